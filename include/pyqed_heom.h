@@ -1,0 +1,145 @@
+/*
+ * pyqed_heom.h - C ABI of the B200-native HEOM/DEOM RK4 propagation path.
+ *
+ * The reference (binggu56/pyqed) has no FFI layer for this path: its boundary is
+ * the Python class API of pyqed/heom/deom.py (DEOMSolver, :953-1114) and
+ * pyqed/HEOM/heom.py (HEOMSolver, :161-205).  The entry points below are what a
+ * ctypes binding inside those classes would call; each one names the reference
+ * code it replaces.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure;
+ *     pyqed_heom_last_error() then describes the failure (thread-local).
+ *   - complex128 is passed as interleaved (re, im) doubles, matrices row-major.
+ *   - "host" pointers are ordinary (or pinned) host memory; "d_" pointers are
+ *     CUDA device memory owned by the caller (e.g. a torch tensor).  The
+ *     library never allocates the large arrays itself.
+ *   - ADO order on the ABI is always the reference's flat id
+ *     (gen_hash_value, deom.py:555-565), whatever the device layout is.
+ *   - no exceptions, no callbacks into the host language; one plan per host
+ *     thread at a time (the reference solver is not re-entrant either).
+ */
+#ifndef PYQED_HEOM_H
+#define PYQED_HEOM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pyqed_heom_plan pyqed_heom_plan;
+
+/* ABI version of this header (bumped on incompatible change). */
+int pyqed_heom_version(void);
+
+/* Message for the last failure on this thread ("" if none). */
+const char* pyqed_heom_last_error(void);
+
+/* nmax = C(lmax + nind, lmax): number of ADOs.  Replaces the Pascal-table
+ * lookup in DEOMSolver.init_ (deom.py:1048-1060).  Returns -1 on overflow or
+ * invalid arguments. */
+int64_t pyqed_heom_hierarchy_size(int nind, int lmax);
+
+/* Create / destroy a plan for an N-level system with K = nind dissipatons
+ * grouped into M = nmod coupling operators, hierarchy depth lmax and `batch`
+ * independent trajectories (batch >= 1; trajectories differ only in their
+ * initial state and field tables).  Replaces DEOMSolver.__init__ / check_
+ * (deom.py:958-1046). */
+int pyqed_heom_plan_create(pyqed_heom_plan** plan, int device, int nsys, int nind,
+                           int nmod, int lmax, int batch);
+void pyqed_heom_plan_destroy(pyqed_heom_plan* plan);
+
+/* System Hamiltonian H and its dipole mu, both N x N complex128 on the host;
+ * H(t) = H + mu * f(t) (generate_time, deom.py:681).  mu may be NULL (= 0).
+ * Replaces set_system / set_system_dipole (deom.py:998-1008). */
+int pyqed_heom_set_system(pyqed_heom_plan* plan, const double* H, const double* mu);
+
+/* Coupling operators Q[M][N][N] and their dipoles; Q_m(t) = Q_m + Qdip_m g(t)
+ * (deom.py:684-686).  Qdip may be NULL.  Replaces set_coupling /
+ * set_coupling_dipole (deom.py:1010-1021). */
+int pyqed_heom_set_coupling(pyqed_heom_plan* plan, const double* Q, const double* Qdip);
+
+/* Bath exponents: expn, etal, etar, etaa complex128[K], mode int64[K] with
+ * values in [0, M).  These are the five attributes the reference solver reads
+ * from its Bath object (deom.py:1040-1041, 1070). */
+int pyqed_heom_set_bath(pyqed_heom_plan* plan, const double* expn, const double* etal,
+                        const double* etar, const double* etaa, const int64_t* mode);
+
+/* ADO storage order on the device: 0 = reference id order (tier-major),
+ * 1 = lexicographic in the multi-index (better gather locality).  Must be
+ * called before pyqed_heom_table_bytes.  Results on the ABI are unaffected. */
+int pyqed_heom_set_order(pyqed_heom_plan* plan, int order);
+
+/* Sizes of the two caller-owned device buffers: the index/coefficient tables
+ * and the ADO state (4 arrays of [batch, nmax, N, N] complex128). */
+int pyqed_heom_table_bytes(pyqed_heom_plan* plan, size_t* bytes);
+int pyqed_heom_state_bytes(pyqed_heom_plan* plan, size_t* bytes);
+
+/* Hand the buffers (256-byte aligned) and a cudaStream_t (as void*, NULL =
+ * default stream) to the plan.  All later calls are enqueued on that stream. */
+int pyqed_heom_bind(pyqed_heom_plan* plan, void* d_tables, size_t table_bytes,
+                    void* d_state, size_t state_bytes, void* stream);
+
+/* Build keys, damping rates and the n+-1 neighbour/coefficient tables on the
+ * device.  Replaces init_ / gen_keys (deom.py:608-638, 1048-1064) and the
+ * per-call hash_plus / hash_minus of generate_dot_element (deom.py:653-661). */
+int pyqed_heom_build_hierarchy(pyqed_heom_plan* plan);
+
+/* keys[nmax][K] (uint8, reference id order) -> host.  DEOMSolver.keys. */
+int pyqed_heom_get_keys(pyqed_heom_plan* plan, uint8_t* keys_host);
+
+/* Zero every ADO and set ADO 0 of trajectory b to rho0[b] (host, [batch][N][N]).
+ * Replaces the allocation block of DEOMSolver.run (deom.py:1084-1092). */
+int pyqed_heom_set_state(pyqed_heom_plan* plan, const double* rho0_host);
+
+/* Whole ADO array [batch][nmax][N][N] host <-> device, reference id order.
+ * get replaces reading DEOMSolver.ddos after run(). */
+int pyqed_heom_load_ados(pyqed_heom_plan* plan, const double* ados_host);
+int pyqed_heom_get_ados(pyqed_heom_plan* plan, double* ados_host);
+
+/* Propagate nt steps of size dt from the current state.
+ *   method 0: classical RK4 with stage times t, t+dt/2, t+dt/2, t+dt
+ *             (rk4, deom.py:725-766; rem_cal / generate_dot_element :641-673)
+ *   method 1: explicit Euler (one stage).
+ * fsys / fcoup: host tables [batch][nt][3] of the pulse functions sampled at
+ * i*dt, i*dt+dt/2, i*dt+dt for every step (NULL = identically zero); they are
+ * what generate_time (deom.py:676-687) would evaluate.
+ * d_traj: device [batch][nt+1][N][N] complex128 or NULL; entry 0 receives the
+ * system density matrix before the first step, entry i+1 after step i
+ * (ddos_save of DEOMSolver.run, deom.py:1094-1113).
+ * Asynchronous on the plan's stream. */
+int pyqed_heom_propagate(pyqed_heom_plan* plan, double dt, int64_t nt, const double* fsys,
+                         const double* fcoup, double* d_traj, int method);
+
+/* Tr(op_e rho) for npts density matrices per trajectory:
+ * d_rho [batch][npts][N][N] (device), ops_host [n_ops][N][N] (host),
+ * d_out [batch][n_ops][npts] complex128 (device).  Replaces
+ * (p1 @ ddos[0]).trace() (deom.py:1104,1113) and obs (superoperator.py:313). */
+int pyqed_heom_expectation(pyqed_heom_plan* plan, const double* d_rho, int64_t npts,
+                           const double* ops_host, int n_ops, double* d_out);
+
+/* Copy `bytes` device<->host on the plan's stream and wait (so a ctypes caller
+ * needs no CUDA runtime binding of its own). */
+int pyqed_heom_memcpy_d2h(pyqed_heom_plan* plan, void* host, const void* dev, size_t bytes);
+int pyqed_heom_memcpy_h2d(pyqed_heom_plan* plan, void* dev, const void* host, size_t bytes);
+int pyqed_heom_synchronize(pyqed_heom_plan* plan);
+
+/* Number of kernels this plan has launched so far (bench.py's gpu_launches),
+ * and CUDA-event timing of the stage kernel accumulated since the last reset:
+ * total milliseconds and launch count (roofline.achieved in bench.py). */
+int64_t pyqed_heom_launch_count(pyqed_heom_plan* plan);
+int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
+                            int64_t* launches);
+
+/* Tuning knobs (0 = library default): kernel 0 auto, 1 row-per-lane kernel
+ * (N <= 8), 2 generic one-CTA-per-ADO kernel; warps per CTA for kernel 1;
+ * use_graph: replay the RK4 step as a CUDA graph. */
+int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
+                          int use_graph);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYQED_HEOM_H */

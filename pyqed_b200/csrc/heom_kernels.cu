@@ -1,0 +1,1153 @@
+// heom_kernels.cu - sm_100a kernels and C ABI for HEOM/DEOM RK4 propagation.
+//
+// What the reference does per RK stage (pyqed/heom/deom.py:641-673, 725-766):
+// for every ADO n, dρ_n/dt = -(Σ n_k γ_k) ρ_n - i[H, ρ_n]
+//        - i Σ_k √n_k/√a_k (η_k Q_m ρ_{n-e_k} - η̄_k ρ_{n-e_k} Q_m)
+//        - i Σ_k √(n_k+1) √a_k [Q_m, ρ_{n+e_k}]
+// followed by separate axpy sweeps.  Here one kernel per stage evaluates the
+// right-hand side and applies the stage update in the same pass:
+//     k = F(y_in);  acc' = (first ? y : acc) + w k;  y_out = y + a k
+// so an RK4 step moves 16 array passes of N*N*16 B per ADO.
+//
+// Layout: ADO arrays are [batch][slot][N][N] complex128, interleaved re/im, so
+// one matrix element is one 128-bit access.  "slot" is the storage order
+// (heom_core.cuh); links hold neighbour slots.
+#include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pyqed_heom.h"
+#include "heom_core.cuh"
+
+using heom::Pascal;
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+#define CU_TRY(expr)                                                                    \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess)                                                          \
+            return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +     \
+                        __FILE__ + ":" + std::to_string(__LINE__) + ")");               \
+    } while (0)
+#define REQUIRE(cond, msg)               \
+    do {                                 \
+        if (!(cond)) return fail(msg);   \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// complex helpers (double2 = re, im)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cfma(double2& acc, const double2 a, const double2 b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfms(double2& acc, const double2 a, const double2 b) {  // acc -= a*b
+    acc.x = fma(-a.x, b.x, acc.x);
+    acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(-a.x, b.y, acc.y);
+    acc.y = fma(-a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct TableLayout {
+    size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
+        ops_t, row_ptr, row_idx, col_ptr, col_idx, step_base, total;
+};
+
+struct pyqed_heom_plan {
+    int device = 0, N = 0, K = 0, M = 0, L = 0, B = 1, order = 0;
+    long long nmax = 0, nlinks = 0;
+    int side = 0;
+    std::vector<long long> pascal;
+    std::vector<std::complex<double>> H, mu, Q, Qd, expn, etal, etar, etaa;
+    std::vector<long long> mode;
+    bool have_sys = false, have_coup = false, have_bath = false, bound = false, built = false;
+    bool mu_nonzero = false, qd_nonzero = false;
+    TableLayout tl{};
+    char* d_tables = nullptr;
+    char* d_state = nullptr;
+    size_t array_bytes = 0;  // one [B][nmax][N][N] array, aligned
+    cudaStream_t stream = nullptr;
+    long long slot0 = 0;  // storage slot of ADO id 0
+    // tuning
+    int kernel = 0, warps = 0, use_graph = 0;
+    // accounting
+    long long launches = 0;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t ev_used = 0;
+    // internal small device buffers for the field tables of one propagate call
+    double* d_fsys = nullptr;
+    double* d_fcoup = nullptr;
+    size_t field_cap = 0;
+    bool debug_sync = false;
+
+    double2* arr(int which) const { return (double2*)(d_state + (size_t)which * array_bytes); }
+    template <typename T> T* tab(size_t off) const { return (T*)(d_tables + off); }
+};
+enum { ARR_Y = 0, ARR_SA = 1, ARR_SB = 2, ARR_ACC = 3 };
+
+static int compute_layout(pyqed_heom_plan* p) {
+    const size_t NN = (size_t)p->N * p->N, M1 = 1 + p->M;
+    TableLayout& t = p->tl;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes);
+        return o;
+    };
+    t.pascal = take(sizeof(long long) * p->side * p->side);
+    t.keys = take((size_t)p->nmax * p->K);
+    t.id_of_slot = take(sizeof(int) * p->nmax);
+    t.slot_of_id = take(sizeof(int) * p->nmax);
+    t.damp = take(sizeof(double2) * p->nmax);
+    t.link_ptr = take(sizeof(int) * (p->nmax + 1));
+    t.links = take(sizeof(int2) * (size_t)std::max(1ll, p->nlinks));
+    t.coef = take(sizeof(double2) * 2 * 2 * p->K * (p->L + 1));
+    t.ops_base = take(sizeof(double2) * M1 * NN);
+    t.ops_dip = take(sizeof(double2) * M1 * NN);
+    t.ops_t = take(sizeof(double2) * (size_t)p->B * M1 * NN);
+    t.row_ptr = take(sizeof(short) * M1 * (p->N + 1));
+    t.row_idx = take(sizeof(short) * M1 * NN);
+    t.col_ptr = take(sizeof(short) * M1 * (p->N + 1));
+    t.col_idx = take(sizeof(short) * M1 * NN);
+    t.step_base = take(sizeof(long long));
+    t.total = off;
+    p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// hierarchy builder kernels
+// ---------------------------------------------------------------------------
+struct HierArgs {
+    const long long* pascal;
+    int side, K, L, order;
+    long long nmax;
+    uint8_t* keys;
+    int* id_of_slot;
+    int* slot_of_id;
+    double2* damp;
+    int* link_ptr;
+    int2* links;
+    const double2* expn;  // [K] device copy (stored at the head of coef scratch)
+    const int* mode;      // [K]
+};
+
+// pass 1: one thread per storage slot - multi-index, damping rate, link count
+__global__ void hier_keys_kernel(HierArgs h) {
+    const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (slot >= h.nmax) return;
+    Pascal P{h.pascal, h.side};
+    uint8_t key[heom::MAX_NIND];
+    heom::unrank_slot(h.order, slot, h.K, h.L, P, key);
+    int tier = 0, nz = 0;
+    double dr = 0.0, di = 0.0;
+    for (int k = 0; k < h.K; ++k) {
+        h.keys[slot * h.K + k] = key[k];
+        tier += key[k];
+        nz += key[k] > 0;
+        const double2 g = h.expn[k];
+        dr += key[k] * g.x;
+        di += key[k] * g.y;
+    }
+    h.damp[slot] = make_double2(dr, di);
+    const long long id = heom::rank_ref(key, h.K, P);
+    h.id_of_slot[slot] = (int)id;
+    h.slot_of_id[id] = (int)slot;
+    h.link_ptr[slot] = nz + (tier < h.L ? h.K : 0);
+    if (slot == 0) h.link_ptr[h.nmax] = 0;
+}
+
+// pass 2: fill links in the reference's summation order (k ascending; for each
+// k the n-e_k term, then the n+e_k term; deom.py:651-664)
+__global__ void hier_links_kernel(HierArgs h) {
+    const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (slot >= h.nmax) return;
+    Pascal P{h.pascal, h.side};
+    uint8_t key[heom::MAX_NIND];
+    int tier = 0;
+    for (int k = 0; k < h.K; ++k) {
+        key[k] = h.keys[slot * h.K + k];
+        tier += key[k];
+    }
+    int w = h.link_ptr[slot];
+    for (int k = 0; k < h.K; ++k) {
+        const int nk = key[k];
+        if (nk > 0) {
+            key[k] = (uint8_t)(nk - 1);
+            const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
+            key[k] = (uint8_t)nk;
+            h.links[w++] = make_int2((int)nb, heom::link_meta(0, k, nk, h.mode[k], h.K, h.L));
+        }
+        if (tier < h.L) {
+            key[k] = (uint8_t)(nk + 1);
+            const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
+            key[k] = (uint8_t)nk;
+            h.links[w++] = make_int2((int)nb, heom::link_meta(1, k, nk + 1, h.mode[k], h.K, h.L));
+        }
+    }
+}
+
+// gather / scatter between storage-slot order and reference id order
+__global__ void permute_kernel(double2* dst, const double2* src, const int* map, long long nmax,
+                               int NN, int dst_is_mapped) {
+    // dst_is_mapped: dst[map[i]] = src[i]   else   dst[i] = src[map[i]]
+    const long long total = nmax * NN;
+    const long long boff = blockIdx.y * total;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / NN;
+        const int r = (int)(e - i * NN);
+        const long long j = map[i];
+        if (dst_is_mapped) dst[boff + j * NN + r] = src[boff + e];
+        else dst[boff + e] = src[boff + j * NN + r];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// time-dependent operators: ops_t[b][o] = base[o] + dip[o] * field_o[b][step][tidx]
+// (generate_time, deom.py:676-687).  Single block; the tables are tiny.
+// ---------------------------------------------------------------------------
+__global__ void prep_ops_kernel(double2* ops_t, const double2* base, const double2* dip,
+                                const double* fsys, const double* fcoup, const long long* step_base,
+                                int local_step, int tidx, long long nt, int B, int M1, int NN) {
+    const long long step = *step_base + local_step;
+    const int per = M1 * NN;
+    for (int e = threadIdx.x; e < B * per; e += blockDim.x) {
+        const int b = e / per, r = e - b * per, o = r / NN;
+        const double* f = (o == 0) ? fsys : fcoup;
+        const double s = f ? f[((long long)b * nt + step) * 3 + tidx] : 0.0;
+        const double2 v = base[r], d = dip[r];
+        ops_t[e] = make_double2(fma(d.x, s, v.x), fma(d.y, s, v.y));
+    }
+}
+
+__global__ void advance_kernel(long long* step_base, long long by) { *step_base += by; }
+
+// rho_sys of every trajectory -> traj[b][index]
+__global__ void record_kernel(double2* traj, const double2* y, long long nmax, long long slot0,
+                              int NN, long long traj_bstride, long long index) {
+    const int b = blockIdx.x;
+    for (int e = threadIdx.x; e < NN; e += blockDim.x)
+        traj[b * traj_bstride + index * NN + e] = y[(b * nmax + slot0) * NN + e];
+}
+
+// out[b][o][p] = Tr(op_o rho[b][p])
+__global__ void expectation_kernel(double2* out, const double2* rho, const double2* ops,
+                                   long long npts, int n_ops, int N) {
+    const long long total = (long long)gridDim.y * n_ops * npts;
+    const int NN = N * N;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_ops * npts;
+         t += (long long)gridDim.x * blockDim.x) {
+        (void)total;
+        const int b = blockIdx.y;
+        const int o = (int)(t / npts);
+        const long long pt = t - (long long)o * npts;
+        const double2* r = rho + ((long long)b * npts + pt) * NN;
+        const double2* a = ops + (long long)o * NN;
+        double2 s = make_double2(0.0, 0.0);
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) cfma(s, a[i * N + j], r[j * N + i]);
+        out[((long long)b * n_ops + o) * npts + pt] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage kernels
+// ---------------------------------------------------------------------------
+struct StageArgs {
+    const double2* yin;   // stage input (read-only in this launch)
+    const double2* y;     // state at the start of the step
+    double2* acc;         // running combination
+    double2* yout;        // next stage input (unused when last)
+    double2* ydst;        // end-of-step state (used when last)
+    const double2* damp;
+    const int* link_ptr;
+    const int2* links;
+    const double2* coef;  // [ci] -> (alphaL, alphaR)
+    const double2* ops;   // [b][1+M][N*N] operators at this stage time
+    long long ops_bstride;
+    const short* row_ptr;
+    const short* row_idx;
+    const short* col_ptr;
+    const short* col_idx;
+    double2* traj;        // may be null
+    const long long* step_base;
+    long long traj_bstride;
+    long long nmax, slot0, ngroups;
+    double a, w;
+    int local_step, first, last, N;
+};
+
+template <int N>
+struct HParam {
+    double2 v[N * N];
+};
+
+// Kernel 1 (N <= 8): a warp owns 32/N consecutive ADOs; lane (sub,row) owns one
+// matrix row in registers.  -i[H,rho] uses H from the constant bank (kernel
+// parameter) or, when H depends on time/trajectory, from shared memory.
+template <int N, bool TDEP>
+__global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
+                                                         const __grid_constant__ HParam<N> hp) {
+    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
+    extern __shared__ double2 smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
+    double2* Hs = smem;
+    double2* rho_s = smem + (TDEP ? NN : 0) + wid * 2 * TILE;
+    double2* k_s = rho_s + TILE;
+    if (TDEP) {
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) Hs[e] = ops[e];
+        __syncthreads();
+    }
+#define HEL(r_, c_) (TDEP ? Hs[(r_) * N + (c_)] : hp.v[(r_) * N + (c_)])
+    const long long boff = (long long)b * a.nmax * NN;
+    const double2* __restrict__ yin = a.yin + boff;
+    const int sub = lane / N, row = lane - sub * N;
+    const bool lane_ok = lane < APW * N;
+    const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
+
+    for (long long g = (long long)blockIdx.x * nwarps + wid; g < a.ngroups;
+         g += (long long)gridDim.x * nwarps) {
+        const long long base = g * APW;
+        const int cnt = (int)min((long long)APW, a.nmax - base);
+        const int nelem = cnt * NN;
+        const double2* src = yin + base * NN;
+        for (int e = lane; e < nelem; e += 32) {
+            const int s = e / NN, r = e - s * NN, i = r / N, j = r - i * N;
+            rho_s[(s * N + i) * LD + j] = ldg2(src + e);
+        }
+        __syncwarp();
+        const bool on = lane_ok && sub < cnt;
+        if (on) {  // column pass: (H rho)[:, row]
+            double2 col[N];
+#pragma unroll
+            for (int l = 0; l < N; ++l) col[l] = rho_s[(sub * N + l) * LD + row];
+#pragma unroll
+            for (int rr = 0; rr < N; ++rr) {
+                double2 c = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int l = 0; l < N; ++l) cfma(c, HEL(rr, l), col[l]);
+                k_s[(sub * N + rr) * LD + row] = c;
+            }
+        }
+        __syncwarp();
+        if (on) {
+            const long long slot = base + sub;
+            double2 r[N];
+            {
+                double2 rv[N];
+#pragma unroll
+                for (int l = 0; l < N; ++l) rv[l] = rho_s[(sub * N + row) * LD + l];
+                const double2 d = a.damp[slot];
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double2 t = k_s[(sub * N + row) * LD + j];
+#pragma unroll
+                    for (int l = 0; l < N; ++l) cfms(t, rv[l], HEL(l, j));
+                    // -i t - damp * rho
+                    r[j] = make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
+                                        -t.x - (d.x * rv[j].y + d.y * rv[j].x));
+                }
+            }
+            const int lend = a.link_ptr[slot + 1];
+            for (int lp = a.link_ptr[slot]; lp < lend; ++lp) {
+                const int2 lk = a.links[lp];
+                const double2* __restrict__ pn = yin + (long long)lk.x * NN;
+                const int ci = heom::meta_ci(lk.y), m1 = 1 + heom::meta_mode(lk.y);
+                const double2 aL = a.coef[2 * ci], aR = a.coef[2 * ci + 1];
+                const double2* __restrict__ Qm = ops + m1 * NN;
+                const short* rp = a.row_ptr + m1 * (N + 1);
+                const short* ri = a.row_idx + m1 * NN;
+                for (int t = rp[row]; t < rp[row + 1]; ++t) {
+                    const int l = ri[t];
+                    const double2 q = cmul(aL, Qm[row * N + l]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) cfma(r[j], q, ldg2(pn + l * N + j));
+                }
+                const short* cp = a.col_ptr + m1 * (N + 1);
+                const short* cidx = a.col_idx + m1 * NN;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    for (int t = cp[j]; t < cp[j + 1]; ++t) {
+                        const int l = cidx[t];
+                        const double2 q = cmul(aR, Qm[l * N + j]);
+                        cfma(r[j], q, ldg2(pn + row * N + l));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < N; ++j) k_s[(sub * N + row) * LD + j] = r[j];
+        }
+        __syncwarp();
+        // flat epilogue: coalesced 128-bit traffic on y / acc / outputs
+        const long long gbase = boff + base * NN;
+        for (int e = lane; e < nelem; e += 32) {
+            const int s = e / NN, rr = e - s * NN, i = rr / N, j = rr - i * N;
+            const int si = (s * N + i) * LD + j;
+            const double2 k = k_s[si];
+            const long long gi = gbase + e;
+            if (a.last) {
+                const double2 bs = a.first ? rho_s[si] : a.acc[gi];
+                const double2 res = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
+                a.ydst[gi] = res;
+                if (a.traj && base + s == a.slot0)
+                    a.traj[b * a.traj_bstride + (step + 1) * NN + rr] = res;
+            } else {
+                const double2 yv = a.first ? rho_s[si] : a.y[gi];
+                const double2 bs = a.first ? yv : a.acc[gi];
+                a.acc[gi] = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
+                a.yout[gi] = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
+            }
+        }
+        __syncwarp();
+    }
+#undef HEL
+}
+
+// Kernel 2 (any N): one CTA per ADO, one thread per matrix element (strided);
+// all operators (H and Q_m) go through their sparsity lists, so cost scales
+// with nnz.  rho_n is staged in shared memory; neighbours are read through L2.
+__global__ void __launch_bounds__(256) stage_generic_kernel(const StageArgs a) {
+    extern __shared__ double2 smem[];
+    const int N = a.N, NN = N * N;
+    double2* rho_s = smem;
+    const int b = blockIdx.y;
+    const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
+    const long long boff = (long long)b * a.nmax * NN;
+    const double2* __restrict__ yin = a.yin + boff;
+    const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
+    for (long long slot = blockIdx.x; slot < a.nmax; slot += gridDim.x) {
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) rho_s[e] = ldg2(yin + slot * NN + e);
+        __syncthreads();
+        const double2 d = a.damp[slot];
+        const int lbeg = a.link_ptr[slot], lend = a.link_ptr[slot + 1];
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+            const int i = e / N, j = e - i * N;
+            const double2 own = rho_s[e];
+            double2 v = make_double2(-(d.x * own.x - d.y * own.y), -(d.x * own.y + d.y * own.x));
+            {   // -i (H rho - rho H)
+                const short* rp = a.row_ptr;
+                for (int t = rp[i]; t < rp[i + 1]; ++t) {
+                    const int l = a.row_idx[t];
+                    const double2 h = ops[i * N + l];
+                    cfma(v, make_double2(h.y, -h.x), rho_s[l * N + j]);
+                }
+                const short* cp = a.col_ptr;
+                for (int t = cp[j]; t < cp[j + 1]; ++t) {
+                    const int l = a.col_idx[t];
+                    const double2 h = ops[l * N + j];
+                    cfma(v, make_double2(-h.y, h.x), rho_s[i * N + l]);
+                }
+            }
+            for (int lp = lbeg; lp < lend; ++lp) {
+                const int2 lk = a.links[lp];
+                const double2* __restrict__ pn = yin + (long long)lk.x * NN;
+                const int ci = heom::meta_ci(lk.y), m1 = 1 + heom::meta_mode(lk.y);
+                const double2 aL = a.coef[2 * ci], aR = a.coef[2 * ci + 1];
+                const double2* __restrict__ Qm = ops + m1 * NN;
+                const short* rp = a.row_ptr + m1 * (N + 1);
+                const short* ri = a.row_idx + m1 * NN;
+                double2 sl = make_double2(0.0, 0.0), sr = make_double2(0.0, 0.0);
+                for (int t = rp[i]; t < rp[i + 1]; ++t) {
+                    const int l = ri[t];
+                    cfma(sl, Qm[i * N + l], ldg2(pn + l * N + j));
+                }
+                const short* cp = a.col_ptr + m1 * (N + 1);
+                const short* cidx = a.col_idx + m1 * NN;
+                for (int t = cp[j]; t < cp[j + 1]; ++t) {
+                    const int l = cidx[t];
+                    cfma(sr, Qm[l * N + j], ldg2(pn + i * N + l));
+                }
+                cfma(v, aL, sl);
+                cfma(v, aR, sr);
+            }
+            const long long gi = boff + slot * NN + e;
+            if (a.last) {
+                const double2 bs = a.first ? own : a.acc[gi];
+                const double2 res = make_double2(fma(a.w, v.x, bs.x), fma(a.w, v.y, bs.y));
+                a.ydst[gi] = res;
+                if (a.traj && slot == a.slot0)
+                    a.traj[b * a.traj_bstride + (step + 1) * NN + e] = res;
+            } else {
+                const double2 yv = a.first ? own : a.y[gi];
+                const double2 bs = a.first ? yv : a.acc[gi];
+                a.acc[gi] = make_double2(fma(a.w, v.x, bs.x), fma(a.w, v.y, bs.y));
+                a.yout[gi] = make_double2(fma(a.a, v.x, yv.x), fma(a.a, v.y, yv.y));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int post_launch(pyqed_heom_plan* p, const char* what) {
+    p->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string(what) + " launch: " + cudaGetErrorString(e));
+    if (p->debug_sync) {
+        e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) return fail(std::string(what) + " exec: " + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+template <int N, bool TDEP>
+static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
+    constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
+    StageArgs args = a;
+    args.ngroups = (p->nmax + APW - 1) / APW;
+    int warps = p->warps > 0 ? std::min(p->warps, 8) : 8;
+    if (p->warps <= 0) {
+        // small hierarchies: prefer more CTAs over fuller CTAs
+        while (warps > 1 && args.ngroups * p->B < (long long)warps * sm_count * 2) warps >>= 1;
+    }
+    const size_t smem = sizeof(double2) * ((TDEP ? N * N : 0) + (size_t)warps * 2 * TILE);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(cudaFuncSetAttribute(stage_rows_kernel<N, TDEP>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        attr_set = true;
+    }
+    long long ctas = (args.ngroups + warps - 1) / warps;
+    const long long cap = (long long)sm_count * 16;
+    dim3 grid((unsigned)std::min(ctas, cap), p->B);
+    HParam<N> hp;
+    for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
+    stage_rows_kernel<N, TDEP><<<grid, warps * 32, smem, p->stream>>>(args, hp);
+    return post_launch(p, "stage_rows_kernel");
+}
+
+static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
+    static int sm_count = 0;
+    if (!sm_count) {
+        CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    }
+    if (p->timing) {
+        if (p->ev_used == p->ev.size()) {
+            cudaEvent_t e0, e1;
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            p->ev.emplace_back(e0, e1);
+        }
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].first, p->stream));
+    }
+    int rc = 0;
+    const int kern = p->kernel ? p->kernel : (p->N <= 8 ? 1 : 2);
+    if (kern == 1) {
+        REQUIRE(p->N >= 2 && p->N <= 8, "kernel 1 needs 2 <= N <= 8");
+#define ROWS_CASE(n)                                                                       \
+    case n:                                                                                \
+        rc = tdep ? launch_rows<n, true>(p, a, sm_count) : launch_rows<n, false>(p, a, sm_count); \
+        break;
+        switch (p->N) {
+            ROWS_CASE(2) ROWS_CASE(3) ROWS_CASE(4) ROWS_CASE(5) ROWS_CASE(6) ROWS_CASE(7) ROWS_CASE(8)
+        }
+#undef ROWS_CASE
+    } else {
+        const int NN = p->N * p->N;
+        int threads = std::min(256, (NN + 31) / 32 * 32);
+        const size_t smem = sizeof(double2) * NN;
+        REQUIRE(smem <= 48 * 1024, "N too large for the generic kernel (N <= 55)");
+        dim3 grid((unsigned)std::min(p->nmax, (long long)sm_count * 32), p->B);
+        stage_generic_kernel<<<grid, threads, smem, p->stream>>>(a);
+        rc = post_launch(p, "stage_generic_kernel");
+    }
+    if (rc) return rc;
+    if (p->timing) {
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].second, p->stream));
+        p->ev_used++;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int pyqed_heom_version(void) { return 1; }
+const char* pyqed_heom_last_error(void) { return g_err.c_str(); }
+
+static bool build_pascal(int side, std::vector<long long>& tab) {
+    tab.assign((size_t)side * side, 0);
+    const long long SAT = (1ll << 62);
+    for (int a = 0; a < side; ++a) {
+        tab[(size_t)a * side] = 1;
+        for (int b = 1; b <= a; ++b) {
+            long long x = tab[(size_t)(a - 1) * side + b - 1] + (b <= a - 1 ? tab[(size_t)(a - 1) * side + b] : 0);
+            tab[(size_t)a * side + b] = x > SAT ? SAT : x;
+        }
+    }
+    return true;
+}
+
+int64_t pyqed_heom_hierarchy_size(int nind, int lmax) {
+    if (nind < 1 || lmax < 0 || nind > heom::MAX_NIND || nind + lmax + 1 > heom::MAX_SIDE) return -1;
+    std::vector<long long> tab;
+    build_pascal(nind + lmax + 1, tab);
+    const long long v = tab[(size_t)(lmax + nind) * (nind + lmax + 1) + lmax];
+    return v >= (1ll << 31) ? -1 : v;
+}
+
+int pyqed_heom_plan_create(pyqed_heom_plan** out, int device, int nsys, int nind, int nmod,
+                           int lmax, int batch) {
+    REQUIRE(out, "plan pointer is null");
+    REQUIRE(nsys >= 1 && nsys <= 55, "nsys must be in [1, 55]");
+    REQUIRE(nind >= 1 && nind <= heom::MAX_NIND, "nind must be in [1, 64]");
+    REQUIRE(nmod >= 1 && nmod <= 127, "nmod must be in [1, 127]");
+    REQUIRE(lmax >= 0 && lmax <= 255 && nind + lmax + 1 <= heom::MAX_SIDE, "lmax out of range");
+    REQUIRE(batch >= 1 && batch <= 65535, "batch must be in [1, 65535]");
+    const int64_t nmax = pyqed_heom_hierarchy_size(nind, lmax);
+    REQUIRE(nmax > 0, "hierarchy too large (nmax must be < 2^31)");
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+    CU_TRY(cudaSetDevice(device));
+    auto* p = new pyqed_heom_plan();
+    p->device = device;
+    p->N = nsys;
+    p->K = nind;
+    p->M = nmod;
+    p->L = lmax;
+    p->B = batch;
+    p->nmax = nmax;
+    p->side = nind + lmax + 1;
+    build_pascal(p->side, p->pascal);
+    // links: every n+e_k edge appears once as a "plus" and once as a "minus" link
+    const long long below = lmax >= 1 ? p->pascal[(size_t)(lmax - 1 + nind) * p->side + nind] : 0;
+    p->nlinks = 2ll * nind * below;
+    if (p->nlinks >= (1ll << 31)) {
+        delete p;
+        return fail("too many links for 32-bit offsets");
+    }
+    const char* dbg = getenv("PYQED_HEOM_DEBUG");
+    p->debug_sync = dbg && dbg[0] == '1';
+    *out = p;
+    return 0;
+}
+
+void pyqed_heom_plan_destroy(pyqed_heom_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (auto& e : p->ev) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (p->d_fsys) cudaFree(p->d_fsys);
+    if (p->d_fcoup) cudaFree(p->d_fcoup);
+    delete p;
+}
+
+static void to_complex(std::vector<std::complex<double>>& dst, const double* src, size_t n) {
+    dst.resize(n);
+    for (size_t i = 0; i < n; ++i)
+        dst[i] = src ? std::complex<double>(src[2 * i], src[2 * i + 1]) : std::complex<double>(0, 0);
+}
+static bool any_nonzero(const std::vector<std::complex<double>>& v) {
+    for (auto& x : v)
+        if (x != std::complex<double>(0, 0)) return true;
+    return false;
+}
+
+int pyqed_heom_set_system(pyqed_heom_plan* p, const double* H, const double* mu) {
+    REQUIRE(p && H, "set_system: null argument");
+    const size_t NN = (size_t)p->N * p->N;
+    to_complex(p->H, H, NN);
+    to_complex(p->mu, mu, NN);
+    p->mu_nonzero = any_nonzero(p->mu);
+    p->have_sys = true;
+    p->built = false;
+    return 0;
+}
+
+int pyqed_heom_set_coupling(pyqed_heom_plan* p, const double* Q, const double* Qdip) {
+    REQUIRE(p && Q, "set_coupling: null argument");
+    const size_t n = (size_t)p->M * p->N * p->N;
+    to_complex(p->Q, Q, n);
+    to_complex(p->Qd, Qdip, n);
+    p->qd_nonzero = any_nonzero(p->Qd);
+    p->have_coup = true;
+    p->built = false;
+    return 0;
+}
+
+int pyqed_heom_set_bath(pyqed_heom_plan* p, const double* expn, const double* etal,
+                        const double* etar, const double* etaa, const int64_t* mode) {
+    REQUIRE(p && expn && etal && etar && etaa && mode, "set_bath: null argument");
+    to_complex(p->expn, expn, p->K);
+    to_complex(p->etal, etal, p->K);
+    to_complex(p->etar, etar, p->K);
+    to_complex(p->etaa, etaa, p->K);
+    p->mode.assign(mode, mode + p->K);
+    for (int k = 0; k < p->K; ++k)
+        REQUIRE(p->mode[k] >= 0 && p->mode[k] < p->M, "set_bath: mode index out of range");
+    p->have_bath = true;
+    p->built = false;
+    return 0;
+}
+
+int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
+    REQUIRE(p, "null plan");
+    REQUIRE(order == 0 || order == 1, "order must be 0 (reference) or 1 (lexicographic)");
+    REQUIRE(!p->bound, "set_order must precede bind");
+    p->order = order;
+    return 0;
+}
+
+int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
+    REQUIRE(p, "null plan");
+    REQUIRE(kernel >= 0 && kernel <= 2, "kernel must be 0, 1 or 2");
+    REQUIRE(warps >= 0 && warps <= 8, "warps_per_cta must be in [0, 8]");
+    p->kernel = kernel;
+    p->warps = warps;
+    p->use_graph = use_graph;
+    return 0;
+}
+
+int pyqed_heom_table_bytes(pyqed_heom_plan* p, size_t* bytes) {
+    REQUIRE(p && bytes, "null argument");
+    compute_layout(p);
+    *bytes = p->tl.total;
+    return 0;
+}
+int pyqed_heom_state_bytes(pyqed_heom_plan* p, size_t* bytes) {
+    REQUIRE(p && bytes, "null argument");
+    compute_layout(p);
+    *bytes = 4 * p->array_bytes;
+    return 0;
+}
+
+int pyqed_heom_bind(pyqed_heom_plan* p, void* d_tables, size_t table_bytes, void* d_state,
+                    size_t state_bytes, void* stream) {
+    REQUIRE(p && d_tables && d_state, "bind: null argument");
+    compute_layout(p);
+    REQUIRE(table_bytes >= p->tl.total, "bind: table buffer too small");
+    REQUIRE(state_bytes >= 4 * p->array_bytes, "bind: state buffer too small");
+    REQUIRE(((uintptr_t)d_tables % 256) == 0 && ((uintptr_t)d_state % 256) == 0,
+            "bind: buffers must be 256-byte aligned");
+    p->d_tables = (char*)d_tables;
+    p->d_state = (char*)d_state;
+    p->stream = (cudaStream_t)stream;
+    p->bound = true;
+    p->built = false;
+    return 0;
+}
+
+// sparsity lists of operator o (union of the static and the dipole pattern)
+static void sparsity(const pyqed_heom_plan* p, int o, std::vector<short>& row_ptr,
+                     std::vector<short>& row_idx, std::vector<short>& col_ptr,
+                     std::vector<short>& col_idx) {
+    const int N = p->N, NN = N * N;
+    const std::complex<double>* base = o == 0 ? p->H.data() : p->Q.data() + (size_t)(o - 1) * NN;
+    const std::complex<double>* dip = o == 0 ? p->mu.data() : p->Qd.data() + (size_t)(o - 1) * NN;
+    auto nz = [&](int i, int j) {
+        return base[i * N + j] != std::complex<double>(0, 0) ||
+               dip[i * N + j] != std::complex<double>(0, 0);
+    };
+    row_ptr.assign(N + 1, 0);
+    col_ptr.assign(N + 1, 0);
+    row_idx.assign(NN, 0);
+    col_idx.assign(NN, 0);
+    int w = 0;
+    for (int i = 0; i < N; ++i) {
+        row_ptr[i] = (short)w;
+        for (int l = 0; l < N; ++l)
+            if (nz(i, l)) row_idx[w++] = (short)l;
+    }
+    row_ptr[N] = (short)w;
+    w = 0;
+    for (int j = 0; j < N; ++j) {
+        col_ptr[j] = (short)w;
+        for (int l = 0; l < N; ++l)
+            if (nz(l, j)) col_idx[w++] = (short)l;
+    }
+    col_ptr[N] = (short)w;
+}
+
+int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
+    REQUIRE(p && p->bound, "build_hierarchy: bind the buffers first");
+    REQUIRE(p->have_sys && p->have_coup && p->have_bath,
+            "build_hierarchy: system, coupling and bath must be set");
+    CU_TRY(cudaSetDevice(p->device));
+    const int N = p->N, NN = N * N, K = p->K, L = p->L, M1 = 1 + p->M;
+    const TableLayout& t = p->tl;
+    cudaStream_t s = p->stream;
+    // small host-built tables -------------------------------------------------
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.pascal, p->pascal.data(),
+                           sizeof(long long) * p->pascal.size(), cudaMemcpyHostToDevice, s));
+    // coefficient pairs (alphaL, alphaR) per (dir, k, n_eff); generate_dot_element,
+    // deom.py:656-664: minus: -i sqrt(n)/sqrt(a) (eta_l Q rho - eta_r rho Q)
+    //                  plus : -i sqrt(n+1) sqrt(a) (Q rho - rho Q)
+    std::vector<double> coef((size_t)2 * 2 * 2 * K * (L + 1), 0.0);
+    const std::complex<double> I(0, 1);
+    for (int k = 0; k < K; ++k) {
+        const std::complex<double> sa = std::sqrt(p->etaa[k]);
+        for (int n = 1; n <= L; ++n) {
+            const std::complex<double> cm = I * std::sqrt((double)n) / sa;
+            const std::complex<double> cp = I * std::sqrt((double)n) * sa;
+            const std::complex<double> vals[2][2] = {{-cm * p->etal[k], cm * p->etar[k]}, {-cp, cp}};
+            for (int dir = 0; dir < 2; ++dir) {
+                const size_t ci = ((size_t)dir * K + k) * (L + 1) + n;
+                coef[4 * ci + 0] = vals[dir][0].real();
+                coef[4 * ci + 1] = vals[dir][0].imag();
+                coef[4 * ci + 2] = vals[dir][1].real();
+                coef[4 * ci + 3] = vals[dir][1].imag();
+            }
+        }
+    }
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.coef, coef.data(), sizeof(double) * coef.size(),
+                           cudaMemcpyHostToDevice, s));
+    // operators and their sparsity lists
+    std::vector<double> base((size_t)M1 * NN * 2), dip((size_t)M1 * NN * 2);
+    std::vector<short> rp((size_t)M1 * (N + 1)), ri((size_t)M1 * NN), cp((size_t)M1 * (N + 1)),
+        cidx((size_t)M1 * NN);
+    for (int o = 0; o < M1; ++o) {
+        const std::complex<double>* bsrc = o == 0 ? p->H.data() : p->Q.data() + (size_t)(o - 1) * NN;
+        const std::complex<double>* dsrc = o == 0 ? p->mu.data() : p->Qd.data() + (size_t)(o - 1) * NN;
+        for (int e = 0; e < NN; ++e) {
+            base[((size_t)o * NN + e) * 2] = bsrc[e].real();
+            base[((size_t)o * NN + e) * 2 + 1] = bsrc[e].imag();
+            dip[((size_t)o * NN + e) * 2] = dsrc[e].real();
+            dip[((size_t)o * NN + e) * 2 + 1] = dsrc[e].imag();
+        }
+        std::vector<short> a, b, c, d;
+        sparsity(p, o, a, b, c, d);
+        std::copy(a.begin(), a.end(), rp.begin() + (size_t)o * (N + 1));
+        std::copy(b.begin(), b.end(), ri.begin() + (size_t)o * NN);
+        std::copy(c.begin(), c.end(), cp.begin() + (size_t)o * (N + 1));
+        std::copy(d.begin(), d.end(), cidx.begin() + (size_t)o * NN);
+    }
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.ops_base, base.data(), sizeof(double) * base.size(),
+                           cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.ops_dip, dip.data(), sizeof(double) * dip.size(),
+                           cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.row_ptr, rp.data(), sizeof(short) * rp.size(),
+                           cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.row_idx, ri.data(), sizeof(short) * ri.size(),
+                           cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.col_ptr, cp.data(), sizeof(short) * cp.size(),
+                           cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.col_idx, cidx.data(), sizeof(short) * cidx.size(),
+                           cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemsetAsync(p->d_tables + t.step_base, 0, sizeof(long long), s));
+    // expn and mode for the builder kernels: staged in ops_t (rebuilt before use)
+    std::vector<double> ex(2 * K);
+    std::vector<int> md(K);
+    for (int k = 0; k < K; ++k) {
+        ex[2 * k] = p->expn[k].real();
+        ex[2 * k + 1] = p->expn[k].imag();
+        md[k] = (int)p->mode[k];
+    }
+    double2* d_expn = nullptr;
+    int* d_mode = nullptr;
+    CU_TRY(cudaMalloc(&d_expn, sizeof(double2) * K));
+    CU_TRY(cudaMalloc(&d_mode, sizeof(int) * K));
+    CU_TRY(cudaMemcpyAsync(d_expn, ex.data(), sizeof(double) * ex.size(), cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(d_mode, md.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));  // host vectors above go out of scope
+    // device-built tables -------------------------------------------------------
+    HierArgs h;
+    h.pascal = p->tab<long long>(t.pascal);
+    h.side = p->side;
+    h.K = K;
+    h.L = L;
+    h.order = p->order;
+    h.nmax = p->nmax;
+    h.keys = p->tab<uint8_t>(t.keys);
+    h.id_of_slot = p->tab<int>(t.id_of_slot);
+    h.slot_of_id = p->tab<int>(t.slot_of_id);
+    h.damp = p->tab<double2>(t.damp);
+    h.link_ptr = p->tab<int>(t.link_ptr);
+    h.links = p->tab<int2>(t.links);
+    h.expn = d_expn;
+    h.mode = d_mode;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((p->nmax + threads - 1) / threads);
+    hier_keys_kernel<<<blocks, threads, 0, s>>>(h);
+    if (post_launch(p, "hier_keys_kernel")) return 1;
+    size_t tmp_bytes = 0;
+    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h.link_ptr, h.link_ptr,
+                                         (int)(p->nmax + 1), s));
+    void* d_tmp = nullptr;
+    CU_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, h.link_ptr, h.link_ptr,
+                                         (int)(p->nmax + 1), s));
+    p->launches++;
+    hier_links_kernel<<<blocks, threads, 0, s>>>(h);
+    if (post_launch(p, "hier_links_kernel")) return 1;
+    int total_links = 0, slot0 = 0;
+    CU_TRY(cudaMemcpyAsync(&total_links, h.link_ptr + p->nmax, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaMemcpyAsync(&slot0, h.slot_of_id, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    cudaFree(d_tmp);
+    cudaFree(d_expn);
+    cudaFree(d_mode);
+    REQUIRE(total_links == p->nlinks, "hierarchy builder: link count mismatch (" +
+                                          std::to_string(total_links) + " vs " +
+                                          std::to_string(p->nlinks) + ")");
+    p->slot0 = slot0;
+    p->built = true;
+    return 0;
+}
+
+int pyqed_heom_get_keys(pyqed_heom_plan* p, uint8_t* keys_host) {
+    REQUIRE(p && p->built && keys_host, "get_keys: build the hierarchy first");
+    CU_TRY(cudaSetDevice(p->device));
+    const size_t bytes = (size_t)p->nmax * p->K;
+    std::vector<uint8_t> slot_keys(bytes);
+    std::vector<int> ids(p->nmax);
+    CU_TRY(cudaMemcpyAsync(slot_keys.data(), p->d_tables + p->tl.keys, bytes, cudaMemcpyDeviceToHost,
+                           p->stream));
+    CU_TRY(cudaMemcpyAsync(ids.data(), p->d_tables + p->tl.id_of_slot, sizeof(int) * p->nmax,
+                           cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    for (long long sidx = 0; sidx < p->nmax; ++sidx)
+        memcpy(keys_host + (size_t)ids[sidx] * p->K, slot_keys.data() + (size_t)sidx * p->K, p->K);
+    return 0;
+}
+
+int pyqed_heom_set_state(pyqed_heom_plan* p, const double* rho0_host) {
+    REQUIRE(p && p->built && rho0_host, "set_state: build the hierarchy first");
+    CU_TRY(cudaSetDevice(p->device));
+    const size_t NN = (size_t)p->N * p->N;
+    CU_TRY(cudaMemsetAsync(p->d_state, 0, 4 * p->array_bytes, p->stream));
+    CU_TRY(cudaMemcpy2DAsync(p->arr(ARR_Y) + (size_t)p->slot0 * NN, sizeof(double2) * p->nmax * NN,
+                             rho0_host, sizeof(double2) * NN, sizeof(double2) * NN, p->B,
+                             cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+static int permute(pyqed_heom_plan* p, double2* dst, const double2* src, bool to_id_order) {
+    const int NN = p->N * p->N;
+    const long long total = p->nmax * NN;
+    dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 148 * 32), p->B);
+    // to id order:   dst[id] = src[slot_of_id[id]]  (gather through slot_of_id)
+    // to slot order: dst[slot] = src[id_of_slot[slot]]
+    const int* map = p->tab<int>(to_id_order ? p->tl.slot_of_id : p->tl.id_of_slot);
+    permute_kernel<<<grid, 256, 0, p->stream>>>(dst, src, map, p->nmax, NN, 0);
+    return post_launch(p, "permute_kernel");
+}
+
+int pyqed_heom_load_ados(pyqed_heom_plan* p, const double* ados_host) {
+    REQUIRE(p && p->built && ados_host, "load_ados: build the hierarchy first");
+    CU_TRY(cudaSetDevice(p->device));
+    const size_t bytes = sizeof(double2) * (size_t)p->B * p->nmax * p->N * p->N;
+    if (p->order == 0) {
+        CU_TRY(cudaMemcpyAsync(p->arr(ARR_Y), ados_host, bytes, cudaMemcpyHostToDevice, p->stream));
+    } else {
+        CU_TRY(cudaMemcpyAsync(p->arr(ARR_ACC), ados_host, bytes, cudaMemcpyHostToDevice, p->stream));
+        if (permute(p, p->arr(ARR_Y), p->arr(ARR_ACC), false)) return 1;
+    }
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int pyqed_heom_get_ados(pyqed_heom_plan* p, double* ados_host) {
+    REQUIRE(p && p->built && ados_host, "get_ados: build the hierarchy first");
+    CU_TRY(cudaSetDevice(p->device));
+    const size_t bytes = sizeof(double2) * (size_t)p->B * p->nmax * p->N * p->N;
+    const double2* src = p->arr(ARR_Y);
+    if (p->order != 0) {
+        if (permute(p, p->arr(ARR_ACC), p->arr(ARR_Y), true)) return 1;
+        src = p->arr(ARR_ACC);
+    }
+    CU_TRY(cudaMemcpyAsync(ados_host, src, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+static int upload_fields(pyqed_heom_plan* p, const double* fsys, const double* fcoup, long long nt) {
+    const size_t n = (size_t)p->B * nt * 3;
+    if (n > p->field_cap) {
+        if (p->d_fsys) cudaFree(p->d_fsys);
+        if (p->d_fcoup) cudaFree(p->d_fcoup);
+        p->d_fsys = p->d_fcoup = nullptr;
+        CU_TRY(cudaMalloc(&p->d_fsys, sizeof(double) * n));
+        CU_TRY(cudaMalloc(&p->d_fcoup, sizeof(double) * n));
+        p->field_cap = n;
+    }
+    if (fsys)
+        CU_TRY(cudaMemcpyAsync(p->d_fsys, fsys, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+    if (fcoup)
+        CU_TRY(cudaMemcpyAsync(p->d_fcoup, fcoup, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+    return 0;
+}
+
+int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double* fsys,
+                         const double* fcoup, double* d_traj, int method) {
+    REQUIRE(p && p->built, "propagate: build the hierarchy first");
+    REQUIRE(nt >= 0, "propagate: nt must be >= 0");
+    REQUIRE(method == 0 || method == 1, "propagate: method must be 0 (rk4) or 1 (euler)");
+    CU_TRY(cudaSetDevice(p->device));
+    const int N = p->N, NN = N * N, M1 = 1 + p->M;
+    const TableLayout& t = p->tl;
+    const bool use_fs = fsys && p->mu_nonzero, use_fc = fcoup && p->qd_nonzero;
+    const bool tdep = use_fs || use_fc;
+    if (tdep) {
+        if (upload_fields(p, use_fs ? fsys : nullptr, use_fc ? fcoup : nullptr, nt)) return 1;
+    }
+    CU_TRY(cudaMemsetAsync(p->d_tables + t.step_base, 0, sizeof(long long), p->stream));
+    double2* traj = (double2*)d_traj;
+    const long long traj_bstride = (long long)(nt + 1) * NN;
+    if (traj) {
+        record_kernel<<<p->B, 64, 0, p->stream>>>(traj, p->arr(ARR_Y), p->nmax, p->slot0, NN,
+                                                  traj_bstride, 0);
+        if (post_launch(p, "record_kernel")) return 1;
+    }
+    StageArgs a;
+    memset(&a, 0, sizeof(a));
+    a.damp = p->tab<double2>(t.damp);
+    a.link_ptr = p->tab<int>(t.link_ptr);
+    a.links = p->tab<int2>(t.links);
+    a.coef = p->tab<double2>(t.coef);
+    a.ops = p->tab<double2>(tdep ? t.ops_t : t.ops_base);
+    a.ops_bstride = tdep ? (long long)M1 * NN : 0;
+    a.row_ptr = p->tab<short>(t.row_ptr);
+    a.row_idx = p->tab<short>(t.row_idx);
+    a.col_ptr = p->tab<short>(t.col_ptr);
+    a.col_idx = p->tab<short>(t.col_idx);
+    a.traj = traj;
+    a.step_base = p->tab<long long>(t.step_base);
+    a.traj_bstride = traj_bstride;
+    a.nmax = p->nmax;
+    a.slot0 = p->slot0;
+    a.N = N;
+    double2 *Y = p->arr(ARR_Y), *SA = p->arr(ARR_SA), *SB = p->arr(ARR_SB), *ACC = p->arr(ARR_ACC);
+
+    auto prep = [&](int local_step, int tidx) -> int {
+        if (!tdep) return 0;
+        prep_ops_kernel<<<1, 256, 0, p->stream>>>(
+            p->tab<double2>(t.ops_t), p->tab<double2>(t.ops_base), p->tab<double2>(t.ops_dip),
+            use_fs ? p->d_fsys : nullptr, use_fc ? p->d_fcoup : nullptr, a.step_base, local_step,
+            tidx, nt, p->B, M1, NN);
+        return post_launch(p, "prep_ops_kernel");
+    };
+    auto stage = [&](const double2* yin, double2* yout, double2* ydst, double ac, double wc,
+                     int first, int last, int local_step) -> int {
+        StageArgs s = a;
+        s.yin = yin;
+        s.y = Y;
+        s.acc = ACC;
+        s.yout = yout;
+        s.ydst = ydst;
+        s.a = ac;
+        s.w = wc;
+        s.first = first;
+        s.last = last;
+        s.local_step = local_step;
+        return launch_stage(p, s, tdep);
+    };
+
+    if (method == 0) {
+        for (int64_t i = 0; i < nt; ++i) {
+            const int ls = (int)i;
+            if (prep(ls, 0) || stage(Y, SA, nullptr, dt / 2, dt / 6, 1, 0, ls)) return 1;
+            if (prep(ls, 1) || stage(SA, SB, nullptr, dt / 2, dt / 3, 0, 0, ls)) return 1;
+            if (stage(SB, SA, nullptr, dt, dt / 3, 0, 0, ls)) return 1;
+            if (prep(ls, 2) || stage(SA, nullptr, Y, 0.0, dt / 6, 0, 1, ls)) return 1;
+        }
+    } else {
+        // explicit Euler: y' = y + dt F(y); ping-pong through SA so that no CTA
+        // reads a neighbour that another CTA has already advanced
+        for (int64_t i = 0; i < nt; ++i) {
+            const int ls = (int)i;
+            if (prep(ls, 0) || stage(Y, nullptr, SA, 0.0, dt, 1, 1, ls)) return 1;
+            CU_TRY(cudaMemcpyAsync(Y, SA, sizeof(double2) * (size_t)p->B * p->nmax * NN,
+                                   cudaMemcpyDeviceToDevice, p->stream));
+        }
+    }
+    return 0;
+}
+
+int pyqed_heom_expectation(pyqed_heom_plan* p, const double* d_rho, int64_t npts,
+                           const double* ops_host, int n_ops, double* d_out) {
+    REQUIRE(p && d_rho && ops_host && d_out && n_ops >= 1 && npts >= 1, "expectation: bad argument");
+    CU_TRY(cudaSetDevice(p->device));
+    const size_t NN = (size_t)p->N * p->N;
+    double2* d_ops = nullptr;
+    CU_TRY(cudaMalloc(&d_ops, sizeof(double2) * n_ops * NN));
+    CU_TRY(cudaMemcpyAsync(d_ops, ops_host, sizeof(double2) * n_ops * NN, cudaMemcpyHostToDevice,
+                           p->stream));
+    dim3 grid((unsigned)std::min<long long>(((long long)n_ops * npts + 127) / 128, 4096), p->B);
+    expectation_kernel<<<grid, 128, 0, p->stream>>>((double2*)d_out, (const double2*)d_rho, d_ops,
+                                                    npts, n_ops, p->N);
+    int rc = post_launch(p, "expectation_kernel");
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    cudaFree(d_ops);
+    return rc;
+}
+
+int pyqed_heom_memcpy_d2h(pyqed_heom_plan* p, void* host, const void* dev, size_t bytes) {
+    REQUIRE(p && host && dev, "memcpy_d2h: null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+int pyqed_heom_memcpy_h2d(pyqed_heom_plan* p, void* dev, const void* host, size_t bytes) {
+    REQUIRE(p && host && dev, "memcpy_h2d: null argument");
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+int pyqed_heom_synchronize(pyqed_heom_plan* p) {
+    REQUIRE(p, "null plan");
+    CU_TRY(cudaSetDevice(p->device));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+int64_t pyqed_heom_launch_count(pyqed_heom_plan* p) { return p ? p->launches : -1; }
+
+int pyqed_heom_stage_timing(pyqed_heom_plan* p, int enable, double* total_ms, int64_t* launches) {
+    REQUIRE(p, "null plan");
+    CU_TRY(cudaSetDevice(p->device));
+    if (total_ms || launches) {
+        CU_TRY(cudaStreamSynchronize(p->stream));
+        double tot = 0.0;
+        for (size_t i = 0; i < p->ev_used; ++i) {
+            float ms = 0.f;
+            CU_TRY(cudaEventElapsedTime(&ms, p->ev[i].first, p->ev[i].second));
+            tot += ms;
+        }
+        if (total_ms) *total_ms = tot;
+        if (launches) *launches = (int64_t)p->ev_used;
+    }
+    p->ev_used = 0;
+    p->timing = enable != 0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):
+
+    python tests/golden/make_golden.py
+
+The reference cannot be imported as a package here, so
+the three entry points on the path are loaded by file:
+
+* ``pyqed/heom/deom.py``  -> ``DEOMSolver``, ``Bath``, decompositions (spec loader)
+* ``pyqed/HEOM/heom.py``  -> ``_heom`` RK4 chain  (AST-extracted, helpers from phys.py)
+* ``pyqed/oqs.py``        -> ``_heom`` Euler chain (AST-extracted)
+
+Nothing from the reference is written into the repo except its numerical
+outputs.  Inputs come from ``pyqed_b200.workloads`` so that the oracle, the
+CUDA path and the reference all see the same arrays; the inputs are stored in
+each fixture too, so the tests do not depend on the builders staying unchanged.
+"""
+from __future__ import annotations
+
+import ast
+import importlib.util
+import io
+import contextlib
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+from pyqed_b200 import workloads as W  # noqa: E402
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+ref_deom = _load("ref_deom", f"{REF}/pyqed/heom/deom.py")
+ref_deom.tqdm = lambda x: x
+ref_phys = _load("ref_phys", f"{REF}/pyqed/phys.py")
+
+
+def _extract(path, fname, ns):
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == fname:
+            code = compile(ast.Module([node], []), path, "exec")
+            exec(code, ns)
+            return ns[fname]
+    raise KeyError(fname)
+
+
+_ns = dict(np=np, comm=ref_phys.comm, commutator=ref_phys.commutator,
+           anticommutator=ref_phys.anticommutator, rk4=ref_phys.rk4, coth=ref_phys.coth,
+           obs=lambda rho, a: np.vdot(ref_phys.dag(a).ravel(), rho))
+ref_heom_rk4 = _extract(f"{REF}/pyqed/HEOM/heom.py", "_heom", dict(_ns))
+ref_heom_euler = _extract(f"{REF}/pyqed/oqs.py", "_heom", dict(_ns))
+
+
+def run_ref_deom(w, nt, p1=None, keep_ados=True):
+    bath = SimpleNamespace(expn=w["expn"].copy(), etal=w["etal"].copy(), etar=w["etar"].copy(),
+                           etaa=w["etaa"].copy(), mode=w["mode"].copy())
+    f = w["pulse_system_func"] or (lambda t: 0.0)
+    g = w["pulse_coupling_func"] or (lambda t: 0.0)
+    s = ref_deom.DEOMSolver(system=w["system"].copy(), system_dipole=w["system_dipole"].copy(),
+                            bath=bath, coupling=w["coupling"].copy(),
+                            coupling_dipole=w["coupling_dipole"].copy(),
+                            pulse_system_func=f, pulse_coupling_func=g, lmax=w["lmax"])
+    t0 = time.time()
+    ts, dd = s.run(w["rho0"].copy(), w["dt"], nt, p1=p1)
+    wall = time.time() - t0
+    if p1 is None:
+        dd = np.stack([np.asarray(x) for x in dd])
+    ados = np.stack([np.asarray(x) if not hasattr(x, "toarray") else x.toarray()
+                     for x in s.ddos]) if keep_ados else None
+    return ts, np.asarray(dd), ados, np.asarray(s.keys), wall
+
+
+def save_deom(tag, w, nt, p1=None, keep_ados=True, stride=1):
+    ts, dd, ados, keys, wall = run_ref_deom(w, nt, p1, keep_ados)
+    f = w["pulse_system_func"]
+    g = w["pulse_coupling_func"]
+    # pulses sampled on the half-step grid so the fixture is self-contained
+    grid = np.arange(2 * nt + 1) * (w["dt"] / 2)
+    fs = np.array([f(t) for t in grid]) if f else np.zeros(2 * nt + 1)
+    gs = np.array([g(t) for t in grid]) if g else np.zeros(2 * nt + 1)
+    out = dict(system=w["system"], system_dipole=w["system_dipole"], coupling=w["coupling"],
+               coupling_dipole=w["coupling_dipole"], expn=w["expn"], etal=w["etal"],
+               etar=w["etar"], etaa=w["etaa"], mode=w["mode"], lmax=w["lmax"], rho0=w["rho0"],
+               dt=w["dt"], nt=nt, t_save=ts[::stride], traj=dd[::stride], stride=stride,
+               pulse_system=fs, pulse_coupling=gs, keys=keys.astype(np.uint8),
+               ref_wall_s=wall)
+    if p1 is not None:
+        out["p1"] = np.asarray(p1, dtype=np.complex128)
+    if keep_ados:
+        out["ados_final"] = ados
+    np.savez_compressed(os.path.join(HERE, f"deom_{tag}.npz"), **out)
+    nmax = keys.shape[0]
+    print(f"deom_{tag}: nmax={nmax} nt={nt} ref wall {wall:.2f}s "
+          f"({nmax * nt / wall:.0f} ADO-steps/s)")
+
+
+def save_chain(tag, fn, kind, nado, dt, nt):
+    s0, sx, sy, sz = ref_phys.pauli()
+    H = -0.5 * sx - 0.5 * sz
+    rho0 = np.zeros((2, 2))
+    rho0[1, 1] = 1
+    with contextlib.redirect_stdout(io.StringIO()):
+        obs = fn(H, rho0.copy(), [sz], [sz, sx], temperature=600, cutoff=5,
+                 reorganization=0.2, nado=nado, dt=dt, nt=nt)
+    np.savez_compressed(os.path.join(HERE, f"chain_{tag}.npz"), H=H, rho0=rho0, c_op=sz,
+                        e_ops=np.stack([sz, sx]), temperature=600.0, cutoff=5.0,
+                        reorganization=0.2, nado=nado, dt=dt, nt=nt, observables=obs, kind=kind)
+    print(f"chain_{tag}: last <sz> = {obs[0, -1].real!r}")
+
+
+def save_bath():
+    import sympy as sp
+    w_sp = sp.symbols("omega", real=True)
+    out = {}
+    cases = {
+        "drude_m1": (2 * 0.2 * 1.0 * w_sp / (1.0 ** 2 + w_sp ** 2), 1.0, 1, 0),
+        "drude_m2": (2 * 6.593 * 20.0 * w_sp / (20.0 ** 2 + w_sp ** 2), 1 / 39.276, 2, 0),
+        "drude_p1": (2 * 0.05 * 1.0 * w_sp / (1.0 ** 2 + w_sp ** 2), 1.0, 1, 1),
+        "drude_p2": (2 * 1.0 * 1.0 * w_sp / (1.0 ** 2 + w_sp ** 2), 1.0, 2, 1),
+        "drude_p5": (2 * 0.5 * 2.0 * w_sp / (2.0 ** 2 + w_sp ** 2), 0.7, 5, 1),
+        "bo_p3": (2 * 0.3 * 0.4 * 1.5 ** 2 * w_sp / ((w_sp ** 2 - 1.5 ** 2) ** 2 + 0.4 ** 2 * w_sp ** 2),
+                  0.8, 3, 1),
+    }
+    for name, (spe, beta, npsd, pade) in cases.items():
+        etal, etar, etaa, expn = ref_deom.decompose_spectrum_pade(spe, w_sp, beta, npsd, pade=pade)
+        out[f"{name}_etal"], out[f"{name}_etar"] = np.asarray(etal), np.asarray(etar)
+        out[f"{name}_etaa"], out[f"{name}_expn"] = np.asarray(etaa), np.asarray(expn)
+        out[f"{name}_args"] = np.array([beta, npsd, pade], dtype=float)
+    for n in (1, 2, 3, 6):
+        p, r = ref_deom.pade_approximation_distribution(n, 1, 1)
+        out[f"psd_pole_{n}"], out[f"psd_resi_{n}"] = np.asarray(p), np.asarray(r)
+    etal, etar, etaa, expn = ref_deom.single_oscillator(1.3, w_sp, 0.9, 2)
+    out["so_etal"], out["so_etar"], out["so_etaa"], out["so_expn"] = etal, etar, etaa, expn
+    np.savez_compressed(os.path.join(HERE, "bath.npz"), **out)
+    print("bath: saved", len(out), "arrays")
+
+
+def main():
+    save_bath()
+    # KAT-1 / KAT-1b / KAT-1e: examples/heom.py inputs
+    save_chain("rk4_nado5", ref_heom_rk4, "rk4", 5, 0.02, 100)
+    save_chain("rk4_nado12", ref_heom_rk4, "rk4", 12, 0.01, 200)
+    save_chain("euler_nado5", ref_heom_euler, "euler", 5, 0.02, 100)
+    # config 1 (DEOM form), depth 10, shortened trajectory
+    save_deom("spin_boson_L10", W.spin_boson(lmax=10), 100)
+    # KAT-2: examples/deom.py inputs, population observable
+    save_deom("example_L10_p1", W.spin_boson_deom_example(lmax=10), 20,
+              p1=np.array([[1, 0], [0, 0]], dtype=np.complex128), keep_ados=False)
+    # config 2, 60 steps (KAT-4)
+    save_deom("fmo_K7_L4", W.fmo(lmax=4, n_matsubara=0), 60)
+    # config 3 shape at reduced depth
+    save_deom("fmo_K21_L2", W.fmo(lmax=2, n_matsubara=2), 8)
+    save_deom("fmo_K21_L3", W.fmo(lmax=3, n_matsubara=2), 2)
+    # config 4 shape at reduced depth (N=32, dense-ish Q, complex H)
+    save_deom("polariton32_L2", W.polariton(lmax=2), 6)
+    save_deom("polariton8_L4", W.polariton(lmax=4, nfock=4), 10)
+    # config 5 with the pump/probe field on, two waiting times, observable Tr(mu rho)
+    for b in (0, 37):
+        w = W.aggregate_2des(lmax=3, waiting_index=b)
+        save_deom(f"aggregate_L3_T{b}", w, 300, p1=w["observable"], keep_ados=False, stride=1)
+    # stress: random dense complex inputs with both pulses on, Hermitian and not
+    save_deom("random4_herm", W.random_dense(4, 2, 3, 3, seed=0, hermitian=True), 20)
+    save_deom("random5_nonherm", W.random_dense(5, 3, 4, 2, seed=1, hermitian=False), 12)
+    save_deom("random3_K1", W.random_dense(3, 1, 1, 5, seed=2, hermitian=True), 15)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+"""CUDA path vs the reference's own outputs (tests/golden) and vs the oracle.
+
+Everything here goes through the public drop-in classes, which call the C ABI.
+Tolerance: the north star asks for max |rho_sys - rho_ref| <= 1e-10 over the
+trajectory in FP64; the kernels differ from NumPy only in summation order, so
+the tests hold them to 1e-12.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, deom_golden_names, pulse_from_samples
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _solver_from(g, **kw):
+    from pyqed_b200.heom import DEOMSolver, Bath
+    dt = float(g["dt"])
+    bath = Bath(expn=g["expn"], etal=g["etal"], etar=g["etar"], etaa=g["etaa"], mode=g["mode"])
+    return DEOMSolver(system=g["system"], system_dipole=g["system_dipole"], bath=bath,
+                      coupling=g["coupling"], coupling_dipole=g["coupling_dipole"],
+                      pulse_system_func=pulse_from_samples(g["pulse_system"], dt),
+                      pulse_coupling_func=pulse_from_samples(g["pulse_coupling"], dt),
+                      lmax=int(g["lmax"]), **kw)
+
+
+def _check_against_golden(g, s):
+    p1 = g["p1"] if "p1" in g else None
+    ts, traj = s.run(g["rho0"].copy(), float(g["dt"]), int(g["nt"]), p1=p1)
+    traj = np.asarray(traj)
+    assert np.allclose(ts, g["t_save"], rtol=0, atol=1e-15)
+    err = np.max(np.abs(traj - g["traj"]))
+    assert err < TOL, err
+    assert np.array_equal(s.keys, g["keys"].astype(np.int64))
+    if "ados_final" in g:
+        err = np.max(np.abs(s.ddos - g["ados_final"]))
+        assert err < TOL, err
+
+
+@pytest.mark.parametrize("name", deom_golden_names())
+def test_deom_matches_reference(name):
+    g = golden(name)
+    _check_against_golden(g, _solver_from(g))
+
+
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_random4_herm", "deom_random5_nonherm",
+                                  "deom_spin_boson_L10", "deom_fmo_K21_L2"])
+def test_lexicographic_storage_order(name):
+    g = golden(name)
+    _check_against_golden(g, _solver_from(g, order=1))
+
+
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_random4_herm", "deom_random5_nonherm",
+                                  "deom_aggregate_L3_T37", "deom_random3_K1"])
+def test_generic_kernel_small_n(name):
+    g = golden(name)
+    s = _solver_from(g)
+    s.tuning = dict(kernel=2, warps_per_cta=0, use_graph=0)
+    _check_against_golden(g, s)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_warps_per_cta(warps):
+    g = golden("deom_fmo_K21_L2")
+    s = _solver_from(g)
+    s.tuning = dict(kernel=1, warps_per_cta=warps, use_graph=0)
+    _check_against_golden(g, s)
+
+
+@pytest.mark.parametrize("tag", ["rk4_nado5", "rk4_nado12"])
+def test_chain_solver_matches_reference(tag):
+    from pyqed_b200.heom import HEOMSolver
+    g = golden("chain_" + tag)
+    sol = HEOMSolver(g["H"], c_ops=[g["c_op"]], e_ops=list(g["e_ops"]), verbose=False)
+    obs = sol.run(rho0=g["rho0"], dt=float(g["dt"]), nt=int(g["nt"]),
+                  temperature=float(g["temperature"]), cutoff=float(g["cutoff"]),
+                  reorganization=float(g["reorganization"]), nado=int(g["nado"]))
+    assert obs.shape == g["observables"].shape
+    err = np.max(np.abs(obs - g["observables"]))
+    assert err < TOL, err
+
+
+def test_batch_of_waiting_times():
+    """Config 5 shape: trajectories that differ only in their field table."""
+    ga, gb = golden("deom_aggregate_L3_T0"), golden("deom_aggregate_L3_T37")
+    s = _solver_from(ga)
+    dt, nt = float(ga["dt"]), int(ga["nt"])
+    fa = pulse_from_samples(ga["pulse_system"], dt)
+    fb = pulse_from_samples(gb["pulse_system"], dt)
+    ts, out = s.run_batch([ga["rho0"], gb["rho0"], ga["rho0"]], dt, nt, p1=ga["p1"],
+                          pulse_system_funcs=[fa, fb, None])
+    assert np.max(np.abs(out[0] - ga["traj"])) < TOL
+    assert np.max(np.abs(out[1] - gb["traj"])) < TOL
+    # no field: the ground state never leaves |g><g|, Tr(mu rho) stays 0
+    assert np.max(np.abs(out[2])) < TOL
+
+
+def test_mid_size_against_oracle():
+    """Config 3 shape at depth 4 (12650 ADOs): too slow for the reference,
+    seconds for the batched oracle (pinned to the reference at depth 2-3)."""
+    from oracle.deom_oracle import DeomOracle
+    from pyqed_b200 import workloads as W
+    from pyqed_b200.heom import DEOMSolver, Bath
+    w = W.fmo(lmax=4, n_matsubara=2)
+    nt = 3
+    o = DeomOracle(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"], w["expn"],
+                   w["etal"], w["etar"], w["etaa"], w["mode"], w["lmax"])
+    _, ref = o.run(w["rho0"], w["dt"], nt)
+    for order in (0, 1):
+        s = DEOMSolver(w["system"], w["system_dipole"],
+                       Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"],
+                            mode=w["mode"]), w["coupling"], w["coupling_dipole"], lmax=w["lmax"],
+                       order=order)
+        _, got = s.run(w["rho0"].copy(), w["dt"], nt)
+        assert np.max(np.abs(np.asarray(got) - np.asarray(ref))) < TOL
+        assert np.max(np.abs(s.ddos - o.ddos)) < TOL
+        assert np.array_equal(s.keys, o.keys)
+
+
+def test_invariants_large():
+    """Size-independent properties on a hierarchy the oracle cannot reach
+    (K=21, L=5: 65780 ADOs): trace 1, Hermitian rho_sys, populations in [0,1]."""
+    from pyqed_b200 import workloads as W
+    from pyqed_b200.heom import DEOMSolver, Bath
+    w = W.fmo(lmax=5, n_matsubara=2)
+    s = DEOMSolver(w["system"], w["system_dipole"],
+                   Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"],
+                        mode=w["mode"]), w["coupling"], w["coupling_dipole"], lmax=w["lmax"])
+    _, traj = s.run(w["rho0"].copy(), w["dt"], 40)
+    traj = np.asarray(traj)
+    tr = np.trace(traj, axis1=1, axis2=2)
+    assert np.max(np.abs(tr - 1.0)) < 1e-12
+    assert np.max(np.abs(traj - traj.conj().transpose(0, 2, 1))) < 1e-12
+    pops = np.real(np.diagonal(traj, axis1=1, axis2=2))
+    assert pops.min() > -1e-9 and pops.max() < 1 + 1e-9
+    assert pops[-1, 0] < 1.0 - 1e-4  # something actually moved
+
+
+def test_empty_and_tiny_inputs():
+    """nt = 0 returns just the initial state; depth 0 is plain von Neumann."""
+    from pyqed_b200.heom import DEOMSolver, Bath
+    g = golden("deom_random4_herm")
+    s = _solver_from(g)
+    ts, traj = s.run(g["rho0"].copy(), 0.01, 0)
+    assert len(traj) == 1 and np.allclose(traj[0], g["rho0"]) and ts.shape == (1,)
+    H = g["system"]
+    bath = Bath(expn=g["expn"], etal=g["etal"], etar=g["etar"], etaa=g["etaa"], mode=g["mode"])
+    s = DEOMSolver(system=H, bath=bath, coupling=g["coupling"], lmax=0)
+    dt, nt = 0.01, 50
+    _, traj = s.run(g["rho0"].copy(), dt, nt)
+    import scipy.linalg as la
+    U = la.expm(-1j * H * dt * nt)
+    assert np.max(np.abs(traj[-1] - U @ g["rho0"] @ U.conj().T)) < 1e-9
+
+
+def test_euler_method_against_oracle():
+    from oracle.deom_oracle import DeomOracle
+    from pyqed_b200._cabi import Plan
+    g = golden("deom_random4_herm")
+    o = DeomOracle(g["system"], g["system_dipole"], g["coupling"], g["coupling_dipole"], g["expn"],
+                   g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]))
+    rho = np.zeros((o.nmax, o.nsys, o.nsys), dtype=np.complex128)
+    rho[0] = g["rho0"]
+    dt, nt = 0.003, 25
+    for i in range(nt):
+        rho = rho + dt * o.rhs_batched(rho, 0.0)
+    p = Plan(o.nsys, o.nind, int(g["coupling"].shape[0]), int(g["lmax"]))
+    p.set_system(g["system"], None)
+    p.set_coupling(g["coupling"], None)
+    p.set_bath(g["expn"], g["etal"], g["etar"], g["etaa"], g["mode"])
+    p.build()
+    p.set_state(g["rho0"][None])
+    p.propagate(dt, nt, method=1)
+    got = p.get_ados()[0]
+    assert np.max(np.abs(got - rho)) < TOL

@@ -1,0 +1,95 @@
+"""Pins the CPU oracle to outputs of the unmodified reference (tests/golden)."""
+import numpy as np
+import pytest
+
+from conftest import golden, deom_golden_names, pulse_from_samples
+from oracle import deom_oracle as DO
+from oracle import chain_oracle as CO
+
+TOL = 1e-12  # oracle vs reference: same arithmetic up to summation order
+
+
+def _oracle_from(g):
+    dt = float(g["dt"])
+    return DO.DeomOracle(g["system"], g["system_dipole"], g["coupling"], g["coupling_dipole"],
+                         g["expn"], g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]),
+                         pulse_from_samples(g["pulse_system"], dt),
+                         pulse_from_samples(g["pulse_coupling"], dt))
+
+
+@pytest.mark.parametrize("name", deom_golden_names())
+def test_deom_batched_matches_reference(name):
+    g = golden(name)
+    o = _oracle_from(g)
+    assert np.array_equal(o.keys, g["keys"].astype(np.int64))
+    p1 = g["p1"] if "p1" in g else None
+    ts, traj = o.run(g["rho0"], float(g["dt"]), int(g["nt"]), p1=p1, batched=True)
+    traj = np.asarray(traj)
+    assert np.allclose(ts, g["t_save"], rtol=0, atol=1e-15)
+    assert np.max(np.abs(traj - g["traj"])) < TOL
+    if "ados_final" in g:
+        assert np.max(np.abs(o.ddos - g["ados_final"])) < TOL
+
+
+@pytest.mark.parametrize("name", ["deom_random4_herm", "deom_random5_nonherm", "deom_random3_K1",
+                                  "deom_polariton8_L4", "deom_fmo_K21_L2"])
+def test_deom_loop_matches_reference(name):
+    g = golden(name)
+    o = _oracle_from(g)
+    nt = min(int(g["nt"]), 4)
+    ts, traj = o.run(g["rho0"], float(g["dt"]), nt, p1=None, batched=False)
+    assert np.max(np.abs(np.asarray(traj) - g["traj"][:nt + 1])) < TOL
+
+
+def test_hash_is_tier_major_bijection():
+    for K, L in [(1, 5), (2, 10), (3, 4), (7, 4), (21, 2)]:
+        tab = DO.pascal_table(K, L)
+        keys = DO.build_keys(K, L, tab)
+        ids = [DO.ado_id(k, tab) for k in keys]
+        assert ids == list(range(len(keys)))
+        tiers = keys.sum(axis=1)
+        assert np.all(np.diff(tiers) >= 0)
+        minus, plus = DO.build_neighbours(keys, L, tab)
+        for n in range(len(keys)):
+            for k in range(K):
+                if minus[n, k] >= 0:
+                    assert plus[minus[n, k], k] == n
+
+
+@pytest.mark.parametrize("tag,fn", [("rk4_nado5", CO.heom_chain_rk4), ("rk4_nado12", CO.heom_chain_rk4),
+                                    ("euler_nado5", CO.heom_chain_euler)])
+def test_chain_matches_reference(tag, fn):
+    g = golden("chain_" + tag)
+    obs = fn(g["H"], g["rho0"], [g["c_op"]], list(g["e_ops"]), float(g["temperature"]),
+             float(g["cutoff"]), float(g["reorganization"]), int(g["nado"]), float(g["dt"]),
+             int(g["nt"]))
+    assert np.max(np.abs(obs - g["observables"])) < TOL
+
+
+def test_known_answers():
+    """KAT values recorded independently in SURVEY.md section 8c."""
+    g = golden("chain_rk4_nado5")
+    assert abs(g["observables"][0, -1].real - (-0.9688066943939262)) < 1e-15
+    g = golden("chain_rk4_nado12")
+    assert abs(g["observables"][0, -1].real - (-0.9165103413782143)) < 1e-15
+    g = golden("chain_euler_nado5")
+    assert abs(g["observables"][0, -1].real - (-0.9690784389436947)) < 1e-15
+    g = golden("deom_example_L10_p1")
+    assert abs(g["traj"][20] - 0.8697707701043433) < 1e-14
+    g = golden("deom_fmo_K7_L4")
+    pops = np.real(np.diagonal(g["traj"][60]))
+    assert np.allclose(pops[:3], [0.50655946, 0.45133341, 0.0160922], atol=1e-8)
+
+
+def test_chain_equals_deom_form():
+    """KAT-3: the chain is the DEOM form with K=1."""
+    g = golden("chain_rk4_nado5")
+    nado, dt, nt = int(g["nado"]), float(g["dt"]), int(g["nt"])
+    D0 = CO.d0_high_temperature(float(g["temperature"]), float(g["cutoff"]), float(g["reorganization"]))
+    expn, etal, etar, etaa, mode, lmax = CO.chain_as_deom(D0, float(g["cutoff"]), nado)
+    n = g["H"].shape[0]
+    o = DO.DeomOracle(g["H"], np.zeros((n, n)), [g["c_op"]], None, expn, etal, etar, etaa, mode, lmax)
+    _, traj = o.run(g["rho0"], dt, nt)
+    sz = g["e_ops"][0]
+    got = np.array([np.trace(sz @ r) for r in traj[1:]])
+    assert np.max(np.abs(got - g["observables"][0])) < 1e-13
