@@ -216,6 +216,7 @@ def run_gpu_arm(args):
                         w["pulse_system_func"], w["pulse_coupling_func"], lmax=lmax, device=local,
                         order=args.order, alias_rho0=False)
     solver.tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
+    solver.options = {"qdiag": args.qdiag, "hermitian": args.herm}
     K, Wm, dt = args.steps, args.warmup, w["dt"]
 
     # ---- e2e: the public call with host buffers (first call also builds the plan)
@@ -291,6 +292,7 @@ def run_gpu_arm(args):
                 "workload": args.workload, "nsys": n, "nind": nind, "nmod": int(w["coupling"].shape[0]),
                 "lmax": lmax, "n_ado": nmax, "dt": dt, "storage_order": ["reference", "lexicographic"][args.order],
                 "state_mb_per_array": state_mb,
+                "fast_paths": {"diagonal_Q": plan.info("qdiag"), "hermitian_ados": plan.info("hermitian")},
                 "l2": ("inputs larger than L2 (4 arrays of %.0f MB); no flush needed" % state_mb) if state_mb > 200
                       else "state is cache-resident by construction (time stepping re-reads its own output); no flush",
                 "parallelism": "single GPU" if world == 1 else
@@ -331,6 +333,8 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--qdiag", type=int, default=-1)
+    ap.add_argument("--herm", type=int, default=-1)
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:

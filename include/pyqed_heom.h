@@ -139,6 +139,17 @@ int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
 int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
                           int use_graph);
 
+/* Named integer options (-1 = automatic, 0 = off, 1 = on):
+ *   "qdiag"      use the element-wise neighbour path when every Q_m is diagonal
+ *   "hermitian"  when H, Q, the bath (real expn, etar = conj(etal), etaa > 0)
+ *                and the loaded state keep every ADO Hermitian, fetch a
+ *                neighbour's column entries as the conjugate of its row
+ *   "debug_sync" synchronise and check after every launch
+ * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian",
+ * "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */
+int pyqed_heom_set_option(pyqed_heom_plan* plan, const char* name, int value);
+int64_t pyqed_heom_get_info(pyqed_heom_plan* plan, const char* name);
+
 #ifdef __cplusplus
 }
 #endif

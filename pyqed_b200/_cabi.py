@@ -52,6 +52,8 @@ SIGNATURES = {
     "pyqed_heom_launch_count": (C.c_int64, [C.c_void_p]),
     "pyqed_heom_stage_timing": (C.c_int, [C.c_void_p, C.c_int, _c_double_p, _c_int64_p]),
     "pyqed_heom_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "pyqed_heom_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "pyqed_heom_get_info": (C.c_int64, [C.c_void_p, C.c_char_p]),
 }
 
 
@@ -164,6 +166,12 @@ class Plan:
     def set_tuning(self, kernel=0, warps_per_cta=0, use_graph=0):
         self._check(self.lib.pyqed_heom_set_tuning(self._h, int(kernel), int(warps_per_cta),
                                                    int(use_graph)))
+
+    def set_option(self, name, value):
+        self._check(self.lib.pyqed_heom_set_option(self._h, name.encode(), int(value)))
+
+    def info(self, name):
+        return int(self.lib.pyqed_heom_get_info(self._h, name.encode()))
 
     def build(self):
         """Allocate the device buffers (torch), bind them and build the tables."""

@@ -75,7 +75,7 @@ __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 // ---------------------------------------------------------------------------
 struct TableLayout {
     size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
-        ops_t, row_ptr, row_idx, col_ptr, col_idx, step_base, total;
+        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, step_base, total;
 };
 
 struct pyqed_heom_plan {
@@ -87,6 +87,11 @@ struct pyqed_heom_plan {
     std::vector<long long> mode;
     bool have_sys = false, have_coup = false, have_bath = false, bound = false, built = false;
     bool mu_nonzero = false, qd_nonzero = false;
+    bool q_diagonal = false;     // every Q_m (and its dipole) is diagonal
+    bool herm_inputs = false;    // operators/bath keep every ADO Hermitian
+    bool herm_state = false;     // ... and so is the state that was loaded
+    bool use_qdiag = false;      // resolved at build time from the options below
+    int opt_qdiag = -1, opt_herm = -1;  // -1 auto, 0 off, 1 on
     TableLayout tl{};
     char* d_tables = nullptr;
     char* d_state = nullptr;
@@ -135,6 +140,7 @@ static int compute_layout(pyqed_heom_plan* p) {
     t.row_idx = take(sizeof(short) * M1 * NN);
     t.col_ptr = take(sizeof(short) * M1 * (p->N + 1));
     t.col_idx = take(sizeof(short) * M1 * NN);
+    t.supp = take((size_t)p->M * (2 * p->N + 1));
     t.step_base = take(sizeof(long long));
     t.total = off;
     p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
@@ -296,12 +302,14 @@ struct StageArgs {
     const short* row_idx;
     const short* col_ptr;
     const short* col_idx;
+    const unsigned char* supp;  // diagonal-Q tables: [M][N+1] (count, rows) then [M][N] membership
     double2* traj;        // may be null
     const long long* step_base;
     long long traj_bstride;
     long long nmax, slot0, ngroups;
     double a, w;
     int local_step, first, last, N;
+    int herm, ncoef, nmod;
 };
 
 template <int N>
@@ -309,29 +317,57 @@ struct HParam {
     double2 v[N * N];
 };
 
+// streaming (evict-first) accesses for the arrays that are touched once per launch
+__device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(double2* p, const double2 v) { __stcs(p, v); }
+
 // Kernel 1 (N <= 8): a warp owns 32/N consecutive ADOs; lane (sub,row) owns one
 // matrix row in registers.  -i[H,rho] uses H from the constant bank (kernel
 // parameter) or, when H depends on time/trajectory, from shared memory.
-template <int N, bool TDEP>
+//
+// Neighbour terms, two variants:
+//  QDIAG (every Q_m diagonal: projectors, sigma_z, occupation numbers): the
+//    coupling is element-wise, (Q rho' - rho' Q)_ij = (q_i - q_j) rho'_ij, so a
+//    link only needs the rows r of rho' with q_r != 0 (plus, for non-Hermitian
+//    ADOs, the matching column entries).  The N lanes of an ADO fetch such a row
+//    with one coalesced 16N-byte request and accumulate into the shared k tile;
+//    U links are fetched per batch to keep U independent loads in flight per lane.
+//  general Q: per-lane sparse row/column products in registers.
+template <int N, bool TDEP, bool QDIAG>
 __global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
                                                          const __grid_constant__ HParam<N> hp) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
+    constexpr int U = 4;
     extern __shared__ double2 smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int b = blockIdx.y;
     const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
     double2* Hs = smem;
-    double2* rho_s = smem + (TDEP ? NN : 0) + wid * 2 * TILE;
+    double2* coef_s = Hs + (TDEP ? NN : 0);
+    double2* qd_s = coef_s + (QDIAG ? 2 * a.ncoef : 0);
+    double2* tiles = qd_s + (QDIAG ? a.nmod * N : 0);
+    double2* rho_s = tiles + wid * 2 * TILE;
     double2* k_s = rho_s + TILE;
+    unsigned char* supp_s = (unsigned char*)(tiles + nwarps * 2 * TILE);
     if (TDEP) {
         for (int e = threadIdx.x; e < NN; e += blockDim.x) Hs[e] = ops[e];
-        __syncthreads();
     }
+    if (QDIAG) {
+        for (int e = threadIdx.x; e < 2 * a.ncoef; e += blockDim.x) coef_s[e] = a.coef[e];
+        for (int e = threadIdx.x; e < a.nmod * N; e += blockDim.x) {
+            const int m = e / N, j = e - m * N;
+            qd_s[e] = ops[(1 + m) * NN + j * N + j];
+        }
+        for (int e = threadIdx.x; e < a.nmod * (2 * N + 1); e += blockDim.x) supp_s[e] = a.supp[e];
+    }
+    if (TDEP || QDIAG) __syncthreads();
 #define HEL(r_, c_) (TDEP ? Hs[(r_) * N + (c_)] : hp.v[(r_) * N + (c_)])
     const long long boff = (long long)b * a.nmax * NN;
     const double2* __restrict__ yin = a.yin + boff;
     const int sub = lane / N, row = lane - sub * N;
     const bool lane_ok = lane < APW * N;
+    const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
+    const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
     const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
 
     for (long long g = (long long)blockIdx.x * nwarps + wid; g < a.ngroups;
@@ -377,37 +413,85 @@ __global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
                                         -t.x - (d.x * rv[j].y + d.y * rv[j].x));
                 }
             }
-            const int lend = a.link_ptr[slot + 1];
-            for (int lp = a.link_ptr[slot]; lp < lend; ++lp) {
-                const int2 lk = a.links[lp];
-                const double2* __restrict__ pn = yin + (long long)lk.x * NN;
-                const int ci = heom::meta_ci(lk.y), m1 = 1 + heom::meta_mode(lk.y);
-                const double2 aL = a.coef[2 * ci], aR = a.coef[2 * ci + 1];
-                const double2* __restrict__ Qm = ops + m1 * NN;
-                const short* rp = a.row_ptr + m1 * (N + 1);
-                const short* ri = a.row_idx + m1 * NN;
-                for (int t = rp[row]; t < rp[row + 1]; ++t) {
-                    const int l = ri[t];
-                    const double2 q = cmul(aL, Qm[row * N + l]);
+            const int lbeg = a.link_ptr[slot], lend = a.link_ptr[slot + 1];
+            if (QDIAG) {
 #pragma unroll
-                    for (int j = 0; j < N; ++j) cfma(r[j], q, ldg2(pn + l * N + j));
-                }
-                const short* cp = a.col_ptr + m1 * (N + 1);
-                const short* cidx = a.col_idx + m1 * NN;
+                for (int j = 0; j < N; ++j) k_s[(sub * N + row) * LD + j] = r[j];
+                __syncwarp(submask);
+                for (int lp = lbeg; lp < lend; lp += U) {
+                    int2 lk[U];
+                    double2 A[U];
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    for (int t = cp[j]; t < cp[j + 1]; ++t) {
-                        const int l = cidx[t];
-                        const double2 q = cmul(aR, Qm[l * N + j]);
-                        cfma(r[j], q, ldg2(pn + row * N + l));
+                    for (int u = 0; u < U; ++u)
+                        lk[u] = (lp + u < lend) ? __ldg(a.links + lp + u) : make_int2((int)slot, 0);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int m = heom::meta_mode(lk[u].y);
+                        const int r0 = supp_s[m * (N + 1) + 1];
+                        A[u] = ldg2(yin + (long long)lk[u].x * NN + r0 * N + row);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int ci = heom::meta_ci(lk[u].y), m = heom::meta_mode(lk[u].y);
+                        const double2 aL = coef_s[2 * ci], aR = coef_s[2 * ci + 1];
+                        const double2* __restrict__ pn = yin + (long long)lk[u].x * NN;
+                        const int ns = supp_s[m * (N + 1)];
+                        const double2 qj = qd_s[m * N + row];
+                        const bool outside = insupp_s[m * N + row] == 0;
+                        for (int t = 0; t < ns; ++t) {
+                            const int rr = supp_s[m * (N + 1) + 1 + t];
+                            const double2 Aj = (t == 0) ? A[u] : ldg2(pn + rr * N + row);
+                            const double2 qr = qd_s[m * N + rr];
+                            double2 c = cmul(aL, qr);
+                            cfma(c, aR, qj);
+                            double2* d1 = &k_s[(sub * N + rr) * LD + row];
+                            double2 v1 = *d1;
+                            cfma(v1, c, Aj);
+                            *d1 = v1;
+                            if (outside) {  // element (row, rr): only the right product survives
+                                const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y)
+                                                          : ldg2(pn + row * N + rr);
+                                double2* d2 = &k_s[(sub * N + row) * LD + rr];
+                                double2 v2 = *d2;
+                                cfma(v2, cmul(aR, qr), Bj);
+                                *d2 = v2;
+                            }
+                        }
+                        __syncwarp(submask);
                     }
                 }
-            }
+            } else {
+                for (int lp = lbeg; lp < lend; ++lp) {
+                    const int2 lk = a.links[lp];
+                    const double2* __restrict__ pn = yin + (long long)lk.x * NN;
+                    const int ci = heom::meta_ci(lk.y), m1 = 1 + heom::meta_mode(lk.y);
+                    const double2 aL = a.coef[2 * ci], aR = a.coef[2 * ci + 1];
+                    const double2* __restrict__ Qm = ops + m1 * NN;
+                    const short* rp = a.row_ptr + m1 * (N + 1);
+                    const short* ri = a.row_idx + m1 * NN;
+                    for (int t = rp[row]; t < rp[row + 1]; ++t) {
+                        const int l = ri[t];
+                        const double2 q = cmul(aL, Qm[row * N + l]);
 #pragma unroll
-            for (int j = 0; j < N; ++j) k_s[(sub * N + row) * LD + j] = r[j];
+                        for (int j = 0; j < N; ++j) cfma(r[j], q, ldg2(pn + l * N + j));
+                    }
+                    const short* cp = a.col_ptr + m1 * (N + 1);
+                    const short* cidx = a.col_idx + m1 * NN;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        for (int t = cp[j]; t < cp[j + 1]; ++t) {
+                            const int l = cidx[t];
+                            const double2 q = cmul(aR, Qm[l * N + j]);
+                            cfma(r[j], q, ldg2(pn + row * N + l));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < N; ++j) k_s[(sub * N + row) * LD + j] = r[j];
+            }
         }
         __syncwarp();
-        // flat epilogue: coalesced 128-bit traffic on y / acc / outputs
+        // flat epilogue: coalesced 128-bit streaming traffic on y / acc / outputs
         const long long gbase = boff + base * NN;
         for (int e = lane; e < nelem; e += 32) {
             const int s = e / NN, rr = e - s * NN, i = rr / N, j = rr - i * N;
@@ -415,16 +499,16 @@ __global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
             const double2 k = k_s[si];
             const long long gi = gbase + e;
             if (a.last) {
-                const double2 bs = a.first ? rho_s[si] : a.acc[gi];
+                const double2 bs = a.first ? rho_s[si] : ld_stream(a.acc + gi);
                 const double2 res = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
-                a.ydst[gi] = res;
+                st_stream(a.ydst + gi, res);
                 if (a.traj && base + s == a.slot0)
                     a.traj[b * a.traj_bstride + (step + 1) * NN + rr] = res;
             } else {
-                const double2 yv = a.first ? rho_s[si] : a.y[gi];
-                const double2 bs = a.first ? yv : a.acc[gi];
-                a.acc[gi] = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
-                a.yout[gi] = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
+                const double2 yv = a.first ? rho_s[si] : ld_stream(a.y + gi);
+                const double2 bs = a.first ? yv : ld_stream(a.acc + gi);
+                st_stream(a.acc + gi, make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y)));
+                st_stream(a.yout + gi, make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
             }
         }
         __syncwarp();
@@ -521,7 +605,7 @@ static int post_launch(pyqed_heom_plan* p, const char* what) {
     return 0;
 }
 
-template <int N, bool TDEP>
+template <int N, bool TDEP, bool QDIAG>
 static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     StageArgs args = a;
@@ -531,11 +615,14 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
         // small hierarchies: prefer more CTAs over fuller CTAs
         while (warps > 1 && args.ngroups * p->B < (long long)warps * sm_count * 2) warps >>= 1;
     }
-    const size_t smem = sizeof(double2) * ((TDEP ? N * N : 0) + (size_t)warps * 2 * TILE);
+    size_t smem = sizeof(double2) * ((TDEP ? N * N : 0) + (size_t)warps * 2 * TILE);
+    if (QDIAG) smem += sizeof(double2) * (2 * (size_t)args.ncoef + (size_t)p->M * N) +
+                       align_up((size_t)p->M * (2 * N + 1), 16);
+    REQUIRE(smem <= 200 * 1024, "shared-memory tables too large for the row kernel");
     static bool attr_set = false;
     if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(stage_rows_kernel<N, TDEP>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CU_TRY(cudaFuncSetAttribute(stage_rows_kernel<N, TDEP, QDIAG>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     long long ctas = (args.ngroups + warps - 1) / warps;
@@ -543,8 +630,14 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     dim3 grid((unsigned)std::min(ctas, cap), p->B);
     HParam<N> hp;
     for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    stage_rows_kernel<N, TDEP><<<grid, warps * 32, smem, p->stream>>>(args, hp);
+    stage_rows_kernel<N, TDEP, QDIAG><<<grid, warps * 32, smem, p->stream>>>(args, hp);
     return post_launch(p, "stage_rows_kernel");
+}
+
+template <int N>
+static int launch_rows_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool qdiag) {
+    if (tdep) return qdiag ? launch_rows<N, true, true>(p, a, sm_count) : launch_rows<N, true, false>(p, a, sm_count);
+    return qdiag ? launch_rows<N, false, true>(p, a, sm_count) : launch_rows<N, false, false>(p, a, sm_count);
 }
 
 static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
@@ -565,9 +658,9 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     const int kern = p->kernel ? p->kernel : (p->N <= 8 ? 1 : 2);
     if (kern == 1) {
         REQUIRE(p->N >= 2 && p->N <= 8, "kernel 1 needs 2 <= N <= 8");
-#define ROWS_CASE(n)                                                                       \
-    case n:                                                                                \
-        rc = tdep ? launch_rows<n, true>(p, a, sm_count) : launch_rows<n, false>(p, a, sm_count); \
+#define ROWS_CASE(n)                                              \
+    case n:                                                       \
+        rc = launch_rows_n<n>(p, a, sm_count, tdep, p->use_qdiag); \
         break;
         switch (p->N) {
             ROWS_CASE(2) ROWS_CASE(3) ROWS_CASE(4) ROWS_CASE(5) ROWS_CASE(6) ROWS_CASE(7) ROWS_CASE(8)
@@ -604,8 +697,9 @@ static bool build_pascal(int side, std::vector<long long>& tab) {
     for (int a = 0; a < side; ++a) {
         tab[(size_t)a * side] = 1;
         for (int b = 1; b <= a; ++b) {
-            long long x = tab[(size_t)(a - 1) * side + b - 1] + (b <= a - 1 ? tab[(size_t)(a - 1) * side + b] : 0);
-            tab[(size_t)a * side + b] = x > SAT ? SAT : x;
+            const long long u = tab[(size_t)(a - 1) * side + b - 1];
+            const long long v = b <= a - 1 ? tab[(size_t)(a - 1) * side + b] : 0;
+            tab[(size_t)a * side + b] = (u >= SAT || v >= SAT || u + v > SAT) ? SAT : u + v;
         }
     }
     return true;
@@ -734,6 +828,29 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_gra
     return 0;
 }
 
+int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
+    REQUIRE(p && name, "null argument");
+    const std::string n(name);
+    if (n == "qdiag") p->opt_qdiag = value;
+    else if (n == "hermitian") p->opt_herm = value;
+    else if (n == "debug_sync") p->debug_sync = value != 0;
+    else return fail("unknown option '" + n + "'");
+    return 0;
+}
+
+int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
+    if (!p || !name) return -1;
+    const std::string n(name);
+    if (n == "qdiag") return p->use_qdiag;
+    if (n == "q_diagonal") return p->q_diagonal;
+    if (n == "hermitian") return p->herm_inputs && p->herm_state && p->opt_herm != 0;
+    if (n == "nlinks") return p->nlinks;
+    if (n == "nmax") return p->nmax;
+    if (n == "slot0") return p->slot0;
+    if (n == "table_bytes") return (int64_t)p->tl.total;
+    return -1;
+}
+
 int pyqed_heom_table_bytes(pyqed_heom_plan* p, size_t* bytes) {
     REQUIRE(p && bytes, "null argument");
     compute_layout(p);
@@ -859,6 +976,47 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
                            cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(p->d_tables + t.col_idx, cidx.data(), sizeof(short) * cidx.size(),
                            cudaMemcpyHostToDevice, s));
+    {   // structure of the coupling operators and of the whole problem
+        const std::complex<double> Z(0, 0);
+        bool diag = true, herm = true;
+        for (int m = 0; m < p->M && diag; ++m)
+            for (int i = 0; i < N && diag; ++i)
+                for (int j = 0; j < N; ++j)
+                    if (i != j && (p->Q[(size_t)m * NN + i * N + j] != Z || p->Qd[(size_t)m * NN + i * N + j] != Z)) {
+                        diag = false;
+                        break;
+                    }
+        auto is_herm = [&](const std::complex<double>* A) {
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j)
+                    if (A[i * N + j] != std::conj(A[j * N + i])) return false;
+            return true;
+        };
+        herm = is_herm(p->H.data()) && is_herm(p->mu.data());
+        for (int m = 0; m < p->M && herm; ++m)
+            herm = is_herm(p->Q.data() + (size_t)m * NN) && is_herm(p->Qd.data() + (size_t)m * NN);
+        for (int k = 0; k < K && herm; ++k)
+            herm = p->expn[k].imag() == 0.0 && p->etaa[k].imag() == 0.0 && p->etaa[k].real() > 0.0 &&
+                   p->etar[k] == std::conj(p->etal[k]);
+        p->q_diagonal = diag;
+        p->herm_inputs = herm;
+        p->use_qdiag = diag && p->opt_qdiag != 0 && N <= 8;
+        std::vector<unsigned char> supp((size_t)p->M * (2 * N + 1), 0);
+        unsigned char* ins = supp.data() + (size_t)p->M * (N + 1);
+        for (int m = 0; m < p->M; ++m) {
+            int c = 0;
+            for (int j = 0; j < N; ++j) {
+                const bool nzd = p->Q[(size_t)m * NN + j * N + j] != Z || p->Qd[(size_t)m * NN + j * N + j] != Z;
+                if (nzd) {
+                    supp[(size_t)m * (N + 1) + 1 + c++] = (unsigned char)j;
+                    ins[(size_t)m * N + j] = 1;
+                }
+            }
+            supp[(size_t)m * (N + 1)] = (unsigned char)c;
+        }
+        CU_TRY(cudaMemcpyAsync(p->d_tables + t.supp, supp.data(), supp.size(), cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaStreamSynchronize(s));
+    }
     CU_TRY(cudaMemsetAsync(p->d_tables + t.step_base, 0, sizeof(long long), s));
     // expn and mode for the builder kernels: staged in ops_t (rebuilt before use)
     std::vector<double> ex(2 * K);
@@ -940,6 +1098,20 @@ int pyqed_heom_set_state(pyqed_heom_plan* p, const double* rho0_host) {
     REQUIRE(p && p->built && rho0_host, "set_state: build the hierarchy first");
     CU_TRY(cudaSetDevice(p->device));
     const size_t NN = (size_t)p->N * p->N;
+    {
+        bool h = true;
+        for (int b = 0; b < p->B && h; ++b)
+            for (int i = 0; i < p->N && h; ++i)
+                for (int j = 0; j < p->N; ++j) {
+                    const double* x = rho0_host + 2 * ((size_t)b * NN + i * p->N + j);
+                    const double* y = rho0_host + 2 * ((size_t)b * NN + j * p->N + i);
+                    if (x[0] != y[0] || x[1] != -y[1]) {
+                        h = false;
+                        break;
+                    }
+                }
+        p->herm_state = h;
+    }
     CU_TRY(cudaMemsetAsync(p->d_state, 0, 4 * p->array_bytes, p->stream));
     CU_TRY(cudaMemcpy2DAsync(p->arr(ARR_Y) + (size_t)p->slot0 * NN, sizeof(double2) * p->nmax * NN,
                              rho0_host, sizeof(double2) * NN, sizeof(double2) * NN, p->B,
@@ -962,6 +1134,7 @@ static int permute(pyqed_heom_plan* p, double2* dst, const double2* src, bool to
 int pyqed_heom_load_ados(pyqed_heom_plan* p, const double* ados_host) {
     REQUIRE(p && p->built && ados_host, "load_ados: build the hierarchy first");
     CU_TRY(cudaSetDevice(p->device));
+    p->herm_state = false;  // arbitrary ADOs: do not assume Hermiticity
     const size_t bytes = sizeof(double2) * (size_t)p->B * p->nmax * p->N * p->N;
     if (p->order == 0) {
         CU_TRY(cudaMemcpyAsync(p->arr(ARR_Y), ados_host, bytes, cudaMemcpyHostToDevice, p->stream));
@@ -1037,6 +1210,10 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
     a.row_idx = p->tab<short>(t.row_idx);
     a.col_ptr = p->tab<short>(t.col_ptr);
     a.col_idx = p->tab<short>(t.col_idx);
+    a.supp = p->tab<unsigned char>(t.supp);
+    a.herm = (p->herm_inputs && p->herm_state && p->opt_herm != 0) ? 1 : 0;
+    a.ncoef = 2 * p->K * (p->L + 1);
+    a.nmod = p->M;
     a.traj = traj;
     a.step_base = p->tab<long long>(t.step_base);
     a.traj_bstride = traj_bstride;

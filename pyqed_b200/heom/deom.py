@@ -71,6 +71,7 @@ class DEOMSolver:
         self.order = order
         self.alias_rho0 = alias_rho0
         self.tuning = dict(kernel=0, warps_per_cta=0, use_graph=0)
+        self.options = {}  # named C-ABI options, e.g. {"qdiag": 0, "hermitian": 0}
         self._plan = None
         self._plan_key = None
         self._keys = None
@@ -154,6 +155,8 @@ class DEOMSolver:
         p.set_coupling(Q, Qd)
         p.set_bath(b.expn, b.etal, b.etar, b.etaa, b.mode)
         p.set_tuning(**self.tuning)
+        for name, value in self.options.items():
+            p.set_option(name, value)
         if fresh:
             p.build()
         else:

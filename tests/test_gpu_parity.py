@@ -60,6 +60,30 @@ def test_generic_kernel_small_n(name):
     _check_against_golden(g, s)
 
 
+@pytest.mark.parametrize("opts", [{"qdiag": 0}, {"hermitian": 0}, {"qdiag": 0, "hermitian": 0}])
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L2", "deom_spin_boson_L10",
+                                  "deom_aggregate_L3_T37"])
+def test_structure_fast_paths_can_be_disabled(name, opts):
+    """The diagonal-Q and Hermitian fast paths are optimisations only: with
+    them off the general code must give the same trajectory."""
+    g = golden(name)
+    s = _solver_from(g)
+    s.options = dict(opts)
+    _check_against_golden(g, s)
+    assert s._plan.info("qdiag") == (0 if opts.get("qdiag") == 0 else 1)
+
+
+def test_fast_path_detection():
+    for name, qdiag, herm in [("deom_fmo_K7_L4", 1, 1), ("deom_random4_herm", 0, 0),
+                              ("deom_random5_nonherm", 0, 0), ("deom_polariton8_L4", 0, 1),
+                              ("deom_spin_boson_L10", 1, 1)]:
+        g = golden(name)
+        s = _solver_from(g)
+        s.run(g["rho0"].copy(), float(g["dt"]), 1)
+        assert s._plan.info("q_diagonal") == qdiag, name
+        assert s._plan.info("hermitian") == herm, name
+
+
 @pytest.mark.parametrize("warps", [1, 2, 4, 8])
 def test_warps_per_cta(warps):
     g = golden("deom_fmo_K21_L2")
