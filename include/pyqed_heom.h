@@ -134,7 +134,8 @@ int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
                             int64_t* launches);
 
 /* Tuning knobs (0 = library default): kernel 0 auto, 1 row-per-lane kernel
- * (N <= 8), 2 generic one-CTA-per-ADO kernel; warps per CTA for kernel 1;
+ * (N <= 8), 2 generic one-CTA-per-ADO kernel, 3 row-per-lane kernel with
+ * cp.async staging (N <= 8, diagonal Q_m); warps per CTA for kernels 1 and 3;
  * use_graph: replay the RK4 step as a CUDA graph. */
 int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
                           int use_graph);

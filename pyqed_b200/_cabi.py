@@ -71,8 +71,8 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if _build.is_stale():
+    path = os.environ.get("PYQED_HEOM_LIB") or _build.LIB  # override: tuning variants
+    if path == _build.LIB and _build.is_stale():
         try:
             _build.build_extension()
         except Exception as exc:  # no nvcc on this box and no prebuilt library

@@ -27,20 +27,23 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build_extension(force: bool = False, verbose: bool = False) -> str:
-    """Compile ``csrc/heom_kernels.cu`` into ``lib/libpyqed_heom.so``."""
-    if not force and not is_stale():
+def build_extension(force: bool = False, verbose: bool = False, defines=None, out=None) -> str:
+    """Compile ``csrc/heom_kernels.cu`` into ``lib/libpyqed_heom.so`` (or ``out``,
+    with extra ``-D`` defines, for tuning variants)."""
+    target = out or LIB
+    if out is None and not force and not is_stale():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(target), exist_ok=True)
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
-           "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB, SRC]
+           "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3"]
+    cmd += [f"-D{d}" for d in (defines or [])]
+    cmd += ["-o", target, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

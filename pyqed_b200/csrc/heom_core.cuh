@@ -99,13 +99,19 @@ HEOM_HD void unrank_slot(int order, long long slot, int K, int L, const Pascal& 
 }
 
 // ---- link metadata ----------------------------------------------------------
-// One link = (neighbour slot, meta); meta packs the coefficient-table index
-// ci = (dir*K + k)*(L+1) + n_eff  (dir 0: n-e_k with n_eff = n_k, dir 1: n+e_k
-// with n_eff = n_k + 1) in the low 24 bits and the coupling mode in the top 8.
-HEOM_HD int link_meta(int dir, int k, int neff, int mode, int K, int L) {
-    return ((dir * K + k) * (L + 1) + neff) | (mode << 24);
+// One link = (neighbour slot, meta).  meta packs n_eff (bits 0-7; n_k for the
+// n-e_k link, n_k+1 for the n+e_k link), the dissipaton k (bits 8-15), the
+// direction (bit 16: 0 = minus, 1 = plus) and the coupling mode (bits 24-31).
+HEOM_HD int link_meta(int dir, int k, int neff, int mode) {
+    return neff | (k << 8) | (dir << 16) | (mode << 24);
 }
-HEOM_HD int meta_ci(int meta) { return meta & 0xffffff; }
+HEOM_HD int meta_neff(int meta) { return meta & 0xff; }
+HEOM_HD int meta_k(int meta) { return (meta >> 8) & 0xff; }
+HEOM_HD int meta_dir(int meta) { return (meta >> 16) & 1; }
 HEOM_HD int meta_mode(int meta) { return (meta >> 24) & 0xff; }
+// index into the full coefficient table [dir][k][n_eff]
+HEOM_HD int meta_ci(int meta, int K, int L) {
+    return (meta_dir(meta) * K + meta_k(meta)) * (L + 1) + meta_neff(meta);
+}
 
 }  // namespace heom

@@ -28,6 +28,14 @@
 
 using heom::Pascal;
 
+// build-time tuning knobs (see pyqed_b200/build.py)
+#ifndef HEOM_U
+#define HEOM_U 4          // links fetched per batch in the diagonal-Q path
+#endif
+#ifndef HEOM_MINBLOCKS
+#define HEOM_MINBLOCKS 2  // __launch_bounds__ min blocks per SM for the row kernel
+#endif
+
 // ---------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------
@@ -75,7 +83,7 @@ __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 // ---------------------------------------------------------------------------
 struct TableLayout {
     size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
-        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, step_base, total;
+        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, step_base, total;
 };
 
 struct pyqed_heom_plan {
@@ -141,6 +149,7 @@ static int compute_layout(pyqed_heom_plan* p) {
     t.col_ptr = take(sizeof(short) * M1 * (p->N + 1));
     t.col_idx = take(sizeof(short) * M1 * NN);
     t.supp = take((size_t)p->M * (2 * p->N + 1));
+    t.cbase = take(sizeof(double2) * 4 * p->K);
     t.step_base = take(sizeof(long long));
     t.total = off;
     p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
@@ -208,13 +217,13 @@ __global__ void hier_links_kernel(HierArgs h) {
             key[k] = (uint8_t)(nk - 1);
             const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
             key[k] = (uint8_t)nk;
-            h.links[w++] = make_int2((int)nb, heom::link_meta(0, k, nk, h.mode[k], h.K, h.L));
+            h.links[w++] = make_int2((int)nb, heom::link_meta(0, k, nk, h.mode[k]));
         }
         if (tier < h.L) {
             key[k] = (uint8_t)(nk + 1);
             const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
             key[k] = (uint8_t)nk;
-            h.links[w++] = make_int2((int)nb, heom::link_meta(1, k, nk + 1, h.mode[k], h.K, h.L));
+            h.links[w++] = make_int2((int)nb, heom::link_meta(1, k, nk + 1, h.mode[k]));
         }
     }
 }
@@ -309,7 +318,8 @@ struct StageArgs {
     long long nmax, slot0, ngroups;
     double a, w;
     int local_step, first, last, N;
-    int herm, ncoef, nmod;
+    int herm, ncoef, nmod, nind, lmax;
+    const double2* cbase;  // [K][4]: minus (L,R) and plus (L,R) coefficients for n_eff = 1
 };
 
 template <int N>
@@ -334,10 +344,10 @@ __device__ __forceinline__ void st_stream(double2* p, const double2 v) { __stcs(
 //    U links are fetched per batch to keep U independent loads in flight per lane.
 //  general Q: per-lane sparse row/column products in registers.
 template <int N, bool TDEP, bool QDIAG>
-__global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
+__global__ void __launch_bounds__(256, HEOM_MINBLOCKS) stage_rows_kernel(const StageArgs a,
                                                          const __grid_constant__ HParam<N> hp) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int U = 4;
+    constexpr int U = HEOM_U;
     extern __shared__ double2 smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int b = blockIdx.y;
@@ -432,7 +442,7 @@ __global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const int ci = heom::meta_ci(lk[u].y), m = heom::meta_mode(lk[u].y);
+                        const int ci = heom::meta_ci(lk[u].y, a.nind, a.lmax), m = heom::meta_mode(lk[u].y);
                         const double2 aL = coef_s[2 * ci], aR = coef_s[2 * ci + 1];
                         const double2* __restrict__ pn = yin + (long long)lk[u].x * NN;
                         const int ns = supp_s[m * (N + 1)];
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
                 for (int lp = lbeg; lp < lend; ++lp) {
                     const int2 lk = a.links[lp];
                     const double2* __restrict__ pn = yin + (long long)lk.x * NN;
-                    const int ci = heom::meta_ci(lk.y), m1 = 1 + heom::meta_mode(lk.y);
+                    const int ci = heom::meta_ci(lk.y, a.nind, a.lmax), m1 = 1 + heom::meta_mode(lk.y);
                     const double2 aL = a.coef[2 * ci], aR = a.coef[2 * ci + 1];
                     const double2* __restrict__ Qm = ops + m1 * NN;
                     const short* rp = a.row_ptr + m1 * (N + 1);
@@ -491,24 +501,344 @@ __global__ void __launch_bounds__(256) stage_rows_kernel(const StageArgs a,
             }
         }
         __syncwarp();
-        // flat epilogue: coalesced 128-bit streaming traffic on y / acc / outputs
+        // flat epilogue: coalesced 128-bit streaming traffic on y / acc / outputs.
+        // All loads of the group are issued before the first store so that they
+        // overlap (the compiler cannot prove the outputs do not alias the inputs).
         const long long gbase = boff + base * NN;
-        for (int e = lane; e < nelem; e += 32) {
-            const int s = e / NN, rr = e - s * NN, i = rr / N, j = rr - i * N;
-            const int si = (s * N + i) * LD + j;
-            const double2 k = k_s[si];
-            const long long gi = gbase + e;
-            if (a.last) {
-                const double2 bs = a.first ? rho_s[si] : ld_stream(a.acc + gi);
+        constexpr int EIT = (APW * NN + 31) / 32;
+        double2 yv[EIT], bs[EIT];
+#pragma unroll
+        for (int it = 0; it < EIT; ++it) {
+            const int e = lane + 32 * it;
+            if (e < nelem) {
+                const long long gi = gbase + e;
+                if (!a.first) {
+                    bs[it] = ld_stream(a.acc + gi);
+                    if (!a.last) yv[it] = ld_stream(a.y + gi);
+                }
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < EIT; ++it) {
+            const int e = lane + 32 * it;
+            if (e < nelem) {
+                const int s = e / NN, rr = e - s * NN, i = rr / N, j = rr - i * N;
+                const int si = (s * N + i) * LD + j;
+                const double2 k = k_s[si];
+                const long long gi = gbase + e;
+                if (a.first) {
+                    yv[it] = rho_s[si];
+                    bs[it] = yv[it];
+                }
+                const double2 res = make_double2(fma(a.w, k.x, bs[it].x), fma(a.w, k.y, bs[it].y));
+                if (a.last) {
+                    st_stream(a.ydst + gi, res);
+                    if (a.traj && base + s == a.slot0)
+                        a.traj[b * a.traj_bstride + (step + 1) * NN + rr] = res;
+                } else {
+                    st_stream(a.acc + gi, res);
+                    st_stream(a.yout + gi,
+                              make_double2(fma(a.a, k.x, yv[it].x), fma(a.a, k.y, yv[it].y)));
+                }
+            }
+        }
+        __syncwarp();
+    }
+#undef HEL
+}
+
+// ---------------------------------------------------------------------------
+// Kernel 3 (N <= 8, every Q_m diagonal): same lane mapping as kernel 1, but every
+// global read of a group goes through cp.async into shared memory so that no
+// registers are tied up by loads in flight:
+//   group A: the group's own y_in tile + one row of each of the first N
+//            neighbours of every ADO (link records are prefetched one group ahead)
+//   group B: the y and acc tiles the epilogue will need
+// The commutator runs while B (and later link chunks) are still in flight.
+// Neighbour contributions are accumulated in registers per target row and
+// flushed to the k tile once per row instead of once per link.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NWAIT>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NWAIT) : "memory");
+}
+
+constexpr int ASYNC_MAX_THREADS = 384;
+
+template <int N, bool TDEP>
+__global__ void __launch_bounds__(ASYNC_MAX_THREADS, 1)
+stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp) {
+    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
+    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT;
+    constexpr int EIT = (FLAT + 31) / 32;
+    extern __shared__ double2 smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
+    double2* Hs = smem;
+    double2* cb_s = Hs + (TDEP ? NN : 0);
+    double2* qd_s = cb_s + 4 * a.nind;
+    double* sq_s = (double*)(qd_s + a.nmod * N);
+    double2* warp0 = (double2*)(sq_s + ((a.lmax + 2) & ~1));
+    double2* rho_s = warp0 + wid * PERWARP;
+    double2* k_s = rho_s + TILE;
+    double2* y_s = k_s + TILE;
+    double2* acc_s = y_s + FLAT;
+    double2* nb_s = acc_s + FLAT;
+    unsigned char* supp_s = (unsigned char*)(warp0 + nwarps * PERWARP);
+    if (TDEP) {
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) Hs[e] = ops[e];
+    }
+    for (int e = threadIdx.x; e < 4 * a.nind; e += blockDim.x) cb_s[e] = a.cbase[e];
+    for (int e = threadIdx.x; e < a.nmod * N; e += blockDim.x) {
+        const int m = e / N, j = e - m * N;
+        qd_s[e] = ops[(1 + m) * NN + j * N + j];
+    }
+    for (int e = threadIdx.x; e <= a.lmax; e += blockDim.x) sq_s[e] = sqrt((double)e);
+    for (int e = threadIdx.x; e < a.nmod * (2 * N + 1); e += blockDim.x) supp_s[e] = a.supp[e];
+    __syncthreads();
+#define HEL(r_, c_) (TDEP ? Hs[(r_) * N + (c_)] : hp.v[(r_) * N + (c_)])
+    const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
+    const long long boff = (long long)b * a.nmax * NN;
+    const double2* __restrict__ yin = a.yin + boff;
+    const int sub = lane / N, row = lane - sub * N;
+    const bool lane_ok = lane < APW * N;
+    const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
+    const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
+    const long long gstride = (long long)gridDim.x * nwarps;
+
+    // link bookkeeping of the group about to be processed, fetched one group ahead
+    int nx_lbeg = 0, nx_lend = 0;
+    int2 nx_rec = make_int2(0, 0);
+    long long g = (long long)blockIdx.x * nwarps + wid;
+    if (g < a.ngroups) {
+        const long long slot = g * APW + sub;
+        if (lane_ok && slot < a.nmax) {
+            nx_lbeg = a.link_ptr[slot];
+            nx_lend = a.link_ptr[slot + 1];
+            if (nx_lbeg + row < nx_lend) nx_rec = __ldg(a.links + nx_lbeg + row);
+        }
+    }
+
+    for (; g < a.ngroups; g += gstride) {
+        const long long base = g * APW;
+        const int cnt = (int)min((long long)APW, a.nmax - base);
+        const int nelem = cnt * NN;
+        const bool on = lane_ok && sub < cnt;
+        const int lbeg = nx_lbeg, lend = nx_lend;
+        const int nl = on ? (lend - lbeg) : 0;
+        int2 rec = nx_rec;
+        int2 rts[N];
+        const long long gbase = boff + base * NN;
+
+        // ---- issue: own tile + first chunk of neighbour rows (group A), y/acc (group B)
+        {
+            const double2* src = yin + base * NN;
+#pragma unroll
+            for (int it = 0; it < EIT; ++it) {
+                const int e = lane + 32 * it;
+                if (e < nelem) {
+                    const int s = e / NN, r = e - s * NN, i = r / N, j = r - i * N;
+                    cp_async16(&rho_s[(s * N + i) * LD + j], src + e);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            const int srcl = (sub * N + t) & 31;
+            rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
+            rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
+            if (on && t < nl) {
+                const int m = heom::meta_mode(rts[t].y);
+                const int r0 = supp_s[m * (N + 1) + 1];
+                cp_async16(&nb_s[(sub * N + t) * N + row], yin + (long long)rts[t].x * NN + r0 * N + row);
+            }
+        }
+        cp_async_commit();
+        if (!a.first) {
+#pragma unroll
+            for (int it = 0; it < EIT; ++it) {
+                const int e = lane + 32 * it;
+                if (e < nelem) {
+                    cp_async16(&acc_s[e], a.acc + gbase + e);
+                    if (!a.last) cp_async16(&y_s[e], a.y + gbase + e);
+                }
+            }
+        }
+        cp_async_commit();
+
+        // ---- start fetching the next group's link offsets
+        {
+            const long long gn = g + gstride;
+            const long long slot = gn * APW + sub;
+            nx_lbeg = nx_lend = 0;
+            if (gn < a.ngroups && lane_ok && slot < a.nmax) {
+                nx_lbeg = a.link_ptr[slot];
+                nx_lend = a.link_ptr[slot + 1];
+            }
+        }
+
+        cp_async_wait<1>();
+        __syncwarp();
+
+        // ---- -i[H, rho] - damp rho  (as kernel 1)
+        if (on) {
+            double2 col[N];
+#pragma unroll
+            for (int l = 0; l < N; ++l) col[l] = rho_s[(sub * N + l) * LD + row];
+#pragma unroll
+            for (int rr = 0; rr < N; ++rr) {
+                double2 c = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int l = 0; l < N; ++l) cfma(c, HEL(rr, l), col[l]);
+                k_s[(sub * N + rr) * LD + row] = c;
+            }
+        }
+        __syncwarp();
+        if (on) {
+            const long long slot = base + sub;
+            double2 rv[N];
+#pragma unroll
+            for (int l = 0; l < N; ++l) rv[l] = rho_s[(sub * N + row) * LD + l];
+            const double2 d = a.damp[slot];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                double2 t = k_s[(sub * N + row) * LD + j];
+#pragma unroll
+                for (int l = 0; l < N; ++l) cfms(t, rv[l], HEL(l, j));
+                k_s[(sub * N + row) * LD + j] =
+                    make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
+                                 -t.x - (d.x * rv[j].y + d.y * rv[j].x));
+            }
+        }
+        // the next group's first link record (its offsets have arrived by now)
+        nx_rec = make_int2(0, 0);
+        if (nx_lbeg + row < nx_lend) nx_rec = __ldg(a.links + nx_lbeg + row);
+        __syncwarp();
+
+        // ---- neighbour terms, N links per chunk
+        const int maxl = __reduce_max_sync(0xffffffffu, nl);
+        double2 X = make_double2(0.0, 0.0), Y = make_double2(0.0, 0.0);
+        int cur_rr = -1;
+        bool yused = false;
+        for (int c0 = 0; c0 < maxl; c0 += N) {
+            if (c0 > 0) {
+                rec = make_int2(0, 0);
+                if (on && lbeg + c0 + row < lend) rec = __ldg(a.links + lbeg + c0 + row);
+                __syncwarp();  // every lane is done with the previous chunk's rows
+#pragma unroll
+                for (int t = 0; t < N; ++t) {
+                    const int srcl = (sub * N + t) & 31;
+                    rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
+                    rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
+                    if (on && c0 + t < nl) {
+                        const int m = heom::meta_mode(rts[t].y);
+                        const int r0 = supp_s[m * (N + 1) + 1];
+                        cp_async16(&nb_s[(sub * N + t) * N + row],
+                                   yin + (long long)rts[t].x * NN + r0 * N + row);
+                    }
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+            }
+            if (on) {
+#pragma unroll
+                for (int t = 0; t < N; ++t) {
+                    if (c0 + t < nl) {
+                        const int meta = rts[t].y;
+                        const int m = heom::meta_mode(meta), kk = heom::meta_k(meta);
+                        const int dir = heom::meta_dir(meta);
+                        const double sq = sq_s[heom::meta_neff(meta)];
+                        const double2 bL = cb_s[4 * kk + 2 * dir], bR = cb_s[4 * kk + 2 * dir + 1];
+                        const double2 aL = make_double2(bL.x * sq, bL.y * sq);
+                        const double2 aR = make_double2(bR.x * sq, bR.y * sq);
+                        const double2* __restrict__ pn = yin + (long long)rts[t].x * NN;
+                        const int ns = supp_s[m * (N + 1)];
+                        const double2 qj = qd_s[m * N + row];
+                        const bool outside = insupp_s[m * N + row] == 0;
+                        for (int t2 = 0; t2 < ns; ++t2) {
+                            const int rr = supp_s[m * (N + 1) + 1 + t2];
+                            const double2 Aj = (t2 == 0) ? nb_s[(sub * N + t) * N + row]
+                                                         : ldg2(pn + rr * N + row);
+                            if (rr != cur_rr) {
+                                if (cur_rr >= 0) {
+                                    double2* d1 = &k_s[(sub * N + cur_rr) * LD + row];
+                                    double2 v1 = *d1;
+                                    v1.x += X.x;
+                                    v1.y += X.y;
+                                    *d1 = v1;
+                                    if (yused) {
+                                        double2* d2 = &k_s[(sub * N + row) * LD + cur_rr];
+                                        double2 v2 = *d2;
+                                        v2.x += Y.x;
+                                        v2.y += Y.y;
+                                        *d2 = v2;
+                                    }
+                                    __syncwarp(submask);
+                                }
+                                cur_rr = rr;
+                                X = make_double2(0.0, 0.0);
+                                Y = make_double2(0.0, 0.0);
+                                yused = false;
+                            }
+                            const double2 qr = qd_s[m * N + rr];
+                            double2 c = cmul(aL, qr);
+                            cfma(c, aR, qj);
+                            cfma(X, c, Aj);
+                            if (outside) {
+                                const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y)
+                                                          : ldg2(pn + row * N + rr);
+                                cfma(Y, cmul(aR, qr), Bj);
+                                yused = true;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (on && cur_rr >= 0) {
+            double2* d1 = &k_s[(sub * N + cur_rr) * LD + row];
+            double2 v1 = *d1;
+            v1.x += X.x;
+            v1.y += X.y;
+            *d1 = v1;
+            if (yused) {
+                double2* d2 = &k_s[(sub * N + row) * LD + cur_rr];
+                double2 v2 = *d2;
+                v2.x += Y.x;
+                v2.y += Y.y;
+                *d2 = v2;
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+
+        // ---- epilogue from shared memory, streaming stores
+#pragma unroll
+        for (int it = 0; it < EIT; ++it) {
+            const int e = lane + 32 * it;
+            if (e < nelem) {
+                const int s = e / NN, rr = e - s * NN, i = rr / N, j = rr - i * N;
+                const int si = (s * N + i) * LD + j;
+                const double2 k = k_s[si];
+                const long long gi = gbase + e;
+                const double2 yv = a.first ? rho_s[si] : (a.last ? make_double2(0.0, 0.0) : y_s[e]);
+                const double2 bs = a.first ? yv : acc_s[e];
                 const double2 res = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
-                st_stream(a.ydst + gi, res);
-                if (a.traj && base + s == a.slot0)
-                    a.traj[b * a.traj_bstride + (step + 1) * NN + rr] = res;
-            } else {
-                const double2 yv = a.first ? rho_s[si] : ld_stream(a.y + gi);
-                const double2 bs = a.first ? yv : ld_stream(a.acc + gi);
-                st_stream(a.acc + gi, make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y)));
-                st_stream(a.yout + gi, make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
+                if (a.last) {
+                    st_stream(a.ydst + gi, res);
+                    if (a.traj && base + s == a.slot0)
+                        a.traj[b * a.traj_bstride + (step + 1) * NN + rr] = res;
+                } else {
+                    st_stream(a.acc + gi, res);
+                    st_stream(a.yout + gi, make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
+                }
             }
         }
         __syncwarp();
@@ -554,7 +884,7 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(const StageArgs a) {
             for (int lp = lbeg; lp < lend; ++lp) {
                 const int2 lk = a.links[lp];
                 const double2* __restrict__ pn = yin + (long long)lk.x * NN;
-                const int ci = heom::meta_ci(lk.y), m1 = 1 + heom::meta_mode(lk.y);
+                const int ci = heom::meta_ci(lk.y, a.nind, a.lmax), m1 = 1 + heom::meta_mode(lk.y);
                 const double2 aL = a.coef[2 * ci], aR = a.coef[2 * ci + 1];
                 const double2* __restrict__ Qm = ops + m1 * NN;
                 const short* rp = a.row_ptr + m1 * (N + 1);
@@ -634,6 +964,39 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     return post_launch(p, "stage_rows_kernel");
 }
 
+template <int N, bool TDEP>
+static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
+    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
+    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT;
+    StageArgs args = a;
+    args.ngroups = (p->nmax + APW - 1) / APW;
+    const size_t table_bytes = sizeof(double2) * ((TDEP ? NN : 0) + 4 * (size_t)p->K + (size_t)p->M * N) +
+                               sizeof(double) * ((p->L + 2) & ~1) + align_up((size_t)p->M * (2 * N + 1), 16);
+    const size_t per_warp = sizeof(double2) * PERWARP;
+    const size_t budget = 227 * 1024;
+    REQUIRE(table_bytes + per_warp <= budget, "shared-memory tables too large for the async row kernel");
+    int maxw = (int)std::min<size_t>(ASYNC_MAX_THREADS / 32, (budget - table_bytes) / per_warp);
+    int warps = p->warps > 0 ? std::min(p->warps, maxw) : maxw;
+    if (p->warps <= 0) {
+        // small hierarchies: spread the groups over all SMs first
+        const long long per_sm = (args.ngroups * p->B + sm_count - 1) / sm_count;
+        warps = (int)std::max<long long>(1, std::min<long long>(maxw, per_sm));
+    }
+    const size_t smem = table_bytes + per_warp * warps;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        attr_set = true;
+    }
+    const long long ctas = (args.ngroups + warps - 1) / warps;
+    dim3 grid((unsigned)std::min<long long>(ctas, sm_count), p->B);
+    HParam<N> hp;
+    for (int e = 0; e < NN; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
+    stage_rows_async_kernel<N, TDEP><<<grid, warps * 32, smem, p->stream>>>(args, hp);
+    return post_launch(p, "stage_rows_async_kernel");
+}
+
 template <int N>
 static int launch_rows_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool qdiag) {
     if (tdep) return qdiag ? launch_rows<N, true, true>(p, a, sm_count) : launch_rows<N, true, false>(p, a, sm_count);
@@ -655,8 +1018,19 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
         CU_TRY(cudaEventRecord(p->ev[p->ev_used].first, p->stream));
     }
     int rc = 0;
-    const int kern = p->kernel ? p->kernel : (p->N <= 8 ? 1 : 2);
-    if (kern == 1) {
+    const int kern = p->kernel ? p->kernel : (p->N <= 8 ? (p->use_qdiag ? 3 : 1) : 2);
+    if (kern == 3) {
+        REQUIRE(p->N >= 2 && p->N <= 8 && p->use_qdiag,
+                "kernel 3 needs 2 <= N <= 8 and diagonal coupling operators");
+#define ASYNC_CASE(n)                                                                              \
+    case n:                                                                                        \
+        rc = tdep ? launch_async<n, true>(p, a, sm_count) : launch_async<n, false>(p, a, sm_count); \
+        break;
+        switch (p->N) {
+            ASYNC_CASE(2) ASYNC_CASE(3) ASYNC_CASE(4) ASYNC_CASE(5) ASYNC_CASE(6) ASYNC_CASE(7) ASYNC_CASE(8)
+        }
+#undef ASYNC_CASE
+    } else if (kern == 1) {
         REQUIRE(p->N >= 2 && p->N <= 8, "kernel 1 needs 2 <= N <= 8");
 #define ROWS_CASE(n)                                              \
     case n:                                                       \
@@ -820,7 +1194,7 @@ int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
 
 int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
     REQUIRE(p, "null plan");
-    REQUIRE(kernel >= 0 && kernel <= 2, "kernel must be 0, 1 or 2");
+    REQUIRE(kernel >= 0 && kernel <= 3, "kernel must be 0..3");
     REQUIRE(warps >= 0 && warps <= 8, "warps_per_cta must be in [0, 8]");
     p->kernel = kernel;
     p->warps = warps;
@@ -944,6 +1318,20 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
     }
     CU_TRY(cudaMemcpyAsync(p->d_tables + t.coef, coef.data(), sizeof(double) * coef.size(),
                            cudaMemcpyHostToDevice, s));
+    {   // per-dissipaton base coefficients (n_eff = 1); the async kernel scales by sqrt(n_eff)
+        std::vector<double> cb((size_t)8 * K);
+        for (int k = 0; k < K; ++k) {
+            const std::complex<double> sa = std::sqrt(p->etaa[k]);
+            const std::complex<double> v[4] = {-(I / sa) * p->etal[k], (I / sa) * p->etar[k], -I * sa, I * sa};
+            for (int q = 0; q < 4; ++q) {
+                cb[(size_t)8 * k + 2 * q] = v[q].real();
+                cb[(size_t)8 * k + 2 * q + 1] = v[q].imag();
+            }
+        }
+        CU_TRY(cudaMemcpyAsync(p->d_tables + t.cbase, cb.data(), sizeof(double) * cb.size(),
+                               cudaMemcpyHostToDevice, s));
+        CU_TRY(cudaStreamSynchronize(s));
+    }
     // operators and their sparsity lists
     std::vector<double> base((size_t)M1 * NN * 2), dip((size_t)M1 * NN * 2);
     std::vector<short> rp((size_t)M1 * (N + 1)), ri((size_t)M1 * NN), cp((size_t)M1 * (N + 1)),
@@ -1214,6 +1602,9 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
     a.herm = (p->herm_inputs && p->herm_state && p->opt_herm != 0) ? 1 : 0;
     a.ncoef = 2 * p->K * (p->L + 1);
     a.nmod = p->M;
+    a.nind = p->K;
+    a.lmax = p->L;
+    a.cbase = p->tab<double2>(t.cbase);
     a.traj = traj;
     a.step_base = p->tab<long long>(t.step_base);
     a.traj_bstride = traj_bstride;

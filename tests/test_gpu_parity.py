@@ -84,11 +84,26 @@ def test_fast_path_detection():
         assert s._plan.info("hermitian") == herm, name
 
 
+@pytest.mark.parametrize("kernel", [1, 3])
 @pytest.mark.parametrize("warps", [1, 2, 4, 8])
-def test_warps_per_cta(warps):
+def test_warps_per_cta(warps, kernel):
     g = golden("deom_fmo_K21_L2")
     s = _solver_from(g)
-    s.tuning = dict(kernel=1, warps_per_cta=warps, use_graph=0)
+    s.tuning = dict(kernel=kernel, warps_per_cta=warps, use_graph=0)
+    _check_against_golden(g, s)
+
+
+@pytest.mark.parametrize("kernel", [1, 3])
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L3", "deom_spin_boson_L10",
+                                  "deom_aggregate_L3_T0"])
+@pytest.mark.parametrize("herm", [-1, 0])
+def test_row_kernels_on_diagonal_coupling(name, kernel, herm):
+    """Both row kernels (plain loads / cp.async staging), with and without
+    the Hermitian row fetch, on projector, sigma_z and occupation couplings."""
+    g = golden(name)
+    s = _solver_from(g)
+    s.tuning = dict(kernel=kernel, warps_per_cta=0, use_graph=0)
+    s.options = {"hermitian": herm}
     _check_against_golden(g, s)
 
 
