@@ -145,8 +145,9 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *   "hermitian"  when H, Q, the bath (real expn, etar = conj(etal), etaa > 0)
  *                and the loaded state keep every ADO Hermitian, fetch a
  *                neighbour's column entries as the conjugate of its row
+ *   "real_h"     use real arithmetic for the H products when H and mu are real
  *   "debug_sync" synchronise and check after every launch
- * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian",
+ * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "real_h",
  * "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */
 int pyqed_heom_set_option(pyqed_heom_plan* plan, const char* name, int value);
 int64_t pyqed_heom_get_info(pyqed_heom_plan* plan, const char* name);

@@ -99,15 +99,20 @@ HEOM_HD void unrank_slot(int order, long long slot, int K, int L, const Pascal& 
 }
 
 // ---- link metadata ----------------------------------------------------------
-// One link = (neighbour slot, meta).  meta packs n_eff (bits 0-7; n_k for the
-// n-e_k link, n_k+1 for the n+e_k link), the dissipaton k (bits 8-15), the
-// direction (bit 16: 0 = minus, 1 = plus) and the coupling mode (bits 24-31).
-HEOM_HD int link_meta(int dir, int k, int neff, int mode) {
-    return neff | (k << 8) | (dir << 16) | (mode << 24);
+// One link = (neighbour slot, meta).  meta packs
+//   bits 0-7   n_eff (n_k for the n-e_k link, n_k+1 for the n+e_k link)
+//   bit  8     direction (0 = minus, 1 = plus)
+//   bits 9-15  dissipaton k          -> bits 8-15 together are 2k+dir
+//   bits 16-19 first row r with (Q_mode)_rr != 0 (used by the diagonal-Q kernels)
+//   bits 24-31 coupling mode
+HEOM_HD int link_meta(int dir, int k, int neff, int mode, int r0) {
+    return neff | (dir << 8) | (k << 9) | ((r0 & 0xf) << 16) | (mode << 24);
 }
 HEOM_HD int meta_neff(int meta) { return meta & 0xff; }
-HEOM_HD int meta_k(int meta) { return (meta >> 8) & 0xff; }
-HEOM_HD int meta_dir(int meta) { return (meta >> 16) & 1; }
+HEOM_HD int meta_dir(int meta) { return (meta >> 8) & 1; }
+HEOM_HD int meta_k(int meta) { return (meta >> 9) & 0x7f; }
+HEOM_HD int meta_kdir(int meta) { return (meta >> 8) & 0xff; }  // 2k + dir
+HEOM_HD int meta_r0(int meta) { return (meta >> 16) & 0xf; }
 HEOM_HD int meta_mode(int meta) { return (meta >> 24) & 0xff; }
 // index into the full coefficient table [dir][k][n_eff]
 HEOM_HD int meta_ci(int meta, int K, int L) {

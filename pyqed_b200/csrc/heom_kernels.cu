@@ -83,7 +83,7 @@ __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 // ---------------------------------------------------------------------------
 struct TableLayout {
     size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
-        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, step_base, total;
+        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, step_base, total;
 };
 
 struct pyqed_heom_plan {
@@ -99,7 +99,9 @@ struct pyqed_heom_plan {
     bool herm_inputs = false;    // operators/bath keep every ADO Hermitian
     bool herm_state = false;     // ... and so is the state that was loaded
     bool use_qdiag = false;      // resolved at build time from the options below
-    int opt_qdiag = -1, opt_herm = -1;  // -1 auto, 0 off, 1 on
+    bool h_real = false;         // H and mu have no imaginary part
+    std::vector<int> r0mode;     // first row with a non-zero diagonal entry, per mode
+    int opt_qdiag = -1, opt_herm = -1, opt_hreal = -1;  // -1 auto, 0 off, 1 on
     TableLayout tl{};
     char* d_tables = nullptr;
     char* d_state = nullptr;
@@ -150,6 +152,7 @@ static int compute_layout(pyqed_heom_plan* p) {
     t.col_idx = take(sizeof(short) * M1 * NN);
     t.supp = take((size_t)p->M * (2 * p->N + 1));
     t.cbase = take(sizeof(double2) * 4 * p->K);
+    t.kmode = take(sizeof(int) * p->K);
     t.step_base = take(sizeof(long long));
     t.total = off;
     p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
@@ -170,7 +173,7 @@ struct HierArgs {
     int* link_ptr;
     int2* links;
     const double2* expn;  // [K] device copy (stored at the head of coef scratch)
-    const int* mode;      // [K]
+    const int* mode;      // [K]: mode | first support row << 8
 };
 
 // pass 1: one thread per storage slot - multi-index, damping rate, link count
@@ -217,13 +220,13 @@ __global__ void hier_links_kernel(HierArgs h) {
             key[k] = (uint8_t)(nk - 1);
             const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
             key[k] = (uint8_t)nk;
-            h.links[w++] = make_int2((int)nb, heom::link_meta(0, k, nk, h.mode[k]));
+            h.links[w++] = make_int2((int)nb, heom::link_meta(0, k, nk, h.mode[k] & 0xff, h.mode[k] >> 8));
         }
         if (tier < h.L) {
             key[k] = (uint8_t)(nk + 1);
             const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
             key[k] = (uint8_t)nk;
-            h.links[w++] = make_int2((int)nb, heom::link_meta(1, k, nk + 1, h.mode[k]));
+            h.links[w++] = make_int2((int)nb, heom::link_meta(1, k, nk + 1, h.mode[k] & 0xff, h.mode[k] >> 8));
         }
     }
 }
@@ -320,6 +323,7 @@ struct StageArgs {
     int local_step, first, last, N;
     int herm, ncoef, nmod, nind, lmax;
     const double2* cbase;  // [K][4]: minus (L,R) and plus (L,R) coefficients for n_eff = 1
+    const int* kmode;      // [K]: mode | first support row << 8
 };
 
 template <int N>
@@ -570,7 +574,25 @@ __device__ __forceinline__ void cp_async_wait() {
 
 constexpr int ASYNC_MAX_THREADS = 384;
 
-template <int N, bool TDEP>
+// shared-memory tables of the async kernel (sizes in double2 units unless noted)
+struct AsyncTables {
+    int H, cb, cq, qd, sq, warp0;   // offsets in double2 units
+    int bytes_tail;                 // supp (cnt/rows, membership) bytes after the warp buffers
+};
+__host__ __device__ inline AsyncTables async_tables(int N, int K, int M, int L, bool tdep) {
+    AsyncTables t;
+    int o = 0;
+    t.H = o;  o += tdep ? N * N : 0;
+    t.cb = o; o += 4 * K;           // general path: (mL, mR, pL, pR) per k
+    t.cq = o; o += 3 * 2 * K;       // single-row path: per 2k+dir (bL q, (bL+bR) q, bR q)
+    t.qd = o; o += M * N;           // diagonal entries of Q_m
+    t.sq = o; o += (L + 2) / 2;     // sqrt(n) as doubles
+    t.warp0 = o;
+    t.bytes_tail = (M * (2 * N + 1) + 15) / 16 * 16;
+    return t;
+}
+
+template <int N, bool TDEP, bool HREAL>
 __global__ void __launch_bounds__(ASYNC_MAX_THREADS, 1)
 stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
@@ -580,11 +602,13 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int b = blockIdx.y;
     const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
-    double2* Hs = smem;
-    double2* cb_s = Hs + (TDEP ? NN : 0);
-    double2* qd_s = cb_s + 4 * a.nind;
-    double* sq_s = (double*)(qd_s + a.nmod * N);
-    double2* warp0 = (double2*)(sq_s + ((a.lmax + 2) & ~1));
+    const AsyncTables T = async_tables(N, a.nind, a.nmod, a.lmax, TDEP);
+    double2* Hs = smem + T.H;
+    double2* cb_s = smem + T.cb;
+    double2* cq_s = smem + T.cq;
+    double2* qd_s = smem + T.qd;
+    double* sq_s = (double*)(smem + T.sq);
+    double2* warp0 = smem + T.warp0;
     double2* rho_s = warp0 + wid * PERWARP;
     double2* k_s = rho_s + TILE;
     double2* y_s = k_s + TILE;
@@ -601,8 +625,17 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     }
     for (int e = threadIdx.x; e <= a.lmax; e += blockDim.x) sq_s[e] = sqrt((double)e);
     for (int e = threadIdx.x; e < a.nmod * (2 * N + 1); e += blockDim.x) supp_s[e] = a.supp[e];
+    for (int e = threadIdx.x; e < 2 * a.nind; e += blockDim.x) {
+        // e = 2k + dir; mode and first support row of dissipaton k
+        const int k = e >> 1, dir = e & 1;
+        const int m = a.kmode[k] & 0xff, r0 = a.kmode[k] >> 8;
+        const double2 q = ops[(1 + m) * NN + r0 * N + r0];
+        const double2 bL = a.cbase[4 * k + 2 * dir], bR = a.cbase[4 * k + 2 * dir + 1];
+        cq_s[3 * e + 0] = cmul(bL, q);
+        cq_s[3 * e + 1] = cmul(make_double2(bL.x + bR.x, bL.y + bR.y), q);
+        cq_s[3 * e + 2] = cmul(bR, q);
+    }
     __syncthreads();
-#define HEL(r_, c_) (TDEP ? Hs[(r_) * N + (c_)] : hp.v[(r_) * N + (c_)])
     const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
     const long long boff = (long long)b * a.nmax * NN;
     const double2* __restrict__ yin = a.yin + boff;
@@ -611,6 +644,20 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
     const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
     const long long gstride = (long long)gridDim.x * nwarps;
+    // flat element e = lane + 32 it  ->  offset in the (possibly padded) tile
+    int pofs[EIT];
+#pragma unroll
+    for (int it = 0; it < EIT; ++it) {
+        const int e = lane + 32 * it;
+        if (LD == N) pofs[it] = e;
+        else {
+            const int s = e / NN, r = e - s * NN, i = r / N, j = r - i * N;
+            pofs[it] = (s * N + i) * LD + j;
+        }
+    }
+    double2* const ksub = k_s + sub * N * LD;     // this ADO's k tile
+    double2* const rsub = rho_s + sub * N * LD;
+    double2* const nbrow = nb_s + sub * NN + row; // + t*N: row element of staged link t
 
     // link bookkeeping of the group about to be processed, fetched one group ahead
     int nx_lbeg = 0, nx_lend = 0;
@@ -638,37 +685,30 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
 
         // ---- issue: own tile + first chunk of neighbour rows (group A), y/acc (group B)
         {
-            const double2* src = yin + base * NN;
+            const double2* src = yin + base * NN + lane;
 #pragma unroll
-            for (int it = 0; it < EIT; ++it) {
-                const int e = lane + 32 * it;
-                if (e < nelem) {
-                    const int s = e / NN, r = e - s * NN, i = r / N, j = r - i * N;
-                    cp_async16(&rho_s[(s * N + i) * LD + j], src + e);
-                }
-            }
+            for (int it = 0; it < EIT; ++it)
+                if (lane + 32 * it < nelem) cp_async16(&rho_s[pofs[it]], src + 32 * it);
         }
 #pragma unroll
         for (int t = 0; t < N; ++t) {
             const int srcl = (sub * N + t) & 31;
             rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
             rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
-            if (on && t < nl) {
-                const int m = heom::meta_mode(rts[t].y);
-                const int r0 = supp_s[m * (N + 1) + 1];
-                cp_async16(&nb_s[(sub * N + t) * N + row], yin + (long long)rts[t].x * NN + r0 * N + row);
-            }
+            if (t < nl)
+                cp_async16(nbrow + t * N,
+                           yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
         }
         cp_async_commit();
         if (!a.first) {
+            const double2* sa = a.acc + gbase + lane;
+            const double2* sy = a.y + gbase + lane;
 #pragma unroll
-            for (int it = 0; it < EIT; ++it) {
-                const int e = lane + 32 * it;
-                if (e < nelem) {
-                    cp_async16(&acc_s[e], a.acc + gbase + e);
-                    if (!a.last) cp_async16(&y_s[e], a.y + gbase + e);
+            for (int it = 0; it < EIT; ++it)
+                if (lane + 32 * it < nelem) {
+                    cp_async16(&acc_s[lane + 32 * it], sa + 32 * it);
+                    if (!a.last) cp_async16(&y_s[lane + 32 * it], sy + 32 * it);
                 }
-            }
         }
         cp_async_commit();
 
@@ -686,136 +726,164 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         cp_async_wait<1>();
         __syncwarp();
 
-        // ---- -i[H, rho] - damp rho  (as kernel 1)
+        // ---- -i[H, rho] - damp rho
+#define HEL(r_, c_) (TDEP ? Hs[(r_) * N + (c_)] : hp.v[(r_) * N + (c_)])
         if (on) {
             double2 col[N];
 #pragma unroll
-            for (int l = 0; l < N; ++l) col[l] = rho_s[(sub * N + l) * LD + row];
+            for (int l = 0; l < N; ++l) col[l] = rsub[l * LD + row];
 #pragma unroll
             for (int rr = 0; rr < N; ++rr) {
                 double2 c = make_double2(0.0, 0.0);
 #pragma unroll
-                for (int l = 0; l < N; ++l) cfma(c, HEL(rr, l), col[l]);
-                k_s[(sub * N + rr) * LD + row] = c;
+                for (int l = 0; l < N; ++l) {
+                    if (HREAL) {
+                        const double h = HEL(rr, l).x;
+                        c.x = fma(h, col[l].x, c.x);
+                        c.y = fma(h, col[l].y, c.y);
+                    } else {
+                        cfma(c, HEL(rr, l), col[l]);
+                    }
+                }
+                ksub[rr * LD + row] = c;
             }
         }
         __syncwarp();
         if (on) {
-            const long long slot = base + sub;
             double2 rv[N];
 #pragma unroll
-            for (int l = 0; l < N; ++l) rv[l] = rho_s[(sub * N + row) * LD + l];
-            const double2 d = a.damp[slot];
+            for (int l = 0; l < N; ++l) rv[l] = rsub[row * LD + l];
+            const double2 d = a.damp[base + sub];
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                double2 t = k_s[(sub * N + row) * LD + j];
+                double2 t = ksub[row * LD + j];
 #pragma unroll
-                for (int l = 0; l < N; ++l) cfms(t, rv[l], HEL(l, j));
-                k_s[(sub * N + row) * LD + j] =
-                    make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
-                                 -t.x - (d.x * rv[j].y + d.y * rv[j].x));
+                for (int l = 0; l < N; ++l) {
+                    if (HREAL) {
+                        const double h = HEL(l, j).x;
+                        t.x = fma(-h, rv[l].x, t.x);
+                        t.y = fma(-h, rv[l].y, t.y);
+                    } else {
+                        cfms(t, rv[l], HEL(l, j));
+                    }
+                }
+                ksub[row * LD + j] = make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
+                                                  -t.x - (d.x * rv[j].y + d.y * rv[j].x));
             }
         }
+#undef HEL
         // the next group's first link record (its offsets have arrived by now)
         nx_rec = make_int2(0, 0);
         if (nx_lbeg + row < nx_lend) nx_rec = __ldg(a.links + nx_lbeg + row);
         __syncwarp();
 
-        // ---- neighbour terms, N links per chunk
+        // ---- neighbour terms, N links per chunk; contributions to one target row
+        //      are summed in registers (X: element (cur_rr,row), Y: element (row,cur_rr))
         const int maxl = __reduce_max_sync(0xffffffffu, nl);
         double2 X = make_double2(0.0, 0.0), Y = make_double2(0.0, 0.0);
         int cur_rr = -1;
         bool yused = false;
+        auto flush = [&]() {
+            double2* d1 = ksub + cur_rr * LD + row;
+            double2 v1 = *d1;
+            v1.x += X.x;
+            v1.y += X.y;
+            *d1 = v1;
+            if (yused) {
+                double2* d2 = ksub + row * LD + cur_rr;
+                double2 v2 = *d2;
+                v2.x += Y.x;
+                v2.y += Y.y;
+                *d2 = v2;
+            }
+        };
         for (int c0 = 0; c0 < maxl; c0 += N) {
             if (c0 > 0) {
                 rec = make_int2(0, 0);
-                if (on && lbeg + c0 + row < lend) rec = __ldg(a.links + lbeg + c0 + row);
+                if (lbeg + c0 + row < lend) rec = __ldg(a.links + lbeg + c0 + row);
                 __syncwarp();  // every lane is done with the previous chunk's rows
 #pragma unroll
                 for (int t = 0; t < N; ++t) {
                     const int srcl = (sub * N + t) & 31;
                     rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
                     rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
-                    if (on && c0 + t < nl) {
-                        const int m = heom::meta_mode(rts[t].y);
-                        const int r0 = supp_s[m * (N + 1) + 1];
-                        cp_async16(&nb_s[(sub * N + t) * N + row],
-                                   yin + (long long)rts[t].x * NN + r0 * N + row);
-                    }
+                    if (c0 + t < nl)
+                        cp_async16(nbrow + t * N,
+                                   yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
                 __syncwarp();
             }
-            if (on) {
+            if (c0 < nl) {
 #pragma unroll
                 for (int t = 0; t < N; ++t) {
                     if (c0 + t < nl) {
                         const int meta = rts[t].y;
-                        const int m = heom::meta_mode(meta), kk = heom::meta_k(meta);
-                        const int dir = heom::meta_dir(meta);
+                        const int m = heom::meta_mode(meta);
+                        const int rr = heom::meta_r0(meta);
+                        const double2 Aj = nbrow[t * N];
                         const double sq = sq_s[heom::meta_neff(meta)];
-                        const double2 bL = cb_s[4 * kk + 2 * dir], bR = cb_s[4 * kk + 2 * dir + 1];
-                        const double2 aL = make_double2(bL.x * sq, bL.y * sq);
-                        const double2 aR = make_double2(bR.x * sq, bR.y * sq);
-                        const double2* __restrict__ pn = yin + (long long)rts[t].x * NN;
-                        const int ns = supp_s[m * (N + 1)];
-                        const double2 qj = qd_s[m * N + row];
-                        const bool outside = insupp_s[m * N + row] == 0;
-                        for (int t2 = 0; t2 < ns; ++t2) {
-                            const int rr = supp_s[m * (N + 1) + 1 + t2];
-                            const double2 Aj = (t2 == 0) ? nb_s[(sub * N + t) * N + row]
-                                                         : ldg2(pn + rr * N + row);
-                            if (rr != cur_rr) {
-                                if (cur_rr >= 0) {
-                                    double2* d1 = &k_s[(sub * N + cur_rr) * LD + row];
-                                    double2 v1 = *d1;
-                                    v1.x += X.x;
-                                    v1.y += X.y;
-                                    *d1 = v1;
-                                    if (yused) {
-                                        double2* d2 = &k_s[(sub * N + row) * LD + cur_rr];
-                                        double2 v2 = *d2;
-                                        v2.x += Y.x;
-                                        v2.y += Y.y;
-                                        *d2 = v2;
-                                    }
-                                    __syncwarp(submask);
-                                }
-                                cur_rr = rr;
-                                X = make_double2(0.0, 0.0);
-                                Y = make_double2(0.0, 0.0);
-                                yused = false;
+                        if (rr != cur_rr) {
+                            if (cur_rr >= 0) {
+                                flush();
+                                __syncwarp(submask);
                             }
-                            const double2 qr = qd_s[m * N + rr];
-                            double2 c = cmul(aL, qr);
-                            cfma(c, aR, qj);
-                            cfma(X, c, Aj);
-                            if (outside) {
-                                const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y)
-                                                          : ldg2(pn + row * N + rr);
-                                cfma(Y, cmul(aR, qr), Bj);
+                            cur_rr = rr;
+                            X = make_double2(0.0, 0.0);
+                            Y = make_double2(0.0, 0.0);
+                            yused = false;
+                        }
+                        const int ns = supp_s[m * (N + 1)];
+                        if (ns == 1) {
+                            const int cid = heom::meta_kdir(meta);
+                            const double2 c1 = cq_s[3 * cid + (row == rr ? 1 : 0)];
+                            cfma(X, make_double2(c1.x * sq, c1.y * sq), Aj);
+                            if (row != rr) {
+                                const double2 c2 = cq_s[3 * cid + 2];
+                                const double2 Bj = a.herm
+                                    ? make_double2(Aj.x, -Aj.y)
+                                    : ldg2(yin + ((long long)rts[t].x * NN + row * N + rr));
+                                cfma(Y, make_double2(c2.x * sq, c2.y * sq), Bj);
                                 yused = true;
+                            }
+                        } else {
+                            // several non-zero diagonal entries: further rows straight from global
+                            const int kd = heom::meta_kdir(meta);
+                            const double2 bL = cb_s[2 * kd], bR = cb_s[2 * kd + 1];
+                            const double2 aL = make_double2(bL.x * sq, bL.y * sq);
+                            const double2 aR = make_double2(bR.x * sq, bR.y * sq);
+                            const double2* __restrict__ pn = yin + (long long)rts[t].x * NN;
+                            const double2 qj = qd_s[m * N + row];
+                            const bool outside = insupp_s[m * N + row] == 0;
+                            for (int t2 = 0; t2 < ns; ++t2) {
+                                const int r2 = supp_s[m * (N + 1) + 1 + t2];
+                                const double2 A2 = (t2 == 0) ? Aj : ldg2(pn + r2 * N + row);
+                                if (r2 != cur_rr) {
+                                    flush();
+                                    __syncwarp(submask);
+                                    cur_rr = r2;
+                                    X = make_double2(0.0, 0.0);
+                                    Y = make_double2(0.0, 0.0);
+                                    yused = false;
+                                }
+                                const double2 qr = qd_s[m * N + r2];
+                                double2 c = cmul(aL, qr);
+                                cfma(c, aR, qj);
+                                cfma(X, c, A2);
+                                if (outside) {
+                                    const double2 B2 = a.herm ? make_double2(A2.x, -A2.y)
+                                                              : ldg2(pn + row * N + r2);
+                                    cfma(Y, cmul(aR, qr), B2);
+                                    yused = true;
+                                }
                             }
                         }
                     }
                 }
             }
         }
-        if (on && cur_rr >= 0) {
-            double2* d1 = &k_s[(sub * N + cur_rr) * LD + row];
-            double2 v1 = *d1;
-            v1.x += X.x;
-            v1.y += X.y;
-            *d1 = v1;
-            if (yused) {
-                double2* d2 = &k_s[(sub * N + row) * LD + cur_rr];
-                double2 v2 = *d2;
-                v2.x += Y.x;
-                v2.y += Y.y;
-                *d2 = v2;
-            }
-        }
+        if (cur_rr >= 0) flush();
         cp_async_wait<0>();
         __syncwarp();
 
@@ -824,17 +892,15 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         for (int it = 0; it < EIT; ++it) {
             const int e = lane + 32 * it;
             if (e < nelem) {
-                const int s = e / NN, rr = e - s * NN, i = rr / N, j = rr - i * N;
-                const int si = (s * N + i) * LD + j;
-                const double2 k = k_s[si];
+                const double2 k = k_s[pofs[it]];
                 const long long gi = gbase + e;
-                const double2 yv = a.first ? rho_s[si] : (a.last ? make_double2(0.0, 0.0) : y_s[e]);
+                const double2 yv = a.first ? rho_s[pofs[it]] : (a.last ? make_double2(0.0, 0.0) : y_s[e]);
                 const double2 bs = a.first ? yv : acc_s[e];
                 const double2 res = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
                 if (a.last) {
                     st_stream(a.ydst + gi, res);
-                    if (a.traj && base + s == a.slot0)
-                        a.traj[b * a.traj_bstride + (step + 1) * NN + rr] = res;
+                    if (a.traj && base + e / NN == a.slot0)
+                        a.traj[b * a.traj_bstride + (step + 1) * NN + e % NN] = res;
                 } else {
                     st_stream(a.acc + gi, res);
                     st_stream(a.yout + gi, make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
@@ -843,7 +909,6 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         }
         __syncwarp();
     }
-#undef HEL
 }
 
 // Kernel 2 (any N): one CTA per ADO, one thread per matrix element (strided);
@@ -964,14 +1029,14 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     return post_launch(p, "stage_rows_kernel");
 }
 
-template <int N, bool TDEP>
+template <int N, bool TDEP, bool HREAL>
 static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT;
     StageArgs args = a;
     args.ngroups = (p->nmax + APW - 1) / APW;
-    const size_t table_bytes = sizeof(double2) * ((TDEP ? NN : 0) + 4 * (size_t)p->K + (size_t)p->M * N) +
-                               sizeof(double) * ((p->L + 2) & ~1) + align_up((size_t)p->M * (2 * N + 1), 16);
+    const AsyncTables T = async_tables(N, p->K, p->M, p->L, TDEP);
+    const size_t table_bytes = sizeof(double2) * T.warp0 + T.bytes_tail;
     const size_t per_warp = sizeof(double2) * PERWARP;
     const size_t budget = 227 * 1024;
     REQUIRE(table_bytes + per_warp <= budget, "shared-memory tables too large for the async row kernel");
@@ -985,7 +1050,7 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     const size_t smem = table_bytes + per_warp * warps;
     static bool attr_set = false;
     if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP>,
+        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP, HREAL>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set = true;
     }
@@ -993,8 +1058,14 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     dim3 grid((unsigned)std::min<long long>(ctas, sm_count), p->B);
     HParam<N> hp;
     for (int e = 0; e < NN; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    stage_rows_async_kernel<N, TDEP><<<grid, warps * 32, smem, p->stream>>>(args, hp);
+    stage_rows_async_kernel<N, TDEP, HREAL><<<grid, warps * 32, smem, p->stream>>>(args, hp);
     return post_launch(p, "stage_rows_async_kernel");
+}
+
+template <int N>
+static int launch_async_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool hreal) {
+    if (tdep) return hreal ? launch_async<N, true, true>(p, a, sm_count) : launch_async<N, true, false>(p, a, sm_count);
+    return hreal ? launch_async<N, false, true>(p, a, sm_count) : launch_async<N, false, false>(p, a, sm_count);
 }
 
 template <int N>
@@ -1022,9 +1093,9 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     if (kern == 3) {
         REQUIRE(p->N >= 2 && p->N <= 8 && p->use_qdiag,
                 "kernel 3 needs 2 <= N <= 8 and diagonal coupling operators");
-#define ASYNC_CASE(n)                                                                              \
-    case n:                                                                                        \
-        rc = tdep ? launch_async<n, true>(p, a, sm_count) : launch_async<n, false>(p, a, sm_count); \
+#define ASYNC_CASE(n)                                                                  \
+    case n:                                                                            \
+        rc = launch_async_n<n>(p, a, sm_count, tdep, p->h_real && p->opt_hreal != 0); \
         break;
         switch (p->N) {
             ASYNC_CASE(2) ASYNC_CASE(3) ASYNC_CASE(4) ASYNC_CASE(5) ASYNC_CASE(6) ASYNC_CASE(7) ASYNC_CASE(8)
@@ -1207,6 +1278,7 @@ int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
     const std::string n(name);
     if (n == "qdiag") p->opt_qdiag = value;
     else if (n == "hermitian") p->opt_herm = value;
+    else if (n == "real_h") p->opt_hreal = value;
     else if (n == "debug_sync") p->debug_sync = value != 0;
     else return fail("unknown option '" + n + "'");
     return 0;
@@ -1218,6 +1290,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "qdiag") return p->use_qdiag;
     if (n == "q_diagonal") return p->q_diagonal;
     if (n == "hermitian") return p->herm_inputs && p->herm_state && p->opt_herm != 0;
+    if (n == "real_h") return p->h_real && p->opt_hreal != 0;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
     if (n == "slot0") return p->slot0;
@@ -1402,6 +1475,11 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
             }
             supp[(size_t)m * (N + 1)] = (unsigned char)c;
         }
+        p->r0mode.assign(p->M, 0);
+        for (int m = 0; m < p->M; ++m) p->r0mode[m] = supp[(size_t)m * (N + 1)] ? supp[(size_t)m * (N + 1) + 1] : 0;
+        p->h_real = true;
+        for (int e = 0; e < NN; ++e)
+            if (p->H[e].imag() != 0.0 || p->mu[e].imag() != 0.0) p->h_real = false;
         CU_TRY(cudaMemcpyAsync(p->d_tables + t.supp, supp.data(), supp.size(), cudaMemcpyHostToDevice, s));
         CU_TRY(cudaStreamSynchronize(s));
     }
@@ -1412,7 +1490,7 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
     for (int k = 0; k < K; ++k) {
         ex[2 * k] = p->expn[k].real();
         ex[2 * k + 1] = p->expn[k].imag();
-        md[k] = (int)p->mode[k];
+        md[k] = (int)p->mode[k] | (p->r0mode[p->mode[k]] << 8);
     }
     double2* d_expn = nullptr;
     int* d_mode = nullptr;
@@ -1420,6 +1498,7 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
     CU_TRY(cudaMalloc(&d_mode, sizeof(int) * K));
     CU_TRY(cudaMemcpyAsync(d_expn, ex.data(), sizeof(double) * ex.size(), cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(d_mode, md.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaMemcpyAsync(p->d_tables + t.kmode, md.data(), sizeof(int) * K, cudaMemcpyHostToDevice, s));
     CU_TRY(cudaStreamSynchronize(s));  // host vectors above go out of scope
     // device-built tables -------------------------------------------------------
     HierArgs h;
@@ -1605,6 +1684,7 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
     a.nind = p->K;
     a.lmax = p->L;
     a.cbase = p->tab<double2>(t.cbase);
+    a.kmode = p->tab<int>(t.kmode);
     a.traj = traj;
     a.step_base = p->tab<long long>(t.step_base);
     a.traj_bstride = traj_bstride;

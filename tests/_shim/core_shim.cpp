@@ -30,6 +30,6 @@ void shim_unrank_all(int order, long long nmax, int K, int L, unsigned char* key
     for (long long s = 0; s < nmax; ++s) heom::unrank_slot(order, s, K, L, P, keys + s * K);
 }
 int shim_link_meta(int dir, int k, int neff, int mode, int K, int L) {
-    (void)K; (void)L; return heom::link_meta(dir, k, neff, mode);
+    (void)K; (void)L; return heom::link_meta(dir, k, neff, mode, 0);
 }
 }
