@@ -659,18 +659,37 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     double2* const rsub = rho_s + sub * N * LD;
     double2* const nbrow = nb_s + sub * NN + row; // + t*N: row element of staged link t
 
-    // link bookkeeping of the group about to be processed, fetched one group ahead
-    int nx_lbeg = 0, nx_lend = 0;
-    int2 nx_rec = make_int2(0, 0);
+    // Bookkeeping pipeline, carried in registers across iterations so that no
+    // dependent global load sits on the critical path of a group:
+    //   two groups ahead : link offsets (link_ptr)
+    //   one group ahead  : damping rate and the first NCH*N link records
+    constexpr int NCH = (32 + N - 1) / N > 4 ? 4 : (32 + N - 1) / N;  // record chunks prefetched
     long long g = (long long)blockIdx.x * nwarps + wid;
-    if (g < a.ngroups) {
-        const long long slot = g * APW + sub;
-        if (lane_ok && slot < a.nmax) {
-            nx_lbeg = a.link_ptr[slot];
-            nx_lend = a.link_ptr[slot + 1];
-            if (nx_lbeg + row < nx_lend) nx_rec = __ldg(a.links + nx_lbeg + row);
+    int nx_lbeg = 0, nx_lend = 0, nn_lbeg = 0, nn_lend = 0;
+    int2 nx_rec[NCH];
+    double2 nx_damp = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) nx_rec[c] = make_int2(0, 0);
+    auto fetch_ptr = [&](long long gg, int& lb, int& le) {
+        const long long slot = gg * APW + sub;
+        lb = le = 0;
+        if (gg < a.ngroups && lane_ok && slot < a.nmax) {
+            lb = a.link_ptr[slot];
+            le = a.link_ptr[slot + 1];
         }
-    }
+    };
+    auto fetch_rec = [&](long long gg, int lb, int le) {
+        const long long slot = gg * APW + sub;
+        if (gg < a.ngroups && lane_ok && slot < a.nmax) nx_damp = a.damp[slot];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            nx_rec[c] = make_int2(0, 0);
+            if (lb + c * N + row < le) nx_rec[c] = __ldg(a.links + lb + c * N + row);
+        }
+    };
+    fetch_ptr(g, nx_lbeg, nx_lend);
+    fetch_rec(g, nx_lbeg, nx_lend);
+    fetch_ptr(g + gstride, nn_lbeg, nn_lend);
 
     for (; g < a.ngroups; g += gstride) {
         const long long base = g * APW;
@@ -679,9 +698,19 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         const bool on = lane_ok && sub < cnt;
         const int lbeg = nx_lbeg, lend = nx_lend;
         const int nl = on ? (lend - lbeg) : 0;
-        int2 rec = nx_rec;
+        int2 recs[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) recs[c] = nx_rec[c];
+        int2 rec = recs[0];
+        const double2 d = nx_damp;
         int2 rts[N];
         const long long gbase = boff + base * NN;
+        // next group's records / damping (offsets arrived during the previous
+        // iteration), and the offsets of the group after that
+        nx_lbeg = nn_lbeg;
+        nx_lend = nn_lend;
+        fetch_rec(g + gstride, nx_lbeg, nx_lend);
+        fetch_ptr(g + 2 * gstride, nn_lbeg, nn_lend);
 
         // ---- issue: own tile + first chunk of neighbour rows (group A), y/acc (group B)
         {
@@ -711,17 +740,6 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                 }
         }
         cp_async_commit();
-
-        // ---- start fetching the next group's link offsets
-        {
-            const long long gn = g + gstride;
-            const long long slot = gn * APW + sub;
-            nx_lbeg = nx_lend = 0;
-            if (gn < a.ngroups && lane_ok && slot < a.nmax) {
-                nx_lbeg = a.link_ptr[slot];
-                nx_lend = a.link_ptr[slot + 1];
-            }
-        }
 
         cp_async_wait<1>();
         __syncwarp();
@@ -753,7 +771,6 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             double2 rv[N];
 #pragma unroll
             for (int l = 0; l < N; ++l) rv[l] = rsub[row * LD + l];
-            const double2 d = a.damp[base + sub];
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 double2 t = ksub[row * LD + j];
@@ -772,9 +789,6 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             }
         }
 #undef HEL
-        // the next group's first link record (its offsets have arrived by now)
-        nx_rec = make_int2(0, 0);
-        if (nx_lbeg + row < nx_lend) nx_rec = __ldg(a.links + nx_lbeg + row);
         __syncwarp();
 
         // ---- neighbour terms, N links per chunk; contributions to one target row
@@ -800,7 +814,17 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         for (int c0 = 0; c0 < maxl; c0 += N) {
             if (c0 > 0) {
                 rec = make_int2(0, 0);
-                if (lbeg + c0 + row < lend) rec = __ldg(a.links + lbeg + c0 + row);
+                {
+                    const int c = c0 / N;
+                    bool have = false;
+#pragma unroll
+                    for (int cc = 1; cc < NCH; ++cc)
+                        if (c == cc) {
+                            rec = recs[cc];
+                            have = true;
+                        }
+                    if (!have && lbeg + c0 + row < lend) rec = __ldg(a.links + lbeg + c0 + row);
+                }
                 __syncwarp();  // every lane is done with the previous chunk's rows
 #pragma unroll
                 for (int t = 0; t < N; ++t) {
