@@ -82,6 +82,11 @@ def rational_exponents(numer, denom, beta, npsd, pade=1):
     temp = 1.0 / beta
     pole_b, resi_b = bose_poles(npsd, pade)
 
+    # the reference takes the poles in sympy.nroots order (real part, then
+    # imaginary part, ascending) and then sorts by |Im expn| descending with a
+    # reversed argsort, which fixes the order inside a conjugate pair
+    scale = max(1.0, float(np.max(np.abs(poles)))) if len(poles) else 1.0
+    poles = np.array(sorted(poles, key=lambda z: (round(z.real / scale, 10), z.imag)))
     lower = [z for z in poles if z.imag < 0]
     expn_sys = np.array([1j * z for z in lower], dtype=C128)
     order = np.argsort(np.abs(expn_sys.imag), kind="stable")[::-1]
