@@ -113,6 +113,25 @@ int pyqed_heom_get_ados(pyqed_heom_plan* plan, double* ados_host);
 int pyqed_heom_propagate(pyqed_heom_plan* plan, double dt, int64_t nt, const double* fsys,
                          const double* fcoup, double* d_traj, int method);
 
+/* The same propagation split up so that a multi-GPU driver can interleave the
+ * halo exchange: propagate_begin takes the arguments of pyqed_heom_propagate
+ * (RK4 only), propagate_stage launches stage 0..3 of step `step`.  The stage
+ * outputs live in arrays 1 (stages 0, 2), 2 (stage 1) and 0 (stage 3). */
+int pyqed_heom_propagate_begin(pyqed_heom_plan* plan, double dt, int64_t nt, const double* fsys,
+                               const double* fcoup, double* d_traj);
+int pyqed_heom_propagate_stage(pyqed_heom_plan* plan, int64_t step, int stage);
+
+/* Multi-GPU (one process per GPU): this rank owns storage slots [lo, hi) and
+ * only advances those; all four ADO arrays stay full-size so that neighbour
+ * reads use global slot numbers.  halo_pack copies the listed items of array
+ * `array_id` (0 state, 1/2 stage buffers, 3 accumulator) into a contiguous
+ * buffer [batch][n_items][N or N*N] (unpack = 0) or back (unpack = 1).
+ * An item is slot*8+row when row_items = 1 (one matrix row, the only part of a
+ * neighbour a diagonal Q_m needs) or a slot when row_items = 0 (whole ADO). */
+int pyqed_heom_set_partition(pyqed_heom_plan* plan, int64_t slot_lo, int64_t slot_hi);
+int pyqed_heom_halo_pack(pyqed_heom_plan* plan, int array_id, const int32_t* d_items,
+                         int64_t n_items, int row_items, double* d_buf, int unpack);
+
 /* Tr(op_e rho) for npts density matrices per trajectory:
  * d_rho [batch][npts][N][N] (device), ops_host [n_ops][N][N] (host),
  * d_out [batch][n_ops][npts] complex128 (device).  Replaces
@@ -147,8 +166,8 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *                neighbour's column entries as the conjugate of its row
  *   "real_h"     use real arithmetic for the H products when H and mu are real
  *   "debug_sync" synchronise and check after every launch
- * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "real_h",
- * "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */
+ * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
+ * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */
 int pyqed_heom_set_option(pyqed_heom_plan* plan, const char* name, int value);
 int64_t pyqed_heom_get_info(pyqed_heom_plan* plan, const char* name);
 

@@ -44,6 +44,12 @@ SIGNATURES = {
     "pyqed_heom_get_ados": (C.c_int, [C.c_void_p, _c_double_p]),
     "pyqed_heom_propagate": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, _c_double_p, _c_double_p,
                                        C.c_void_p, C.c_int]),
+    "pyqed_heom_propagate_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, _c_double_p, _c_double_p,
+                                             C.c_void_p]),
+    "pyqed_heom_propagate_stage": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
+    "pyqed_heom_set_partition": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "pyqed_heom_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                       C.c_int]),
     "pyqed_heom_expectation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _c_double_p, C.c_int,
                                          C.c_void_p]),
     "pyqed_heom_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

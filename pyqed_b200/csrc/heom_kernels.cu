@@ -108,6 +108,7 @@ struct pyqed_heom_plan {
     size_t array_bytes = 0;  // one [B][nmax][N][N] array, aligned
     cudaStream_t stream = nullptr;
     long long slot0 = 0;  // storage slot of ADO id 0
+    long long part_lo = 0, part_hi = 0;  // owned slot range (multi-GPU); [0, nmax) by default
     // tuning
     int kernel = 0, warps = 0, use_graph = 0;
     // accounting
@@ -120,6 +121,11 @@ struct pyqed_heom_plan {
     double* d_fcoup = nullptr;
     size_t field_cap = 0;
     bool debug_sync = false;
+    // context of the propagation in progress (propagate_begin)
+    bool ctx_valid = false, ctx_tdep = false, ctx_use_fs = false, ctx_use_fc = false;
+    double ctx_dt = 0.0;
+    long long ctx_nt = 0;
+    double2* ctx_traj = nullptr;
 
     double2* arr(int which) const { return (double2*)(d_state + (size_t)which * array_bytes); }
     template <typename T> T* tab(size_t off) const { return (T*)(d_tables + off); }
@@ -319,6 +325,7 @@ struct StageArgs {
     const long long* step_base;
     long long traj_bstride;
     long long nmax, slot0, ngroups;
+    long long slot_lo, slot_hi;  // owned slot range of this rank (whole hierarchy on one GPU)
     double a, w;
     int local_step, first, last, N;
     int herm, ncoef, nmod, nind, lmax;
@@ -386,8 +393,8 @@ __global__ void __launch_bounds__(256, HEOM_MINBLOCKS) stage_rows_kernel(const S
 
     for (long long g = (long long)blockIdx.x * nwarps + wid; g < a.ngroups;
          g += (long long)gridDim.x * nwarps) {
-        const long long base = g * APW;
-        const int cnt = (int)min((long long)APW, a.nmax - base);
+        const long long base = a.slot_lo + g * APW;
+        const int cnt = (int)min((long long)APW, a.slot_hi - base);
         const int nelem = cnt * NN;
         const double2* src = yin + base * NN;
         for (int e = lane; e < nelem; e += 32) {
@@ -671,16 +678,16 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
 #pragma unroll
     for (int c = 0; c < NCH; ++c) nx_rec[c] = make_int2(0, 0);
     auto fetch_ptr = [&](long long gg, int& lb, int& le) {
-        const long long slot = gg * APW + sub;
+        const long long slot = a.slot_lo + gg * APW + sub;
         lb = le = 0;
-        if (gg < a.ngroups && lane_ok && slot < a.nmax) {
+        if (gg < a.ngroups && lane_ok && slot < a.slot_hi) {
             lb = a.link_ptr[slot];
             le = a.link_ptr[slot + 1];
         }
     };
     auto fetch_rec = [&](long long gg, int lb, int le) {
-        const long long slot = gg * APW + sub;
-        if (gg < a.ngroups && lane_ok && slot < a.nmax) nx_damp = a.damp[slot];
+        const long long slot = a.slot_lo + gg * APW + sub;
+        if (gg < a.ngroups && lane_ok && slot < a.slot_hi) nx_damp = a.damp[slot];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             nx_rec[c] = make_int2(0, 0);
@@ -692,8 +699,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     fetch_ptr(g + gstride, nn_lbeg, nn_lend);
 
     for (; g < a.ngroups; g += gstride) {
-        const long long base = g * APW;
-        const int cnt = (int)min((long long)APW, a.nmax - base);
+        const long long base = a.slot_lo + g * APW;
+        const int cnt = (int)min((long long)APW, a.slot_hi - base);
         const int nelem = cnt * NN;
         const bool on = lane_ok && sub < cnt;
         const int lbeg = nx_lbeg, lend = nx_lend;
@@ -947,7 +954,7 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(const StageArgs a) {
     const long long boff = (long long)b * a.nmax * NN;
     const double2* __restrict__ yin = a.yin + boff;
     const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
-    for (long long slot = blockIdx.x; slot < a.nmax; slot += gridDim.x) {
+    for (long long slot = a.slot_lo + blockIdx.x; slot < a.slot_hi; slot += gridDim.x) {
         for (int e = threadIdx.x; e < NN; e += blockDim.x) rho_s[e] = ldg2(yin + slot * NN + e);
         __syncthreads();
         const double2 d = a.damp[slot];
@@ -1028,7 +1035,7 @@ template <int N, bool TDEP, bool QDIAG>
 static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     StageArgs args = a;
-    args.ngroups = (p->nmax + APW - 1) / APW;
+    args.ngroups = (p->part_hi - p->part_lo + APW - 1) / APW;
     int warps = p->warps > 0 ? std::min(p->warps, 8) : 8;
     if (p->warps <= 0) {
         // small hierarchies: prefer more CTAs over fuller CTAs
@@ -1058,7 +1065,7 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT;
     StageArgs args = a;
-    args.ngroups = (p->nmax + APW - 1) / APW;
+    args.ngroups = (p->part_hi - p->part_lo + APW - 1) / APW;
     const AsyncTables T = async_tables(N, p->K, p->M, p->L, TDEP);
     const size_t table_bytes = sizeof(double2) * T.warp0 + T.bytes_tail;
     const size_t per_warp = sizeof(double2) * PERWARP;
@@ -1140,7 +1147,7 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
         int threads = std::min(256, (NN + 31) / 32 * 32);
         const size_t smem = sizeof(double2) * NN;
         REQUIRE(smem <= 48 * 1024, "N too large for the generic kernel (N <= 55)");
-        dim3 grid((unsigned)std::min(p->nmax, (long long)sm_count * 32), p->B);
+        dim3 grid((unsigned)std::max(1ll, std::min(p->part_hi - p->part_lo, (long long)sm_count * 32)), p->B);
         stage_generic_kernel<<<grid, threads, smem, p->stream>>>(a);
         rc = post_launch(p, "stage_generic_kernel");
     }
@@ -1314,11 +1321,17 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "qdiag") return p->use_qdiag;
     if (n == "q_diagonal") return p->q_diagonal;
     if (n == "hermitian") return p->herm_inputs && p->herm_state && p->opt_herm != 0;
+    if (n == "hermitian_inputs") return p->herm_inputs && p->opt_herm != 0;
     if (n == "real_h") return p->h_real && p->opt_hreal != 0;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
     if (n == "slot0") return p->slot0;
     if (n == "table_bytes") return (int64_t)p->tl.total;
+    if (n == "off_link_ptr") return (int64_t)p->tl.link_ptr;
+    if (n == "off_links") return (int64_t)p->tl.links;
+    if (n == "array_bytes") return (int64_t)p->array_bytes;
+    if (n == "part_lo") return p->part_lo;
+    if (n == "part_hi") return p->part_hi;
     return -1;
 }
 
@@ -1565,6 +1578,10 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
                                           std::to_string(total_links) + " vs " +
                                           std::to_string(p->nlinks) + ")");
     p->slot0 = slot0;
+    if (p->part_hi <= p->part_lo) {
+        p->part_lo = 0;
+        p->part_hi = p->nmax;
+    }
     p->built = true;
     return 0;
 }
@@ -1668,35 +1685,17 @@ static int upload_fields(pyqed_heom_plan* p, const double* fsys, const double* f
     return 0;
 }
 
-int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double* fsys,
-                         const double* fcoup, double* d_traj, int method) {
-    REQUIRE(p && p->built, "propagate: build the hierarchy first");
-    REQUIRE(nt >= 0, "propagate: nt must be >= 0");
-    REQUIRE(method == 0 || method == 1, "propagate: method must be 0 (rk4) or 1 (euler)");
-    CU_TRY(cudaSetDevice(p->device));
+// ---- propagation: begin (context) / single stage / whole run -----------------
+static void fill_stage_args(pyqed_heom_plan* p, StageArgs& a) {
     const int N = p->N, NN = N * N, M1 = 1 + p->M;
     const TableLayout& t = p->tl;
-    const bool use_fs = fsys && p->mu_nonzero, use_fc = fcoup && p->qd_nonzero;
-    const bool tdep = use_fs || use_fc;
-    if (tdep) {
-        if (upload_fields(p, use_fs ? fsys : nullptr, use_fc ? fcoup : nullptr, nt)) return 1;
-    }
-    CU_TRY(cudaMemsetAsync(p->d_tables + t.step_base, 0, sizeof(long long), p->stream));
-    double2* traj = (double2*)d_traj;
-    const long long traj_bstride = (long long)(nt + 1) * NN;
-    if (traj) {
-        record_kernel<<<p->B, 64, 0, p->stream>>>(traj, p->arr(ARR_Y), p->nmax, p->slot0, NN,
-                                                  traj_bstride, 0);
-        if (post_launch(p, "record_kernel")) return 1;
-    }
-    StageArgs a;
     memset(&a, 0, sizeof(a));
     a.damp = p->tab<double2>(t.damp);
     a.link_ptr = p->tab<int>(t.link_ptr);
     a.links = p->tab<int2>(t.links);
     a.coef = p->tab<double2>(t.coef);
-    a.ops = p->tab<double2>(tdep ? t.ops_t : t.ops_base);
-    a.ops_bstride = tdep ? (long long)M1 * NN : 0;
+    a.ops = p->tab<double2>(p->ctx_tdep ? t.ops_t : t.ops_base);
+    a.ops_bstride = p->ctx_tdep ? (long long)M1 * NN : 0;
     a.row_ptr = p->tab<short>(t.row_ptr);
     a.row_idx = p->tab<short>(t.row_idx);
     a.col_ptr = p->tab<short>(t.col_ptr);
@@ -1709,57 +1708,138 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
     a.lmax = p->L;
     a.cbase = p->tab<double2>(t.cbase);
     a.kmode = p->tab<int>(t.kmode);
-    a.traj = traj;
+    a.traj = p->ctx_traj;
     a.step_base = p->tab<long long>(t.step_base);
-    a.traj_bstride = traj_bstride;
+    a.traj_bstride = (long long)(p->ctx_nt + 1) * NN;
     a.nmax = p->nmax;
+    a.slot_lo = p->part_lo;
+    a.slot_hi = p->part_hi;
     a.slot0 = p->slot0;
     a.N = N;
+}
+
+static int run_prep(pyqed_heom_plan* p, long long step, int tidx) {
+    if (!p->ctx_tdep) return 0;
+    const int NN = p->N * p->N, M1 = 1 + p->M;
+    const TableLayout& t = p->tl;
+    prep_ops_kernel<<<1, 256, 0, p->stream>>>(
+        p->tab<double2>(t.ops_t), p->tab<double2>(t.ops_base), p->tab<double2>(t.ops_dip),
+        p->ctx_use_fs ? p->d_fsys : nullptr, p->ctx_use_fc ? p->d_fcoup : nullptr,
+        p->tab<long long>(t.step_base), (int)step, tidx, p->ctx_nt, p->B, M1, NN);
+    return post_launch(p, "prep_ops_kernel");
+}
+
+// one RK4 stage (0..3) of step `step`; method 1 (Euler) uses stage -1
+static int run_stage(pyqed_heom_plan* p, long long step, int stage) {
+    StageArgs s;
+    fill_stage_args(p, s);
     double2 *Y = p->arr(ARR_Y), *SA = p->arr(ARR_SA), *SB = p->arr(ARR_SB), *ACC = p->arr(ARR_ACC);
+    const double dt = p->ctx_dt;
+    s.y = Y;
+    s.acc = ACC;
+    s.local_step = (int)step;
+    switch (stage) {
+        case 0: s.yin = Y;  s.yout = SA; s.a = dt / 2; s.w = dt / 6; s.first = 1; break;
+        case 1: s.yin = SA; s.yout = SB; s.a = dt / 2; s.w = dt / 3; break;
+        case 2: s.yin = SB; s.yout = SA; s.a = dt;     s.w = dt / 3; break;
+        case 3: s.yin = SA; s.ydst = Y;  s.w = dt / 6; s.last = 1; break;
+        default: s.yin = Y; s.ydst = SA; s.w = dt; s.first = 1; s.last = 1; break;  // Euler
+    }
+    const int tidx = stage <= 0 ? 0 : (stage == 3 ? 2 : 1);
+    if (stage != 2 && run_prep(p, step, tidx)) return 1;  // stages 1 and 2 share t + dt/2
+    return launch_stage(p, s, p->ctx_tdep);
+}
 
-    auto prep = [&](int local_step, int tidx) -> int {
-        if (!tdep) return 0;
-        prep_ops_kernel<<<1, 256, 0, p->stream>>>(
-            p->tab<double2>(t.ops_t), p->tab<double2>(t.ops_base), p->tab<double2>(t.ops_dip),
-            use_fs ? p->d_fsys : nullptr, use_fc ? p->d_fcoup : nullptr, a.step_base, local_step,
-            tidx, nt, p->B, M1, NN);
-        return post_launch(p, "prep_ops_kernel");
-    };
-    auto stage = [&](const double2* yin, double2* yout, double2* ydst, double ac, double wc,
-                     int first, int last, int local_step) -> int {
-        StageArgs s = a;
-        s.yin = yin;
-        s.y = Y;
-        s.acc = ACC;
-        s.yout = yout;
-        s.ydst = ydst;
-        s.a = ac;
-        s.w = wc;
-        s.first = first;
-        s.last = last;
-        s.local_step = local_step;
-        return launch_stage(p, s, tdep);
-    };
+int pyqed_heom_propagate_begin(pyqed_heom_plan* p, double dt, int64_t nt, const double* fsys,
+                               const double* fcoup, double* d_traj) {
+    REQUIRE(p && p->built, "propagate: build the hierarchy first");
+    REQUIRE(nt >= 0, "propagate: nt must be >= 0");
+    CU_TRY(cudaSetDevice(p->device));
+    const int NN = p->N * p->N;
+    p->ctx_use_fs = fsys && p->mu_nonzero;
+    p->ctx_use_fc = fcoup && p->qd_nonzero;
+    p->ctx_tdep = p->ctx_use_fs || p->ctx_use_fc;
+    p->ctx_dt = dt;
+    p->ctx_nt = nt;
+    p->ctx_traj = (double2*)d_traj;
+    if (p->ctx_tdep) {
+        if (upload_fields(p, p->ctx_use_fs ? fsys : nullptr, p->ctx_use_fc ? fcoup : nullptr, nt)) return 1;
+    }
+    CU_TRY(cudaMemsetAsync(p->d_tables + p->tl.step_base, 0, sizeof(long long), p->stream));
+    if (p->ctx_traj) {
+        record_kernel<<<p->B, 64, 0, p->stream>>>(p->ctx_traj, p->arr(ARR_Y), p->nmax, p->slot0, NN,
+                                                  (long long)(nt + 1) * NN, 0);
+        if (post_launch(p, "record_kernel")) return 1;
+    }
+    p->ctx_valid = true;
+    return 0;
+}
 
+int pyqed_heom_propagate_stage(pyqed_heom_plan* p, int64_t step, int stage) {
+    REQUIRE(p && p->built && p->ctx_valid, "propagate_stage: call propagate_begin first");
+    REQUIRE(stage >= 0 && stage <= 3 && step >= 0 && step < p->ctx_nt, "propagate_stage: bad step/stage");
+    CU_TRY(cudaSetDevice(p->device));
+    return run_stage(p, step, stage);
+}
+
+int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double* fsys,
+                         const double* fcoup, double* d_traj, int method) {
+    REQUIRE(method == 0 || method == 1, "propagate: method must be 0 (rk4) or 1 (euler)");
+    if (pyqed_heom_propagate_begin(p, dt, nt, fsys, fcoup, d_traj)) return 1;
     if (method == 0) {
-        for (int64_t i = 0; i < nt; ++i) {
-            const int ls = (int)i;
-            if (prep(ls, 0) || stage(Y, SA, nullptr, dt / 2, dt / 6, 1, 0, ls)) return 1;
-            if (prep(ls, 1) || stage(SA, SB, nullptr, dt / 2, dt / 3, 0, 0, ls)) return 1;
-            if (stage(SB, SA, nullptr, dt, dt / 3, 0, 0, ls)) return 1;
-            if (prep(ls, 2) || stage(SA, nullptr, Y, 0.0, dt / 6, 0, 1, ls)) return 1;
-        }
+        for (int64_t i = 0; i < nt; ++i)
+            for (int st = 0; st < 4; ++st)
+                if (run_stage(p, i, st)) return 1;
     } else {
-        // explicit Euler: y' = y + dt F(y); ping-pong through SA so that no CTA
-        // reads a neighbour that another CTA has already advanced
+        // explicit Euler: y' = y + dt F(y) through SA so that no CTA reads a
+        // neighbour that another CTA has already advanced
+        const size_t bytes = sizeof(double2) * (size_t)p->B * p->nmax * p->N * p->N;
         for (int64_t i = 0; i < nt; ++i) {
-            const int ls = (int)i;
-            if (prep(ls, 0) || stage(Y, nullptr, SA, 0.0, dt, 1, 1, ls)) return 1;
-            CU_TRY(cudaMemcpyAsync(Y, SA, sizeof(double2) * (size_t)p->B * p->nmax * NN,
-                                   cudaMemcpyDeviceToDevice, p->stream));
+            if (run_stage(p, i, -1)) return 1;
+            CU_TRY(cudaMemcpyAsync(p->arr(ARR_Y), p->arr(ARR_SA), bytes, cudaMemcpyDeviceToDevice, p->stream));
         }
     }
     return 0;
+}
+
+// ---- multi-GPU: owned range and halo rows --------------------------------------
+int pyqed_heom_set_partition(pyqed_heom_plan* p, int64_t slot_lo, int64_t slot_hi) {
+    REQUIRE(p && p->built, "set_partition: build the hierarchy first");
+    REQUIRE(slot_lo >= 0 && slot_lo <= slot_hi && slot_hi <= p->nmax, "set_partition: bad range");
+    p->part_lo = slot_lo;
+    p->part_hi = slot_hi;
+    return 0;
+}
+
+// items: slot * 8 + row  (rows == 1, diagonal-Q row items) or slot (rows == 0, whole ADOs)
+__global__ void halo_pack_kernel(double2* buf, const double2* arr, const int* items, long long n,
+                                 int N, int rows, long long nmax, int unpack) {
+    const int NN = N * N, per = rows ? N : NN;
+    const long long total = n * per;
+    const long long boff = (long long)blockIdx.y * nmax * NN;
+    double2* out = buf + (long long)blockIdx.y * total;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / per;
+        const int j = (int)(e - i * per);
+        const int it = items[i];
+        const long long src = rows ? ((long long)(it >> 3) * NN + (it & 7) * N + j) : ((long long)it * NN + j);
+        if (unpack) const_cast<double2*>(arr)[boff + src] = out[e];
+        else out[e] = arr[boff + src];
+    }
+}
+
+int pyqed_heom_halo_pack(pyqed_heom_plan* p, int array_id, const int32_t* d_items, int64_t n_items,
+                         int row_items, double* d_buf, int unpack) {
+    REQUIRE(p && p->built && array_id >= 0 && array_id <= 3, "halo_pack: bad argument");
+    if (n_items == 0) return 0;
+    REQUIRE(d_items && d_buf, "halo_pack: null buffer");
+    CU_TRY(cudaSetDevice(p->device));
+    const long long total = n_items * (row_items ? p->N : p->N * p->N);
+    dim3 grid((unsigned)std::min<long long>((total + 255) / 256, 148 * 16), p->B);
+    halo_pack_kernel<<<grid, 256, 0, p->stream>>>((double2*)d_buf, p->arr(array_id), d_items, n_items,
+                                                  p->N, row_items, p->nmax, unpack);
+    return post_launch(p, unpack ? "halo_unpack_kernel" : "halo_pack_kernel");
 }
 
 int pyqed_heom_expectation(pyqed_heom_plan* p, const double* d_rho, int64_t npts,

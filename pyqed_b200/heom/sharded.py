@@ -1,0 +1,283 @@
+"""Multi-GPU propagation: the hierarchy is split into contiguous ranges of the
+lexicographic storage order, one range per rank (one process per GPU), and the
+neighbour rows that cross a range boundary are exchanged once per RK stage.
+
+What the reference does: nothing - it is a single Python loop
+(``pyqed/heom/deom.py:1072-1114``).  SURVEY.md section 8e describes the shard:
+owner-computes over a partition of the ADOs plus one halo exchange per stage.
+
+Layout per rank: all four ADO arrays keep the full ``[nmax, N, N]`` index space
+(links hold global slot numbers, the stage kernel is unchanged) but a rank only
+advances its own slots ``[lo, hi)``; the halo consists of *items*: for diagonal
+coupling operators one matrix row of a foreign ADO (``16 N`` bytes, the only
+part the element-wise coupling needs), otherwise the whole ADO.
+
+The exchange logic (``HaloPlan``) is independent of CUDA so that it is tested
+with ``gloo`` on CPU; the device work (stage kernel, pack/unpack kernels) goes
+through the C ABI.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+C128 = np.complex128
+STAGE_OUTPUT_ARRAY = (1, 2, 1, 0)  # array written by RK4 stage 0..3 (include/pyqed_heom.h)
+
+
+def cost_balanced_bounds(link_ptr, world, base_cost=12):
+    """Range boundaries ``b[0]=0 <= ... <= b[world]=nmax`` that equalise
+    ``sum(base_cost + links)`` per rank; ``link_ptr`` is the CSR offset array."""
+    lp = np.asarray(link_ptr, dtype=np.int64)
+    nmax = len(lp) - 1
+    cost = base_cost * np.arange(nmax + 1, dtype=np.int64) + (lp - lp[0])
+    targets = cost[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(cost, targets).astype(np.int64)
+    return [0] + [int(x) for x in inner] + [nmax]
+
+
+def needed_items(nbr, meta, lo, hi, row_items, supp_rows=None):
+    """Sorted unique halo items of the links ``(nbr, meta)`` of the owned slots
+    ``[lo, hi)``.  ``row_items``: ``slot*8 + row`` for every row in the support
+    of the link's coupling mode (``supp_rows[mode]``; default: the single row
+    stored in bits 16-19 of ``meta``); otherwise just ``slot``."""
+    nbr = nbr.to(torch.int64)
+    outside = (nbr < lo) | (nbr >= hi)
+    nb = nbr[outside]
+    if not row_items:
+        return torch.unique(nb)
+    mt = meta[outside].to(torch.int64)
+    if supp_rows is None:
+        return torch.unique(nb * 8 + ((mt >> 16) & 0xF))
+    mode = (mt >> 24) & 0xFF
+    parts = []
+    for m, rows in enumerate(supp_rows):
+        sel = nb[mode == m]
+        for r in rows:
+            parts.append(sel * 8 + int(r))
+    if not parts:
+        return torch.zeros(0, dtype=torch.int64, device=nbr.device)
+    return torch.unique(torch.cat(parts))
+
+
+class HaloPlan:
+    """Who sends which items to whom.  ``need`` is this rank's sorted item list;
+    construction is collective over ``transport`` (see ``DistTransport`` /
+    ``LocalTransport``)."""
+
+    def __init__(self, bounds, rank, world, need, row_items, transport):
+        self.bounds, self.rank, self.world, self.row_items = list(bounds), rank, world, row_items
+        self.need = need.to(torch.int64)
+        slots = (self.need >> 3) if row_items else self.need
+        upper = torch.tensor(self.bounds[1:], dtype=torch.int64, device=slots.device)
+        owner = torch.searchsorted(upper, slots, right=True)
+        self.recv_counts = [int(x) for x in torch.bincount(owner, minlength=world).tolist()]
+        assert self.recv_counts[rank] == 0, "a rank never needs its own slots"
+        # counts[q][r] = number of items rank q needs from rank r
+        all_counts = transport.allgather_counts(self.recv_counts)
+        self.send_counts = [int(all_counts[q][rank]) for q in range(world)]
+        chunks = torch.split(self.need, self.recv_counts)
+        got = transport.exchange_lists(list(chunks), self.send_counts)
+        self.send_items = (torch.cat(got) if sum(self.send_counts) else
+                           torch.zeros(0, dtype=torch.int64, device=self.need.device))
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        s = (self.send_items >> 3) if row_items else self.send_items
+        assert bool(((s >= lo) & (s < hi)).all()), "asked for items this rank does not own"
+
+
+class DistTransport:
+    """torch.distributed transport.  NCCL moves device buffers directly
+    (``all_to_all_single`` over NVLink); with gloo (CPU tests, or several ranks
+    sharing one GPU) buffers are staged through host memory and sent pairwise."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+        self.nccl = self.backend == "nccl"
+
+    def allgather_counts(self, counts):
+        mine = torch.tensor(counts, dtype=torch.int64, device="cuda" if self.nccl else "cpu")
+        out = [torch.zeros_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(out, mine, group=self.group)
+        return [o.tolist() for o in out]
+
+    def exchange_lists(self, chunks, send_counts):
+        dev = chunks[0].device
+        wire = dev if self.nccl else torch.device("cpu")
+        send = [c.to(wire).contiguous() for c in chunks]
+        recv = [torch.zeros(n, dtype=torch.int64, device=wire) for n in send_counts]
+        self._p2p(send, recv)
+        return [r.to(dev) for r in recv]
+
+    def _p2p(self, send, recv):
+        ops = []
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            if recv[q].numel():
+                ops.append(self.dist.P2POp(self.dist.irecv, recv[q], q, self.group))
+            if send[q].numel():
+                ops.append(self.dist.P2POp(self.dist.isend, send[q], q, self.group))
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def all_to_all(self, sendbuf, send_counts, recvbuf, recv_counts, elems):
+        """Buffers are flat float64; counts are in items of ``elems`` reals."""
+        ss = [c * elems for c in send_counts]
+        rs = [c * elems for c in recv_counts]
+        if self.nccl:
+            self.dist.all_to_all_single(recvbuf, sendbuf, rs, ss, group=self.group)
+            return
+        host_send = sendbuf.cpu()
+        host_recv = torch.empty(recvbuf.shape, dtype=recvbuf.dtype)
+        self._p2p(list(torch.split(host_send, ss)), list(torch.split(host_recv, rs)))
+        recvbuf.copy_(host_recv)
+
+    def broadcast(self, t, src):
+        if self.nccl or not t.is_cuda:
+            self.dist.broadcast(t, src, group=self.group)
+            return
+        h = t.cpu()
+        self.dist.broadcast(h, src, group=self.group)
+        t.copy_(h)
+
+    def allreduce_sum(self, t):
+        self.dist.all_reduce(t, group=self.group)
+
+
+class ShardedDEOM:
+    """One rank's share of a sharded RK4 propagation.
+
+    Parameters are those of ``DEOMSolver`` given as arrays; ``transport`` is a
+    ``DistTransport`` (one process per GPU).  Only ``batch = 1``.
+    """
+
+    def __init__(self, system, system_dipole, coupling, coupling_dipole, expn, etal, etar, etaa,
+                 mode, lmax, transport, device=0, order=1, options=None, tuning=None):
+        from .._cabi import Plan
+        self.tr = transport
+        self.rank, self.world = transport.rank, transport.world
+        n = np.shape(system)[0]
+        m = int(np.max(mode)) + 1
+        self.n = n
+        self.plan = p = Plan(n, len(expn), m, lmax, batch=1, device=device, order=order)
+        p.set_system(system, system_dipole)
+        p.set_coupling(np.asarray(coupling)[:m], coupling_dipole)
+        p.set_bath(expn, etal, etar, etaa, mode)
+        if tuning:
+            p.set_tuning(**tuning)
+        for k, v in (options or {}).items():
+            p.set_option(k, v)
+        p.build()
+        self.nmax = p.nmax
+        # a diagonal Q_m only reads the rows r of a neighbour with (Q_m)_rr != 0, and
+        # (for Hermitian ADOs) gets the column entries as their conjugates
+        self.row_items = bool(p.info("qdiag")) and bool(p.info("hermitian_inputs"))
+        Qa = np.asarray(coupling, dtype=C128)[:m]
+        Qd = (np.zeros_like(Qa) if coupling_dipole is None
+              else np.broadcast_to(np.asarray(coupling_dipole, dtype=C128), Qa.shape))
+        self.supp_rows = [[r for r in range(n) if Qa[mm, r, r] != 0 or Qd[mm, r, r] != 0]
+                          for mm in range(m)]
+        tables = p._tables
+        lp_off, lk_off = p.info("off_link_ptr"), p.info("off_links")
+        self.link_ptr = tables[lp_off:lp_off + 4 * (self.nmax + 1)].view(torch.int32)
+        nlinks = p.info("nlinks")
+        links = tables[lk_off:lk_off + 8 * nlinks].view(torch.int32).view(nlinks, 2)
+        self.bounds = cost_balanced_bounds(self.link_ptr.cpu().numpy(), self.world)
+        self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
+        p._check(p.lib.pyqed_heom_set_partition(p._h, self.lo, self.hi))
+        l0, l1 = int(self.link_ptr[self.lo]), int(self.link_ptr[self.hi])
+        need = needed_items(links[l0:l1, 0], links[l0:l1, 1], self.lo, self.hi, self.row_items,
+                            self.supp_rows)
+        self.halo = HaloPlan(self.bounds, self.rank, self.world, need, self.row_items, transport)
+        dev = tables.device
+        self.elems = 2 * (n if self.row_items else n * n)  # reals per item
+        self.need32 = self.halo.need.to(torch.int32).contiguous()
+        self.send32 = self.halo.send_items.to(torch.int32).contiguous()
+        self.sendbuf = torch.empty(self.send32.numel() * self.elems, dtype=torch.float64, device=dev)
+        self.recvbuf = torch.empty(self.need32.numel() * self.elems, dtype=torch.float64, device=dev)
+        self.owner_of_sys = next(r for r in range(self.world)
+                                 if self.bounds[r] <= p.info("slot0") < self.bounds[r + 1])
+
+    # -- one halo exchange of array `array_id` -----------------------------
+    def exchange(self, array_id):
+        import ctypes as C
+        p = self.plan
+        p._check(p.lib.pyqed_heom_halo_pack(p._h, array_id, C.c_void_p(self.send32.data_ptr()),
+                                            self.send32.numel(), int(self.row_items),
+                                            C.c_void_p(self.sendbuf.data_ptr()), 0))
+        self.tr.all_to_all(self.sendbuf, self.halo.send_counts, self.recvbuf, self.halo.recv_counts,
+                           self.elems)
+        p._check(p.lib.pyqed_heom_halo_pack(p._h, array_id, C.c_void_p(self.need32.data_ptr()),
+                                            self.need32.numel(), int(self.row_items),
+                                            C.c_void_p(self.recvbuf.data_ptr()), 1))
+
+    def halo_bytes_per_stage(self):
+        return self.need32.numel() * self.elems * 8
+
+    # -- propagation ---------------------------------------------------------
+    def set_state(self, rho0):
+        rho0 = np.asarray(rho0, dtype=C128).reshape(1, self.n, self.n)
+        if self.row_items and not np.array_equal(rho0[0], rho0[0].conj().T):
+            raise ValueError("row halos assume Hermitian ADOs; rho0 is not Hermitian")
+        self.plan.set_state(rho0)
+
+    def propagate(self, dt, nt, traj=None):
+        """RK4 for ``nt`` steps; ``traj`` (torch complex128 [1, nt+1, N, N]) is
+        filled on the rank that owns the system density matrix."""
+        import ctypes as C
+        p = self.plan
+        tp = None if traj is None else C.c_void_p(traj.data_ptr())
+        p._check(p.lib.pyqed_heom_propagate_begin(p._h, float(dt), int(nt), None, None, tp))
+        for i in range(nt):
+            for st in range(4):
+                p._check(p.lib.pyqed_heom_propagate_stage(p._h, i, st))
+                self.exchange(STAGE_OUTPUT_ARRAY[st])
+
+    def run(self, rho0, dt, nt):
+        """Returns ``(t_save, rho_sys[nt+1, N, N])`` on every rank."""
+        self.set_state(rho0)
+        dev = self.plan._tables.device
+        traj = torch.zeros((1, nt + 1, self.n, self.n), dtype=torch.complex128, device=dev)
+        self.propagate(dt, nt, traj)
+        flat = torch.view_as_real(traj).contiguous()
+        self.tr.broadcast(flat, self.owner_of_sys)
+        t_save = np.arange(nt + 1, dtype=np.float64) * dt
+        return t_save, torch.view_as_complex(flat)[0].cpu().numpy()
+
+    def gather_ados(self):
+        """All ADOs in reference id order on every rank (test helper: each rank
+        contributes the slots it owns)."""
+        p = self.plan
+        full = p.get_ados()[0]
+        keys = p.get_keys()
+        # owned slots -> reference ids: recompute the storage rank of every key on the host
+        owned = np.zeros(self.nmax, dtype=bool)
+        slots = _lex_rank(keys.astype(np.int64), p.lmax) if p.order == 1 else np.arange(self.nmax)
+        owned[(slots >= self.lo) & (slots < self.hi)] = True
+        full = np.where(owned[:, None, None], full, 0)
+        t = torch.from_numpy(np.ascontiguousarray(full).view(np.float64))
+        if self.tr.nccl:
+            t = t.cuda()
+        self.tr.allreduce_sum(t)
+        return t.cpu().numpy().view(C128).reshape(self.nmax, self.n, self.n)
+
+
+def _lex_rank(keys, lmax):
+    """Lexicographic storage slot of every multi-index (``rank_lex`` in
+    ``csrc/heom_core.cuh``), vectorised on the host."""
+    from math import comb
+    nmax, K = keys.shape
+    side = K + lmax + 2
+    tab = np.array([[comb(a, b) if 0 <= b <= a else 0 for b in range(side)] for a in range(side)],
+                   dtype=np.int64)
+    r = np.zeros(nmax, dtype=np.int64)
+    b = np.full(nmax, lmax, dtype=np.int64)
+    for i in range(K):
+        d = K - 1 - i
+        r += tab[b + d + 1, d + 1] - tab[b - keys[:, i] + d + 1, d + 1]
+        b -= keys[:, i]
+    return r

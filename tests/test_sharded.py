@@ -1,0 +1,63 @@
+"""Multi-rank path: halo bookkeeping + sharded RK4 (world_size 2 and 3)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+WORKER = os.path.join(ROOT, "tests", "_dist_worker.py")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _launch(world, args, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER] + args
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    return res.stdout
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_and_sharded_rk4_gloo_cpu(world):
+    out = _launch(world, ["cpu"])
+    assert out.count("cpu sharded ok") == world
+
+
+def test_cost_balanced_bounds():
+    import numpy as np
+    from pyqed_b200.heom.sharded import cost_balanced_bounds
+    lp = np.concatenate([[0], np.cumsum([20] * 10 + [4] * 90)])
+    b = cost_balanced_bounds(lp, 4, base_cost=12)
+    assert b[0] == 0 and b[-1] == 100 and b == sorted(b)
+    cost = [sum(12 + (lp[i + 1] - lp[i]) for i in range(b[r], b[r + 1])) for r in range(4)]
+    assert max(cost) - min(cost) <= 2 * 32
+    assert cost_balanced_bounds(lp, 1) == [0, 100]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,order", [(2, 1), (3, 1), (2, 0)])
+def test_sharded_gpu_ranks_sharing_one_device(world, order):
+    """The real kernels and pack/unpack with several ranks on one GPU (gloo
+    transport staged through the host); projector, sigma_z and dense couplings."""
+    out = _launch(world, ["gpu", "--backend", "gloo", "--order", str(order), "--cases",
+                          "deom_fmo_K21_L2,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
+    assert out.count(" ok (owned") == 4 * world
+
+
+@pytest.mark.gpu
+def test_sharded_nccl_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _launch(2, ["gpu", "--backend", "nccl", "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4"])
+    assert out.count(" ok (owned") == 4
