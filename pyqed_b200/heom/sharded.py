@@ -225,24 +225,36 @@ class ShardedDEOM:
             raise ValueError("row halos assume Hermitian ADOs; rho0 is not Hermitian")
         self.plan.set_state(rho0)
 
-    def propagate(self, dt, nt, traj=None):
+    def propagate(self, dt, nt, traj=None, fsys=None, fcoup=None):
         """RK4 for ``nt`` steps; ``traj`` (torch complex128 [1, nt+1, N, N]) is
-        filled on the rank that owns the system density matrix."""
+        filled on the rank that owns the system density matrix; ``fsys`` /
+        ``fcoup``: pulse tables [nt, 3] as in ``Plan.propagate``."""
         import ctypes as C
         p = self.plan
+        dp = C.POINTER(C.c_double)
+
+        def field(f):
+            if f is None:
+                return None, None
+            f = np.ascontiguousarray(np.broadcast_to(np.asarray(f, dtype=np.float64), (1, nt, 3)))
+            return f, f.ctypes.data_as(dp)
+        fs, fsp = field(fsys)
+        fc, fcp = field(fcoup)
         tp = None if traj is None else C.c_void_p(traj.data_ptr())
-        p._check(p.lib.pyqed_heom_propagate_begin(p._h, float(dt), int(nt), None, None, tp))
+        p._check(p.lib.pyqed_heom_propagate_begin(p._h, float(dt), int(nt), fsp, fcp, tp))
         for i in range(nt):
             for st in range(4):
                 p._check(p.lib.pyqed_heom_propagate_stage(p._h, i, st))
                 self.exchange(STAGE_OUTPUT_ARRAY[st])
 
-    def run(self, rho0, dt, nt):
+    def run(self, rho0, dt, nt, pulse_system_func=None, pulse_coupling_func=None):
         """Returns ``(t_save, rho_sys[nt+1, N, N])`` on every rank."""
+        from .deom import sample_pulse
         self.set_state(rho0)
         dev = self.plan._tables.device
         traj = torch.zeros((1, nt + 1, self.n, self.n), dtype=torch.complex128, device=dev)
-        self.propagate(dt, nt, traj)
+        self.propagate(dt, nt, traj, sample_pulse(pulse_system_func, dt, nt),
+                       sample_pulse(pulse_coupling_func, dt, nt))
         flat = torch.view_as_real(traj).contiguous()
         self.tr.broadcast(flat, self.owner_of_sys)
         t_save = np.arange(nt + 1, dtype=np.float64) * dt

@@ -144,7 +144,10 @@ def gpu_mode(args):
                            g["expn"], g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]),
                            tr, device=dev, order=args.order)
         nt = int(g["nt"])
-        ts, traj = sh.run(g["rho0"], float(g["dt"]), nt)
+        from conftest import pulse_from_samples
+        dt = float(g["dt"])
+        ts, traj = sh.run(g["rho0"], dt, nt, pulse_from_samples(g["pulse_system"], dt),
+                          pulse_from_samples(g["pulse_coupling"], dt))
         err = np.max(np.abs(traj - g["traj"]))
         assert err < 1e-12, (name, err)
         if "ados_final" in g:
