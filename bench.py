@@ -205,46 +205,74 @@ def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     multi = world > 1
+    torch.cuda.set_device(local)
     if multi:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
+    order = args.order if args.order >= 0 else (1 if multi else 0)
 
     w = WORKLOADS[args.workload]()
     n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
-    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
-    solver = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
-                        w["pulse_system_func"], w["pulse_coupling_func"], lmax=lmax, device=local,
-                        order=args.order, alias_rho0=False)
-    solver.tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
-    solver.options = {"qdiag": args.qdiag, "hermitian": args.herm}
     K, Wm, dt = args.steps, args.warmup, w["dt"]
-
-    # ---- e2e: the public call with host buffers (first call also builds the plan)
-    t0 = time.perf_counter()
-    solver.run(w["rho0"].copy(), dt, 1)
-    setup_s = time.perf_counter() - t0
-    plan = solver._plan
-    nmax = plan.nmax
-    if multi:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    _, traj = solver.run(w["rho0"].copy(), dt, K)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
+    options = {"qdiag": args.qdiag, "hermitian": args.herm}
     in_bytes = sum(np.asarray(w[k]).nbytes for k in
                    ("rho0", "system", "system_dipole", "coupling", "coupling_dipole", "expn", "etal",
                     "etar", "etaa", "mode"))
     out_bytes = (K + 1) * n * n * 16
-
-    # ---- device-resident timing
-    fs = fc = None
+    fs = None
     if w["pulse_system_func"] is not None:
         from pyqed_b200.heom.deom import sample_pulse
-        s = sample_pulse(w["pulse_system_func"], dt, max(K, Wm))
-        fs = None if s is None else s[None]
-    plan.set_state(w["rho0"][None])
-    plan.propagate(dt, Wm, None if fs is None else fs[:, :Wm], fc, None, 0)
+        fs = sample_pulse(w["pulse_system_func"], dt, max(K, Wm))
+
+    if not multi:
+        bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+        solver = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
+                            w["pulse_system_func"], w["pulse_coupling_func"], lmax=lmax, device=local,
+                            order=order, alias_rho0=False)
+        solver.tuning, solver.options = tuning, options
+        # ---- e2e: the public call with host buffers (first call also builds the plan)
+        t0 = time.perf_counter()
+        solver.run(w["rho0"].copy(), dt, 1)
+        setup_s = time.perf_counter() - t0
+        plan = solver._plan
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, traj = solver.run(w["rho0"].copy(), dt, K)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        rho_end = np.asarray(traj[-1])
+        owned = plan.nmax
+        halo_bytes = 0
+
+        def propagate(nsteps):
+            plan.propagate(dt, nsteps, None if fs is None else fs[None, :nsteps], None, None, 0)
+        plan.set_state(w["rho0"][None])
+    else:
+        from pyqed_b200.heom.sharded import ShardedDEOM, DistTransport
+        t0 = time.perf_counter()
+        sh = ShardedDEOM(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"],
+                         w["expn"], w["etal"], w["etar"], w["etaa"], w["mode"], lmax,
+                         DistTransport(), device=local, order=order, options=options, tuning=tuning)
+        sh.run(w["rho0"], dt, 1, w["pulse_system_func"], w["pulse_coupling_func"])
+        setup_s = time.perf_counter() - t0
+        plan = sh.plan
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, traj = sh.run(w["rho0"], dt, K, w["pulse_system_func"], w["pulse_coupling_func"])
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        rho_end = np.asarray(traj[-1])
+        owned = sh.hi - sh.lo
+        halo_bytes = sh.halo_bytes_per_stage()
+
+        def propagate(nsteps):
+            sh.propagate(dt, nsteps, None, None if fs is None else fs[:nsteps], None)
+        sh.set_state(w["rho0"])
+    nmax = plan.nmax
+
+    # ---- device-resident timing
+    propagate(Wm)
     plan.synchronize()
     launches0 = plan.launch_count()
     plan.stage_timing(True)
@@ -256,7 +284,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    plan.propagate(dt, K, None if fs is None else fs[:, :K], fc, None, 0)
+    propagate(K)
     ev1.record()
     torch.cuda.synchronize()
     if multi:
@@ -265,6 +293,7 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else {}
     stage_ms, stage_n = plan.stage_timing(False)
     launches = plan.launch_count() - launches0
+    per_rank = None
     if multi:
         tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -272,46 +301,58 @@ def run_gpu_arm(args):
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(lt)
         launches = int(lt[0])
+        mine = torch.tensor([owned, halo_bytes, stage_ms / max(stage_n, 1)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [dict(owned_ados=int(x[0]), halo_bytes_per_stage=int(x[1]), avg_stage_kernel_ms=float(x[2]))
+                    for x in allr]
 
-    # sanity of the timed state: trace of rho_sys must still be 1
-    ados0 = np.asarray(traj[-1])
-    tr = complex(np.trace(ados0))
-
+    tr = complex(np.trace(rho_end))
     if rank == 0:
         peak, peak_src = peaks()
         bytes_per_step = 256.0 * n * n * nmax          # 16 array passes x 16 B x N^2
-        value = world * nmax * K / (ms * 1e-3)
+        value = nmax * K / (ms * 1e-3)
         avg_launch_ms = stage_ms / max(stage_n, 1)
-        achieved = (bytes_per_step / 4.0) / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
+        # dominant kernel on this rank: its share of the algorithmic bytes / its mean duration
+        achieved = (256.0 * n * n * owned / 4.0) / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
         state_mb = nmax * n * n * 16 / 1e6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if multi else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": args.workload, "nsys": n, "nind": nind, "nmod": int(w["coupling"].shape[0]),
-                "lmax": lmax, "n_ado": nmax, "dt": dt, "storage_order": ["reference", "lexicographic"][args.order],
+                "lmax": lmax, "n_ado": nmax, "dt": dt, "storage_order": ["reference", "lexicographic"][order],
                 "state_mb_per_array": state_mb,
-                "fast_paths": {"diagonal_Q": plan.info("qdiag"), "hermitian_ados": plan.info("hermitian")},
+                "fast_paths": {"diagonal_Q": plan.info("qdiag"), "hermitian_ados": plan.info("hermitian"),
+                               "real_H": plan.info("real_h")},
                 "l2": ("inputs larger than L2 (4 arrays of %.0f MB); no flush needed" % state_mb) if state_mb > 200
                       else "state is cache-resident by construction (time stepping re-reads its own output); no flush",
-                "parallelism": "single GPU" if world == 1 else
-                               f"{world} independent replicas, one per GPU (hierarchy sharding not in this round)",
+                "parallelism": "single GPU" if not multi else
+                               (f"hierarchy sharded over {world} GPUs (contiguous ranges of the lexicographic order, "
+                                f"cost balanced); one halo exchange of neighbour rows per RK stage "
+                                f"(NCCL all_to_all_single)"),
                 "setup_s_first_call": setup_s,
             },
             "clocks": clocks,
-            "e2e": {"value": world * nmax * K / e2e_s, "unit": UNIT,
+            "e2e": {"value": nmax * K / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": in_bytes / K, "d2h_bytes_per_step": out_bytes / K,
-                    "call": "DEOMSolver.run(rho0, dt, nt=steps) with host arrays, plan cached"},
+                    "call": ("DEOMSolver.run(rho0, dt, nt=steps)" if not multi else "ShardedDEOM.run(rho0, dt, nt=steps)")
+                            + " with host arrays, plan cached"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": peak_src, "kernel": "stage_rows_kernel" if n <= 8 else "stage_generic_kernel",
-                         "algorithmic_bytes_per_launch": bytes_per_step / 4.0,
+                         "peak_source": peak_src,
+                         "kernel": {1: "stage_rows_kernel", 2: "stage_generic_kernel", 3: "stage_rows_async_kernel"}[
+                             args.kernel or (2 if n > 8 else (3 if plan.info("qdiag") else 1))],
+                         "algorithmic_bytes_per_launch": 256.0 * n * n * owned / 4.0,
                          "avg_launch_ms": avg_launch_ms, "launches_timed": stage_n,
-                         "whole_step_gbs": bytes_per_step * K / (ms * 1e-3) / 1e9},
+                         "whole_job_gbs": bytes_per_step * K / (ms * 1e-3) / 1e9,
+                         "whole_job_frac_of_aggregate_peak": bytes_per_step * K / (ms * 1e-3) / 1e9 / (peak * world)},
             "check": {"trace_rho_sys": [tr.real, tr.imag]},
         }
+        if per_rank:
+            line["ranks"] = per_rank
         if world == 1 and not args.no_cpu:
             cb, _, _ = cpu_reference_leg(args.workload)
             line["cpu_baseline"] = cb
@@ -328,7 +369,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--order", type=int, default=0)
+    ap.add_argument("--order", type=int, default=-1, help="storage order: 0 reference, 1 lexicographic; default 0 on one GPU, 1 when sharded")
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--graph", type=int, default=0)
