@@ -208,7 +208,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     if multi:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    order = args.order if args.order >= 0 else (1 if multi else 0)
+    order = args.order if args.order >= 0 else (2 if multi else 0)
 
     w = WORKLOADS[args.workload]()
     n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
@@ -322,7 +322,7 @@ def run_gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": args.workload, "nsys": n, "nind": nind, "nmod": int(w["coupling"].shape[0]),
-                "lmax": lmax, "n_ado": nmax, "dt": dt, "storage_order": ["reference", "lexicographic"][order],
+                "lmax": lmax, "n_ado": nmax, "dt": dt, "storage_order": ["reference", "lexicographic", "blocked lexicographic"][order],
                 "state_mb_per_array": state_mb,
                 "fast_paths": {"diagonal_Q": plan.info("qdiag"), "hermitian_ados": plan.info("hermitian"),
                                "real_H": plan.info("real_h")},

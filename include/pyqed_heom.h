@@ -68,8 +68,10 @@ int pyqed_heom_set_bath(pyqed_heom_plan* plan, const double* expn, const double*
                         const double* etar, const double* etaa, const int64_t* mode);
 
 /* ADO storage order on the device: 0 = reference id order (tier-major),
- * 1 = lexicographic in the multi-index (better gather locality).  Must be
- * called before pyqed_heom_table_bytes.  Results on the ABI are unaffected. */
+ * 1 = lexicographic in the multi-index (gather locality, small halos),
+ * 2 = lexicographic with top-tier ADOs grouped inside aligned 64-slot blocks
+ *     (same locality, balanced link counts per warp).  Must be called before
+ * pyqed_heom_table_bytes.  Results on the ABI are unaffected. */
 int pyqed_heom_set_order(pyqed_heom_plan* plan, int order);
 
 /* Sizes of the two caller-owned device buffers: the index/coefficient tables

@@ -83,7 +83,7 @@ __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 // ---------------------------------------------------------------------------
 struct TableLayout {
     size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
-        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, step_base, total;
+        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, lex2slot, slot2lex, step_base, total;
 };
 
 struct pyqed_heom_plan {
@@ -159,6 +159,8 @@ static int compute_layout(pyqed_heom_plan* p) {
     t.supp = take((size_t)p->M * (2 * p->N + 1));
     t.cbase = take(sizeof(double2) * 4 * p->K);
     t.kmode = take(sizeof(int) * p->K);
+    t.lex2slot = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
+    t.slot2lex = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
     t.step_base = take(sizeof(long long));
     t.total = off;
     p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
@@ -180,7 +182,46 @@ struct HierArgs {
     int2* links;
     const double2* expn;  // [K] device copy (stored at the head of coef scratch)
     const int* mode;      // [K]: mode | first support row << 8
+    int* lex2slot;        // order 2 only: lexicographic rank <-> storage slot
+    int* slot2lex;
 };
+
+// Storage order 2 = lexicographic order with a stable partition inside every
+// aligned block of ORDER2_BLOCK ranks: ADOs below the top tier (which carry the
+// K extra n+e_k links) first, top-tier ADOs after them.  Consecutive slots then
+// have similar link counts (warps stay balanced) while the locality and the
+// small rank-boundary halos of the lexicographic order are kept.
+constexpr int ORDER2_BLOCK = 64;
+__global__ void hier_blockperm_kernel(HierArgs h) {
+    const long long blk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long r0 = blk * ORDER2_BLOCK;
+    if (r0 >= h.nmax) return;
+    Pascal P{h.pascal, h.side};
+    const int cnt = (int)min((long long)ORDER2_BLOCK, h.nmax - r0);
+    unsigned long long top = 0ull;
+    uint8_t key[heom::MAX_NIND];
+    for (int i = 0; i < cnt; ++i) {
+        heom::unrank_lex(r0 + i, h.K, h.L, P, key);
+        int tier = 0;
+        for (int k = 0; k < h.K; ++k) tier += key[k];
+        if (tier == h.L) top |= 1ull << i;
+    }
+    const int nlow = cnt - __popcll(top);
+    int a = 0, b = nlow;
+    for (int i = 0; i < cnt; ++i) {
+        const int pos = ((top >> i) & 1ull) ? b++ : a++;
+        h.lex2slot[r0 + i] = (int)(r0 + pos);
+        h.slot2lex[r0 + pos] = (int)(r0 + i);
+    }
+}
+__device__ __forceinline__ void unrank_any(const HierArgs& h, long long slot, const Pascal& P, uint8_t* key) {
+    if (h.order == 2) heom::unrank_lex(h.slot2lex[slot], h.K, h.L, P, key);
+    else heom::unrank_slot(h.order, slot, h.K, h.L, P, key);
+}
+__device__ __forceinline__ long long rank_any(const HierArgs& h, const uint8_t* key, const Pascal& P) {
+    if (h.order == 2) return h.lex2slot[heom::rank_lex(key, h.K, h.L, P)];
+    return heom::rank_slot(h.order, key, h.K, h.L, P);
+}
 
 // pass 1: one thread per storage slot - multi-index, damping rate, link count
 __global__ void hier_keys_kernel(HierArgs h) {
@@ -188,7 +229,7 @@ __global__ void hier_keys_kernel(HierArgs h) {
     if (slot >= h.nmax) return;
     Pascal P{h.pascal, h.side};
     uint8_t key[heom::MAX_NIND];
-    heom::unrank_slot(h.order, slot, h.K, h.L, P, key);
+    unrank_any(h, slot, P, key);
     int tier = 0, nz = 0;
     double dr = 0.0, di = 0.0;
     for (int k = 0; k < h.K; ++k) {
@@ -224,13 +265,13 @@ __global__ void hier_links_kernel(HierArgs h) {
         const int nk = key[k];
         if (nk > 0) {
             key[k] = (uint8_t)(nk - 1);
-            const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
+            const long long nb = rank_any(h, key, P);
             key[k] = (uint8_t)nk;
             h.links[w++] = make_int2((int)nb, heom::link_meta(0, k, nk, h.mode[k] & 0xff, h.mode[k] >> 8));
         }
         if (tier < h.L) {
             key[k] = (uint8_t)(nk + 1);
-            const long long nb = heom::rank_slot(h.order, key, h.K, h.L, P);
+            const long long nb = rank_any(h, key, P);
             key[k] = (uint8_t)nk;
             h.links[w++] = make_int2((int)nb, heom::link_meta(1, k, nk + 1, h.mode[k] & 0xff, h.mode[k] >> 8));
         }
@@ -1288,7 +1329,7 @@ int pyqed_heom_set_bath(pyqed_heom_plan* p, const double* expn, const double* et
 
 int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
     REQUIRE(p, "null plan");
-    REQUIRE(order == 0 || order == 1, "order must be 0 (reference) or 1 (lexicographic)");
+    REQUIRE(order >= 0 && order <= 2, "order must be 0 (reference), 1 (lexicographic) or 2 (blocked lexicographic)");
     REQUIRE(!p->bound, "set_order must precede bind");
     p->order = order;
     return 0;
@@ -1327,6 +1368,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "nmax") return p->nmax;
     if (n == "slot0") return p->slot0;
     if (n == "table_bytes") return (int64_t)p->tl.total;
+    if (n == "off_id_of_slot") return (int64_t)p->tl.id_of_slot;
     if (n == "off_link_ptr") return (int64_t)p->tl.link_ptr;
     if (n == "off_links") return (int64_t)p->tl.links;
     if (n == "array_bytes") return (int64_t)p->array_bytes;
@@ -1553,8 +1595,15 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
     h.links = p->tab<int2>(t.links);
     h.expn = d_expn;
     h.mode = d_mode;
+    h.lex2slot = p->tab<int>(t.lex2slot);
+    h.slot2lex = p->tab<int>(t.slot2lex);
     const int threads = 128;
     const unsigned blocks = (unsigned)((p->nmax + threads - 1) / threads);
+    if (p->order == 2) {
+        const long long nblk = (p->nmax + ORDER2_BLOCK - 1) / ORDER2_BLOCK;
+        hier_blockperm_kernel<<<(unsigned)((nblk + 63) / 64), 64, 0, s>>>(h);
+        if (post_launch(p, "hier_blockperm_kernel")) return 1;
+    }
     hier_keys_kernel<<<blocks, threads, 0, s>>>(h);
     if (post_launch(p, "hier_keys_kernel")) return 1;
     size_t tmp_bytes = 0;

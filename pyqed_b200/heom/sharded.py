@@ -187,6 +187,9 @@ class ShardedDEOM:
         nlinks = p.info("nlinks")
         links = tables[lk_off:lk_off + 8 * nlinks].view(torch.int32).view(nlinks, 2)
         self.bounds = cost_balanced_bounds(self.link_ptr.cpu().numpy(), self.world)
+        if order == 2:  # keep the 64-slot blocks of storage order 2 whole
+            self.bounds = ([0] + [min(self.nmax, (b + 32) // 64 * 64) for b in self.bounds[1:-1]]
+                           + [self.nmax])
         self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         p._check(p.lib.pyqed_heom_set_partition(p._h, self.lo, self.hi))
         l0, l1 = int(self.link_ptr[self.lo]), int(self.link_ptr[self.hi])
@@ -265,11 +268,10 @@ class ShardedDEOM:
         contributes the slots it owns)."""
         p = self.plan
         full = p.get_ados()[0]
-        keys = p.get_keys()
-        # owned slots -> reference ids: recompute the storage rank of every key on the host
+        off = p.info("off_id_of_slot")
+        id_of_slot = p._tables[off:off + 4 * self.nmax].view(torch.int32).cpu().numpy()
         owned = np.zeros(self.nmax, dtype=bool)
-        slots = _lex_rank(keys.astype(np.int64), p.lmax) if p.order == 1 else np.arange(self.nmax)
-        owned[(slots >= self.lo) & (slots < self.hi)] = True
+        owned[id_of_slot[self.lo:self.hi]] = True
         full = np.where(owned[:, None, None], full, 0)
         t = torch.from_numpy(np.ascontiguousarray(full).view(np.float64))
         if self.tr.nccl:

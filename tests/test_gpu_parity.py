@@ -46,9 +46,10 @@ def test_deom_matches_reference(name):
 
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_random4_herm", "deom_random5_nonherm",
                                   "deom_spin_boson_L10", "deom_fmo_K21_L2"])
-def test_lexicographic_storage_order(name):
+@pytest.mark.parametrize("order", [1, 2])
+def test_lexicographic_storage_order(name, order):
     g = golden(name)
-    _check_against_golden(g, _solver_from(g, order=1))
+    _check_against_golden(g, _solver_from(g, order=order))
 
 
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_random4_herm", "deom_random5_nonherm",
@@ -147,7 +148,7 @@ def test_mid_size_against_oracle():
     o = DeomOracle(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"], w["expn"],
                    w["etal"], w["etar"], w["etaa"], w["mode"], w["lmax"])
     _, ref = o.run(w["rho0"], w["dt"], nt)
-    for order in (0, 1):
+    for order in (0, 1, 2):
         s = DEOMSolver(w["system"], w["system_dipole"],
                        Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"],
                             mode=w["mode"]), w["coupling"], w["coupling_dipole"], lmax=w["lmax"],

@@ -45,7 +45,7 @@ def test_cost_balanced_bounds():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,order", [(2, 1), (3, 1), (2, 0)])
+@pytest.mark.parametrize("world,order", [(2, 1), (3, 1), (2, 0), (2, 2), (3, 2)])
 def test_sharded_gpu_ranks_sharing_one_device(world, order):
     """The real kernels and pack/unpack with several ranks on one GPU (gloo
     transport staged through the host); projector, sigma_z and dense couplings."""
@@ -59,5 +59,5 @@ def test_sharded_nccl_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _launch(2, ["gpu", "--backend", "nccl", "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4"])
+    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4"])
     assert out.count(" ok (owned") == 4
