@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(256, HEOM_MINBLOCKS) stage_rows_kernel(const S
 
     for (long long g = (long long)blockIdx.x * nwarps + wid; g < a.ngroups;
          g += (long long)gridDim.x * nwarps) {
-        const long long base = a.slot_lo + g * APW;
+        const long long gm = g < (a.ngroups & ~15ll) ? ((g & ~15ll) | ((g + (g >> 4)) & 15ll)) : g;
+        const long long base = a.slot_lo + gm * APW;
         const int cnt = (int)min((long long)APW, a.slot_hi - base);
         const int nelem = cnt * NN;
         const double2* src = yin + base * NN;
@@ -718,8 +719,16 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     double2 nx_damp = make_double2(0.0, 0.0);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) nx_rec[c] = make_int2(0, 0);
+    // Groups are visited in a scrambled order: the position inside every run of
+    // 16 groups is rotated by the run index, so a warp (whose stride is a
+    // multiple of 16) does not see the same position of the 64-slot blocks of
+    // storage order 2 every time (their head holds the link-heavy ADOs).
+    const long long gfull = a.ngroups & ~15ll;
+    auto gmap = [&](long long gg) {
+        return gg < gfull ? ((gg & ~15ll) | ((gg + (gg >> 4)) & 15ll)) : gg;
+    };
     auto fetch_ptr = [&](long long gg, int& lb, int& le) {
-        const long long slot = a.slot_lo + gg * APW + sub;
+        const long long slot = a.slot_lo + gmap(gg) * APW + sub;
         lb = le = 0;
         if (gg < a.ngroups && lane_ok && slot < a.slot_hi) {
             lb = a.link_ptr[slot];
@@ -727,7 +736,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         }
     };
     auto fetch_rec = [&](long long gg, int lb, int le) {
-        const long long slot = a.slot_lo + gg * APW + sub;
+        const long long slot = a.slot_lo + gmap(gg) * APW + sub;
         if (gg < a.ngroups && lane_ok && slot < a.slot_hi) nx_damp = a.damp[slot];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -740,7 +749,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     fetch_ptr(g + gstride, nn_lbeg, nn_lend);
 
     for (; g < a.ngroups; g += gstride) {
-        const long long base = a.slot_lo + g * APW;
+        const long long base = a.slot_lo + gmap(g) * APW;
         const int cnt = (int)min((long long)APW, a.slot_hi - base);
         const int nelem = cnt * NN;
         const bool on = lane_ok && sub < cnt;
@@ -1147,6 +1156,7 @@ static int launch_rows_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, b
 }
 
 static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
+    if (p->part_hi <= p->part_lo) return 0;  // this rank owns nothing (tiny hierarchy, many ranks)
     static int sm_count = 0;
     if (!sm_count) {
         CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, p->device));
