@@ -154,7 +154,8 @@ def gpu_mode(args):
             ados = sh.gather_ados()
             e2 = np.max(np.abs(ados - g["ados_final"]))
             assert e2 < 1e-12, (name, e2)
-        assert sum(sh.halo.recv_counts) > 0
+        if 0 < sh.hi - sh.lo < sh.nmax:
+            assert sum(sh.halo.recv_counts) > 0   # a proper sub-range always has foreign neighbours
         print(f"rank {tr.rank}: {name} ok (owned {sh.hi - sh.lo} of {sh.nmax}, halo items "
               f"{sh.need32.numel()}, row items {sh.row_items}, err {err:.1e})", flush=True)
 
