@@ -156,7 +156,9 @@ int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
 
 /* Tuning knobs (0 = library default): kernel 0 auto, 1 row-per-lane kernel
  * (N <= 8), 2 generic one-CTA-per-ADO kernel, 3 row-per-lane kernel with
- * cp.async staging (N <= 8, diagonal Q_m); warps per CTA for kernels 1 and 3;
+ * cp.async staging (N <= 8, diagonal Q_m), 4 cluster-resident propagation
+ * (whole hierarchy in distributed shared memory, small hierarchies only;
+ * chosen automatically when it fits); warps per CTA for kernels 1 and 3;
  * use_graph: replay the RK4 step as a CUDA graph. */
 int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
                           int use_graph);
@@ -167,6 +169,7 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *                and the loaded state keep every ADO Hermitian, fetch a
  *                neighbour's column entries as the conjugate of its row
  *   "real_h"     use real arithmetic for the H products when H and mu are real
+ *   "resident"   allow the cluster-resident kernel for small hierarchies
  *   "debug_sync" synchronise and check after every launch
  * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
  * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */

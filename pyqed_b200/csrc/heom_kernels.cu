@@ -13,6 +13,7 @@
 // one matrix element is one 128-bit access.  "slot" is the storage order
 // (heom_core.cuh); links hold neighbour slots.
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -101,7 +102,8 @@ struct pyqed_heom_plan {
     bool use_qdiag = false;      // resolved at build time from the options below
     bool h_real = false;         // H and mu have no imaginary part
     std::vector<int> r0mode;     // first row with a non-zero diagonal entry, per mode
-    int opt_qdiag = -1, opt_herm = -1, opt_hreal = -1;  // -1 auto, 0 off, 1 on
+    int opt_qdiag = -1, opt_herm = -1, opt_hreal = -1, opt_resident = -1;  // -1 auto, 0 off, 1 on
+    long long resident_launches = 0;
     TableLayout tl{};
     char* d_tables = nullptr;
     char* d_state = nullptr;
@@ -992,6 +994,282 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Kernel 4: cluster-resident propagation for small hierarchies (N <= 8, diagonal
+// Q_m).  One thread-block cluster per trajectory keeps the whole hierarchy - y,
+// acc and both stage buffers - in distributed shared memory for all nt steps;
+// neighbour rows are read from the owning CTA's shared memory (DSMEM) and the
+// only synchronisation per RK stage is a hardware cluster barrier.  Hierarchies
+// of a few hundred ADOs (BASELINE configs 1, 2, 5) are otherwise bound by
+// launch and L2 latency, not bandwidth.
+// ---------------------------------------------------------------------------
+struct ResidentArgs {
+    StageArgs s;          // tables, traj, herm, ...; array pointers: s.y = state (global)
+    const double* fsys;   // [B][nt][3] or null
+    const double* fcoup;
+    const double2* ops_base;  // [1+M][NN]
+    const double2* ops_dip;
+    double dt;
+    long long nt;
+    int apc;              // ADOs per CTA (multiple of 32/N)
+    int tdep;
+};
+
+template <int N, bool HREAL>
+__global__ void __launch_bounds__(512, 1)
+resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N> hp) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const StageArgs& a = ra.s;
+    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, ADO = N * LD;
+    constexpr int FLAT = APW * NN, EIT = (FLAT + 31) / 32;
+    extern __shared__ double2 smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+    const int b = blockIdx.x / csize;       // trajectory
+    const int apc = ra.apc;
+    const AsyncTables T = async_tables(N, a.nind, a.nmod, a.lmax, true);
+    double2* Hs = smem + T.H;
+    double2* cb_s = smem + T.cb;
+    double2* cq_s = smem + T.cq;
+    double2* qd_s = smem + T.qd;
+    double* sq_s = (double*)(smem + T.sq);
+    double2* arr0 = smem + T.warp0;          // 4 arrays of apc ADOs each
+    double2* Yb = arr0;
+    double2* ACCb = Yb + (size_t)apc * ADO;
+    double2* SAb = ACCb + (size_t)apc * ADO;
+    double2* SBb = SAb + (size_t)apc * ADO;
+    unsigned char* supp_s = (unsigned char*)(SBb + (size_t)apc * ADO);
+    const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
+
+    // ---- static tables
+    for (int e = threadIdx.x; e < 4 * a.nind; e += blockDim.x) cb_s[e] = a.cbase[e];
+    for (int e = threadIdx.x; e <= a.lmax; e += blockDim.x) sq_s[e] = sqrt((double)e);
+    for (int e = threadIdx.x; e < a.nmod * (2 * N + 1); e += blockDim.x) supp_s[e] = a.supp[e];
+    auto load_ops = [&](long long step, int tidx) {
+        // H(t), diag Q_m(t) and the single-row coefficient table (generate_time, deom.py:676-687)
+        const double fs = (ra.tdep && ra.fsys) ? ra.fsys[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
+        const double fc = (ra.tdep && ra.fcoup) ? ra.fcoup[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+            const double2 v = ra.ops_base[e], d = ra.ops_dip[e];
+            Hs[e] = make_double2(fma(d.x, fs, v.x), fma(d.y, fs, v.y));
+        }
+        for (int e = threadIdx.x; e < a.nmod * N; e += blockDim.x) {
+            const int m = e / N, j = e - m * N, o = (1 + m) * NN + j * N + j;
+            const double2 v = ra.ops_base[o], d = ra.ops_dip[o];
+            qd_s[e] = make_double2(fma(d.x, fc, v.x), fma(d.y, fc, v.y));
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 2 * a.nind; e += blockDim.x) {
+            const int k = e >> 1, dir = e & 1;
+            const int m = a.kmode[k] & 0xff, r0 = a.kmode[k] >> 8;
+            const double2 q = qd_s[m * N + r0];
+            const double2 bL = cb_s[4 * k + 2 * dir], bR = cb_s[4 * k + 2 * dir + 1];
+            cq_s[3 * e + 0] = cmul(bL, q);
+            cq_s[3 * e + 1] = cmul(make_double2(bL.x + bR.x, bL.y + bR.y), q);
+            cq_s[3 * e + 2] = cmul(bR, q);
+        }
+        __syncthreads();
+    };
+    __syncthreads();
+    load_ops(0, 0);
+
+    // ---- this warp's ADOs
+    const int sub = lane / N, row = lane - sub * N;
+    const bool lane_ok = lane < APW * N;
+    const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
+    const int li0 = wid * APW;                                   // first local ADO of the warp
+    const long long slot_w = (long long)crank * apc + li0;       // its global slot
+    const long long slot = slot_w + sub;
+    const int cnt = (int)max(0ll, min((long long)APW, a.nmax - slot_w));
+    const bool on = lane_ok && sub < cnt;
+    const int nelem = cnt * NN;
+    const long long boff = (long long)b * a.nmax * NN;
+    int pofs[EIT];   // flat element -> offset inside the warp's (padded) tile
+#pragma unroll
+    for (int it = 0; it < EIT; ++it) {
+        const int e = lane + 32 * it;
+        const int s2 = e / NN, r = e - s2 * NN, i = r / N, j = r - i * N;
+        pofs[it] = (s2 * N + i) * LD + j;
+    }
+    const int woff = li0 * ADO;                                   // warp tile offset in each array
+    double2 damp = make_double2(0.0, 0.0);
+    int lbeg = 0, lend = 0;
+    if (on) {
+        damp = a.damp[slot];
+        lbeg = a.link_ptr[slot];
+        lend = a.link_ptr[slot + 1];
+    }
+    const int nl = lend - lbeg;
+    const int maxl = __reduce_max_sync(0xffffffffu, nl);
+    // initial state from global memory; the other arrays start at zero
+#pragma unroll
+    for (int it = 0; it < EIT; ++it) {
+        const int e = lane + 32 * it;
+        if (e < FLAT) {
+            const double2 z = make_double2(0.0, 0.0);
+            Yb[woff + pofs[it]] = e < nelem ? a.y[boff + slot_w * NN + e] : z;
+            ACCb[woff + pofs[it]] = z;
+            SAb[woff + pofs[it]] = z;
+            SBb[woff + pofs[it]] = z;
+        }
+    }
+    cluster.sync();
+
+#define HEL(r_, c_) (Hs[(r_) * N + (c_)])
+    for (long long step = 0; step < ra.nt; ++step) {
+        for (int st = 0; st < 4; ++st) {
+            double2* inb = st == 0 ? Yb : (st == 2 ? SBb : SAb);
+            double2* outb = st == 0 ? SAb : (st == 1 ? SBb : (st == 2 ? SAb : Yb));
+            const double ac = st == 2 ? ra.dt : ra.dt * 0.5;
+            const double wc = (st == 0 || st == 3) ? ra.dt / 6.0 : ra.dt / 3.0;
+            if (ra.tdep && st != 2 && !(step == 0 && st == 0)) load_ops(step, st == 0 ? 0 : (st == 3 ? 2 : 1));
+            // stage 3 writes y in place: its k tile lives in SB (free at that point)
+            double2* kt = (st == 3 ? SBb : outb) + woff;
+            const double2* rsub = inb + woff + sub * ADO;
+            double2* ksub = kt + sub * ADO;
+            if (on) {
+                double2 col[N];
+#pragma unroll
+                for (int l = 0; l < N; ++l) col[l] = rsub[l * LD + row];
+#pragma unroll
+                for (int rr = 0; rr < N; ++rr) {
+                    double2 c = make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int l = 0; l < N; ++l) {
+                        if (HREAL) {
+                            const double h = HEL(rr, l).x;
+                            c.x = fma(h, col[l].x, c.x);
+                            c.y = fma(h, col[l].y, c.y);
+                        } else {
+                            cfma(c, HEL(rr, l), col[l]);
+                        }
+                    }
+                    ksub[rr * LD + row] = c;
+                }
+            }
+            __syncwarp();
+            if (on) {
+                double2 rv[N];
+#pragma unroll
+                for (int l = 0; l < N; ++l) rv[l] = rsub[row * LD + l];
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    double2 t = ksub[row * LD + j];
+#pragma unroll
+                    for (int l = 0; l < N; ++l) {
+                        if (HREAL) {
+                            const double h = HEL(l, j).x;
+                            t.x = fma(-h, rv[l].x, t.x);
+                            t.y = fma(-h, rv[l].y, t.y);
+                        } else {
+                            cfms(t, rv[l], HEL(l, j));
+                        }
+                    }
+                    ksub[row * LD + j] = make_double2(t.y - (damp.x * rv[j].x - damp.y * rv[j].y),
+                                                      -t.x - (damp.x * rv[j].y + damp.y * rv[j].x));
+                }
+            }
+            __syncwarp();
+            // ---- neighbour terms: rows read through distributed shared memory
+            if (on) {
+                double2 X = make_double2(0.0, 0.0), Y = make_double2(0.0, 0.0);
+                int cur_rr = -1;
+                bool yused = false;
+                auto flush = [&]() {
+                    double2* d1 = ksub + cur_rr * LD + row;
+                    double2 v1 = *d1;
+                    v1.x += X.x;
+                    v1.y += X.y;
+                    *d1 = v1;
+                    if (yused) {
+                        double2* d2 = ksub + row * LD + cur_rr;
+                        double2 v2 = *d2;
+                        v2.x += Y.x;
+                        v2.y += Y.y;
+                        *d2 = v2;
+                    }
+                };
+                for (int lp = lbeg; lp < lend; ++lp) {
+                    const int2 lk = __ldg(a.links + lp);
+                    const int meta = lk.y;
+                    const int m = heom::meta_mode(meta);
+                    const int orank = lk.x / apc, oli = lk.x - orank * apc;
+                    const double2* rin = cluster.map_shared_rank(inb, orank) + (size_t)oli * ADO;
+                    const double sq = sq_s[heom::meta_neff(meta)];
+                    const int ns = supp_s[m * (N + 1)];
+                    const int kd = heom::meta_kdir(meta);
+                    const double2 qj = qd_s[m * N + row];
+                    const bool outside = insupp_s[m * N + row] == 0;
+                    for (int t2 = 0; t2 < ns; ++t2) {
+                        const int rr = supp_s[m * (N + 1) + 1 + t2];
+                        const double2 Aj = rin[rr * LD + row];
+                        if (rr != cur_rr) {
+                            if (cur_rr >= 0) {
+                                flush();
+                                __syncwarp(submask);
+                            }
+                            cur_rr = rr;
+                            X = make_double2(0.0, 0.0);
+                            Y = make_double2(0.0, 0.0);
+                            yused = false;
+                        }
+                        double2 c;
+                        if (ns == 1) {
+                            const double2 c1 = cq_s[3 * kd + (row == rr ? 1 : 0)];
+                            c = make_double2(c1.x * sq, c1.y * sq);
+                        } else {
+                            const double2 bL = cb_s[2 * kd], bR = cb_s[2 * kd + 1];
+                            c = cmul(make_double2(bL.x * sq, bL.y * sq), qd_s[m * N + rr]);
+                            cfma(c, make_double2(bR.x * sq, bR.y * sq), qj);
+                        }
+                        cfma(X, c, Aj);
+                        if (outside) {
+                            const double2 bR = cb_s[2 * kd + 1];
+                            const double2 cr = cmul(make_double2(bR.x * sq, bR.y * sq), qd_s[m * N + rr]);
+                            const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y) : rin[row * LD + rr];
+                            cfma(Y, cr, Bj);
+                            yused = true;
+                        }
+                    }
+                }
+                if (cur_rr >= 0) flush();
+            }
+            (void)maxl;
+            __syncwarp();
+            // ---- stage update in shared memory
+#pragma unroll
+            for (int it = 0; it < EIT; ++it) {
+                const int e = lane + 32 * it;
+                if (e < nelem) {
+                    const int o = woff + pofs[it];
+                    const double2 k = kt[pofs[it]];
+                    if (st == 3) {
+                        const double2 bs = ACCb[o];
+                        const double2 res = make_double2(fma(wc, k.x, bs.x), fma(wc, k.y, bs.y));
+                        Yb[o] = res;
+                        if (a.traj && slot_w + e / NN == a.slot0)
+                            a.traj[b * a.traj_bstride + (step + 1) * NN + e % NN] = res;
+                    } else {
+                        const double2 yv = Yb[o];
+                        const double2 bs = st == 0 ? yv : ACCb[o];
+                        ACCb[o] = make_double2(fma(wc, k.x, bs.x), fma(wc, k.y, bs.y));
+                        outb[o] = make_double2(fma(ac, k.x, yv.x), fma(ac, k.y, yv.y));
+                    }
+                }
+            }
+            cluster.sync();
+        }
+    }
+#undef HEL
+    // ---- final state back to global memory
+#pragma unroll
+    for (int it = 0; it < EIT; ++it) {
+        const int e = lane + 32 * it;
+        if (e < nelem) const_cast<double2*>(a.y)[boff + slot_w * NN + e] = Yb[woff + pofs[it]];
+    }
+}
+
 // Kernel 2 (any N): one CTA per ADO, one thread per matrix element (strided);
 // all operators (H and Q_m) go through their sparsity lists, so cost scales
 // with nnz.  rho_n is staged in shared memory; neighbours are read through L2.
@@ -1155,6 +1433,136 @@ static int launch_rows_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, b
     return qdiag ? launch_rows<N, false, true>(p, a, sm_count) : launch_rows<N, false, false>(p, a, sm_count);
 }
 
+extern "C" {
+static void fill_stage_args(pyqed_heom_plan* p, StageArgs& a);
+}
+
+// ---- cluster-resident propagation (kernel 4) -----------------------------------
+struct ResidentConfig {
+    int cluster = 0, warps = 0, apc = 0;
+    size_t smem = 0;
+};
+
+template <int N>
+static bool resident_fits(const pyqed_heom_plan* p, ResidentConfig& rc) {
+    constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N;
+    const AsyncTables T = async_tables(N, p->K, p->M, p->L, true);
+    const size_t table_bytes = sizeof(double2) * T.warp0 + T.bytes_tail;
+    const size_t per_warp = sizeof(double2) * 4 * APW * N * LD;
+    const size_t budget = 227 * 1024;
+    if (table_bytes + per_warp > budget) return false;
+    const int maxw = (int)std::min<size_t>(16, (budget - table_bytes) / per_warp);
+    const long long groups = (p->nmax + APW - 1) / APW;
+    int cs_min = 1;
+    while (cs_min <= 16 && (groups + cs_min - 1) / cs_min > maxw) cs_min <<= 1;
+    if (cs_min > 16) return false;
+    int cs = cs_min;
+    if (p->B <= 8)  // few trajectories: spread one hierarchy over as many SMs as a cluster allows
+        while (cs < 16 && cs < groups) cs <<= 1;
+    rc.cluster = cs;
+    rc.warps = (int)((groups + cs - 1) / cs);
+    rc.apc = rc.warps * APW;
+    rc.smem = table_bytes + per_warp * rc.warps;
+    return true;
+}
+
+template <int N, bool HREAL>
+static int launch_resident_t(pyqed_heom_plan* p, const ResidentArgs& ra_in, ResidentConfig rc) {
+    auto kern = resident_cluster_kernel<N, HREAL>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    HParam<N> hp;
+    for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
+    for (;;) {
+        ResidentArgs ra = ra_in;
+        ra.apc = rc.apc;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(rc.cluster * p->B));
+        cfg.blockDim = dim3((unsigned)(rc.warps * 32));
+        cfg.dynamicSmemBytes = rc.smem;
+        cfg.stream = p->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)rc.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+        if (e == cudaSuccess && nclusters >= 1) {
+            CU_TRY(cudaLaunchKernelEx(&cfg, kern, ra, hp));
+            return post_launch(p, "resident_cluster_kernel");
+        }
+        cudaGetLastError();
+        // this cluster shape cannot be co-scheduled: halve the cluster if the
+        // hierarchy still fits, otherwise report that kernel 4 is unavailable
+        constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N;
+        const long long groups = (p->nmax + APW - 1) / APW;
+        const int cs = rc.cluster / 2;
+        if (cs < 1) return -1;
+        const int warps = (int)((groups + cs - 1) / cs);
+        const size_t per_warp = sizeof(double2) * 4 * APW * N * LD;
+        const size_t smem = rc.smem - per_warp * rc.warps + per_warp * warps;
+        if (warps > 16 || smem > 227 * 1024) return -1;
+        rc.cluster = cs;
+        rc.warps = warps;
+        rc.apc = warps * APW;
+        rc.smem = smem;
+    }
+}
+
+// returns 0 = done, -1 = not applicable (caller falls back to per-stage launches), 1 = error
+static int try_resident(pyqed_heom_plan* p) {
+    const bool whole = p->part_lo == 0 && p->part_hi == p->nmax;
+    const bool want = p->kernel == 4 || (p->kernel == 0 && p->opt_resident != 0);
+    if (!want || !p->use_qdiag || p->N < 2 || p->N > 8 || !whole || p->ctx_nt <= 0) return -1;
+    ResidentConfig rc;
+    bool fits = false;
+    switch (p->N) {
+        case 2: fits = resident_fits<2>(p, rc); break;
+        case 3: fits = resident_fits<3>(p, rc); break;
+        case 4: fits = resident_fits<4>(p, rc); break;
+        case 5: fits = resident_fits<5>(p, rc); break;
+        case 6: fits = resident_fits<6>(p, rc); break;
+        case 7: fits = resident_fits<7>(p, rc); break;
+        case 8: fits = resident_fits<8>(p, rc); break;
+    }
+    if (!fits) return -1;
+    ResidentArgs ra;
+    fill_stage_args(p, ra.s);
+    ra.s.y = p->arr(ARR_Y);
+    ra.fsys = p->ctx_use_fs ? p->d_fsys : nullptr;
+    ra.fcoup = p->ctx_use_fc ? p->d_fcoup : nullptr;
+    ra.ops_base = p->tab<double2>(p->tl.ops_base);
+    ra.ops_dip = p->tab<double2>(p->tl.ops_dip);
+    ra.dt = p->ctx_dt;
+    ra.nt = p->ctx_nt;
+    ra.apc = 0;
+    ra.tdep = p->ctx_tdep ? 1 : 0;
+    if (p->timing) {
+        if (p->ev_used == p->ev.size()) {
+            cudaEvent_t e0, e1;
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            p->ev.emplace_back(e0, e1);
+        }
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].first, p->stream));
+    }
+    const bool hr = p->h_real && p->opt_hreal != 0;
+    int rcode = -1;
+#define RES_CASE(n) \
+    case n: rcode = hr ? launch_resident_t<n, true>(p, ra, rc) : launch_resident_t<n, false>(p, ra, rc); break;
+    switch (p->N) { RES_CASE(2) RES_CASE(3) RES_CASE(4) RES_CASE(5) RES_CASE(6) RES_CASE(7) RES_CASE(8) }
+#undef RES_CASE
+    if (rcode == 0 && p->timing) {
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].second, p->stream));
+        p->ev_used++;
+    }
+    if (rcode == 0) p->resident_launches++;
+    return rcode;
+}
+
 static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     if (p->part_hi <= p->part_lo) return 0;  // this rank owns nothing (tiny hierarchy, many ranks)
     static int sm_count = 0;
@@ -1171,7 +1579,7 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
         CU_TRY(cudaEventRecord(p->ev[p->ev_used].first, p->stream));
     }
     int rc = 0;
-    const int kern = p->kernel ? p->kernel : (p->N <= 8 ? (p->use_qdiag ? 3 : 1) : 2);
+    const int kern = (p->kernel && p->kernel != 4) ? p->kernel : (p->N <= 8 ? (p->use_qdiag ? 3 : 1) : 2);
     if (kern == 3) {
         REQUIRE(p->N >= 2 && p->N <= 8 && p->use_qdiag,
                 "kernel 3 needs 2 <= N <= 8 and diagonal coupling operators");
@@ -1347,7 +1755,7 @@ int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
 
 int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
     REQUIRE(p, "null plan");
-    REQUIRE(kernel >= 0 && kernel <= 3, "kernel must be 0..3");
+    REQUIRE(kernel >= 0 && kernel <= 4, "kernel must be 0..4");
     REQUIRE(warps >= 0 && warps <= 8, "warps_per_cta must be in [0, 8]");
     p->kernel = kernel;
     p->warps = warps;
@@ -1361,6 +1769,7 @@ int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
     if (n == "qdiag") p->opt_qdiag = value;
     else if (n == "hermitian") p->opt_herm = value;
     else if (n == "real_h") p->opt_hreal = value;
+    else if (n == "resident") p->opt_resident = value;
     else if (n == "debug_sync") p->debug_sync = value != 0;
     else return fail("unknown option '" + n + "'");
     return 0;
@@ -1374,6 +1783,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "hermitian") return p->herm_inputs && p->herm_state && p->opt_herm != 0;
     if (n == "hermitian_inputs") return p->herm_inputs && p->opt_herm != 0;
     if (n == "real_h") return p->h_real && p->opt_hreal != 0;
+    if (n == "resident_launches") return p->resident_launches;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
     if (n == "slot0") return p->slot0;
@@ -1846,6 +2256,10 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
     REQUIRE(method == 0 || method == 1, "propagate: method must be 0 (rk4) or 1 (euler)");
     if (pyqed_heom_propagate_begin(p, dt, nt, fsys, fcoup, d_traj)) return 1;
     if (method == 0) {
+        const int rr = try_resident(p);
+        if (rr == 0) return 0;
+        if (rr > 0) return 1;
+        REQUIRE(p->kernel != 4, "kernel 4 (cluster-resident) is not applicable to this problem");
         for (int64_t i = 0; i < nt; ++i)
             for (int st = 0; st < 4; ++st)
                 if (run_stage(p, i, st)) return 1;

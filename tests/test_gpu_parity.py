@@ -109,6 +109,37 @@ def test_row_kernels_on_diagonal_coupling(name, kernel, herm):
     _check_against_golden(g, s)
 
 
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L2", "deom_spin_boson_L10",
+                                  "deom_aggregate_L3_T0", "deom_aggregate_L3_T37"])
+@pytest.mark.parametrize("resident", [0, 1])
+def test_cluster_resident_kernel(name, resident):
+    """Small hierarchies are propagated by one cluster-resident launch; with the
+    option off the per-stage kernels must give the same trajectory."""
+    g = golden(name)
+    s = _solver_from(g)
+    s.options = {"resident": resident}
+    if resident:
+        s.tuning = dict(kernel=4, warps_per_cta=0, use_graph=0)
+    _check_against_golden(g, s)
+    assert (s._plan.info("resident_launches") > 0) == bool(resident)
+
+
+def test_cluster_resident_batch_and_restart():
+    """Batch of trajectories (one cluster each) and two consecutive run() calls."""
+    ga, gb = golden("deom_aggregate_L3_T0"), golden("deom_aggregate_L3_T37")
+    s = _solver_from(ga)
+    dt, nt = float(ga["dt"]), int(ga["nt"])
+    fa = pulse_from_samples(ga["pulse_system"], dt)
+    fb = pulse_from_samples(gb["pulse_system"], dt)
+    for _ in range(2):
+        ts, out = s.run_batch([ga["rho0"]] * 5, dt, nt, p1=ga["p1"],
+                              pulse_system_funcs=[fa, fb, None, fb, fa])
+        assert np.max(np.abs(out[0] - ga["traj"])) < TOL and np.max(np.abs(out[4] - ga["traj"])) < TOL
+        assert np.max(np.abs(out[1] - gb["traj"])) < TOL and np.max(np.abs(out[3] - gb["traj"])) < TOL
+        assert np.max(np.abs(out[2])) < TOL
+    assert s._plan.info("resident_launches") == 2
+
+
 @pytest.mark.parametrize("tag", ["rk4_nado5", "rk4_nado12"])
 def test_chain_solver_matches_reference(tag):
     from pyqed_b200.heom import HEOMSolver
