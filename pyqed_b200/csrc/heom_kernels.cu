@@ -1013,6 +1013,7 @@ struct ResidentArgs {
     long long nt;
     int apc;              // ADOs per CTA (multiple of 32/N)
     int tdep;
+    int maxlinks;         // links per ADO, upper bound (sizes the per-warp link cache)
 };
 
 template <int N, bool HREAL>
@@ -1039,7 +1040,10 @@ resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N>
     double2* ACCb = Yb + (size_t)apc * ADO;
     double2* SAb = ACCb + (size_t)apc * ADO;
     double2* SBb = SAb + (size_t)apc * ADO;
-    unsigned char* supp_s = (unsigned char*)(SBb + (size_t)apc * ADO);
+    // per-ADO link cache: (generic pointer to the neighbour's row in its CTA's Y array, meta)
+    struct LinkEnt { const double2* rowp; int meta; int pad; };
+    LinkEnt* lk_s = (LinkEnt*)(SBb + (size_t)apc * ADO);
+    unsigned char* supp_s = (unsigned char*)(lk_s + (size_t)apc * ra.maxlinks);
     const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
 
     // ---- static tables
@@ -1101,7 +1105,18 @@ resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N>
         lend = a.link_ptr[slot + 1];
     }
     const int nl = lend - lbeg;
-    const int maxl = __reduce_max_sync(0xffffffffu, nl);
+    LinkEnt* const mylk = lk_s + (size_t)(li0 + sub) * ra.maxlinks;
+    if (on) {
+        for (int t = row; t < nl; t += N) {
+            const int2 lk = __ldg(a.links + lbeg + t);
+            const int orank = lk.x / apc, oli = lk.x - orank * apc;
+            LinkEnt en;
+            en.rowp = cluster.map_shared_rank(Yb, orank) + (size_t)oli * ADO + heom::meta_r0(lk.y) * LD;
+            en.meta = lk.y;
+            en.pad = 0;
+            mylk[t] = en;
+        }
+    }
     // initial state from global memory; the other arrays start at zero
 #pragma unroll
     for (int it = 0; it < EIT; ++it) {
@@ -1190,52 +1205,65 @@ resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N>
                         *d2 = v2;
                     }
                 };
-                for (int lp = lbeg; lp < lend; ++lp) {
-                    const int2 lk = __ldg(a.links + lp);
-                    const int meta = lk.y;
-                    const int m = heom::meta_mode(meta);
-                    const int orank = lk.x / apc, oli = lk.x - orank * apc;
-                    const double2* rin = cluster.map_shared_rank(inb, orank) + (size_t)oli * ADO;
-                    const double sq = sq_s[heom::meta_neff(meta)];
-                    const int ns = supp_s[m * (N + 1)];
-                    const int kd = heom::meta_kdir(meta);
-                    const double2 qj = qd_s[m * N + row];
-                    const bool outside = insupp_s[m * N + row] == 0;
-                    for (int t2 = 0; t2 < ns; ++t2) {
-                        const int rr = supp_s[m * (N + 1) + 1 + t2];
-                        const double2 Aj = rin[rr * LD + row];
-                        if (rr != cur_rr) {
-                            if (cur_rr >= 0) {
-                                flush();
-                                __syncwarp(submask);
+                const ptrdiff_t boffs = inb - Yb;   // same layout in every CTA of the cluster
+                constexpr int U = 4;
+                for (int c0 = 0; c0 < nl; c0 += U) {
+                    LinkEnt en[U];
+                    double2 A[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        en[u] = mylk[min(c0 + u, nl - 1)];
+                        A[u] = en[u].rowp[boffs + row];   // first support row, element `row`
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (c0 + u < nl) {
+                            const int meta = en[u].meta;
+                            const int m = heom::meta_mode(meta);
+                            const int r0 = heom::meta_r0(meta);
+                            const double2* rin = en[u].rowp + boffs - r0 * LD;   // neighbour ADO base
+                            const double sq = sq_s[heom::meta_neff(meta)];
+                            const int ns = supp_s[m * (N + 1)];
+                            const int kd = heom::meta_kdir(meta);
+                            const double2 qj = qd_s[m * N + row];
+                            const bool outside = insupp_s[m * N + row] == 0;
+                            for (int t2 = 0; t2 < ns; ++t2) {
+                                const int rr = supp_s[m * (N + 1) + 1 + t2];
+                                const double2 Aj = (t2 == 0) ? A[u] : rin[rr * LD + row];
+                                if (rr != cur_rr) {
+                                    if (cur_rr >= 0) {
+                                        flush();
+                                        __syncwarp(submask);
+                                    }
+                                    cur_rr = rr;
+                                    X = make_double2(0.0, 0.0);
+                                    Y = make_double2(0.0, 0.0);
+                                    yused = false;
+                                }
+                                double2 c;
+                                if (ns == 1) {
+                                    const double2 c1 = cq_s[3 * kd + (row == rr ? 1 : 0)];
+                                    c = make_double2(c1.x * sq, c1.y * sq);
+                                } else {
+                                    const double2 bL = cb_s[2 * kd], bR = cb_s[2 * kd + 1];
+                                    c = cmul(make_double2(bL.x * sq, bL.y * sq), qd_s[m * N + rr]);
+                                    cfma(c, make_double2(bR.x * sq, bR.y * sq), qj);
+                                }
+                                cfma(X, c, Aj);
+                                if (outside) {
+                                    const double2 bR = cb_s[2 * kd + 1];
+                                    const double2 cr =
+                                        cmul(make_double2(bR.x * sq, bR.y * sq), qd_s[m * N + rr]);
+                                    const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y) : rin[row * LD + rr];
+                                    cfma(Y, cr, Bj);
+                                    yused = true;
+                                }
                             }
-                            cur_rr = rr;
-                            X = make_double2(0.0, 0.0);
-                            Y = make_double2(0.0, 0.0);
-                            yused = false;
-                        }
-                        double2 c;
-                        if (ns == 1) {
-                            const double2 c1 = cq_s[3 * kd + (row == rr ? 1 : 0)];
-                            c = make_double2(c1.x * sq, c1.y * sq);
-                        } else {
-                            const double2 bL = cb_s[2 * kd], bR = cb_s[2 * kd + 1];
-                            c = cmul(make_double2(bL.x * sq, bL.y * sq), qd_s[m * N + rr]);
-                            cfma(c, make_double2(bR.x * sq, bR.y * sq), qj);
-                        }
-                        cfma(X, c, Aj);
-                        if (outside) {
-                            const double2 bR = cb_s[2 * kd + 1];
-                            const double2 cr = cmul(make_double2(bR.x * sq, bR.y * sq), qd_s[m * N + rr]);
-                            const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y) : rin[row * LD + rr];
-                            cfma(Y, cr, Bj);
-                            yused = true;
                         }
                     }
                 }
                 if (cur_rr >= 0) flush();
             }
-            (void)maxl;
             __syncwarp();
             // ---- stage update in shared memory
 #pragma unroll
@@ -1448,7 +1476,8 @@ static bool resident_fits(const pyqed_heom_plan* p, ResidentConfig& rc) {
     constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N;
     const AsyncTables T = async_tables(N, p->K, p->M, p->L, true);
     const size_t table_bytes = sizeof(double2) * T.warp0 + T.bytes_tail;
-    const size_t per_warp = sizeof(double2) * 4 * APW * N * LD;
+    const int maxlinks = std::max(1, std::min(p->L, p->K) + p->K);
+    const size_t per_warp = sizeof(double2) * 4 * APW * N * LD + (size_t)16 * APW * maxlinks;
     const size_t budget = 227 * 1024;
     if (table_bytes + per_warp > budget) return false;
     const int maxw = (int)std::min<size_t>(16, (budget - table_bytes) / per_warp);
@@ -1502,7 +1531,8 @@ static int launch_resident_t(pyqed_heom_plan* p, const ResidentArgs& ra_in, Resi
         const int cs = rc.cluster / 2;
         if (cs < 1) return -1;
         const int warps = (int)((groups + cs - 1) / cs);
-        const size_t per_warp = sizeof(double2) * 4 * APW * N * LD;
+        const int maxlinks = std::max(1, std::min(p->L, p->K) + p->K);
+        const size_t per_warp = sizeof(double2) * 4 * APW * N * LD + (size_t)16 * APW * maxlinks;
         const size_t smem = rc.smem - per_warp * rc.warps + per_warp * warps;
         if (warps > 16 || smem > 227 * 1024) return -1;
         rc.cluster = cs;
@@ -1540,6 +1570,7 @@ static int try_resident(pyqed_heom_plan* p) {
     ra.nt = p->ctx_nt;
     ra.apc = 0;
     ra.tdep = p->ctx_tdep ? 1 : 0;
+    ra.maxlinks = std::max(1, std::min(p->L, p->K) + p->K);
     if (p->timing) {
         if (p->ev_used == p->ev.size()) {
             cudaEvent_t e0, e1;
