@@ -46,6 +46,20 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "fmo7_K21_L8"
 
 
+def measured_traffic(workload, kernel, order):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/r01_traffic.json), if it was taken for this workload/kernel/order."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        if (t["workload"], t["kernel"]) == (workload, kernel) and t["storage_order"] == order:
+            return t["dram_bytes_per_launch_avg"]
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -316,6 +330,11 @@ def run_gpu_arm(args):
         # dominant kernel on this rank: its share of the algorithmic bytes / its mean duration
         achieved = (256.0 * n * n * owned / 4.0) / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
         state_mb = nmax * n * n * 16 / 1e6
+        kname = {1: "stage_rows_kernel", 2: "stage_generic_kernel", 3: "stage_rows_async_kernel",
+                 4: "resident_cluster_kernel"}[
+            4 if plan.info("resident_launches") > 0 else
+            (args.kernel or (2 if n > 8 else (3 if plan.info("qdiag") else 1)))]
+        order_name = ["reference", "lexicographic", "blocked lexicographic"][order]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if multi else "weak",
@@ -341,10 +360,9 @@ def run_gpu_arm(args):
                             + " with host arrays, plan cached"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": peak_src,
-                         "kernel": {1: "stage_rows_kernel", 2: "stage_generic_kernel", 3: "stage_rows_async_kernel"}[
-                             args.kernel or (2 if n > 8 else (3 if plan.info("qdiag") else 1))],
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": measured_traffic(args.workload, kname, order_name) if not multi else None,
+                         "peak_source": peak_src, "kernel": kname,
                          "algorithmic_bytes_per_launch": 256.0 * n * n * owned / 4.0,
                          "avg_launch_ms": avg_launch_ms, "launches_timed": stage_n,
                          "whole_job_gbs": bytes_per_step * K / (ms * 1e-3) / 1e9,

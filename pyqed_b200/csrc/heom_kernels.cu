@@ -623,7 +623,10 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NWAIT) : "memory");
 }
 
-constexpr int ASYNC_MAX_THREADS = 384;
+#ifndef HEOM_ASYNC_THREADS
+#define HEOM_ASYNC_THREADS 448
+#endif
+constexpr int ASYNC_MAX_THREADS = HEOM_ASYNC_THREADS;
 
 // shared-memory tables of the async kernel (sizes in double2 units unless noted)
 struct AsyncTables {
