@@ -266,7 +266,8 @@ def run_gpu_arm(args):
         t0 = time.perf_counter()
         sh = ShardedDEOM(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"],
                          w["expn"], w["etal"], w["etar"], w["etaa"], w["mode"], lmax,
-                         DistTransport(), device=local, order=order, options=options, tuning=tuning)
+                         DistTransport(), device=local, order=order, options=options, tuning=tuning,
+                         peer_push={-1: None, 0: False, 1: True}[args.push])
         sh.run(w["rho0"], dt, 1, w["pulse_system_func"], w["pulse_coupling_func"])
         setup_s = time.perf_counter() - t0
         plan = sh.plan
@@ -350,7 +351,8 @@ def run_gpu_arm(args):
                 "parallelism": "single GPU" if not multi else
                                (f"hierarchy sharded over {world} GPUs (contiguous ranges of the lexicographic order, "
                                 f"cost balanced); one halo exchange of neighbour rows per RK stage "
-                                f"(NCCL all_to_all_single)"),
+                                + ("(direct stores into peer memory over NVLink + symmetric-memory barrier)"
+                                   if sh.symm is not None else "(NCCL all_to_all_single)")),
                 "setup_s_first_call": setup_s,
             },
             "clocks": clocks,
@@ -394,6 +396,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--qdiag", type=int, default=-1)
     ap.add_argument("--herm", type=int, default=-1)
+    ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:

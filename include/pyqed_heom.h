@@ -134,6 +134,17 @@ int pyqed_heom_set_partition(pyqed_heom_plan* plan, int64_t slot_lo, int64_t slo
 int pyqed_heom_halo_pack(pyqed_heom_plan* plan, int array_id, const int32_t* d_items,
                          int64_t n_items, int row_items, double* d_buf, int unpack);
 
+/* Peer-memory variant of the halo exchange: the ranks' state buffers are mapped
+ * into each other's address space (e.g. torch symmetric memory); this rank
+ * stores the listed items of its array `array_id` directly into the same
+ * positions of the destination ranks' arrays.  d_items holds the items grouped
+ * by destination, dest_offsets[world+1] (host) the group boundaries and
+ * peer_state_ptrs[world] (host) the device address of every rank's state
+ * buffer.  The caller synchronises the ranks before the next stage reads. */
+int pyqed_heom_halo_push(pyqed_heom_plan* plan, int array_id, const int32_t* d_items,
+                         int64_t n_items, int row_items, const int64_t* dest_offsets,
+                         const uint64_t* peer_state_ptrs, int world);
+
 /* Tr(op_e rho) for npts density matrices per trajectory:
  * d_rho [batch][npts][N][N] (device), ops_host [n_ops][N][N] (host),
  * d_out [batch][n_ops][npts] complex128 (device).  Replaces

@@ -50,6 +50,8 @@ SIGNATURES = {
     "pyqed_heom_set_partition": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "pyqed_heom_halo_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                        C.c_int]),
+    "pyqed_heom_halo_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, _c_int64_p,
+                                       C.POINTER(C.c_uint64), C.c_int]),
     "pyqed_heom_expectation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _c_double_p, C.c_int,
                                          C.c_void_p]),
     "pyqed_heom_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -179,15 +181,23 @@ class Plan:
     def info(self, name):
         return int(self.lib.pyqed_heom_get_info(self._h, name.encode()))
 
-    def build(self):
-        """Allocate the device buffers (torch), bind them and build the tables."""
+    def state_bytes(self):
+        sb = C.c_size_t()
+        self._check(self.lib.pyqed_heom_state_bytes(self._h, C.byref(sb)))
+        return sb.value
+
+    def build(self, state=None):
+        """Allocate the device buffers (torch), bind them and build the tables.
+        ``state``: optional caller-provided uint8 tensor for the ADO arrays
+        (e.g. symmetric memory shared with peer ranks)."""
         torch = self.torch
         tb, sb = C.c_size_t(), C.c_size_t()
         self._check(self.lib.pyqed_heom_table_bytes(self._h, C.byref(tb)))
         self._check(self.lib.pyqed_heom_state_bytes(self._h, C.byref(sb)))
         dev = torch.device("cuda", self.device)
         self._tables = torch.empty(tb.value, dtype=torch.uint8, device=dev)
-        self._state = torch.empty(sb.value, dtype=torch.uint8, device=dev)
+        self._state = state if state is not None else torch.empty(sb.value, dtype=torch.uint8, device=dev)
+        assert self._state.numel() >= sb.value and self._state.dtype == torch.uint8
         self.table_bytes, self.state_bytes = tb.value, sb.value
         stream = torch.cuda.current_stream(dev).cuda_stream
         self._check(self.lib.pyqed_heom_bind(self._h, self._tables.data_ptr(), tb.value,

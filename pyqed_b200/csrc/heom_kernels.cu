@@ -2336,6 +2336,53 @@ __global__ void halo_pack_kernel(double2* buf, const double2* arr, const int* it
     }
 }
 
+// Peer-memory halo: every rank maps the other ranks' state buffers (symmetric
+// memory / CUDA IPC) and stores the requested rows straight into their arrays
+// over NVLink - no pack buffer, no collective, no unpack on the receiver.
+struct PushArgs {
+    long long off[17];             // items [off[q], off[q+1]) go to rank q
+    unsigned long long peer[16];   // base address of rank q's state buffer
+    int world;
+};
+__global__ void halo_push_kernel(const double2* arr, long long arr_elem_off, const int* items,
+                                 long long n, int N, int rows, PushArgs pa) {
+    const int NN = N * N, per = rows ? N : NN;
+    const long long total = n * per;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / per;
+        const int j = (int)(e - i * per);
+        const int it = items[i];
+        const long long src = rows ? ((long long)(it >> 3) * NN + (it & 7) * N + j) : ((long long)it * NN + j);
+        int q = 0;
+        while (q + 1 < pa.world && i >= pa.off[q + 1]) ++q;
+        double2* dst = reinterpret_cast<double2*>(pa.peer[q]) + arr_elem_off + src;
+        *dst = arr[src];
+    }
+}
+
+int pyqed_heom_halo_push(pyqed_heom_plan* p, int array_id, const int32_t* d_items, int64_t n_items,
+                         int row_items, const int64_t* dest_offsets, const uint64_t* peer_state_ptrs,
+                         int world) {
+    REQUIRE(p && p->built && array_id >= 0 && array_id <= 3, "halo_push: bad argument");
+    REQUIRE(world >= 1 && world <= 16 && dest_offsets && peer_state_ptrs, "halo_push: bad peer table");
+    REQUIRE(p->B == 1, "halo_push: batch must be 1");
+    if (n_items == 0) return 0;
+    REQUIRE(d_items, "halo_push: null item list");
+    CU_TRY(cudaSetDevice(p->device));
+    PushArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.world = world;
+    for (int q = 0; q <= world; ++q) pa.off[q] = dest_offsets[q];
+    for (int q = 0; q < world; ++q) pa.peer[q] = peer_state_ptrs[q];
+    const long long total = n_items * (row_items ? p->N : p->N * p->N);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+    const long long arr_elem_off = (long long)((size_t)array_id * p->array_bytes / sizeof(double2));
+    halo_push_kernel<<<grid, 256, 0, p->stream>>>(p->arr(array_id), arr_elem_off, d_items, n_items, p->N,
+                                                  row_items, pa);
+    return post_launch(p, "halo_push_kernel");
+}
+
 int pyqed_heom_halo_pack(pyqed_heom_plan* p, int array_id, const int32_t* d_items, int64_t n_items,
                          int row_items, double* d_buf, int unpack) {
     REQUIRE(p && p->built && array_id >= 0 && array_id <= 3, "halo_pack: bad argument");

@@ -156,7 +156,7 @@ class ShardedDEOM:
     """
 
     def __init__(self, system, system_dipole, coupling, coupling_dipole, expn, etal, etar, etaa,
-                 mode, lmax, transport, device=0, order=1, options=None, tuning=None):
+                 mode, lmax, transport, device=0, order=1, options=None, tuning=None, peer_push=None):
         from .._cabi import Plan
         self.tr = transport
         self.rank, self.world = transport.rank, transport.world
@@ -171,7 +171,20 @@ class ShardedDEOM:
             p.set_tuning(**tuning)
         for k, v in (options or {}).items():
             p.set_option(k, v)
-        p.build()
+        # peer_push: None = use it when NCCL + symmetric memory are available
+        self.symm = None
+        state = None
+        if peer_push is not False and getattr(transport, "nccl", False):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                state = symm_mem.empty(p.state_bytes(), dtype=torch.uint8,
+                                       device=torch.device("cuda", device))
+                self.symm = symm_mem.rendezvous(state, transport.group or transport.dist.group.WORLD)
+            except Exception as exc:  # noqa: BLE001 - fall back to the NCCL exchange
+                if peer_push:
+                    raise
+                self.symm, state, self.symm_error = None, None, repr(exc)
+        p.build(state)
         self.nmax = p.nmax
         # a diagonal Q_m only reads the rows r of a neighbour with (Q_m)_rr != 0, and
         # (for Hermitian ADOs) gets the column entries as their conjugates
@@ -202,6 +215,11 @@ class ShardedDEOM:
         self.send32 = self.halo.send_items.to(torch.int32).contiguous()
         self.sendbuf = torch.empty(self.send32.numel() * self.elems, dtype=torch.float64, device=dev)
         self.recvbuf = torch.empty(self.need32.numel() * self.elems, dtype=torch.float64, device=dev)
+        if self.symm is not None:
+            import ctypes as C
+            offs = np.concatenate([[0], np.cumsum(self.halo.send_counts)]).astype(np.int64)
+            self._push_offs = offs
+            self._push_ptrs = (C.c_uint64 * self.world)(*[int(x) for x in self.symm.buffer_ptrs])
         self.owner_of_sys = next(r for r in range(self.world)
                                  if self.bounds[r] <= p.info("slot0") < self.bounds[r + 1])
 
@@ -209,6 +227,15 @@ class ShardedDEOM:
     def exchange(self, array_id):
         import ctypes as C
         p = self.plan
+        if self.symm is not None:
+            # store the requested rows straight into the peers' arrays, then a
+            # device-side barrier over the symmetric-memory signal pads
+            p._check(p.lib.pyqed_heom_halo_push(
+                p._h, array_id, C.c_void_p(self.send32.data_ptr()), self.send32.numel(),
+                int(self.row_items), self._push_offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                self._push_ptrs, self.world))
+            self.symm.barrier(channel=0)
+            return
         p._check(p.lib.pyqed_heom_halo_pack(p._h, array_id, C.c_void_p(self.send32.data_ptr()),
                                             self.send32.numel(), int(self.row_items),
                                             C.c_void_p(self.sendbuf.data_ptr()), 0))

@@ -55,9 +55,13 @@ def test_sharded_gpu_ranks_sharing_one_device(world, order):
 
 
 @pytest.mark.gpu
-def test_sharded_nccl_two_gpus():
+@pytest.mark.parametrize("push", [0, 1])
+def test_sharded_nccl_two_gpus(push):
+    """NCCL all_to_all halo (push=0) and direct peer-memory stores (push=1)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4"])
-    assert out.count(" ok (owned") == 4
+    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", str(push), "--cases",
+                      "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_random4_herm"])
+    assert out.count(" ok (owned") == 6
+    assert out.count(f"push={bool(push)}") == 6
