@@ -2359,6 +2359,9 @@ __global__ void halo_push_kernel(const double2* arr, long long arr_elem_off, con
         double2* dst = reinterpret_cast<double2*>(pa.peer[q]) + arr_elem_off + src;
         *dst = arr[src];
     }
+    // the rows must have landed in the peers' memory before this rank signals the
+    // barrier that follows on the stream
+    __threadfence_system();
 }
 
 int pyqed_heom_halo_push(pyqed_heom_plan* p, int array_id, const int32_t* d_items, int64_t n_items,

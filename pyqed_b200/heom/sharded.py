@@ -254,6 +254,10 @@ class ShardedDEOM:
         if self.row_items and not np.array_equal(rho0[0], rho0[0].conj().T):
             raise ValueError("row halos assume Hermitian ADOs; rho0 is not Hermitian")
         self.plan.set_state(rho0)
+        if self.symm is not None:
+            # peers store into this rank's arrays: nobody may start pushing before
+            # every rank has finished (re)initialising its state
+            self.symm.barrier(channel=0)
 
     def propagate(self, dt, nt, traj=None, fsys=None, fcoup=None):
         """RK4 for ``nt`` steps; ``traj`` (torch complex128 [1, nt+1, N, N]) is
