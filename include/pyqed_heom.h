@@ -145,6 +145,19 @@ int pyqed_heom_halo_push(pyqed_heom_plan* plan, int array_id, const int32_t* d_i
                          int64_t n_items, int row_items, const int64_t* dest_offsets,
                          const uint64_t* peer_state_ptrs, int world);
 
+/* Single-exponential chain HEOM by explicit Euler with the reference's in-place
+ * sequential sweep: the Euler `_heom` of pyqed/oqs.py:1808-1875 (what
+ * examples/heom.py imports) and, with the N*N unit matrices as a batch, the
+ * Liouville-space `_heom_propagator` (pyqed/HEOM/heom.py:349-413;
+ * double_update0 = 1 gives the pyqed/oqs.py:1877-1941 variant, whose loop
+ * advances ADO 0 twice per step).  d_ado [batch][nado][N][N] is read and
+ * updated in place; d_obs [batch][n_e][nt] receives Tr(e rho_0) after each step
+ * (n_e may be 0).  Plan-free; synchronous on `stream`. */
+int pyqed_heom_chain_euler(int device, void* stream, int N, int nado, int batch, const double* H,
+                           const double* S, double gamma, double c_re, double c_im, double dt,
+                           int64_t nt, int double_update0, double* d_ado, const double* e_ops_host,
+                           int n_e, double* d_obs);
+
 /* Tr(op_e rho) for npts density matrices per trajectory:
  * d_rho [batch][npts][N][N] (device), ops_host [n_ops][N][N] (host),
  * d_out [batch][n_ops][npts] complex128 (device).  Replaces

@@ -52,6 +52,9 @@ SIGNATURES = {
                                        C.c_int]),
     "pyqed_heom_halo_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, _c_int64_p,
                                        C.POINTER(C.c_uint64), C.c_int]),
+    "pyqed_heom_chain_euler": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p,
+                                         _c_double_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         C.c_int64, C.c_int, C.c_void_p, _c_double_p, C.c_int, C.c_void_p]),
     "pyqed_heom_expectation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, _c_double_p, C.c_int,
                                          C.c_void_p]),
     "pyqed_heom_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -270,3 +273,32 @@ class Plan:
         self._check(self.lib.pyqed_heom_stage_timing(self._h, int(bool(enable)), C.byref(ms),
                                                      C.byref(n)))
         return ms.value, n.value
+
+
+def chain_euler(H, S, ado0, gamma, c, dt, nt, e_ops=None, double_update0=False, device=0):
+    """Explicit-Euler chain HEOM on the GPU (``pyqed_heom_chain_euler``).
+
+    ``ado0``: complex [batch, nado, N, N] initial ADOs.  Returns
+    ``(ado_final[batch, nado, N, N], obs[batch, n_e, nt] or None)``."""
+    import torch
+    if not torch.cuda.is_available():
+        raise HeomError("no CUDA device: the HEOM path has no CPU fallback")
+    lib = load()
+    ado0 = _c128(ado0)
+    batch, nado, n, _ = ado0.shape
+    H, S = _c128(H, (n, n)), _c128(S, (n, n))
+    dev = torch.device("cuda", device)
+    d_ado = torch.from_numpy(ado0).to(dev)
+    n_e = 0 if e_ops is None else len(e_ops)
+    ops = None if n_e == 0 else _c128(np.stack([np.asarray(e) for e in e_ops]), (n_e, n, n))
+    d_obs = None if n_e == 0 else torch.empty((batch, n_e, nt), dtype=torch.complex128, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    rc = lib.pyqed_heom_chain_euler(device, C.c_void_p(stream), n, nado, batch, _dptr(H.view(np.float64)),
+                                    _dptr(S.view(np.float64)), float(gamma), float(np.real(c)),
+                                    float(np.imag(c)), float(dt), int(nt), int(bool(double_update0)),
+                                    C.c_void_p(d_ado.data_ptr()),
+                                    None if ops is None else _dptr(ops.view(np.float64)), n_e,
+                                    None if d_obs is None else C.c_void_p(d_obs.data_ptr()))
+    if rc != 0:
+        raise HeomError(lib.pyqed_heom_last_error().decode())
+    return d_ado.cpu().numpy(), (None if d_obs is None else d_obs.cpu().numpy())

@@ -2399,6 +2399,121 @@ int pyqed_heom_halo_pack(pyqed_heom_plan* p, int array_id, const int32_t* d_item
     return post_launch(p, unpack ? "halo_unpack_kernel" : "halo_pack_kernel");
 }
 
+// ---- single-exponential chain, explicit Euler with in-place sequential sweep ------
+// Restates the Euler `_heom` of pyqed/oqs.py:1808-1875 and the Liouville-space
+// `_heom_propagator` (pyqed/HEOM/heom.py:349-413, pyqed/oqs.py:1877-1941):
+//   ado[0] += dt (-i[H,ado0] - [S,ado1])
+//   ado[n] += dt (-i[H,adon] - [S,ado_{n+1}] - n gamma adon
+//                 + n (c_re [S,ado_{n-1}] + i c_im {S,ado_{n-1}})),  n = 1..nado-2
+// where ado_{n-1} has already been advanced (Gauss-Seidel order); the last ADO
+// never changes.  One CTA per trajectory (the propagator is the batch of the N^2
+// unit matrices), one thread per matrix element.  double0 reproduces the second
+// update of ado[0] per step that the loop bounds of oqs.py:1930 cause.
+__global__ void chain_euler_kernel(double2* ado, const double2* Hg, const double2* Sg, int N, int nado,
+                                   double gamma, double c_re, double c_im, double dt, long long nt,
+                                   int double0, const double2* eops, int n_e, double2* obs) {
+    extern __shared__ double2 smem[];
+    const int NN = N * N;
+    double2* H = smem;
+    double2* S = smem + NN;
+    double2* red = smem + 2 * NN;   // [n_e] partial traces
+    for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+        H[e] = Hg[e];
+        S[e] = Sg[e];
+    }
+    double2* a = ado + (long long)blockIdx.x * nado * NN;
+    __syncthreads();
+    const int e = threadIdx.x, i = e / N, j = e - i * N;
+    const bool act = e < NN;
+    for (long long step = 0; step < nt; ++step) {
+        const int first = double0 ? -1 : 0;
+        for (int nn = first; nn < nado - 1; ++nn) {
+            const int n = nn < 0 ? 0 : nn;
+            double2 v = make_double2(0.0, 0.0);
+            if (act) {
+                const double2* A = a + (long long)n * NN;
+                const double2* Ap = a + (long long)(n + 1) * NN;
+                double2 cH = make_double2(0.0, 0.0), cS = make_double2(0.0, 0.0);
+                for (int l = 0; l < N; ++l) {
+                    cfma(cH, H[i * N + l], A[l * N + j]);
+                    cfms(cH, A[i * N + l], H[l * N + j]);
+                    cfma(cS, S[i * N + l], Ap[l * N + j]);
+                    cfms(cS, Ap[i * N + l], S[l * N + j]);
+                }
+                // -i [H, A] - [S, A+]
+                v = make_double2(cH.y - cS.x, -cH.x - cS.y);
+                if (n >= 1) {
+                    const double2* Am = a + (long long)(n - 1) * NN;
+                    double2 cm = make_double2(0.0, 0.0), am = make_double2(0.0, 0.0);
+                    for (int l = 0; l < N; ++l) {
+                        const double2 sa = cmul(S[i * N + l], Am[l * N + j]);
+                        const double2 as = cmul(Am[i * N + l], S[l * N + j]);
+                        cm.x += sa.x - as.x;
+                        cm.y += sa.y - as.y;
+                        am.x += sa.x + as.x;
+                        am.y += sa.y + as.y;
+                    }
+                    const double2 own = A[e];
+                    // - n gamma A + n (c_re [S,A-] + i c_im {S,A-})
+                    v.x += -n * gamma * own.x + n * (c_re * cm.x - c_im * am.y);
+                    v.y += -n * gamma * own.y + n * (c_re * cm.y + c_im * am.x);
+                }
+            }
+            __syncthreads();   // everyone has read ado[n] before it is overwritten
+            if (act) {
+                double2* A = a + (long long)n * NN;
+                const double2 own = A[e];
+                A[e] = make_double2(own.x + dt * v.x, own.y + dt * v.y);
+            }
+            __syncthreads();
+        }
+        if (obs) {   // Tr(e rho_0) after the step (obs, superoperator.py:313)
+            for (int o = 0; o < n_e; ++o) {
+                if (threadIdx.x == 0) red[o] = make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            if (threadIdx.x < n_e) {
+                double2 s = make_double2(0.0, 0.0);
+                const double2* op = eops + (long long)threadIdx.x * NN;
+                for (int r = 0; r < N; ++r)
+                    for (int c = 0; c < N; ++c) cfma(s, op[r * N + c], a[c * N + r]);
+                obs[((long long)blockIdx.x * n_e + threadIdx.x) * nt + step] = s;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+int pyqed_heom_chain_euler(int device, void* stream, int N, int nado, int batch, const double* H,
+                           const double* S, double gamma, double c_re, double c_im, double dt,
+                           int64_t nt, int double_update0, double* d_ado, const double* e_ops_host,
+                           int n_e, double* d_obs) {
+    REQUIRE(N >= 1 && N <= 32 && nado >= 2 && batch >= 1 && nt >= 0 && H && S && d_ado,
+            "chain_euler: bad argument (1 <= N <= 32, nado >= 2)");
+    REQUIRE(n_e >= 0 && n_e <= 32 && (n_e == 0 || (e_ops_host && d_obs)), "chain_euler: bad observables");
+    CU_TRY(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t NN = (size_t)N * N;
+    double2* d_ops = nullptr;
+    CU_TRY(cudaMalloc(&d_ops, sizeof(double2) * NN * (2 + (size_t)std::max(n_e, 1))));
+    CU_TRY(cudaMemcpyAsync(d_ops, H, sizeof(double2) * NN, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_ops + NN, S, sizeof(double2) * NN, cudaMemcpyHostToDevice, st));
+    if (n_e)
+        CU_TRY(cudaMemcpyAsync(d_ops + 2 * NN, e_ops_host, sizeof(double2) * NN * n_e,
+                               cudaMemcpyHostToDevice, st));
+    const int threads = (int)std::max<size_t>(32, (NN + 31) / 32 * 32);
+    const size_t smem = sizeof(double2) * (2 * NN + 32);
+    chain_euler_kernel<<<batch, threads, smem, st>>>((double2*)d_ado, d_ops, d_ops + NN, N, nado, gamma,
+                                                     c_re, c_im, dt, nt, double_update0,
+                                                     n_e ? d_ops + 2 * NN : nullptr, n_e, (double2*)d_obs);
+    cudaError_t e = cudaGetLastError();
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(d_ops);
+    if (e != cudaSuccess) return fail(std::string("chain_euler_kernel launch: ") + cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail(std::string("chain_euler_kernel: ") + cudaGetErrorString(e2));
+    return 0;
+}
+
 int pyqed_heom_expectation(pyqed_heom_plan* p, const double* d_rho, int64_t npts,
                            const double* ops_host, int n_ops, double* d_out) {
     REQUIRE(p && d_rho && ops_host && d_out && n_ops >= 1 && npts >= 1, "expectation: bad argument");

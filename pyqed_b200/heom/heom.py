@@ -47,6 +47,18 @@ class HEOMSolver:
         """``D0`` of ``heom.py:312`` (temperature already in energy units)."""
         return reorganization * (2.0 * temperature - 1j * cutoff)
 
+    def propagator(self, dt, nt, temperature, cutoff, reorganization, nado):
+        """Liouville-space Euler propagator ``u[nado, N^2, N^2]`` of
+        ``pyqed/HEOM/heom.py:349-413`` (temperature in kelvin)."""
+        from ..oqs import liouville_propagator
+
+        def say(*lines):
+            if self.verbose:
+                for line in lines:
+                    print(line)
+        return liouville_propagator(self.H, self.c_ops[0], dt, nt, temperature, cutoff, reorganization,
+                                    nado, double_update0=False, device=self.device, say=say)
+
     def run(self, rho0, dt, nt, temperature, cutoff, reorganization, nado):
         if self.H is None or self.c_ops is None or self.e_ops is None:
             raise ValueError('H, c_ops and e_ops must be set.')

@@ -151,7 +151,43 @@ def save_bath():
     print("bath: saved", len(out), "arrays")
 
 
+def save_propagators():
+    """Liouville-space Euler propagators: HEOM/heom.py:349-413 and oqs.py:1877-1941."""
+    from scipy.sparse import kron, identity
+    sup_ns = dict(np=np, kron=kron, identity=identity)
+    o2s = _extract(f"{REF}/pyqed/superoperator.py", "operator_to_superoperator", sup_ns)
+    au2k = 315775.13  # pyqed/units.py:6
+    ns = dict(np=np, operator_to_superoperator=o2s, au2k=au2k)
+    prop_heom = _extract(f"{REF}/pyqed/HEOM/heom.py", "_heom_propagator", dict(ns))
+    prop_oqs = _extract(f"{REF}/pyqed/oqs.py", "_heom_propagator", dict(ns))
+    s0, sx, sy, sz = ref_phys.pauli()
+    H = -0.5 * sx - 0.5 * sz
+    out = dict(H=H, c_op=sz, temperature=300.0 * 100, cutoff=5.0, reorganization=0.2, nado=5, dt=0.001,
+               nt=40, au2k=au2k)
+    for tag, fn in (("heom", prop_heom), ("oqs", prop_oqs)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            u = fn(H, [sz], [sz], out["temperature"], out["cutoff"], out["reorganization"],
+                   out["nado"], out["dt"], out["nt"])
+        out[f"u_{tag}"] = np.asarray(u)
+    # a 3-level case with a complex Hermitian H and non-diagonal coupling
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+    H3 = (A + A.conj().T) / 2
+    S3 = np.diag([1.0, 0.0, -1.0]).astype(complex)
+    S3[0, 1] = S3[1, 0] = 0.3
+    with contextlib.redirect_stdout(io.StringIO()):
+        u3 = prop_heom(H3, [S3], [S3], 2.0e5, 3.0, 0.1, 6, 0.002, 25)
+    out.update(H3=H3, S3=S3, u3_heom=np.asarray(u3), t3=np.array([2.0e5, 3.0, 0.1, 6, 0.002, 25]))
+    np.savez_compressed(os.path.join(HERE, "chain_propagator.npz"), **out)
+    print("chain_propagator: |u_heom[0]| max", np.abs(out["u_heom"][0]).max(),
+          "diff heom/oqs", np.abs(out["u_heom"] - out["u_oqs"]).max())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "propagators":
+        save_propagators()
+        return
+    save_propagators()
     save_bath()
     # KAT-1 / KAT-1b / KAT-1e: examples/heom.py inputs
     save_chain("rk4_nado5", ref_heom_rk4, "rk4", 5, 0.02, 100)

@@ -247,3 +247,31 @@ def test_euler_method_against_oracle():
     p.propagate(dt, nt, method=1)
     got = p.get_ados()[0]
     assert np.max(np.abs(got - rho)) < TOL
+
+
+def test_euler_chain_solver_matches_reference():
+    """pyqed/oqs.py HEOMSolver (what examples/heom.py runs): KAT-1e."""
+    from pyqed_b200.oqs import HEOMSolver
+    g = golden("chain_euler_nado5")
+    sol = HEOMSolver(g["H"], c_ops=[g["c_op"]], e_ops=list(g["e_ops"]), verbose=False)
+    obs = sol.run(rho0=g["rho0"], dt=float(g["dt"]), nt=int(g["nt"]), temperature=float(g["temperature"]),
+                  cutoff=float(g["cutoff"]), reorganization=float(g["reorganization"]), nado=int(g["nado"]))
+    assert obs.shape == g["observables"].shape
+    assert np.max(np.abs(obs - g["observables"])) < TOL
+    assert abs(obs[0, -1].real - (-0.9690784389436947)) < 1e-13
+
+
+def test_liouville_propagators_match_reference():
+    from pyqed_b200.heom import HEOMSolver as RK4Solver
+    from pyqed_b200.oqs import HEOMSolver as EulerSolver, liouville_propagator
+    g = golden("chain_propagator")
+    args = dict(dt=float(g["dt"]), nt=int(g["nt"]), temperature=float(g["temperature"]),
+                cutoff=float(g["cutoff"]), reorganization=float(g["reorganization"]), nado=int(g["nado"]))
+    u = RK4Solver(g["H"], [g["c_op"]], [g["c_op"]], verbose=False).propagator(**args)
+    assert u.shape == g["u_heom"].shape and np.max(np.abs(u - g["u_heom"])) < TOL
+    u = EulerSolver(g["H"], [g["c_op"]], [g["c_op"]], verbose=False).propagator(**args)
+    assert np.max(np.abs(u - g["u_oqs"])) < TOL
+    assert np.max(np.abs(g["u_oqs"] - g["u_heom"])) > 1e-6   # the two variants really differ
+    T, gam, lam, nado, dt, nt = g["t3"]
+    u3 = liouville_propagator(g["H3"], g["S3"], dt, int(nt), T, gam, lam, int(nado))
+    assert np.max(np.abs(u3 - g["u3_heom"])) < TOL
