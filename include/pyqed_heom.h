@@ -145,6 +145,12 @@ int pyqed_heom_halo_push(pyqed_heom_plan* plan, int array_id, const int32_t* d_i
                          int64_t n_items, int row_items, const int64_t* dest_offsets,
                          const uint64_t* peer_state_ptrs, int world);
 
+/* rho_n <- A rho_n (side 0) or rho_n A (side 1) for every ADO of every
+ * trajectory, A an N x N complex128 host matrix.  Replaces operator_action_ddos
+ * (deom.py:945-950); with propagate it gives HEOM-space correlation functions
+ * by time propagation (pyqed/deom.py:921-952). */
+int pyqed_heom_apply_operator(pyqed_heom_plan* plan, const double* op_host, int side);
+
 /* Single-exponential chain HEOM by explicit Euler with the reference's in-place
  * sequential sweep: the Euler `_heom` of pyqed/oqs.py:1808-1875 (what
  * examples/heom.py imports) and, with the N*N unit matrices as a batch, the

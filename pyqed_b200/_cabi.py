@@ -52,6 +52,7 @@ SIGNATURES = {
                                        C.c_int]),
     "pyqed_heom_halo_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, _c_int64_p,
                                        C.POINTER(C.c_uint64), C.c_int]),
+    "pyqed_heom_apply_operator": (C.c_int, [C.c_void_p, _c_double_p, C.c_int]),
     "pyqed_heom_chain_euler": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p,
                                          _c_double_p, C.c_double, C.c_double, C.c_double, C.c_double,
                                          C.c_int64, C.c_int, C.c_void_p, _c_double_p, C.c_int, C.c_void_p]),
@@ -259,6 +260,12 @@ class Plan:
                                                     _dptr(ops.view(np.float64)), ops.shape[0],
                                                     C.c_void_p(out.data_ptr())))
         return out
+
+    def apply_operator(self, op, side="left"):
+        """All ADOs <- op @ ADO (``left``) or ADO @ op (``right``), in place."""
+        op = _c128(op, (self.nsys, self.nsys))
+        self._check(self.lib.pyqed_heom_apply_operator(self._h, _dptr(op.view(np.float64)),
+                                                       {"left": 0, "right": 1}[side]))
 
     def synchronize(self):
         self._check(self.lib.pyqed_heom_synchronize(self._h))

@@ -2399,6 +2399,52 @@ int pyqed_heom_halo_pack(pyqed_heom_plan* p, int array_id, const int32_t* d_item
     return post_launch(p, unpack ? "halo_unpack_kernel" : "halo_pack_kernel");
 }
 
+// ---- operator action on every ADO (operator_action_ddos, deom.py:945-950) ---------
+// rho_n <- A rho_n (side 0) or rho_n A (side 1), for all n and all trajectories;
+// the building block of HEOM-space correlation functions
+// <A(t) B(0)> = Tr[A G(t) (B rho)] (intent of pyqed/deom.py:921-952).
+__global__ void apply_operator_kernel(double2* y, const double2* A, long long nado_total, int N, int side) {
+    extern __shared__ double2 smem[];
+    const int NN = N * N;
+    double2* As = smem;
+    double2* rs = smem + NN;
+    for (int e = threadIdx.x; e < NN; e += blockDim.x) As[e] = A[e];
+    for (long long n = blockIdx.x; n < nado_total; n += gridDim.x) {
+        double2* r = y + n * NN;
+        __syncthreads();
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) rs[e] = r[e];
+        __syncthreads();
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+            const int i = e / N, j = e - i * N;
+            double2 v = make_double2(0.0, 0.0);
+            if (side == 0)
+                for (int l = 0; l < N; ++l) cfma(v, As[i * N + l], rs[l * N + j]);
+            else
+                for (int l = 0; l < N; ++l) cfma(v, rs[i * N + l], As[l * N + j]);
+            r[e] = v;
+        }
+    }
+}
+
+int pyqed_heom_apply_operator(pyqed_heom_plan* p, const double* op_host, int side) {
+    REQUIRE(p && p->built && op_host && (side == 0 || side == 1), "apply_operator: bad argument");
+    CU_TRY(cudaSetDevice(p->device));
+    const size_t NN = (size_t)p->N * p->N;
+    double2* d_op = nullptr;
+    CU_TRY(cudaMalloc(&d_op, sizeof(double2) * NN));
+    CU_TRY(cudaMemcpyAsync(d_op, op_host, sizeof(double2) * NN, cudaMemcpyHostToDevice, p->stream));
+    const long long total = (long long)p->B * p->nmax;
+    const int threads = (int)std::min<size_t>(256, (NN + 31) / 32 * 32);
+    const unsigned grid = (unsigned)std::min<long long>(total, 148 * 16);
+    apply_operator_kernel<<<grid, threads, sizeof(double2) * 2 * NN, p->stream>>>(p->arr(ARR_Y), d_op, total,
+                                                                             p->N, side);
+    int rc = post_launch(p, "apply_operator_kernel");
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    cudaFree(d_op);
+    p->herm_state = false;  // A rho is not Hermitian in general
+    return rc;
+}
+
 // ---- single-exponential chain, explicit Euler with in-place sequential sweep ------
 // Restates the Euler `_heom` of pyqed/oqs.py:1808-1875 and the Liouville-space
 // `_heom_propagator` (pyqed/HEOM/heom.py:349-413, pyqed/oqs.py:1877-1941):

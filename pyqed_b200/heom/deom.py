@@ -213,6 +213,48 @@ class DEOMSolver:
         fc = pulse_coupling_funcs or [self.pulse_coupling_func] * nb
         return self._run(list(rho0s), dt, nt, p1, fs, fc)
 
+    # ---- HEOM-space correlation functions by time propagation ------------------
+    def operator_action_ddos(self, operator, side="left"):
+        """Apply ``operator`` to every ADO currently on the device
+        (``operator_action_ddos``, ``deom.py:945-950``; ``side='right'`` multiplies
+        from the right).  Call after ``run`` / ``prepare``."""
+        if self._plan is None:
+            raise RuntimeError("no state on the device: call run() or prepare() first")
+        self._plan.apply_operator(operator, side)
+        self._ddos = None
+
+    def prepare(self, rho0, dt=None, nt=0):
+        """Load ``rho0`` as ADO 0 (all other ADOs zero) and optionally propagate
+        ``nt`` steps, e.g. towards the correlated system-bath stationary state."""
+        self.check_()
+        self.init_()
+        plan = self._ensure_plan(1)
+        plan.set_state(np.asarray(rho0, dtype=C128).reshape(1, self.nsys, self.nsys))
+        if nt:
+            plan.propagate(dt, nt, None, None, None, method=0)
+        self._ddos = None
+
+    def correlation_2op_1t(self, a_op, b_op, dt, nt, rho0=None, side="left"):
+        """``C(t_i) = Tr[A G(t_i) (B rho)]`` for ``t_i = i dt``, ``i = 0..nt``:
+        the two-time correlation function <A(t) B(0)> in HEOM space, where the
+        operator acts on every ADO and the whole hierarchy is propagated (the
+        scheme sketched in ``pyqed/deom.py:921-952``).  ``rho`` is the state
+        currently on the device (``prepare`` / ``run``) or ``rho0`` if given.
+        Returns ``(t, C)``; the device state is consumed."""
+        import torch
+        if rho0 is not None:
+            self.prepare(rho0)
+        if self._plan is None:
+            raise RuntimeError("no state on the device: pass rho0 or call prepare() first")
+        plan, n = self._plan, self.nsys
+        plan.apply_operator(b_op, side)
+        traj = torch.empty((1, nt + 1, n, n), dtype=torch.complex128,
+                           device=torch.device("cuda", self.device))
+        plan.propagate(dt, nt, None, None, traj, method=0)
+        corr = plan.expectation(traj, np.asarray(a_op, dtype=C128))[0, 0].cpu().numpy()
+        self._ddos = None
+        return np.arange(nt + 1) * dt, corr
+
     def _run(self, rho0s, dt, nt, p1, fs, fc):
         import torch
         nb = len(rho0s)

@@ -275,3 +275,34 @@ def test_liouville_propagators_match_reference():
     T, gam, lam, nado, dt, nt = g["t3"]
     u3 = liouville_propagator(g["H3"], g["S3"], dt, int(nt), T, gam, lam, int(nado))
     assert np.max(np.abs(u3 - g["u3_heom"])) < TOL
+
+
+def test_heom_space_correlation_function():
+    """<A(t)B(0)> by applying B to every ADO and propagating, against the same
+    sequence done with the oracle; also operator_action_ddos on both sides."""
+    from oracle.deom_oracle import DeomOracle
+    g = golden("deom_random4_herm")
+    s = _solver_from(g)
+    s.pulse_system_func = s.pulse_coupling_func = None
+    o = DeomOracle(g["system"], g["system_dipole"], g["coupling"], g["coupling_dipole"], g["expn"],
+                   g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]))
+    rng = np.random.default_rng(3)
+    n = o.nsys
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    dt, n_eq, nt = 0.01, 30, 25
+    # oracle: equilibrate, apply B to all ADOs, propagate, trace with A
+    _, _ = o.run(g["rho0"], dt, n_eq)
+    rho = B @ o.ddos
+    ref = [np.trace(A @ rho[0])]
+    for _ in range(nt):
+        rho = o.rk4_step(rho, dt, 0.0, o.rhs_batched)
+        ref.append(np.trace(A @ rho[0]))
+    s.prepare(g["rho0"], dt, n_eq)
+    t, c = s.correlation_2op_1t(A, B, dt, nt)
+    assert np.allclose(t, np.arange(nt + 1) * dt)
+    assert np.max(np.abs(c - np.array(ref))) < TOL
+    # right action
+    s.prepare(g["rho0"], dt, n_eq)
+    s.operator_action_ddos(B, side="right")
+    assert np.max(np.abs(s.ddos - o.ddos @ B)) < TOL
