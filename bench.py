@@ -267,7 +267,8 @@ def run_gpu_arm(args):
         sh = ShardedDEOM(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"],
                          w["expn"], w["etal"], w["etar"], w["etaa"], w["mode"], lmax,
                          DistTransport(), device=local, order=order, options=options, tuning=tuning,
-                         peer_push={-1: None, 0: False, 1: True}[args.push])
+                         peer_push={-1: None, 0: False, 1: True}[args.push],
+                         fused_push={-1: None, 0: False, 1: True}[args.fused])
         sh.run(w["rho0"], dt, 1, w["pulse_system_func"], w["pulse_coupling_func"])
         setup_s = time.perf_counter() - t0
         plan = sh.plan
@@ -351,7 +352,9 @@ def run_gpu_arm(args):
                 "parallelism": "single GPU" if not multi else
                                (f"hierarchy sharded over {world} GPUs (contiguous ranges of the lexicographic order, "
                                 f"cost balanced); one halo exchange of neighbour rows per RK stage "
-                                + ("(direct stores into peer memory over NVLink + symmetric-memory barrier)"
+                                + (("(rows stored into peer memory over NVLink by the stage kernel's epilogue"
+                                    if sh.fused else "(rows stored into peer memory over NVLink by a push kernel")
+                                   + " + symmetric-memory barrier)"
                                    if sh.symm is not None else "(NCCL all_to_all_single)")),
                 "setup_s_first_call": setup_s,
             },
@@ -396,6 +399,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--qdiag", type=int, default=-1)
     ap.add_argument("--herm", type=int, default=-1)
+    ap.add_argument("--fused", type=int, default=-1, help="multi-GPU: stage kernel stores halo rows itself")
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
     args = ap.parse_args()
     args.steps_given = args.steps is not None

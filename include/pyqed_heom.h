@@ -164,6 +164,15 @@ int pyqed_heom_chain_euler(int device, void* stream, int N, int nado, int batch,
                            int64_t nt, int double_update0, double* d_ado, const double* e_ops_host,
                            int n_e, double* d_obs);
 
+/* Fused form of the peer-memory halo for the async row kernel (kernel 3): the
+ * stage kernel's epilogue stores every output row another rank needs straight
+ * into that rank's array, so the exchange overlaps the stage itself.
+ * d_push_ptr[owned+1] / d_push_ent: CSR over this rank's owned slots, entry =
+ * peer << 4 | row (row 15 = every row of the ADO).  Pass d_push_ptr = NULL to
+ * switch it off.  The caller still synchronises the ranks between stages. */
+int pyqed_heom_set_push_table(pyqed_heom_plan* plan, const int32_t* d_push_ptr,
+                              const uint8_t* d_push_ent, const uint64_t* peer_state_ptrs, int world);
+
 /* Tr(op_e rho) for npts density matrices per trajectory:
  * d_rho [batch][npts][N][N] (device), ops_host [n_ops][N][N] (host),
  * d_out [batch][n_ops][npts] complex128 (device).  Replaces

@@ -52,6 +52,8 @@ SIGNATURES = {
                                        C.c_int]),
     "pyqed_heom_halo_push": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int, _c_int64_p,
                                        C.POINTER(C.c_uint64), C.c_int]),
+    "pyqed_heom_set_push_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
+                                            C.c_int]),
     "pyqed_heom_apply_operator": (C.c_int, [C.c_void_p, _c_double_p, C.c_int]),
     "pyqed_heom_chain_euler": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p,
                                          _c_double_p, C.c_double, C.c_double, C.c_double, C.c_double,

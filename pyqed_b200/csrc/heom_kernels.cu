@@ -123,6 +123,10 @@ struct pyqed_heom_plan {
     double* d_fcoup = nullptr;
     size_t field_cap = 0;
     bool debug_sync = false;
+    // fused peer push (multi-GPU)
+    const int* push_ptr = nullptr;
+    const unsigned char* push_ent = nullptr;
+    unsigned long long* d_peer = nullptr;
     // context of the propagation in progress (propagate_begin)
     bool ctx_valid = false, ctx_tdep = false, ctx_use_fs = false, ctx_use_fc = false;
     double ctx_dt = 0.0;
@@ -374,6 +378,12 @@ struct StageArgs {
     int herm, ncoef, nmod, nind, lmax;
     const double2* cbase;  // [K][4]: minus (L,R) and plus (L,R) coefficients for n_eff = 1
     const int* kmode;      // [K]: mode | first support row << 8
+    // fused multi-GPU halo (async kernel): rows of the stage output that other
+    // ranks need are stored into their arrays by the epilogue
+    const int* push_ptr;            // [owned+1] CSR over the owned slots, or null
+    const unsigned char* push_ent;  // entries: peer << 4 | row (15 = every row)
+    const unsigned long long* peer; // [world] base address of every rank's state buffer (device array)
+    long long out_elem_off;         // offset (double2) of this stage's output array in the state buffer
 };
 
 template <int N>
@@ -720,6 +730,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     constexpr int NCH = (32 + N - 1) / N > 4 ? 4 : (32 + N - 1) / N;  // record chunks prefetched
     long long g = (long long)blockIdx.x * nwarps + wid;
     int nx_lbeg = 0, nx_lend = 0, nn_lbeg = 0, nn_lend = 0;
+    int nx_pb = 0, nx_pe = 0, nn_pb = 0, nn_pe = 0, nx_pent = 0;   // fused halo push bookkeeping
+    const bool pushing = a.push_ptr != nullptr;
     int2 nx_rec[NCH];
     double2 nx_damp = make_double2(0.0, 0.0);
 #pragma unroll
@@ -732,26 +744,32 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     auto gmap = [&](long long gg) {
         return gg < gfull ? ((gg & ~15ll) | ((gg + (gg >> 4)) & 15ll)) : gg;
     };
-    auto fetch_ptr = [&](long long gg, int& lb, int& le) {
+    auto fetch_ptr = [&](long long gg, int& lb, int& le, int& pb, int& pe) {
         const long long slot = a.slot_lo + gmap(gg) * APW + sub;
-        lb = le = 0;
+        lb = le = pb = pe = 0;
         if (gg < a.ngroups && lane_ok && slot < a.slot_hi) {
             lb = a.link_ptr[slot];
             le = a.link_ptr[slot + 1];
+            if (pushing) {
+                pb = a.push_ptr[slot - a.slot_lo];
+                pe = a.push_ptr[slot - a.slot_lo + 1];
+            }
         }
     };
     auto fetch_rec = [&](long long gg, int lb, int le) {
         const long long slot = a.slot_lo + gmap(gg) * APW + sub;
         if (gg < a.ngroups && lane_ok && slot < a.slot_hi) nx_damp = a.damp[slot];
+        nx_pent = 0;
+        if (pushing && nx_pb + row < nx_pe) nx_pent = a.push_ent[nx_pb + row];
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             nx_rec[c] = make_int2(0, 0);
             if (lb + c * N + row < le) nx_rec[c] = __ldg(a.links + lb + c * N + row);
         }
     };
-    fetch_ptr(g, nx_lbeg, nx_lend);
+    fetch_ptr(g, nx_lbeg, nx_lend, nx_pb, nx_pe);
     fetch_rec(g, nx_lbeg, nx_lend);
-    fetch_ptr(g + gstride, nn_lbeg, nn_lend);
+    fetch_ptr(g + gstride, nn_lbeg, nn_lend, nn_pb, nn_pe);
 
     for (; g < a.ngroups; g += gstride) {
         const long long base = a.slot_lo + gmap(g) * APW;
@@ -765,14 +783,17 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         for (int c = 0; c < NCH; ++c) recs[c] = nx_rec[c];
         int2 rec = recs[0];
         const double2 d = nx_damp;
+        const int pb = nx_pb, npush = on ? (nx_pe - nx_pb) : 0, pent = nx_pent;
         int2 rts[N];
         const long long gbase = boff + base * NN;
         // next group's records / damping (offsets arrived during the previous
         // iteration), and the offsets of the group after that
         nx_lbeg = nn_lbeg;
         nx_lend = nn_lend;
+        nx_pb = nn_pb;
+        nx_pe = nn_pe;
         fetch_rec(g + gstride, nx_lbeg, nx_lend);
-        fetch_ptr(g + 2 * gstride, nn_lbeg, nn_lend);
+        fetch_ptr(g + 2 * gstride, nn_lbeg, nn_lend, nn_pb, nn_pe);
 
         // ---- issue: own tile + first chunk of neighbour rows (group A), y/acc (group B)
         {
@@ -973,28 +994,53 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         cp_async_wait<0>();
         __syncwarp();
 
-        // ---- epilogue from shared memory, streaming stores
+        // ---- epilogue from shared memory, streaming stores; rows that other ranks
+        //      need go straight into their arrays (peer memory over NVLink)
+        const int maxpush = pushing ? __reduce_max_sync(0xffffffffu, npush) : 0;
 #pragma unroll
         for (int it = 0; it < EIT; ++it) {
             const int e = lane + 32 * it;
-            if (e < nelem) {
+            const bool live = e < nelem;
+            double2 outv = make_double2(0.0, 0.0);
+            long long gi = 0;
+            if (live) {
                 const double2 k = k_s[pofs[it]];
-                const long long gi = gbase + e;
+                gi = gbase + e;
                 const double2 yv = a.first ? rho_s[pofs[it]] : (a.last ? make_double2(0.0, 0.0) : y_s[e]);
                 const double2 bs = a.first ? yv : acc_s[e];
                 const double2 res = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
                 if (a.last) {
+                    outv = res;
                     st_stream(a.ydst + gi, res);
                     if (a.traj && base + e / NN == a.slot0)
                         a.traj[b * a.traj_bstride + (step + 1) * NN + e % NN] = res;
                 } else {
+                    outv = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
                     st_stream(a.acc + gi, res);
-                    st_stream(a.yout + gi, make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
+                    st_stream(a.yout + gi, outv);
+                }
+            }
+            if (maxpush > 0) {   // warp-uniform
+                const int s2 = min(e / NN, APW - 1), erow = (e - (e / NN) * NN) / N;
+                const int cnt2 = __shfl_sync(0xffffffffu, npush, s2 * N);
+                const int pb2 = __shfl_sync(0xffffffffu, pb, s2 * N);
+                for (int t = 0; t < maxpush; ++t) {
+                    int ent = __shfl_sync(0xffffffffu, pent, (s2 * N + min(t, N - 1)) & 31);
+                    if (live && t < cnt2) {
+                        if (t >= N) ent = a.push_ent[pb2 + t];
+                        const int r = ent & 15;
+                        if (r == 15 || r == erow) {
+                            double2* dst = reinterpret_cast<double2*>(__ldg(a.peer + (ent >> 4))) + a.out_elem_off + gi;
+                            *dst = outv;
+                        }
+                    }
                 }
             }
         }
         __syncwarp();
     }
+    // remote rows must have landed before the stream-ordered barrier that follows the kernel
+    if (pushing) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------
@@ -1728,6 +1774,7 @@ void pyqed_heom_plan_destroy(pyqed_heom_plan* p) {
     }
     if (p->d_fsys) cudaFree(p->d_fsys);
     if (p->d_fcoup) cudaFree(p->d_fcoup);
+    if (p->d_peer) cudaFree(p->d_peer);
     delete p;
 }
 
@@ -2248,6 +2295,13 @@ static int run_stage(pyqed_heom_plan* p, long long step, int stage) {
         case 3: s.yin = SA; s.ydst = Y;  s.w = dt / 6; s.last = 1; break;
         default: s.yin = Y; s.ydst = SA; s.w = dt; s.first = 1; s.last = 1; break;  // Euler
     }
+    if (p->push_ptr && stage >= 0) {
+        const int out_arr = stage == 0 ? ARR_SA : (stage == 1 ? ARR_SB : (stage == 2 ? ARR_SA : ARR_Y));
+        s.push_ptr = p->push_ptr;
+        s.push_ent = p->push_ent;
+        s.peer = p->d_peer;
+        s.out_elem_off = (long long)((size_t)out_arr * p->array_bytes / sizeof(double2));
+    }
     const int tidx = stage <= 0 ? 0 : (stage == 3 ? 2 : 1);
     if (stage != 2 && run_prep(p, step, tidx)) return 1;  // stages 1 and 2 share t + dt/2
     return launch_stage(p, s, p->ctx_tdep);
@@ -2384,6 +2438,28 @@ int pyqed_heom_halo_push(pyqed_heom_plan* p, int array_id, const int32_t* d_item
     halo_push_kernel<<<grid, 256, 0, p->stream>>>(p->arr(array_id), arr_elem_off, d_items, n_items, p->N,
                                                   row_items, pa);
     return post_launch(p, "halo_push_kernel");
+}
+
+int pyqed_heom_set_push_table(pyqed_heom_plan* p, const int32_t* d_push_ptr, const uint8_t* d_push_ent,
+                              const uint64_t* peer_state_ptrs, int world) {
+    REQUIRE(p && p->built, "set_push_table: build the hierarchy first");
+    CU_TRY(cudaSetDevice(p->device));
+    if (!d_push_ptr) {   // switch the fused push off
+        p->push_ptr = nullptr;
+        p->push_ent = nullptr;
+        return 0;
+    }
+    REQUIRE(d_push_ent && peer_state_ptrs && world >= 1 && world <= 16, "set_push_table: bad argument");
+    REQUIRE(p->B == 1, "set_push_table: batch must be 1");
+    const int kern = (p->kernel && p->kernel != 4) ? p->kernel : (p->N <= 8 ? (p->use_qdiag ? 3 : 1) : 2);
+    REQUIRE(kern == 3, "set_push_table: the fused push needs the async row kernel (kernel 3)");
+    if (!p->d_peer) CU_TRY(cudaMalloc(&p->d_peer, sizeof(unsigned long long) * 16));
+    CU_TRY(cudaMemcpyAsync(p->d_peer, peer_state_ptrs, sizeof(unsigned long long) * world,
+                           cudaMemcpyHostToDevice, p->stream));
+    CU_TRY(cudaStreamSynchronize(p->stream));
+    p->push_ptr = d_push_ptr;
+    p->push_ent = d_push_ent;
+    return 0;
 }
 
 int pyqed_heom_halo_pack(pyqed_heom_plan* p, int array_id, const int32_t* d_items, int64_t n_items,

@@ -156,7 +156,8 @@ class ShardedDEOM:
     """
 
     def __init__(self, system, system_dipole, coupling, coupling_dipole, expn, etal, etar, etaa,
-                 mode, lmax, transport, device=0, order=1, options=None, tuning=None, peer_push=None):
+                 mode, lmax, transport, device=0, order=1, options=None, tuning=None, peer_push=None,
+                 fused_push=None):
         from .._cabi import Plan
         self.tr = transport
         self.rank, self.world = transport.rank, transport.world
@@ -220,6 +221,31 @@ class ShardedDEOM:
             offs = np.concatenate([[0], np.cumsum(self.halo.send_counts)]).astype(np.int64)
             self._push_offs = offs
             self._push_ptrs = (C.c_uint64 * self.world)(*[int(x) for x in self.symm.buffer_ptrs])
+        # fused push: the stage kernel itself stores the rows into the peers' arrays
+        self.fused = False
+        kern = (tuning or {}).get("kernel", 0)
+        if (self.symm is not None and fused_push is not False and bool(p.info("qdiag"))
+                and n <= 8 and kern in (0, 3)):
+            import ctypes as C
+            si = self.halo.send_items
+            dest = torch.repeat_interleave(
+                torch.arange(self.world, device=si.device),
+                torch.tensor(self.halo.send_counts, device=si.device))
+            if self.row_items:
+                loc, rowc = (si >> 3) - self.lo, si & 7
+            else:
+                loc, rowc = si - self.lo, torch.full_like(si, 15)
+            ent = (dest * 16 + rowc).to(torch.uint8)
+            order_ix = torch.argsort(loc, stable=True)
+            counts = torch.bincount(loc, minlength=self.hi - self.lo)
+            ptr = torch.zeros(self.hi - self.lo + 1, dtype=torch.int32, device=si.device)
+            ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            self._push_ptr = ptr.contiguous()
+            self._push_ent = ent[order_ix].contiguous() if ent.numel() else torch.zeros(1, dtype=torch.uint8, device=si.device)
+            p._check(p.lib.pyqed_heom_set_push_table(p._h, C.c_void_p(self._push_ptr.data_ptr()),
+                                                     C.c_void_p(self._push_ent.data_ptr()),
+                                                     self._push_ptrs, self.world))
+            self.fused = True
         self.owner_of_sys = next(r for r in range(self.world)
                                  if self.bounds[r] <= p.info("slot0") < self.bounds[r + 1])
 
@@ -227,6 +253,10 @@ class ShardedDEOM:
     def exchange(self, array_id):
         import ctypes as C
         p = self.plan
+        if self.fused:
+            # the stage kernel already stored the rows into the peers' arrays
+            self.symm.barrier(channel=0)
+            return
         if self.symm is not None:
             # store the requested rows straight into the peers' arrays, then a
             # device-side barrier over the symmetric-memory signal pads

@@ -143,7 +143,8 @@ def gpu_mode(args):
         sh = S.ShardedDEOM(g["system"], g["system_dipole"], g["coupling"], g["coupling_dipole"],
                            g["expn"], g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]),
                            tr, device=dev, order=args.order,
-                           peer_push={-1: None, 0: False, 1: True}[args.push])
+                           peer_push={-1: None, 0: False, 1: True}[args.push],
+                           fused_push={-1: None, 0: False, 1: True}[args.fused])
         nt = int(g["nt"])
         from conftest import pulse_from_samples
         dt = float(g["dt"])
@@ -157,7 +158,7 @@ def gpu_mode(args):
             assert e2 < 1e-12, (name, e2)
         if 0 < sh.hi - sh.lo < sh.nmax:
             assert sum(sh.halo.recv_counts) > 0   # a proper sub-range always has foreign neighbours
-        print(f"rank {tr.rank}: {name} push={sh.symm is not None} ok (owned {sh.hi - sh.lo} of {sh.nmax}, halo items "
+        print(f"rank {tr.rank}: {name} push={sh.symm is not None} fused={sh.fused} ok (owned {sh.hi - sh.lo} of {sh.nmax}, halo items "
               f"{sh.need32.numel()}, row items {sh.row_items}, err {err:.1e})", flush=True)
 
 
@@ -168,6 +169,7 @@ if __name__ == "__main__":
     ap.add_argument("--cases", default="deom_fmo_K21_L2")
     ap.add_argument("--order", type=int, default=1)
     ap.add_argument("--push", type=int, default=-1)
+    ap.add_argument("--fused", type=int, default=-1)
     a = ap.parse_args()
     dist.init_process_group(a.backend)
     try:

@@ -55,13 +55,16 @@ def test_sharded_gpu_ranks_sharing_one_device(world, order):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("push", [0, 1])
-def test_sharded_nccl_two_gpus(push):
-    """NCCL all_to_all halo (push=0) and direct peer-memory stores (push=1)."""
+@pytest.mark.parametrize("push,fused", [(0, 0), (1, 0), (1, 1)])
+def test_sharded_nccl_two_gpus(push, fused):
+    """NCCL all_to_all halo (push=0), peer-memory stores by a separate kernel
+    (push=1, fused=0) and by the stage kernel's epilogue (fused=1)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", str(push), "--cases",
-                      "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_random4_herm"])
-    assert out.count(" ok (owned") == 6
-    assert out.count(f"push={bool(push)}") == 6
+    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", str(push), "--fused", str(fused),
+                      "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
+    assert out.count(" ok (owned") == 8
+    assert out.count(f"push={bool(push)}") == 8
+    # the dense-Q case cannot use the fused path (it needs the diagonal-Q kernel)
+    assert out.count("fused=True") == (6 if fused else 0)
