@@ -656,7 +656,7 @@ __host__ __device__ inline AsyncTables async_tables(int N, int K, int M, int L, 
     return t;
 }
 
-template <int N, bool TDEP, bool HREAL>
+template <int N, bool TDEP, bool HREAL, bool PUSH>
 __global__ void __launch_bounds__(ASYNC_MAX_THREADS, 1)
 stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
@@ -731,7 +731,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     long long g = (long long)blockIdx.x * nwarps + wid;
     int nx_lbeg = 0, nx_lend = 0, nn_lbeg = 0, nn_lend = 0;
     int nx_pb = 0, nx_pe = 0, nn_pb = 0, nn_pe = 0, nx_pent = 0;   // fused halo push bookkeeping
-    const bool pushing = a.push_ptr != nullptr;
+    constexpr bool pushing = PUSH;
     int2 nx_rec[NCH];
     double2 nx_damp = make_double2(0.0, 0.0);
 #pragma unroll
@@ -996,7 +996,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
 
         // ---- epilogue from shared memory, streaming stores; rows that other ranks
         //      need go straight into their arrays (peer memory over NVLink)
-        const int maxpush = pushing ? __reduce_max_sync(0xffffffffu, npush) : 0;
+        const int maxpush = PUSH ? __reduce_max_sync(0xffffffffu, npush) : 0;
 #pragma unroll
         for (int it = 0; it < EIT; ++it) {
             const int e = lane + 32 * it;
@@ -1020,7 +1020,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                     st_stream(a.yout + gi, outv);
                 }
             }
-            if (maxpush > 0) {   // warp-uniform
+            if (PUSH && maxpush > 0) {   // warp-uniform
                 const int s2 = min(e / NN, APW - 1), erow = (e - (e / NN) * NN) / N;
                 const int cnt2 = __shfl_sync(0xffffffffu, npush, s2 * N);
                 const int pb2 = __shfl_sync(0xffffffffu, pb, s2 * N);
@@ -1465,7 +1465,7 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     return post_launch(p, "stage_rows_kernel");
 }
 
-template <int N, bool TDEP, bool HREAL>
+template <int N, bool TDEP, bool HREAL, bool PUSH>
 static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT;
@@ -1486,7 +1486,7 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     const size_t smem = table_bytes + per_warp * warps;
     static bool attr_set = false;
     if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP, HREAL>,
+        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP, HREAL, PUSH>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set = true;
     }
@@ -1494,14 +1494,19 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     dim3 grid((unsigned)std::min<long long>(ctas, sm_count), p->B);
     HParam<N> hp;
     for (int e = 0; e < NN; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    stage_rows_async_kernel<N, TDEP, HREAL><<<grid, warps * 32, smem, p->stream>>>(args, hp);
+    stage_rows_async_kernel<N, TDEP, HREAL, PUSH><<<grid, warps * 32, smem, p->stream>>>(args, hp);
     return post_launch(p, "stage_rows_async_kernel");
 }
 
+template <int N, bool PUSH>
+static int launch_async_p(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool hreal) {
+    if (tdep) return hreal ? launch_async<N, true, true, PUSH>(p, a, sm_count) : launch_async<N, true, false, PUSH>(p, a, sm_count);
+    return hreal ? launch_async<N, false, true, PUSH>(p, a, sm_count) : launch_async<N, false, false, PUSH>(p, a, sm_count);
+}
 template <int N>
 static int launch_async_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool hreal) {
-    if (tdep) return hreal ? launch_async<N, true, true>(p, a, sm_count) : launch_async<N, true, false>(p, a, sm_count);
-    return hreal ? launch_async<N, false, true>(p, a, sm_count) : launch_async<N, false, false>(p, a, sm_count);
+    return a.push_ptr ? launch_async_p<N, true>(p, a, sm_count, tdep, hreal)
+                      : launch_async_p<N, false>(p, a, sm_count, tdep, hreal);
 }
 
 template <int N>
