@@ -224,7 +224,8 @@ class ShardedDEOM:
         # fused push: the stage kernel itself stores the rows into the peers' arrays
         self.fused = False
         kern = (tuning or {}).get("kernel", 0)
-        if (self.symm is not None and fused_push is not False and bool(p.info("qdiag"))
+        # (opt-in: measured slower than the separate push kernel in round 1)
+        if (self.symm is not None and fused_push is True and bool(p.info("qdiag"))
                 and n <= 8 and kern in (0, 3)):
             import ctypes as C
             si = self.halo.send_items
