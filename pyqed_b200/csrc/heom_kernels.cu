@@ -2407,16 +2407,32 @@ __global__ void halo_push_kernel(const double2* arr, long long arr_elem_off, con
                                  long long n, int N, int rows, PushArgs pa) {
     const int NN = N * N, per = rows ? N : NN;
     const long long total = n * per;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const long long i = e / per;
-        const int j = (int)(e - i * per);
-        const int it = items[i];
-        const long long src = rows ? ((long long)(it >> 3) * NN + (it & 7) * N + j) : ((long long)it * NN + j);
-        int q = 0;
-        while (q + 1 < pa.world && i >= pa.off[q + 1]) ++q;
-        double2* dst = reinterpret_cast<double2*>(pa.peer[q]) + arr_elem_off + src;
-        *dst = arr[src];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    constexpr int U = 4;   // independent element copies in flight per thread
+    for (long long e0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; e0 < total; e0 += U * stride) {
+        long long src[U];
+        int q[U];
+        double2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long e = e0 + u * stride;
+            src[u] = -1;
+            if (e < total) {
+                const long long i = e / per;
+                const int j = (int)(e - i * per);
+                const int it = __ldg(items + i);
+                src[u] = rows ? ((long long)(it >> 3) * NN + (it & 7) * N + j) : ((long long)it * NN + j);
+                int qq = 0;
+                while (qq + 1 < pa.world && i >= pa.off[qq + 1]) ++qq;
+                q[u] = qq;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (src[u] >= 0) v[u] = arr[src[u]];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (src[u] >= 0) reinterpret_cast<double2*>(pa.peer[q[u]])[arr_elem_off + src[u]] = v[u];
     }
     // the rows must have landed in the peers' memory before this rank signals the
     // barrier that follows on the stream
