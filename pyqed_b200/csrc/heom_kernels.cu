@@ -1132,7 +1132,10 @@ resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N>
     const bool lane_ok = lane < APW * N;
     const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
     const int li0 = wid * APW;                                   // first local ADO of the warp
-    const long long slot_w = (long long)crank * apc + li0;       // its global slot
+    // groups of APW consecutive slots are dealt round-robin to the CTAs of the
+    // cluster, so the link-heavy low tiers (which are contiguous in the reference
+    // order) do not all land in one CTA: group g lives in CTA g % csize
+    const long long slot_w = ((long long)wid * csize + crank) * APW;   // its global slot
     const long long slot = slot_w + sub;
     const int cnt = (int)max(0ll, min((long long)APW, a.nmax - slot_w));
     const bool on = lane_ok && sub < cnt;
@@ -1158,7 +1161,8 @@ resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N>
     if (on) {
         for (int t = row; t < nl; t += N) {
             const int2 lk = __ldg(a.links + lbeg + t);
-            const int orank = lk.x / apc, oli = lk.x - orank * apc;
+            const int og = lk.x / APW;                       // owner group of the neighbour
+            const int orank = og % csize, oli = (og / csize) * APW + (lk.x - og * APW);
             LinkEnt en;
             en.rowp = cluster.map_shared_rank(Yb, orank) + (size_t)oli * ADO + heom::meta_r0(lk.y) * LD;
             en.meta = lk.y;
