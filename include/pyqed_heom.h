@@ -208,7 +208,9 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *                and the loaded state keep every ADO Hermitian, fetch a
  *                neighbour's column entries as the conjugate of its row
  *   "real_h"     use real arithmetic for the H products when H and mu are real
- *   "resident"   allow the cluster-resident kernel for small hierarchies
+ *   "resident"   allow the cluster-resident kernels for small hierarchies
+ *                (4 = prefer the row-per-lane variant, kernel 4, over the
+ *                element-parallel kernel 5)
  *   "debug_sync" synchronise and check after every launch
  * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
  * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */

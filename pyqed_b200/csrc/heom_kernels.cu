@@ -1351,6 +1351,199 @@ resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N>
     }
 }
 
+// ---------------------------------------------------------------------------
+// Kernel 5: cluster-resident propagation, element-parallel.  Same residency as
+// kernel 4 (whole hierarchy in distributed shared memory, one cluster per
+// trajectory, one hardware cluster barrier per RK stage) but a whole warp works
+// on one ADO, one or two matrix elements per lane: the dependent chain per lane
+// is 2N complex FMAs instead of 2N^2, which is what bounds tiny hierarchies.
+// For diagonal Q_m the coupling is element-wise, so a lane reads exactly its own
+// element of each neighbour through DSMEM - no Hermiticity assumption needed.
+// ADOs are dealt round-robin to the CTAs of the cluster (slot s -> CTA s % C).
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(512, 1)
+resident_elem_kernel(const ResidentArgs ra) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const StageArgs& a = ra.s;
+    constexpr int NN = N * N, EPL = (NN + 31) / 32;
+    extern __shared__ double2 smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+    const int b = blockIdx.x / csize;
+    const int apc = ra.apc;
+    struct LinkEnt { const double2* tile; int meta; int pad; };
+    struct AdoMeta { double2 damp; int nl; int pad; };
+    // shared-memory carve-up
+    double2* Hs = smem;
+    double2* qd_s = Hs + NN;
+    double2* cb_s = qd_s + a.nmod * N;
+    double* sq_s = (double*)(cb_s + 4 * a.nind);
+    double2* Yb = (double2*)(sq_s + ((a.lmax + 2) & ~1));
+    double2* ACCb = Yb + (size_t)apc * NN;
+    double2* SAb = ACCb + (size_t)apc * NN;
+    double2* SBb = SAb + (size_t)apc * NN;
+    LinkEnt* lk_s = (LinkEnt*)(SBb + (size_t)apc * NN);
+    AdoMeta* am_s = (AdoMeta*)(lk_s + (size_t)apc * ra.maxlinks);
+
+    for (int e = threadIdx.x; e < 4 * a.nind; e += blockDim.x) cb_s[e] = a.cbase[e];
+    for (int e = threadIdx.x; e <= a.lmax; e += blockDim.x) sq_s[e] = sqrt((double)e);
+    auto load_ops = [&](long long step, int tidx) {
+        const double fs = (ra.tdep && ra.fsys) ? ra.fsys[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
+        const double fc = (ra.tdep && ra.fcoup) ? ra.fcoup[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+            const double2 v = ra.ops_base[e], d = ra.ops_dip[e];
+            Hs[e] = make_double2(fma(d.x, fs, v.x), fma(d.y, fs, v.y));
+        }
+        for (int e = threadIdx.x; e < a.nmod * N; e += blockDim.x) {
+            const int m = e / N, j = e - m * N, o = (1 + m) * NN + j * N + j;
+            const double2 v = ra.ops_base[o], d = ra.ops_dip[o];
+            qd_s[e] = make_double2(fma(d.x, fc, v.x), fma(d.y, fc, v.y));
+        }
+        __syncthreads();
+    };
+    load_ops(0, 0);
+
+    int ei[EPL], ej[EPL];
+    bool ev[EPL];
+#pragma unroll
+    for (int t = 0; t < EPL; ++t) {
+        const int e = lane + 32 * t;
+        ev[t] = e < NN;
+        ei[t] = ev[t] ? e / N : 0;
+        ej[t] = ev[t] ? e - (e / N) * N : 0;
+    }
+    const long long boff = (long long)b * a.nmax * NN;
+    // ---- per-ADO setup: state from global memory, link cache, damping
+    for (int li = wid; li < apc; li += nwarps) {
+        const long long slot = (long long)li * csize + crank;
+        const bool on = slot < a.nmax;
+        int lbeg = 0, nl = 0;
+        double2 damp = make_double2(0.0, 0.0);
+        if (on) {
+            lbeg = a.link_ptr[slot];
+            nl = a.link_ptr[slot + 1] - lbeg;
+            damp = a.damp[slot];
+        }
+        if (lane == 0) {
+            AdoMeta m;
+            m.damp = damp;
+            m.nl = nl;
+            m.pad = 0;
+            am_s[li] = m;
+        }
+        for (int t = lane; t < nl; t += 32) {
+            const int2 lk = __ldg(a.links + lbeg + t);
+            LinkEnt en;
+            en.tile = cluster.map_shared_rank(Yb, lk.x % csize) + (size_t)(lk.x / csize) * NN;
+            en.meta = lk.y;
+            en.pad = 0;
+            lk_s[(size_t)li * ra.maxlinks + t] = en;
+        }
+#pragma unroll
+        for (int t = 0; t < EPL; ++t)
+            if (ev[t]) {
+                const int e = lane + 32 * t;
+                const double2 z = make_double2(0.0, 0.0);
+                Yb[li * NN + e] = on ? a.y[boff + slot * NN + e] : z;
+                ACCb[li * NN + e] = z;
+                SAb[li * NN + e] = z;
+                SBb[li * NN + e] = z;
+            }
+    }
+    cluster.sync();
+
+    for (long long step = 0; step < ra.nt; ++step) {
+        for (int st = 0; st < 4; ++st) {
+            double2* inb = st == 0 ? Yb : (st == 2 ? SBb : SAb);
+            double2* outb = st == 0 ? SAb : (st == 1 ? SBb : (st == 2 ? SAb : Yb));
+            const double ac = st == 2 ? ra.dt : ra.dt * 0.5;
+            const double wc = (st == 0 || st == 3) ? ra.dt / 6.0 : ra.dt / 3.0;
+            if (ra.tdep && st != 2 && !(step == 0 && st == 0)) load_ops(step, st == 0 ? 0 : (st == 3 ? 2 : 1));
+            const ptrdiff_t boffs = inb - Yb;
+            for (int li = wid; li < apc; li += nwarps) {
+                const long long slot = (long long)li * csize + crank;
+                if (slot >= a.nmax) continue;   // warp-uniform
+                const double2* in = inb + (size_t)li * NN;
+                const AdoMeta am = am_s[li];
+                const LinkEnt* mylk = lk_s + (size_t)li * ra.maxlinks;
+                double2 k[EPL];
+#pragma unroll
+                for (int t = 0; t < EPL; ++t) {
+                    k[t] = make_double2(0.0, 0.0);
+                    if (ev[t]) {
+                        double2 c = make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int l = 0; l < N; ++l) {
+                            cfma(c, Hs[ei[t] * N + l], in[l * N + ej[t]]);
+                            cfms(c, in[ei[t] * N + l], Hs[l * N + ej[t]]);
+                        }
+                        const double2 own = in[lane + 32 * t];
+                        k[t] = make_double2(c.y - (am.damp.x * own.x - am.damp.y * own.y),
+                                            -c.x - (am.damp.x * own.y + am.damp.y * own.x));
+                    }
+                }
+                constexpr int U = 4;
+                for (int c0 = 0; c0 < am.nl; c0 += U) {
+                    LinkEnt en[U];
+                    double2 A[U][EPL];
+                    double2 cf[U][EPL];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool live = c0 + u < am.nl;
+                        en[u] = mylk[min(c0 + u, am.nl - 1)];
+                        const int meta = en[u].meta;
+                        const int m = heom::meta_mode(meta), kd = heom::meta_kdir(meta);
+                        const double sq = live ? sq_s[heom::meta_neff(meta)] : 0.0;
+                        const double2 bL = cb_s[2 * kd], bR = cb_s[2 * kd + 1];
+#pragma unroll
+                        for (int t = 0; t < EPL; ++t) {
+                            const double2 qi = qd_s[m * N + ei[t]], qj = qd_s[m * N + ej[t]];
+                            double2 c = cmul(make_double2(bL.x * sq, bL.y * sq), qi);
+                            cfma(c, make_double2(bR.x * sq, bR.y * sq), qj);
+                            cf[u][t] = c;
+                            const bool need = ev[t] && live && (c.x != 0.0 || c.y != 0.0);
+                            A[u][t] = need ? en[u].tile[boffs + lane + 32 * t] : make_double2(0.0, 0.0);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int t = 0; t < EPL; ++t) cfma(k[t], cf[u][t], A[u][t]);
+                }
+                // stage update in shared memory (each lane owns its elements)
+#pragma unroll
+                for (int t = 0; t < EPL; ++t)
+                    if (ev[t]) {
+                        const int o = li * NN + lane + 32 * t;
+                        if (st == 3) {
+                            const double2 bs = ACCb[o];
+                            const double2 res = make_double2(fma(wc, k[t].x, bs.x), fma(wc, k[t].y, bs.y));
+                            Yb[o] = res;
+                            if (a.traj && slot == a.slot0)
+                                a.traj[b * a.traj_bstride + (step + 1) * NN + lane + 32 * t] = res;
+                        } else {
+                            const double2 yv = Yb[o];
+                            const double2 bs = st == 0 ? yv : ACCb[o];
+                            ACCb[o] = make_double2(fma(wc, k[t].x, bs.x), fma(wc, k[t].y, bs.y));
+                            outb[o] = make_double2(fma(ac, k[t].x, yv.x), fma(ac, k[t].y, yv.y));
+                        }
+                    }
+            }
+            cluster.sync();
+        }
+    }
+    for (int li = wid; li < apc; li += nwarps) {
+        const long long slot = (long long)li * csize + crank;
+        if (slot >= a.nmax) continue;
+#pragma unroll
+        for (int t = 0; t < EPL; ++t)
+            if (ev[t]) const_cast<double2*>(a.y)[boff + slot * NN + lane + 32 * t] = Yb[li * NN + lane + 32 * t];
+    }
+}
+
 // Kernel 2 (any N): one CTA per ADO, one thread per matrix element (strided);
 // all operators (H and Q_m) go through their sparsity lists, so cost scales
 // with nnz.  rho_n is staged in shared memory; neighbours are read through L2.
@@ -1600,6 +1793,53 @@ static int launch_resident_t(pyqed_heom_plan* p, const ResidentArgs& ra_in, Resi
     }
 }
 
+template <int N>
+static int launch_resident_elem(pyqed_heom_plan* p, const ResidentArgs& ra_in) {
+    constexpr int NN = N * N;
+    const int maxlinks = ra_in.maxlinks;
+    const size_t table_bytes = sizeof(double2) * (NN + (size_t)p->M * N + 4 * (size_t)p->K) +
+                               sizeof(double) * ((p->L + 2) & ~1);
+    const size_t per_ado = sizeof(double2) * 4 * NN + (size_t)16 * maxlinks + 32;
+    const size_t budget = 227 * 1024;
+    if (table_bytes + per_ado > budget) return -1;
+    const long long cap = (long long)((budget - table_bytes) / per_ado);   // ADOs per CTA
+    int cs = 1;
+    while (cs <= 16 && (p->nmax + cs - 1) / cs > cap) cs <<= 1;
+    if (cs > 16) return -1;
+    if (p->B <= 8)
+        while (cs < 16 && cs < p->nmax) cs <<= 1;
+    auto kern = resident_elem_kernel<N>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    for (; cs >= 1; cs >>= 1) {
+        const long long apc = (p->nmax + cs - 1) / cs;
+        if (apc > cap) return -1;
+        ResidentArgs ra = ra_in;
+        ra.apc = (int)apc;
+        const int warps = (int)std::min<long long>(16, apc);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(cs * p->B));
+        cfg.blockDim = dim3((unsigned)(warps * 32));
+        cfg.dynamicSmemBytes = table_bytes + per_ado * apc;
+        cfg.stream = p->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+        if (e == cudaSuccess && nclusters >= 1) {
+            CU_TRY(cudaLaunchKernelEx(&cfg, kern, ra));
+            return post_launch(p, "resident_elem_kernel");
+        }
+        cudaGetLastError();
+    }
+    return -1;
+}
+
 // returns 0 = done, -1 = not applicable (caller falls back to per-stage launches), 1 = error
 static int try_resident(pyqed_heom_plan* p) {
     const bool whole = p->part_lo == 0 && p->part_hi == p->nmax;
@@ -1616,7 +1856,7 @@ static int try_resident(pyqed_heom_plan* p) {
         case 7: fits = resident_fits<7>(p, rc); break;
         case 8: fits = resident_fits<8>(p, rc); break;
     }
-    if (!fits) return -1;
+    if (!fits && p->opt_resident == 4) return -1;
     ResidentArgs ra;
     fill_stage_args(p, ra.s);
     ra.s.y = p->arr(ARR_Y);
@@ -1640,10 +1880,19 @@ static int try_resident(pyqed_heom_plan* p) {
     }
     const bool hr = p->h_real && p->opt_hreal != 0;
     int rcode = -1;
+    if (p->opt_resident != 4) {   // default: element-parallel kernel 5; "resident" = 4 forces kernel 4
+#define RESE_CASE(n) \
+    case n: rcode = launch_resident_elem<n>(p, ra); break;
+        switch (p->N) { RESE_CASE(2) RESE_CASE(3) RESE_CASE(4) RESE_CASE(5) RESE_CASE(6) RESE_CASE(7) RESE_CASE(8) }
+#undef RESE_CASE
+        if (rcode > 0) return rcode;
+    }
+    if (rcode != 0 && fits) {
 #define RES_CASE(n) \
     case n: rcode = hr ? launch_resident_t<n, true>(p, ra, rc) : launch_resident_t<n, false>(p, ra, rc); break;
-    switch (p->N) { RES_CASE(2) RES_CASE(3) RES_CASE(4) RES_CASE(5) RES_CASE(6) RES_CASE(7) RES_CASE(8) }
+        switch (p->N) { RES_CASE(2) RES_CASE(3) RES_CASE(4) RES_CASE(5) RES_CASE(6) RES_CASE(7) RES_CASE(8) }
 #undef RES_CASE
+    }
     if (rcode == 0 && p->timing) {
         CU_TRY(cudaEventRecord(p->ev[p->ev_used].second, p->stream));
         p->ev_used++;

@@ -111,10 +111,11 @@ def test_row_kernels_on_diagonal_coupling(name, kernel, herm):
 
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L2", "deom_spin_boson_L10",
                                   "deom_aggregate_L3_T0", "deom_aggregate_L3_T37"])
-@pytest.mark.parametrize("resident", [0, 1])
+@pytest.mark.parametrize("resident", [0, 1, 4])
 def test_cluster_resident_kernel(name, resident):
-    """Small hierarchies are propagated by one cluster-resident launch; with the
-    option off the per-stage kernels must give the same trajectory."""
+    """Small hierarchies are propagated by one cluster-resident launch (1: the
+    element-parallel kernel 5, 4: the row-per-lane kernel 4); with the option off
+    the per-stage kernels must give the same trajectory."""
     g = golden(name)
     s = _solver_from(g)
     s.options = {"resident": resident}
