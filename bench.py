@@ -228,7 +228,7 @@ def run_gpu_arm(args):
     n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
     K, Wm, dt = args.steps, args.warmup, w["dt"]
     tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
-    options = {"qdiag": args.qdiag, "hermitian": args.herm}
+    options = {"qdiag": args.qdiag, "hermitian": args.herm, "resident": args.resident}
     in_bytes = sum(np.asarray(w[k]).nbytes for k in
                    ("rho0", "system", "system_dipole", "coupling", "coupling_dipole", "expn", "etal",
                     "etar", "etaa", "mode"))
@@ -333,8 +333,8 @@ def run_gpu_arm(args):
         achieved = (256.0 * n * n * owned / 4.0) / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
         state_mb = nmax * n * n * 16 / 1e6
         kname = {1: "stage_rows_kernel", 2: "stage_generic_kernel", 3: "stage_rows_async_kernel",
-                 4: "resident_cluster_kernel"}[
-            4 if plan.info("resident_launches") > 0 else
+                 4: "resident_cluster_kernel", 5: "resident_elem_kernel"}[
+            plan.info("resident_kind") if plan.info("resident_launches") > 0 else
             (args.kernel or (2 if n > 8 else (3 if plan.info("qdiag") else 1)))]
         order_name = ["reference", "lexicographic", "blocked lexicographic"][order]
         line = {
@@ -399,6 +399,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--qdiag", type=int, default=-1)
     ap.add_argument("--herm", type=int, default=-1)
+    ap.add_argument("--resident", type=int, default=-1, help="0 off, 4 force kernel 4, default auto (kernel 5)")
     ap.add_argument("--fused", type=int, default=-1, help="multi-GPU: stage kernel stores halo rows itself")
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
     args = ap.parse_args()

@@ -104,6 +104,7 @@ struct pyqed_heom_plan {
     std::vector<int> r0mode;     // first row with a non-zero diagonal entry, per mode
     int opt_qdiag = -1, opt_herm = -1, opt_hreal = -1, opt_resident = -1;  // -1 auto, 0 off, 1 on
     long long resident_launches = 0;
+    int resident_kind = 0;  // 4 or 5: which resident kernel ran last
     TableLayout tl{};
     char* d_tables = nullptr;
     char* d_state = nullptr;
@@ -1886,12 +1887,14 @@ static int try_resident(pyqed_heom_plan* p) {
         switch (p->N) { RESE_CASE(2) RESE_CASE(3) RESE_CASE(4) RESE_CASE(5) RESE_CASE(6) RESE_CASE(7) RESE_CASE(8) }
 #undef RESE_CASE
         if (rcode > 0) return rcode;
+        if (rcode == 0) p->resident_kind = 5;
     }
     if (rcode != 0 && fits) {
 #define RES_CASE(n) \
     case n: rcode = hr ? launch_resident_t<n, true>(p, ra, rc) : launch_resident_t<n, false>(p, ra, rc); break;
         switch (p->N) { RES_CASE(2) RES_CASE(3) RES_CASE(4) RES_CASE(5) RES_CASE(6) RES_CASE(7) RES_CASE(8) }
 #undef RES_CASE
+        if (rcode == 0) p->resident_kind = 4;
     }
     if (rcode == 0 && p->timing) {
         CU_TRY(cudaEventRecord(p->ev[p->ev_used].second, p->stream));
@@ -2123,6 +2126,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "hermitian_inputs") return p->herm_inputs && p->opt_herm != 0;
     if (n == "real_h") return p->h_real && p->opt_hreal != 0;
     if (n == "resident_launches") return p->resident_launches;
+    if (n == "resident_kind") return p->resident_kind;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
     if (n == "slot0") return p->slot0;
