@@ -255,7 +255,7 @@ def run_gpu_arm(args):
     n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
     K, Wm, dt = args.steps, args.warmup, w["dt"]
     tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
-    options = {"qdiag": args.qdiag, "hermitian": args.herm, "resident": args.resident}
+    options = {"qdiag": args.qdiag, "hermitian": args.herm, "resident": args.resident, "rk13": args.rk13}
     in_bytes = sum(np.asarray(w[k]).nbytes for k in
                    ("rho0", "system", "system_dipole", "coupling", "coupling_dipole", "expn", "etal",
                     "etar", "etaa", "mode"))
@@ -375,7 +375,8 @@ def run_gpu_arm(args):
                 "lmax": lmax, "n_ado": nmax, "dt": dt, "storage_order": ["reference", "lexicographic", "blocked lexicographic"][order],
                 "state_mb_per_array": state_mb,
                 "fast_paths": {"diagonal_Q": plan.info("qdiag"), "hermitian_ados": plan.info("hermitian"),
-                               "real_H": plan.info("real_h")},
+                               "real_H": plan.info("real_h"),
+                               "rk4_array_passes_per_step": 13 if plan.info("rk_scheme") else 16},
                 "l2": ("inputs larger than L2 (4 arrays of %.0f MB); no flush needed" % state_mb) if state_mb > 200
                       else "state is cache-resident by construction (time stepping re-reads its own output); no flush",
                 "parallelism": "single GPU" if not multi else
@@ -432,6 +433,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--qdiag", type=int, default=-1)
     ap.add_argument("--herm", type=int, default=-1)
+    ap.add_argument("--rk13", type=int, default=-1, help="0: accumulator RK4 (16 passes), default: difference form (13)")
     ap.add_argument("--resident", type=int, default=-1, help="0 off, 4 force kernel 4, default auto (kernel 5)")
     ap.add_argument("--fused", type=int, default=-1, help="multi-GPU: stage kernel stores halo rows itself")
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")

@@ -36,6 +36,9 @@ using heom::Pascal;
 #ifndef HEOM_MINBLOCKS
 #define HEOM_MINBLOCKS 2  // __launch_bounds__ min blocks per SM for the row kernel
 #endif
+#ifndef HEOM_L2_HINTS
+#define HEOM_L2_HINTS 0   // async kernel: L2 eviction-priority hints on the cp.async loads
+#endif
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -103,6 +106,7 @@ struct pyqed_heom_plan {
     bool h_real = false;         // H and mu have no imaginary part
     std::vector<int> r0mode;     // first row with a non-zero diagonal entry, per mode
     int opt_qdiag = -1, opt_herm = -1, opt_hreal = -1, opt_resident = -1;  // -1 auto, 0 off, 1 on
+    int opt_rk13 = -1;  // difference-form RK4 in the async kernel (-1/1 on, 0 off)
     long long resident_launches = 0;
     int resident_kind = 0;  // 4 or 5: which resident kernel ran last
     TableLayout tl{};
@@ -376,6 +380,7 @@ struct StageArgs {
     long long slot_lo, slot_hi;  // owned slot range of this rank (whole hierarchy on one GPU)
     double a, w;
     int local_step, first, last, N;
+    int scheme;  // 0: running accumulator (16 passes/step); 1: difference form (13 passes/step, async kernel)
     int herm, ncoef, nmod, nind, lmax;
     const double2* cbase;  // [K][4]: minus (L,R) and plus (L,R) coefficients for n_eff = 1
     const int* kmode;      // [K]: mode | first support row << 8
@@ -628,6 +633,24 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+// same with an L2 eviction-priority hint (createpolicy): the stage input and the
+// neighbour rows are the only data with reuse (evict_last), y/acc are read once
+// per launch (evict_first)
+__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, unsigned long long pol) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int NWAIT>
 __device__ __forceinline__ void cp_async_wait() {
@@ -709,6 +732,14 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
     const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
     const long long gstride = (long long)gridDim.x * nwarps;
+#if HEOM_L2_HINTS
+    const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+#define CP_KEEP(d_, s_) cp_async16_hint(d_, s_, pol_keep)
+#define CP_STREAM(d_, s_) cp_async16_hint(d_, s_, pol_stream)
+#else
+#define CP_KEEP(d_, s_) cp_async16(d_, s_)
+#define CP_STREAM(d_, s_) cp_async16(d_, s_)
+#endif
     // flat element e = lane + 32 it  ->  offset in the (possibly padded) tile
     int pofs[EIT];
 #pragma unroll
@@ -801,7 +832,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             const double2* src = yin + base * NN + lane;
 #pragma unroll
             for (int it = 0; it < EIT; ++it)
-                if (lane + 32 * it < nelem) cp_async16(&rho_s[pofs[it]], src + 32 * it);
+                if (lane + 32 * it < nelem) CP_KEEP(&rho_s[pofs[it]], src + 32 * it);
         }
 #pragma unroll
         for (int t = 0; t < N; ++t) {
@@ -809,18 +840,22 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
             rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
             if (t < nl)
-                cp_async16(nbrow + t * N,
-                           yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
+                CP_KEEP(nbrow + t * N,
+                        yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
         }
         cp_async_commit();
         if (!a.first) {
+            // scheme 0: acc (+ y unless last).  scheme 1: y (+ the first stage buffer,
+            // passed in a.acc, when last; the second one follows into rho_s later)
             const double2* sa = a.acc + gbase + lane;
             const double2* sy = a.y + gbase + lane;
+            const bool want_acc = a.scheme == 0 || a.last;
+            const bool want_y = a.scheme == 1 || !a.last;
 #pragma unroll
             for (int it = 0; it < EIT; ++it)
                 if (lane + 32 * it < nelem) {
-                    cp_async16(&acc_s[lane + 32 * it], sa + 32 * it);
-                    if (!a.last) cp_async16(&y_s[lane + 32 * it], sy + 32 * it);
+                    if (want_acc) CP_STREAM(&acc_s[lane + 32 * it], sa + 32 * it);
+                    if (want_y) CP_STREAM(&y_s[lane + 32 * it], sy + 32 * it);
                 }
         }
         cp_async_commit();
@@ -868,12 +903,26 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                         cfms(t, rv[l], HEL(l, j));
                     }
                 }
-                ksub[row * LD + j] = make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
-                                                  -t.x - (d.x * rv[j].y + d.y * rv[j].x));
+                double2 kv = make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
+                                          -t.x - (d.x * rv[j].y + d.y * rv[j].x));
+                if (a.scheme == 1 && a.last) {
+                    // fold the stage input's own weight into k: w (k + (2/dt) y_in) = w k + y_in / 3
+                    kv.x = fma(a.a, rv[j].x, kv.x);
+                    kv.y = fma(a.a, rv[j].y, kv.y);
+                }
+                ksub[row * LD + j] = kv;
             }
         }
 #undef HEL
         __syncwarp();
+        if (a.scheme == 1 && a.last) {
+            // rho_s is free now: fetch the second stage buffer (a.yout) into it for the epilogue
+            const double2* sb = a.yout + gbase + lane;
+#pragma unroll
+            for (int it = 0; it < EIT; ++it)
+                if (lane + 32 * it < nelem) CP_STREAM(&rho_s[pofs[it]], sb + 32 * it);
+            cp_async_commit();
+        }
 
         // ---- neighbour terms, N links per chunk; contributions to one target row
         //      are summed in registers (X: element (cur_rr,row), Y: element (row,cur_rr))
@@ -916,8 +965,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                     rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
                     rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
                     if (c0 + t < nl)
-                        cp_async16(nbrow + t * N,
-                                   yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
+                        CP_KEEP(nbrow + t * N,
+                                yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
@@ -1007,6 +1056,25 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             if (live) {
                 const double2 k = k_s[pofs[it]];
                 gi = gbase + e;
+                if (a.scheme == 1) {
+                    if (a.last) {
+                        // y' = -y/3 + S1/3 + 2 S2/3 + w (k4 + (2/dt) S3)   (S3's share is already in k)
+                        const double2 y0 = y_s[e], s1 = acc_s[e], s2 = rho_s[pofs[it]];
+                        const double third = 1.0 / 3.0;
+                        double2 res = make_double2(fma(a.w, k.x, third * (s1.x - y0.x)),
+                                                   fma(a.w, k.y, third * (s1.y - y0.y)));
+                        res.x = fma(2.0 * third, s2.x, res.x);
+                        res.y = fma(2.0 * third, s2.y, res.y);
+                        outv = res;
+                        st_stream(a.ydst + gi, res);
+                        if (a.traj && base + e / NN == a.slot0)
+                            a.traj[b * a.traj_bstride + (step + 1) * NN + e % NN] = res;
+                    } else {
+                        const double2 yv = a.first ? rho_s[pofs[it]] : y_s[e];
+                        outv = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
+                        st_stream(a.yout + gi, outv);
+                    }
+                } else {
                 const double2 yv = a.first ? rho_s[pofs[it]] : (a.last ? make_double2(0.0, 0.0) : y_s[e]);
                 const double2 bs = a.first ? yv : acc_s[e];
                 const double2 res = make_double2(fma(a.w, k.x, bs.x), fma(a.w, k.y, bs.y));
@@ -1019,6 +1087,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                     outv = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
                     st_stream(a.acc + gi, res);
                     st_stream(a.yout + gi, outv);
+                }
                 }
             }
             if (PUSH && maxpush > 0) {   // warp-uniform
@@ -1623,6 +1692,12 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(const StageArgs a) {
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
+// 13-pass difference form of RK4: only the async row kernel implements it
+static bool rk_scheme(const pyqed_heom_plan* p) {
+    const int kern = (p->kernel && p->kernel != 4) ? p->kernel : (p->N <= 8 ? (p->use_qdiag ? 3 : 1) : 2);
+    return kern == 3 && p->opt_rk13 != 0;
+}
+
 static int post_launch(pyqed_heom_plan* p, const char* what) {
     p->launches++;
     cudaError_t e = cudaGetLastError();
@@ -2112,6 +2187,7 @@ int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
     else if (n == "hermitian") p->opt_herm = value;
     else if (n == "real_h") p->opt_hreal = value;
     else if (n == "resident") p->opt_resident = value;
+    else if (n == "rk13") p->opt_rk13 = value;
     else if (n == "debug_sync") p->debug_sync = value != 0;
     else return fail("unknown option '" + n + "'");
     return 0;
@@ -2127,6 +2203,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "real_h") return p->h_real && p->opt_hreal != 0;
     if (n == "resident_launches") return p->resident_launches;
     if (n == "resident_kind") return p->resident_kind;
+    if (n == "rk_scheme") return rk_scheme(p) ? 1 : 0;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
     if (n == "slot0") return p->slot0;
@@ -2550,6 +2627,18 @@ static int run_stage(pyqed_heom_plan* p, long long step, int stage) {
     s.y = Y;
     s.acc = ACC;
     s.local_step = (int)step;
+    const int scheme = (stage >= 0 && rk_scheme(p)) ? 1 : 0;
+    s.scheme = scheme;
+    if (scheme == 1) {
+        // difference form: the stage buffers SA, SB, SC (= the accumulator array) are all
+        // kept and the last stage combines them, y' = -y/3 + SA/3 + 2SB/3 + SC/3 + dt/6 k4
+        switch (stage) {
+            case 0: s.yin = Y;  s.yout = SA;  s.a = dt / 2; s.first = 1; break;
+            case 1: s.yin = SA; s.yout = SB;  s.a = dt / 2; break;
+            case 2: s.yin = SB; s.yout = ACC; s.a = dt; break;
+            default: s.yin = ACC; s.acc = SA; s.yout = SB; s.ydst = Y; s.a = 2.0 / dt; s.w = dt / 6; s.last = 1; break;
+        }
+    } else
     switch (stage) {
         case 0: s.yin = Y;  s.yout = SA; s.a = dt / 2; s.w = dt / 6; s.first = 1; break;
         case 1: s.yin = SA; s.yout = SB; s.a = dt / 2; s.w = dt / 3; break;
@@ -2558,7 +2647,8 @@ static int run_stage(pyqed_heom_plan* p, long long step, int stage) {
         default: s.yin = Y; s.ydst = SA; s.w = dt; s.first = 1; s.last = 1; break;  // Euler
     }
     if (p->push_ptr && stage >= 0) {
-        const int out_arr = stage == 0 ? ARR_SA : (stage == 1 ? ARR_SB : (stage == 2 ? ARR_SA : ARR_Y));
+        const int out_arr = scheme == 1 ? (stage == 0 ? ARR_SA : (stage == 1 ? ARR_SB : (stage == 2 ? ARR_ACC : ARR_Y)))
+                                        : (stage == 0 ? ARR_SA : (stage == 1 ? ARR_SB : (stage == 2 ? ARR_SA : ARR_Y)));
         s.push_ptr = p->push_ptr;
         s.push_ent = p->push_ent;
         s.peer = p->d_peer;

@@ -310,7 +310,7 @@ class ShardedDEOM:
         for i in range(nt):
             for st in range(4):
                 p._check(p.lib.pyqed_heom_propagate_stage(p._h, i, st))
-                self.exchange(STAGE_OUTPUT_ARRAY[st])
+                self.exchange((1, 2, 3, 0)[st] if p.info("rk_scheme") else STAGE_OUTPUT_ARRAY[st])
 
     def run(self, rho0, dt, nt, pulse_system_func=None, pulse_coupling_func=None):
         """Returns ``(t_save, rho_sys[nt+1, N, N])`` on every rank."""

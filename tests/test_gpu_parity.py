@@ -62,7 +62,7 @@ def test_generic_kernel_small_n(name):
 
 
 @pytest.mark.parametrize("opts", [{"qdiag": 0}, {"hermitian": 0}, {"qdiag": 0, "hermitian": 0},
-                                  {"real_h": 0}])
+                                  {"real_h": 0}, {"rk13": 0, "resident": 0}, {"rk13": 1, "resident": 0}])
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L2", "deom_spin_boson_L10",
                                   "deom_aggregate_L3_T37"])
 def test_structure_fast_paths_can_be_disabled(name, opts):
