@@ -208,10 +208,11 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *                and the loaded state keep every ADO Hermitian, fetch a
  *                neighbour's column entries as the conjugate of its row
  *   "real_h"     use real arithmetic for the H products when H and mu are real
- *   "rk13"       difference-form RK4 in the async row kernel: the three stage
- *                buffers are kept and combined in the last stage instead of a
- *                running accumulator (13 instead of 16 array passes per step;
- *                stage outputs then live in arrays 1, 2, 3, 0)
+ *   "rk13"       0 = do not use the async row kernel (kernel 3), whose RK4 is in
+ *                difference form - the three stage buffers are kept and combined
+ *                in the last stage instead of a running accumulator, 13 instead
+ *                of 16 array passes per step (stage outputs then live in arrays
+ *                1, 2, 3, 0) - and fall back to the accumulator form of kernel 1
  *   "resident"   allow the cluster-resident kernels for small hierarchies
  *                (4 = prefer the row-per-lane variant, kernel 4, over the
  *                element-parallel kernel 5)

@@ -225,8 +225,7 @@ class ShardedDEOM:
         self.fused = False
         kern = (tuning or {}).get("kernel", 0)
         # (opt-in: measured slower than the separate push kernel in round 1)
-        if (self.symm is not None and fused_push is True and bool(p.info("qdiag"))
-                and n <= 8 and kern in (0, 3)):
+        if self.symm is not None and fused_push is True and bool(p.info("rk_scheme")):
             import ctypes as C
             si = self.halo.send_items
             dest = torch.repeat_interleave(
