@@ -36,6 +36,9 @@ using heom::Pascal;
 #ifndef HEOM_MINBLOCKS
 #define HEOM_MINBLOCKS 2  // __launch_bounds__ min blocks per SM for the row kernel
 #endif
+#ifndef HEOM_TMA_BULK
+#define HEOM_TMA_BULK 1   // async kernel: contiguous tiles via cp.async.bulk + mbarrier
+#endif
 #ifndef HEOM_L2_HINTS
 #define HEOM_L2_HINTS 0   // async kernel: L2 eviction-priority hints on the cp.async loads
 #endif
@@ -655,6 +658,38 @@ __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
     return p;
 }
+// ---- TMA bulk copies (cp.async.bulk, 1-D) completing on an mbarrier: the
+// contiguous tiles of a group (own y_in, y, stage buffers) are fetched with one
+// instruction each by one lane instead of 16 bytes per lane per LDGSTS
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int NWAIT>
 __device__ __forceinline__ void cp_async_wait() {
@@ -688,7 +723,9 @@ template <int N, bool TDEP, bool HREAL, bool PUSH>
 __global__ void __launch_bounds__(ASYNC_MAX_THREADS, 1)
 stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT;
+    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 1;   // +1: two mbarriers
+    constexpr bool BULK_TILE = HEOM_TMA_BULK && (LD == N);   // padded tiles cannot be one bulk copy
+    constexpr bool BULK_FLAT = HEOM_TMA_BULK != 0;
     constexpr int EIT = (FLAT + 31) / 32;
     extern __shared__ double2 smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -706,6 +743,14 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     double2* y_s = k_s + TILE;
     double2* acc_s = y_s + FLAT;
     double2* nb_s = acc_s + FLAT;
+    unsigned long long* barA = (unsigned long long*)(nb_s + FLAT);   // own tile (and 2nd stage buffer)
+    unsigned long long* barB = barA + 1;                              // y / 1st stage buffer
+    unsigned phA = 0, phB = 0;
+    if (BULK_FLAT && lane == 0) {
+        mbar_init(barA, 1);
+        mbar_init(barB, 1);
+        fence_proxy_async();
+    }
     unsigned char* supp_s = (unsigned char*)(warp0 + nwarps * PERWARP);
     if (TDEP) {
         for (int e = threadIdx.x; e < NN; e += blockDim.x) Hs[e] = ops[e];
@@ -832,7 +877,13 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         fetch_ptr(g + 2 * gstride, nn_lbeg, nn_lend, nn_pb, nn_pe);
 
         // ---- issue: own tile + first chunk of neighbour rows (group A), y/acc (group B)
-        {
+        if (BULK_TILE) {
+            if (lane == 0) {
+                fence_proxy_async();   // earlier generic-proxy reads of these buffers are done (warp sync)
+                mbar_expect_tx(barA, nelem * 16u);
+                bulk_g2s(rho_s, yin + base * NN, nelem * 16u, barA);
+            }
+        } else {
             const double2* src = yin + base * NN + lane;
 #pragma unroll
             for (int it = 0; it < EIT; ++it)
@@ -851,18 +902,31 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         if (!a.first) {
             // y always; in the last stage also the first stage buffer (passed in a.acc) -
             // the second one follows into rho_s once the commutator has consumed it
-            const double2* sa = a.acc + gbase + lane;
-            const double2* sy = a.y + gbase + lane;
-#pragma unroll
-            for (int it = 0; it < EIT; ++it)
-                if (lane + 32 * it < nelem) {
-                    if (a.last) CP_STREAM(&acc_s[lane + 32 * it], sa + 32 * it);
-                    CP_STREAM(&y_s[lane + 32 * it], sy + 32 * it);
+            if (BULK_FLAT) {
+                if (lane == 0) {
+                    if (!BULK_TILE) fence_proxy_async();
+                    mbar_expect_tx(barB, nelem * 16u * (a.last ? 2u : 1u));
+                    bulk_g2s(y_s, a.y + gbase, nelem * 16u, barB);
+                    if (a.last) bulk_g2s(acc_s, a.acc + gbase, nelem * 16u, barB);
                 }
+            } else {
+                const double2* sa = a.acc + gbase + lane;
+                const double2* sy = a.y + gbase + lane;
+#pragma unroll
+                for (int it = 0; it < EIT; ++it)
+                    if (lane + 32 * it < nelem) {
+                        if (a.last) CP_STREAM(&acc_s[lane + 32 * it], sa + 32 * it);
+                        CP_STREAM(&y_s[lane + 32 * it], sy + 32 * it);
+                    }
+            }
         }
         cp_async_commit();
 
         cp_async_wait<1>();
+        if (BULK_TILE) {
+            mbar_wait(barA, phA);
+            phA ^= 1u;
+        }
         __syncwarp();
 
         // ---- -i[H, rho] - damp rho
@@ -919,11 +983,19 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         __syncwarp();
         if (a.last) {
             // rho_s is free now: fetch the second stage buffer (a.yout) into it for the epilogue
-            const double2* sb = a.yout + gbase + lane;
+            if (BULK_TILE) {
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(barA, nelem * 16u);
+                    bulk_g2s(rho_s, a.yout + gbase, nelem * 16u, barA);
+                }
+            } else {
+                const double2* sb = a.yout + gbase + lane;
 #pragma unroll
-            for (int it = 0; it < EIT; ++it)
-                if (lane + 32 * it < nelem) CP_STREAM(&rho_s[pofs[it]], sb + 32 * it);
-            cp_async_commit();
+                for (int it = 0; it < EIT; ++it)
+                    if (lane + 32 * it < nelem) CP_STREAM(&rho_s[pofs[it]], sb + 32 * it);
+                cp_async_commit();
+            }
         }
 
         // ---- neighbour terms, N links per chunk; contributions to one target row
@@ -1044,6 +1116,14 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         }
         if (cur_rr >= 0) flush();
         cp_async_wait<0>();
+        if (BULK_FLAT && !a.first) {
+            mbar_wait(barB, phB);
+            phB ^= 1u;
+        }
+        if (BULK_TILE && a.last) {
+            mbar_wait(barA, phA);
+            phA ^= 1u;
+        }
         __syncwarp();
 
         // ---- epilogue from shared memory, streaming stores; rows that other ranks
@@ -1728,7 +1808,7 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
 template <int N, bool TDEP, bool HREAL, bool PUSH>
 static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT;
+    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 1;
     StageArgs args = a;
     args.ngroups = (p->part_hi - p->part_lo + APW - 1) / APW;
     const AsyncTables T = async_tables(N, p->K, p->M, p->L, TDEP);
