@@ -37,7 +37,7 @@ using heom::Pascal;
 #define HEOM_MINBLOCKS 2  // __launch_bounds__ min blocks per SM for the row kernel
 #endif
 #ifndef HEOM_TMA_BULK
-#define HEOM_TMA_BULK 1   // async kernel: contiguous tiles via cp.async.bulk + mbarrier
+#define HEOM_TMA_BULK 1   // async kernel: 1 = contiguous tiles via cp.async.bulk + mbarrier, 2 = neighbour rows too
 #endif
 #ifndef HEOM_L2_HINTS
 #define HEOM_L2_HINTS 0   // async kernel: L2 eviction-priority hints on the cp.async loads
@@ -723,9 +723,10 @@ template <int N, bool TDEP, bool HREAL, bool PUSH>
 __global__ void __launch_bounds__(ASYNC_MAX_THREADS, 1)
 stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 1;   // +1: two mbarriers
+    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 2;   // +2: four mbarriers
     constexpr bool BULK_TILE = HEOM_TMA_BULK && (LD == N);   // padded tiles cannot be one bulk copy
     constexpr bool BULK_FLAT = HEOM_TMA_BULK != 0;
+    constexpr bool BULK_ROWS = HEOM_TMA_BULK >= 2 && BULK_TILE;   // neighbour rows as 16N-byte bulk copies
     constexpr int EIT = (FLAT + 31) / 32;
     extern __shared__ double2 smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -745,10 +746,14 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     double2* nb_s = acc_s + FLAT;
     unsigned long long* barA = (unsigned long long*)(nb_s + FLAT);   // own tile (and 2nd stage buffer)
     unsigned long long* barB = barA + 1;                              // y / 1st stage buffer
-    unsigned phA = 0, phB = 0;
+    unsigned long long* barC = barA + 2;                              // neighbour rows of later chunks
+    unsigned long long* barD = barA + 3;                              // 2nd stage buffer (last stage)
+    unsigned phA = 0, phB = 0, phC = 0, phD = 0;
     if (BULK_FLAT && lane == 0) {
         mbar_init(barA, 1);
         mbar_init(barB, 1);
+        mbar_init(barC, 1);
+        mbar_init(barD, 1);
         fence_proxy_async();
     }
     unsigned char* supp_s = (unsigned char*)(warp0 + nwarps * PERWARP);
@@ -878,10 +883,21 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
 
         // ---- issue: own tile + first chunk of neighbour rows (group A), y/acc (group B)
         if (BULK_TILE) {
+            unsigned rowbytes = 0;
+            if (BULK_ROWS) {
+                const int mine = (on && row == 0) ? min(nl, N) : 0;
+                rowbytes = (unsigned)__reduce_add_sync(0xffffffffu, mine) * (unsigned)(N * 16);
+            }
             if (lane == 0) {
                 fence_proxy_async();   // earlier generic-proxy reads of these buffers are done (warp sync)
-                mbar_expect_tx(barA, nelem * 16u);
+                mbar_expect_tx(barA, nelem * 16u + rowbytes);
                 bulk_g2s(rho_s, yin + base * NN, nelem * 16u, barA);
+            }
+            if (BULK_ROWS) {
+                __syncwarp();          // the transaction count is posted before any row copy can complete
+                if (on && row < nl)    // lane `row` of an ADO fetches the row its link number `row` needs
+                    bulk_g2s(nb_s + (sub * N + row) * N,
+                             yin + ((long long)rec.x * NN + heom::meta_r0(rec.y) * N), N * 16u, barA);
             }
         } else {
             const double2* src = yin + base * NN + lane;
@@ -894,7 +910,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             const int srcl = (sub * N + t) & 31;
             rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
             rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
-            if (t < nl)
+            if (!BULK_ROWS && t < nl)
                 CP_KEEP(nbrow + t * N,
                         yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
         }
@@ -986,8 +1002,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             if (BULK_TILE) {
                 if (lane == 0) {
                     fence_proxy_async();
-                    mbar_expect_tx(barA, nelem * 16u);
-                    bulk_g2s(rho_s, a.yout + gbase, nelem * 16u, barA);
+                    mbar_expect_tx(barD, nelem * 16u);
+                    bulk_g2s(rho_s, a.yout + gbase, nelem * 16u, barD);
                 }
             } else {
                 const double2* sb = a.yout + gbase + lane;
@@ -1038,12 +1054,27 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                     const int srcl = (sub * N + t) & 31;
                     rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
                     rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
-                    if (c0 + t < nl)
+                    if (!BULK_ROWS && c0 + t < nl)
                         CP_KEEP(nbrow + t * N,
                                 yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
                 }
-                cp_async_commit();
-                cp_async_wait<0>();
+                if (BULK_ROWS) {
+                    const int mine = (on && row == 0) ? max(0, min(nl - c0, N)) : 0;
+                    const unsigned rowbytes = (unsigned)__reduce_add_sync(0xffffffffu, mine) * (unsigned)(N * 16);
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(barC, rowbytes);
+                    }
+                    __syncwarp();
+                    if (on && c0 + row < nl)
+                        bulk_g2s(nb_s + (sub * N + row) * N,
+                                 yin + ((long long)rec.x * NN + heom::meta_r0(rec.y) * N), N * 16u, barC);
+                    mbar_wait(barC, phC);
+                    phC ^= 1u;
+                } else {
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                }
                 __syncwarp();
             }
             if (c0 < nl) {
@@ -1121,8 +1152,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             phB ^= 1u;
         }
         if (BULK_TILE && a.last) {
-            mbar_wait(barA, phA);
-            phA ^= 1u;
+            mbar_wait(barD, phD);
+            phD ^= 1u;
         }
         __syncwarp();
 
@@ -1808,7 +1839,7 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
 template <int N, bool TDEP, bool HREAL, bool PUSH>
 static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 1;
+    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 2;
     StageArgs args = a;
     args.ngroups = (p->part_hi - p->part_lo + APW - 1) / APW;
     const AsyncTables T = async_tables(N, p->K, p->M, p->L, TDEP);
