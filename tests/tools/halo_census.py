@@ -1,8 +1,8 @@
 """Halo size per rank for contiguous partitions of a storage order (offline)."""
 import sys, time
 import numpy as np
-sys.path.insert(0, '.')
-from tools.l2_order_sim import tables, order_of
+sys.path.insert(0, "."); sys.path.insert(0, "tests/tools")
+from l2_order_sim import tables, order_of
 
 K, L, world = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 names = sys.argv[4].split(',')

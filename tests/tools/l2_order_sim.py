@@ -3,7 +3,8 @@
 Models the stage kernel's sweep over the hierarchy in storage order and an L2
 of given capacity with an LRU-by-age approximation (a line hits if fewer than
 `cap` bytes were filled since its last touch).  Used to choose the storage
-order before spending GPU time; not part of the product path.
+order before spending GPU time.  Development/test tooling: it uses the oracle's
+index tables and is not part of the product path.
 """
 import sys, time
 import numpy as np
