@@ -383,6 +383,7 @@ struct StageArgs {
     long long slot_lo, slot_hi;  // owned slot range of this rank (whole hierarchy on one GPU)
     double a, w;
     int local_step, first, last, N;
+    int scramble;  // rotate the visiting order inside runs of 16 groups (storage order 2)
     int scheme;  // 0: running accumulator (16 passes/step); 1: difference form (13 passes/step, async kernel)
     int herm, ncoef, nmod, nind, lmax;
     const double2* cbase;  // [K][4]: minus (L,R) and plus (L,R) coefficients for n_eff = 1
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(256, HEOM_MINBLOCKS) stage_rows_kernel(const S
 
     for (long long g = (long long)blockIdx.x * nwarps + wid; g < a.ngroups;
          g += (long long)gridDim.x * nwarps) {
-        const long long gm = g < (a.ngroups & ~15ll) ? ((g & ~15ll) | ((g + (g >> 4)) & 15ll)) : g;
+        const long long gm = (a.scramble && g < (a.ngroups & ~15ll)) ? ((g & ~15ll) | ((g + (g >> 4)) & 15ll)) : g;
         const long long base = a.slot_lo + gm * APW;
         const int cnt = (int)min((long long)APW, a.slot_hi - base);
         const int nelem = cnt * NN;
@@ -697,7 +698,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 #ifndef HEOM_ASYNC_THREADS
-#define HEOM_ASYNC_THREADS 448
+#define HEOM_ASYNC_THREADS 512
 #endif
 constexpr int ASYNC_MAX_THREADS = HEOM_ASYNC_THREADS;
 
@@ -739,12 +740,15 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     double2* qd_s = smem + T.qd;
     double* sq_s = (double*)(smem + T.sq);
     double2* warp0 = smem + T.warp0;
-    double2* rho_s = warp0 + wid * PERWARP;
+    // per-warp buffers; the first-stage-buffer tile (acc_s) exists only in the last
+    // stage, so the other three stages fit more warps per SM
+    const int perwarp = a.last ? PERWARP : PERWARP - FLAT;
+    double2* rho_s = warp0 + wid * perwarp;
     double2* k_s = rho_s + TILE;
     double2* y_s = k_s + TILE;
-    double2* acc_s = y_s + FLAT;
-    double2* nb_s = acc_s + FLAT;
-    unsigned long long* barA = (unsigned long long*)(nb_s + FLAT);   // own tile (and 2nd stage buffer)
+    double2* nb_s = y_s + FLAT;
+    double2* acc_s = nb_s + FLAT;   // valid only when a.last
+    unsigned long long* barA = (unsigned long long*)(rho_s + perwarp - 2);   // own tile (+ rows)
     unsigned long long* barB = barA + 1;                              // y / 1st stage buffer
     unsigned long long* barC = barA + 2;                              // neighbour rows of later chunks
     unsigned long long* barD = barA + 3;                              // 2nd stage buffer (last stage)
@@ -756,7 +760,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         mbar_init(barD, 1);
         fence_proxy_async();
     }
-    unsigned char* supp_s = (unsigned char*)(warp0 + nwarps * PERWARP);
+    unsigned char* supp_s = (unsigned char*)(warp0 + nwarps * perwarp);
     if (TDEP) {
         for (int e = threadIdx.x; e < NN; e += blockDim.x) Hs[e] = ops[e];
     }
@@ -826,7 +830,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     // 16 groups is rotated by the run index, so a warp (whose stride is a
     // multiple of 16) does not see the same position of the 64-slot blocks of
     // storage order 2 every time (their head holds the link-heavy ADOs).
-    const long long gfull = a.ngroups & ~15ll;
+    const long long gfull = a.scramble ? (a.ngroups & ~15ll) : 0;
     auto gmap = [&](long long gg) {
         return gg < gfull ? ((gg & ~15ll) | ((gg + (gg >> 4)) & 15ll)) : gg;
     };
@@ -1844,7 +1848,7 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     args.ngroups = (p->part_hi - p->part_lo + APW - 1) / APW;
     const AsyncTables T = async_tables(N, p->K, p->M, p->L, TDEP);
     const size_t table_bytes = sizeof(double2) * T.warp0 + T.bytes_tail;
-    const size_t per_warp = sizeof(double2) * PERWARP;
+    const size_t per_warp = sizeof(double2) * (a.last ? PERWARP : PERWARP - FLAT);
     const size_t budget = 227 * 1024;
     REQUIRE(table_bytes + per_warp <= budget, "shared-memory tables too large for the async row kernel");
     int maxw = (int)std::min<size_t>(ASYNC_MAX_THREADS / 32, (budget - table_bytes) / per_warp);
@@ -2704,6 +2708,7 @@ static void fill_stage_args(pyqed_heom_plan* p, StageArgs& a) {
     a.slot_hi = p->part_hi;
     a.slot0 = p->slot0;
     a.N = N;
+    a.scramble = p->order == 2;
 }
 
 static int run_prep(pyqed_heom_plan* p, long long step, int tidx) {
