@@ -456,7 +456,9 @@ __global__ void __launch_bounds__(256, HEOM_MINBLOCKS) stage_rows_kernel(const S
 
     for (long long g = (long long)blockIdx.x * nwarps + wid; g < a.ngroups;
          g += (long long)gridDim.x * nwarps) {
-        const long long gm = (a.scramble && g < (a.ngroups & ~15ll)) ? ((g & ~15ll) | ((g + (g >> 4)) & 15ll)) : g;
+        const long long gm = (a.scramble && g < (a.ngroups & ~15ll))
+                                 ? ((g & ~15ll) | ((g + (((unsigned)(g >> 4) * 2654435761u) >> 28)) & 15ll))
+                                 : g;
         const long long base = a.slot_lo + gm * APW;
         const int cnt = (int)min((long long)APW, a.slot_hi - base);
         const int nelem = cnt * NN;
@@ -832,7 +834,10 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     // storage order 2 every time (their head holds the link-heavy ADOs).
     const long long gfull = a.scramble ? (a.ngroups & ~15ll) : 0;
     auto gmap = [&](long long gg) {
-        return gg < gfull ? ((gg & ~15ll) | ((gg + (gg >> 4)) & 15ll)) : gg;
+        // rotation amount = top bits of a multiplicative hash of the run index, so that
+        // every warp sees all 16 positions whatever its stride is
+        const unsigned rot = ((unsigned)(gg >> 4) * 2654435761u) >> 28;
+        return gg < gfull ? ((gg & ~15ll) | ((gg + rot) & 15ll)) : gg;
     };
     auto fetch_ptr = [&](long long gg, int& lb, int& le, int& pb, int& pe) {
         const long long slot = a.slot_lo + gmap(gg) * APW + sub;
