@@ -198,7 +198,8 @@ int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
  * cp.async staging (N <= 8, diagonal Q_m), 4 cluster-resident propagation
  * (whole hierarchy in distributed shared memory, small hierarchies only;
  * chosen automatically when it fits); warps per CTA for kernels 1 and 3;
- * use_graph: replay the RK4 step as a CUDA graph. */
+ * use_graph: reserved (ignored): small hierarchies are propagated by a single
+ * cluster-resident launch instead of a graph. */
 int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
                           int use_graph);
 

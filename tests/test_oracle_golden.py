@@ -93,3 +93,21 @@ def test_chain_equals_deom_form():
     sz = g["e_ops"][0]
     got = np.array([np.trace(sz @ r) for r in traj[1:]])
     assert np.max(np.abs(got - g["observables"][0])) < 1e-13
+
+
+def test_difference_form_rk4_is_classical_rk4():
+    """The async CUDA kernel keeps the three stage inputs and combines them in
+    the last stage, y' = -y/3 + S1/3 + 2 S2/3 + S3/3 + dt/6 k4 (DESIGN.md section 4);
+    algebraically this is the reference's RK4 (deom.py:725-766)."""
+    g = golden("deom_random5_nonherm")
+    o = _oracle_from(g)
+    rng = np.random.default_rng(11)
+    y = rng.standard_normal((o.nmax, o.nsys, o.nsys)) + 1j * rng.standard_normal((o.nmax, o.nsys, o.nsys))
+    dt, t = 0.013, 0.2
+    ref = o.rk4_step(y, dt, t, o.rhs_batched)
+    s1 = y + dt / 2 * o.rhs_batched(y, t)
+    s2 = y + dt / 2 * o.rhs_batched(s1, t + dt / 2)
+    s3 = y + dt * o.rhs_batched(s2, t + dt / 2)
+    k4 = o.rhs_batched(s3, t + dt)
+    new = -y / 3 + s1 / 3 + 2 * s2 / 3 + s3 / 3 + dt / 6 * k4
+    assert np.max(np.abs(new - ref)) < 1e-13
