@@ -103,7 +103,7 @@ def test_difference_form_rk4_is_classical_rk4():
     o = _oracle_from(g)
     rng = np.random.default_rng(11)
     y = rng.standard_normal((o.nmax, o.nsys, o.nsys)) + 1j * rng.standard_normal((o.nmax, o.nsys, o.nsys))
-    dt, t = 0.013, 0.2
+    dt, t = float(g["dt"]), 2 * float(g["dt"])   # on the fixture's pulse grid
     ref = o.rk4_step(y, dt, t, o.rhs_batched)
     s1 = y + dt / 2 * o.rhs_batched(y, t)
     s2 = y + dt / 2 * o.rhs_batched(s1, t + dt / 2)
