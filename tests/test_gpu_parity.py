@@ -307,3 +307,81 @@ def test_heom_space_correlation_function():
     s.prepare(g["rho0"], dt, n_eq)
     s.operator_action_ddos(B, side="right")
     assert np.max(np.abs(s.ddos - o.ddos @ B)) < TOL
+
+
+def _random_problem(n, nmod, nind, lmax, seed, diag, herm):
+    """Random inputs: diagonal or dense couplings, Hermitian-preserving bath or a
+    general one (complex exponents, unrelated etal/etar)."""
+    rng = np.random.default_rng(seed)
+
+    def rnd(*shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    H = rnd(n, n)
+    H = (H + H.conj().T) / 2
+    if rng.integers(2) and herm:
+        H = H.real.astype(np.complex128)          # exercises the real-H kernels
+    if diag:
+        Q = np.zeros((nmod, n, n), np.complex128)
+        for m in range(nmod):
+            k = int(rng.integers(1, min(3, n) + 1))
+            idx = rng.choice(n, size=k, replace=False)
+            Q[m, idx, idx] = rng.uniform(0.5, 1.5, k) * rng.choice([-1, 1], k)
+    else:
+        Q = rnd(nmod, n, n)
+        Q = (Q + Q.conj().transpose(0, 2, 1)) / 2
+    mode = rng.integers(0, nmod, nind)
+    mode[0] = nmod - 1
+    if herm:
+        expn = rng.uniform(0.5, 2.0, nind).astype(np.complex128)
+        etal = rnd(nind) * 0.3
+        etar = np.conj(etal)
+        etaa = np.abs(etal).astype(np.complex128)
+        psi = rnd(n)
+        rho0 = np.outer(psi, psi.conj())
+    else:
+        expn = rng.uniform(0.5, 2.0, nind) + 1j * rng.uniform(-1, 1, nind)
+        etal, etar = rnd(nind) * 0.3, rnd(nind) * 0.3
+        etaa = rng.uniform(0.1, 0.5, nind).astype(np.complex128)
+        rho0 = rnd(n, n)
+    rho0 = rho0 / np.trace(rho0)
+    return dict(H=H, Q=Q, expn=expn, etal=etal, etar=etar, etaa=etaa, mode=mode, lmax=lmax, rho0=rho0)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("diag,herm", [(True, True), (True, False), (False, True), (False, False)])
+def test_every_system_size_against_oracle(n, diag, herm):
+    """All template instantiations N = 2..8 of the row kernels (and the resident
+    kernels where they apply), diagonal and dense couplings, Hermitian-preserving
+    and general baths, in all three storage orders, against the batched oracle."""
+    from oracle.deom_oracle import DeomOracle
+    from pyqed_b200.heom import DEOMSolver, Bath
+    q = _random_problem(n, nmod=2, nind=3, lmax=3, seed=100 * n + 2 * diag + herm, diag=diag, herm=herm)
+    o = DeomOracle(q["H"], None, q["Q"], None, q["expn"], q["etal"], q["etar"], q["etaa"], q["mode"], q["lmax"])
+    dt, nt = 0.004, 12
+    _, ref = o.run(q["rho0"], dt, nt)
+    bath = Bath(expn=q["expn"], etal=q["etal"], etar=q["etar"], etaa=q["etaa"], mode=q["mode"])
+    for order, opts in [(0, {}), (1, {"resident": 0}), (2, {"resident": 0}), (0, {"resident": 4}),
+                        (0, {"resident": 0, "rk13": 0})]:
+        s = DEOMSolver(q["H"], None, bath, q["Q"], None, lmax=q["lmax"], order=order)
+        s.options = opts
+        _, got = s.run(q["rho0"].copy(), dt, nt)
+        assert np.max(np.abs(np.asarray(got) - np.asarray(ref))) < TOL, (order, opts)
+        assert np.max(np.abs(s.ddos - o.ddos)) < TOL, (order, opts)
+        assert s._plan.info("q_diagonal") == int(diag)
+        assert s._plan.info("hermitian") == int(herm)
+
+
+def test_batched_general_coupling_and_large_k():
+    """Batch > 1 on the dense-coupling path and a wide hierarchy (K = 12)."""
+    from oracle.deom_oracle import DeomOracle
+    from pyqed_b200.heom import DEOMSolver, Bath
+    q = _random_problem(3, nmod=3, nind=12, lmax=2, seed=77, diag=False, herm=True)
+    o = DeomOracle(q["H"], None, q["Q"], None, q["expn"], q["etal"], q["etar"], q["etaa"], q["mode"], q["lmax"])
+    bath = Bath(expn=q["expn"], etal=q["etal"], etar=q["etar"], etaa=q["etaa"], mode=q["mode"])
+    s = DEOMSolver(q["H"], None, bath, q["Q"], None, lmax=q["lmax"])
+    rho_b = np.diag([0.2, 0.3, 0.5]).astype(np.complex128)
+    dt, nt = 0.005, 10
+    _, out = s.run_batch([q["rho0"], rho_b], dt, nt)
+    for b, r0 in enumerate((q["rho0"], rho_b)):
+        _, ref = o.run(r0, dt, nt)
+        assert np.max(np.abs(out[b] - np.asarray(ref))) < TOL
