@@ -338,6 +338,7 @@ def _random_problem(n, nmod, nind, lmax, seed, diag, herm):
         etaa = np.abs(etal).astype(np.complex128)
         psi = rnd(n)
         rho0 = np.outer(psi, psi.conj())
+        rho0 = (rho0 + rho0.conj().T) / 2 / np.trace(rho0).real   # exactly Hermitian
     else:
         expn = rng.uniform(0.5, 2.0, nind) + 1j * rng.uniform(-1, 1, nind)
         etal, etar = rnd(nind) * 0.3, rnd(nind) * 0.3
