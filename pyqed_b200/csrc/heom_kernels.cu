@@ -2104,7 +2104,16 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     int rc = 0;
     const int kern = (p->kernel && p->kernel != 4) ? p->kernel
                                                    : (p->N <= 8 ? ((p->use_qdiag && p->opt_rk13 != 0) ? 3 : 1) : 2);
-    if (kern == 3) {
+    if (kern == 3 && a.first && a.last) {
+        // single-stage (Euler) update: the async kernel only implements the difference-form
+        // RK4 stages, so the plain-load row kernel takes it
+        switch (p->N) {
+#define ROWS_EULER_CASE(n) case n: rc = launch_rows_n<n>(p, a, sm_count, tdep, p->use_qdiag); break;
+            ROWS_EULER_CASE(2) ROWS_EULER_CASE(3) ROWS_EULER_CASE(4) ROWS_EULER_CASE(5) ROWS_EULER_CASE(6)
+            ROWS_EULER_CASE(7) ROWS_EULER_CASE(8)
+#undef ROWS_EULER_CASE
+        }
+    } else if (kern == 3) {
         REQUIRE(p->N >= 2 && p->N <= 8 && p->use_qdiag,
                 "kernel 3 needs 2 <= N <= 8 and diagonal coupling operators");
 #define ASYNC_CASE(n)                                                                  \

@@ -228,10 +228,11 @@ def test_empty_and_tiny_inputs():
     assert np.max(np.abs(traj[-1] - U @ g["rho0"] @ U.conj().T)) < 1e-7
 
 
-def test_euler_method_against_oracle():
+@pytest.mark.parametrize("name", ["deom_random4_herm", "deom_fmo_K7_L4", "deom_spin_boson_L10"])
+def test_euler_method_against_oracle(name):
     from oracle.deom_oracle import DeomOracle
     from pyqed_b200._cabi import Plan
-    g = golden("deom_random4_herm")
+    g = golden(name)
     o = DeomOracle(g["system"], g["system_dipole"], g["coupling"], g["coupling_dipole"], g["expn"],
                    g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]))
     rho = np.zeros((o.nmax, o.nsys, o.nsys), dtype=np.complex128)
