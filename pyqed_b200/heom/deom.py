@@ -76,6 +76,7 @@ class DEOMSolver:
         self._plan_key = None
         self._keys = None
         self._ddos = None
+        self.propgator = None
 
     # ---- setters (deom.py:992-1033) ---------------------------------------
     def set_hierarchy(self, lmax):
@@ -264,6 +265,47 @@ class DEOMSolver:
         corr = plan.expectation(traj, np.asarray(a_op, dtype=C128))[0, 0].cpu().numpy()
         self._ddos = None
         return np.arange(nt + 1) * dt, corr
+
+    # ---- dense generator (deom.py:1116-1125) ---------------------------------------
+    def gen_generate_propgator(self, chunk=256, max_dim=20000):
+        """Dense HEOM generator ``self.propgator`` with the reference's flat
+        index ``iado*N*N + i*N + j`` (``gen_index2``, ``deom.py:769-771``), such
+        that ``d vec(ddos)/dt = propgator @ vec(ddos)`` (static H and Q, as in
+        ``generate_propgator``, ``deom.py:879-886``).
+
+        Built column by column from the stage kernel itself: a batch of unit
+        vectors is advanced by one explicit-Euler stage of step 1, so column c is
+        ``F(e_c)``.  Meant for small hierarchies (spectroscopy, cross-checks);
+        the dense matrix has ``(nmax N^2)^2`` entries."""
+        self.check_()
+        self.init_()
+        n, nmax = self.nsys, self.nmax
+        dim = nmax * n * n
+        if dim > max_dim:
+            raise MemoryError(f"dense generator of dimension {dim} exceeds max_dim={max_dim}")
+        H, mu, Q, Qd = self._operators()
+        b = self.bath
+        chunk = int(min(chunk, dim))
+        plan = Plan(n, self.nind, self.nmod, self.lmax, batch=chunk, device=self.device, order=0)
+        try:
+            plan.set_system(H, None)
+            plan.set_coupling(Q, None)
+            plan.set_bath(b.expn, b.etal, b.etar, b.etaa, b.mode)
+            plan.set_option("resident", 0)
+            plan.build()
+            gen = np.zeros((dim, dim), dtype=C128)
+            for c0 in range(0, dim, chunk):
+                cols = np.arange(c0, min(dim, c0 + chunk))
+                unit = np.zeros((chunk, dim), dtype=C128)
+                unit[np.arange(len(cols)), cols] = 1.0
+                plan.load_ados(unit.reshape(chunk, nmax, n, n))
+                plan.propagate(1.0, 1, None, None, None, method=1)
+                out = plan.get_ados().reshape(chunk, dim)
+                gen[:, cols] = (out - unit)[:len(cols)].T
+        finally:
+            plan.close()
+        self.propgator = gen
+        return gen
 
     def _run(self, rho0s, dt, nt, p1, fs, fc):
         import torch

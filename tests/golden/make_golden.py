@@ -183,9 +183,34 @@ def save_propagators():
           "diff heom/oqs", np.abs(out["u_heom"] - out["u_oqs"]).max())
 
 
+def save_generator():
+    """Dense HEOM generator (gen_generate_propgator, deom.py:1116-1125) for small cases."""
+    out = {}
+    for tag, w in (("random3_K1", W.random_dense(3, 1, 1, 5, seed=2, hermitian=True)),
+                   ("random4_herm", W.random_dense(4, 2, 3, 2, seed=0, hermitian=True)),
+                   ("spin_boson_L3", W.spin_boson(lmax=3))):
+        bath = SimpleNamespace(expn=w["expn"].copy(), etal=w["etal"].copy(), etar=w["etar"].copy(),
+                               etaa=w["etaa"].copy(), mode=w["mode"].copy())
+        s = ref_deom.DEOMSolver(system=w["system"].copy(), system_dipole=w["system_dipole"].copy(),
+                                bath=bath, coupling=w["coupling"].copy(),
+                                coupling_dipole=w["coupling_dipole"].copy(),
+                                pulse_system_func=lambda t: 0.0, pulse_coupling_func=lambda t: 0.0,
+                                lmax=w["lmax"])
+        s.gen_generate_propgator()
+        for k in ("system", "coupling", "expn", "etal", "etar", "etaa", "mode", "rho0"):
+            out[f"{tag}_{k}"] = w[k]
+        out[f"{tag}_lmax"] = w["lmax"]
+        out[f"{tag}_generator"] = np.asarray(s.propgator)
+        print("generator", tag, s.propgator.shape, np.abs(s.propgator).max())
+    np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "propagators":
         save_propagators()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "generator":
+        save_generator()
         return
     save_propagators()
     save_bath()

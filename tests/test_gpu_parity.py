@@ -387,3 +387,28 @@ def test_batched_general_coupling_and_large_k():
     for b, r0 in enumerate((q["rho0"], rho_b)):
         _, ref = o.run(r0, dt, nt)
         assert np.max(np.abs(out[b] - np.asarray(ref))) < TOL
+
+
+@pytest.mark.parametrize("tag", ["random3_K1", "random4_herm", "spin_boson_L3"])
+def test_dense_generator_matches_reference(tag):
+    """gen_generate_propgator: the dense generator equals the reference's
+    (deom.py:1116-1125) and exponentiating it reproduces the RK4 trajectory,
+    the consistency check of pyqed/heom/propagator.py:67-84."""
+    import scipy.linalg as la
+    from pyqed_b200.heom import DEOMSolver, Bath
+    g = golden("generator")
+    get = lambda k: g[f"{tag}_{k}"]
+    bath = Bath(expn=get("expn"), etal=get("etal"), etar=get("etar"), etaa=get("etaa"), mode=get("mode"))
+    s = DEOMSolver(system=get("system"), bath=bath, coupling=get("coupling"), lmax=int(get("lmax")))
+    gen = s.gen_generate_propgator(chunk=37)     # chunk that does not divide the dimension
+    ref = get("generator")
+    assert gen.shape == ref.shape
+    assert np.max(np.abs(gen - ref)) < 1e-12
+    # exp(G t) on vec(rho0, 0, 0, ...) against the RK4 trajectory
+    dt, nt = 0.002, 100
+    _, traj = s.run(get("rho0").copy(), dt, nt)
+    n = s.nsys
+    v0 = np.zeros(gen.shape[0], dtype=np.complex128)
+    v0[:n * n] = get("rho0").ravel()
+    vt = la.expm(gen * dt * nt) @ v0
+    assert np.max(np.abs(vt[:n * n].reshape(n, n) - traj[-1])) < 1e-9
