@@ -412,3 +412,34 @@ def test_dense_generator_matches_reference(tag):
     v0[:n * n] = get("rho0").ravel()
     vt = la.expm(gen * dt * nt) @ v0
     assert np.max(np.abs(vt[:n * n].reshape(n, n) - traj[-1])) < 1e-9
+
+
+def test_examples_deom_script_flow():
+    """The call sequence of the reference's examples/deom.py:23-74 (Mol.deom
+    factory, setters, run with p1) against KAT-2."""
+    import sympy as sp
+    from pyqed_b200.mol import Mol
+    from pyqed_b200.heom import Bath
+    from pyqed_b200.heom.spectrum import decompose_spectrum_pade as pade
+    g = golden("deom_example_L10_p1")
+    sz = np.array([[1, 0], [0, -1]], dtype=complex)
+    sx = np.array([[0, 1], [1, 0]], dtype=complex)
+    H = sz + sx
+    mol = Mol(H, np.zeros_like(H))
+    sdip = np.zeros((2, 2), np.complex128)
+    rho = np.zeros((2, 2), dtype=np.complex128)
+    rho[0, 0] = 1
+    w_sp, lamd_sp, gams_sp = sp.symbols(r"\omega , \lambda, \gamma", real=True)
+    spe_sp = (2 * lamd_sp * gams_sp * w_sp / (gams_sp ** 2 + w_sp ** 2)).subs({lamd_sp: 1, gams_sp: 1})
+    bath = Bath([spe_sp], w_sp, [1.0], [2], [0, 0, 0], [pade])
+    assert np.allclose(bath.expn, g["expn"], rtol=1e-12) and np.allclose(bath.etal, g["etal"], rtol=1e-11)
+    solver = mol.deom(bath, [sx])
+    solver.set_hierarchy(10)
+    solver.set_pulse_system_func(lambda t: 0)
+    solver.set_coupling_dipole(sdip)
+    solver.set_pulse_coupling_func(lambda t: 0)
+    t_save, ddos_save = solver.run(rho0=rho, dt=0.01, nt=20, p1=[[1, 0], [0, 0]])
+    assert np.max(np.abs(ddos_save - g["traj"])) < 1e-11
+    assert abs(ddos_save[20] - 0.8697707701043433) < 1e-11
+    assert solver.nmax == 286 and np.array_equal(solver.keys[:4], [[0, 0, 0], [0, 0, 1], [0, 1, 0], [1, 0, 0]])
+    assert abs(rho[0, 0] - ddos_save[20]) < 1e-12   # rho0 is aliased and advanced in place, as in the reference
