@@ -307,6 +307,56 @@ class DEOMSolver:
         self.propgator = gen
         return gen
 
+    def _action_matrix(self, op, lcr):
+        """Block-diagonal superoperator of ``generate_actions`` (``deom.py:825-892``):
+        'l' -> A rho_n, 'r' -> rho_n A, 'c' -> A rho_n + rho_n A, for every ADO."""
+        n = self.nsys
+        a = np.asarray(op, dtype=C128).copy()
+        a[np.abs(a) <= 1e-10] = 0.0          # the reference skips entries below 1e-10
+        eye = np.eye(n, dtype=C128)
+        blk = np.zeros((n * n, n * n), dtype=C128)
+        if lcr in ("l", "c"):
+            blk += np.kron(a, eye)
+        if lcr in ("r", "c"):
+            blk += np.kron(eye, a.T)
+        return np.kron(np.eye(self.nmax, dtype=C128), blk)
+
+    def correlation_4op_3t(self, operator_a, operator_b, operator_c, operator_d, rho0, T, w_x, w_y,
+                           if_full=True, cut_off_min=0.5, cut_off_max=1.1, lcr='llll'):
+        """Frequency-domain four-operator response at waiting time ``T``
+        (``deom.py:1127-1210``): with ``G(w) = (-L - i w)^-1`` from the
+        eigen-decomposition of the dense generator ``L``,
+        ``c[i, j] = Tr{ D G(w_x[i]) C exp(L T) B G(w_y[j]) A rho0 }`` where every
+        operator acts on all ADOs from the side given in ``lcr`` (letters for
+        a, b, c, d).  The generator comes from the GPU (``gen_generate_propgator``);
+        the eigen-decomposition and the contraction are host linear algebra, as in
+        the reference.  ``if_full=False`` keeps only the eigenvalues with real part
+        in ``(cut_off_min * min Re, cut_off_max * max Re)``."""
+        import scipy.linalg as la
+        if self.propgator is None:
+            self.gen_generate_propgator()
+        if getattr(self, "_eig", None) is None or self._eig[0] is not self.propgator:
+            delta, V = la.eig(self.propgator)
+            self._eig = (self.propgator, delta, V, la.pinv(V))
+        _, delta, V, Vinv = self._eig
+        if not if_full:
+            lo, hi = np.min(delta.real) * cut_off_min, np.max(delta.real) * cut_off_max
+            keep = (delta.real > lo) & (delta.real < hi)
+            delta, V, Vinv = delta[keep], V[:, keep], Vinv[keep, :]
+        n = self.nsys
+        a1, a2 = self._action_matrix(operator_d, lcr[3]), self._action_matrix(operator_c, lcr[2])
+        a3, a4 = self._action_matrix(operator_b, lcr[1]), self._action_matrix(operator_a, lcr[0])
+        rho = np.zeros(self.propgator.shape[0], dtype=C128)
+        rho[:n * n] = np.asarray(rho0, dtype=C128).ravel()
+        v4 = Vinv @ (a4 @ rho)
+        m23 = (Vinv @ a2 @ V) @ (np.exp(delta * T)[:, None] * (Vinv @ a3 @ V))
+        w_x, w_y = np.asarray(w_x, dtype=float), np.asarray(w_y, dtype=float)
+        gx = 1.0 / (-delta[:, None] - 1j * w_x[None, :])
+        gy = 1.0 / (-delta[:, None] - 1j * w_y[None, :])
+        t = m23 @ (gy * v4[:, None])                       # [modes, len(w_y)]
+        tr_row = (a1 @ V)[[k * n + k for k in range(n)], :].sum(axis=0)   # trace over the system block
+        return (tr_row[:, None] * gx).T @ t
+
     def _run(self, rho0s, dt, nt, p1, fs, fc):
         import torch
         nb = len(rho0s)

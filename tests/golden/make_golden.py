@@ -202,6 +202,20 @@ def save_generator():
         out[f"{tag}_lmax"] = w["lmax"]
         out[f"{tag}_generator"] = np.asarray(s.propgator)
         print("generator", tag, s.propgator.shape, np.abs(s.propgator).max())
+        if tag in ("spin_boson_L3", "random3_K1"):
+            # frequency-domain four-operator response (correlation_4op_3t, deom.py:1127-1210)
+            n = w["system"].shape[0]
+            rng = np.random.default_rng(9)
+            ops = [rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)) for _ in range(4)]
+            w_x, w_y = np.linspace(-2, 2, 5), np.linspace(-1.5, 2.5, 4)
+            ref_deom.tqdm = lambda x: x
+            for lcr in ("llll", "lrcl"):
+                with contextlib.redirect_stdout(io.StringIO()):
+                    s.Δ = None
+                    c = s.correlation_4op_3t(ops[0], ops[1], ops[2], ops[3], w["rho0"], 0.7, w_x, w_y, lcr=lcr)
+                out[f"{tag}_c4_{lcr}"] = np.asarray(c)
+            out[f"{tag}_c4_ops"] = np.stack(ops)
+            out[f"{tag}_c4_wx"], out[f"{tag}_c4_wy"] = w_x, w_y
     np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
 
 

@@ -443,3 +443,19 @@ def test_examples_deom_script_flow():
     assert abs(ddos_save[20] - 0.8697707701043433) < 1e-11
     assert solver.nmax == 286 and np.array_equal(solver.keys[:4], [[0, 0, 0], [0, 0, 1], [0, 1, 0], [1, 0, 0]])
     assert abs(rho[0, 0] - ddos_save[20]) < 1e-12   # rho0 is aliased and advanced in place, as in the reference
+
+
+@pytest.mark.parametrize("tag", ["random3_K1", "spin_boson_L3"])
+@pytest.mark.parametrize("lcr", ["llll", "lrcl"])
+def test_frequency_domain_four_operator_response(tag, lcr):
+    """correlation_4op_3t (deom.py:1127-1210) on the GPU-built generator."""
+    from pyqed_b200.heom import DEOMSolver, Bath
+    g = golden("generator")
+    get = lambda k: g[f"{tag}_{k}"]
+    bath = Bath(expn=get("expn"), etal=get("etal"), etar=get("etar"), etaa=get("etaa"), mode=get("mode"))
+    s = DEOMSolver(system=get("system"), bath=bath, coupling=get("coupling"), lmax=int(get("lmax")))
+    ops = get("c4_ops")
+    c = s.correlation_4op_3t(ops[0], ops[1], ops[2], ops[3], get("rho0"), 0.7, get("c4_wx"), get("c4_wy"), lcr=lcr)
+    ref = get(f"c4_{lcr}")
+    assert c.shape == ref.shape
+    assert np.max(np.abs(c - ref)) < 1e-8 * max(1.0, np.max(np.abs(ref)))
