@@ -207,7 +207,7 @@ def save_generator():
             n = w["system"].shape[0]
             rng = np.random.default_rng(9)
             ops = [rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)) for _ in range(4)]
-            w_x, w_y = np.linspace(-2, 2, 5), np.linspace(-1.5, 2.5, 4)
+            w_x, w_y = np.linspace(0.3, 2.3, 5), np.linspace(-2.1, -0.2, 4)  # away from the zero mode
             ref_deom.tqdm = lambda x: x
             for lcr in ("llll", "lrcl"):
                 with contextlib.redirect_stdout(io.StringIO()):
