@@ -704,6 +704,13 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 constexpr int ASYNC_MAX_THREADS = HEOM_ASYNC_THREADS;
 
+// Column entry (row, rr) of a neighbour, needed only when the ADOs are not
+// Hermitian.  Kept out of line so that the address arithmetic is not hoisted
+// into the common (Hermitian) path of the link loop.
+__device__ __noinline__ double2 load_neighbour_entry(const double2* yin, int nbr, int NN, int off) {
+    return __ldg(yin + ((long long)nbr * NN + off));
+}
+
 // shared-memory tables of the async kernel (sizes in double2 units unless noted)
 struct AsyncTables {
     int H, cb, cq, qd, sq, warp0;   // offsets in double2 units
@@ -1112,9 +1119,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                             cfma(X, make_double2(c1.x * sq, c1.y * sq), Aj);
                             if (row != rr) {
                                 const double2 c2 = cq_s[3 * cid + 2];
-                                const double2 Bj = a.herm
-                                    ? make_double2(Aj.x, -Aj.y)
-                                    : ldg2(yin + ((long long)rts[t].x * NN + row * N + rr));
+                                double2 Bj = make_double2(Aj.x, -Aj.y);
+                                if (!a.herm) Bj = load_neighbour_entry(yin, rts[t].x, NN, row * N + rr);
                                 cfma(Y, make_double2(c2.x * sq, c2.y * sq), Bj);
                                 yused = true;
                             }
