@@ -37,6 +37,9 @@ WORKLOADS = {
     # documented fallback of SURVEY.md section 8d ("3alt")
     "fmo7_K14_L8": lambda: W.fmo(lmax=8, n_matsubara=1),
     "fmo7_K21_L6": lambda: W.fmo(lmax=6, n_matsubara=2),
+    "fmo7_K21_L5": lambda: W.fmo(lmax=5, n_matsubara=2),
+    "fmo7_K21_L4": lambda: W.fmo(lmax=4, n_matsubara=2),
+    "fmo7_K21_L3": lambda: W.fmo(lmax=3, n_matsubara=2),
     # BASELINE.json configs[1]: 330 ADOs, 259 kB - cache resident, latency bound
     "fmo7_K7_L4": lambda: W.fmo(lmax=4, n_matsubara=0),
     "spin_boson_K2_L10": lambda: W.spin_boson(lmax=10),
