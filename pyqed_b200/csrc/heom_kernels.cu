@@ -1729,7 +1729,7 @@ resident_elem_kernel(const ResidentArgs ra) {
 // Kernel 2 (any N): one CTA per ADO, one thread per matrix element (strided);
 // all operators (H and Q_m) go through their sparsity lists, so cost scales
 // with nnz.  rho_n is staged in shared memory; neighbours are read through L2.
-__global__ void __launch_bounds__(256) stage_generic_kernel(const StageArgs a) {
+__global__ void __launch_bounds__(1024) stage_generic_kernel(const StageArgs a) {
     extern __shared__ double2 smem[];
     const int N = a.N, NN = N * N;
     double2* rho_s = smem;
@@ -2142,7 +2142,9 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
 #undef ROWS_CASE
     } else {
         const int NN = p->N * p->N;
-        int threads = std::min(256, (NN + 31) / 32 * 32);
+        // one thread per matrix element where possible: the per-thread chain of dependent
+        // neighbour loads is what bounds small hierarchies
+        int threads = std::min(1024, (NN + 31) / 32 * 32);
         const size_t smem = sizeof(double2) * NN;
         REQUIRE(smem <= 48 * 1024, "N too large for the generic kernel (N <= 55)");
         dim3 grid((unsigned)std::max(1ll, std::min(p->part_hi - p->part_lo, (long long)sm_count * 32)), p->B);
