@@ -209,7 +209,7 @@ class DEOMSolver:
             ddos_save = out[0]
         if (self.alias_rho0 and isinstance(rho0, np.ndarray) and rho0.dtype == C128
                 and rho0.flags.writeable):
-            rho0[...] = self.ddos[0]
+            rho0[...] = self._rho_sys_final[0]   # only the N x N block, not the whole hierarchy
         return t_save, ddos_save
 
     def run_batch(self, rho0s, dt, nt, p1=None, pulse_system_funcs=None,
@@ -379,7 +379,9 @@ class DEOMSolver:
             t_save[i + 1] = (i + 1) * dt
         if p1 is None:
             out = traj.cpu().numpy()
+            self._rho_sys_final = out[:, -1]
         else:
             out = plan.expectation(traj, np.asarray(p1, dtype=C128))[:, 0, :].cpu().numpy()
+            self._rho_sys_final = traj[:, -1].cpu().numpy()
         self._ddos = None
         return t_save, out
