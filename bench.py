@@ -185,7 +185,8 @@ def cpu_batched_leg(workload_name, budget_s=6.0):
         rho = o.rk4_step(rho, w["dt"], 0.0, o.rhs_batched)
         done += 1
     el = time.perf_counter() - t0
-    return dict(value=o.nmax * done / el, unit=UNIT, cores=os.cpu_count(), kind="port",
+    return dict(value=o.nmax * done / el, unit=UNIT,
+                cores=int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)), kind="port",
                 sample=f"batched-NumPy oracle at depth {depth} ({o.nmax} ADOs), {done} steps in {el:.1f} s")
 
 
