@@ -16,6 +16,9 @@ those fixtures.
 Modules
 -------
 deom_oracle   multi-exponential DEOM (``pyqed/heom/deom.py:555-766, 1048-1114``)
+heom_oracle.c the same DEOM RK4 path in plain C with an OpenMP loop over ADOs
+              (``c_oracle.py`` builds and binds it); checker for mid-size cases
+              and the multi-threaded CPU baseline of ``bench.py``
 chain_oracle  single-exponential chain HEOM, RK4 (``pyqed/HEOM/heom.py:275-347``
               + ``pyqed/phys.py:1051-1064``) and Euler (``pyqed/oqs.py:1808-1875``)
 """
