@@ -191,6 +191,32 @@ def test_mid_size_against_oracle():
         assert np.array_equal(s.keys, o.keys)
 
 
+def test_beyond_l2_against_c_oracle():
+    """Config 3 shape at depth 6 (296 010 ADOs, 232 MB per array: the state no
+    longer fits L2, the per-stage async kernel runs from HBM) against the
+    C/OpenMP oracle, every ADO compared; with and without pulses."""
+    from oracle import c_oracle
+    from pyqed_b200 import workloads as W
+    from pyqed_b200.heom import DEOMSolver, Bath
+    w = W.fmo(lmax=6, n_matsubara=2)
+    nt = 4
+    mu = np.diag(np.linspace(-1.0, 1.0, 7)) * 20.0
+    for pulse in (None, lambda t: np.exp(-((t - 0.02) / 0.01) ** 2)):
+        dip = w["system_dipole"] if pulse is None else mu
+        ref, ref_ados = c_oracle.run(w["system"], dip, w["coupling"], w["coupling_dipole"], w["expn"],
+                                     w["etal"], w["etar"], w["etaa"], w["mode"], w["lmax"], w["rho0"],
+                                     w["dt"], nt, pulse_system=pulse)
+        s = DEOMSolver(w["system"], dip,
+                       Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"],
+                            mode=w["mode"]), w["coupling"], w["coupling_dipole"],
+                       pulse_system_func=pulse, lmax=w["lmax"])
+        _, got = s.run(w["rho0"].copy(), w["dt"], nt)
+        assert s._plan.info("resident_launches") == 0
+        assert np.max(np.abs(np.asarray(got) - ref)) < TOL
+        assert np.max(np.abs(s.ddos - ref_ados)) < TOL
+        del s
+
+
 def test_invariants_large():
     """Size-independent properties on a hierarchy the oracle cannot reach
     (K=21, L=5: 65780 ADOs): trace 1, Hermitian rho_sys, populations in [0,1]."""
