@@ -208,6 +208,10 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *   "hermitian"  when H, Q, the bath (real expn, etar = conj(etal), etaa > 0)
  *                and the loaded state keep every ADO Hermitian, fetch a
  *                neighbour's column entries as the conjugate of its row
+ *   "sym"        async row kernel: when "hermitian" holds and every Q_m has a
+ *                single non-zero diagonal entry, k is Hermitian as well; form
+ *                -i[H, rho] from one product (rho H = (H rho)^dagger) and take a
+ *                link's column update as the conjugate of its row update
  *   "real_h"     use real arithmetic for the H products when H and mu are real
  *   "rk13"       0 = do not use the async row kernel (kernel 3), whose RK4 is in
  *                difference form - the three stage buffers are kept and combined
@@ -218,7 +222,7 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *                (4 = prefer the row-per-lane variant, kernel 4, over the
  *                element-parallel kernel 5)
  *   "debug_sync" synchronise and check after every launch
- * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
+ * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "sym", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
  * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */
 int pyqed_heom_set_option(pyqed_heom_plan* plan, const char* name, int value);
 int64_t pyqed_heom_get_info(pyqed_heom_plan* plan, const char* name);

@@ -109,6 +109,8 @@ struct pyqed_heom_plan {
     bool h_real = false;         // H and mu have no imaginary part
     std::vector<int> r0mode;     // first row with a non-zero diagonal entry, per mode
     int opt_qdiag = -1, opt_herm = -1, opt_hreal = -1, opt_resident = -1;  // -1 auto, 0 off, 1 on
+    int opt_sym = -1;            // async kernel: Hermitian-symmetric shortcuts (0 off)
+    bool single_support = false; // every Q_m has exactly one non-zero diagonal entry
     int opt_rk13 = -1;  // difference-form RK4 in the async kernel (-1/1 on, 0 off)
     long long resident_launches = 0;
     int resident_kind = 0;  // 4 or 5: which resident kernel ran last
@@ -729,7 +731,11 @@ __host__ __device__ inline AsyncTables async_tables(int N, int K, int M, int L, 
     return t;
 }
 
-template <int N, bool TDEP, bool HREAL, bool PUSH>
+// SYM: every ADO is Hermitian and every Q_m has exactly one non-zero diagonal
+// entry.  Then k is Hermitian too, so (i) rho H = (H rho)^dagger and one product
+// gives the commutator, and (ii) a link's column update is the conjugate of its
+// row update; the multi-row branch of the link loop is not compiled at all.
+template <int N, bool TDEP, bool HREAL, bool PUSH, bool SYM>
 __global__ void __launch_bounds__(ASYNC_MAX_THREADS, 1)
 stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
@@ -963,6 +969,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
 
         // ---- -i[H, rho] - damp rho
 #define HEL(r_, c_) (TDEP ? Hs[(r_) * N + (c_)] : hp.v[(r_) * N + (c_)])
+        double2 ccol[SYM ? N : 1];   // SYM: (H rho)[rr][row], this lane's column
         if (on) {
             double2 col[N];
 #pragma unroll
@@ -981,6 +988,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                     }
                 }
                 ksub[rr * LD + row] = c;
+                if constexpr (SYM) ccol[rr] = c;
             }
         }
         __syncwarp();
@@ -991,14 +999,20 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 double2 t = ksub[row * LD + j];
+                if constexpr (SYM) {
+                    // (rho H)[row][j] = conj((H rho)[j][row])
+                    t.x -= ccol[j].x;
+                    t.y += ccol[j].y;
+                } else {
 #pragma unroll
-                for (int l = 0; l < N; ++l) {
-                    if (HREAL) {
-                        const double h = HEL(l, j).x;
-                        t.x = fma(-h, rv[l].x, t.x);
-                        t.y = fma(-h, rv[l].y, t.y);
-                    } else {
-                        cfms(t, rv[l], HEL(l, j));
+                    for (int l = 0; l < N; ++l) {
+                        if (HREAL) {
+                            const double h = HEL(l, j).x;
+                            t.x = fma(-h, rv[l].x, t.x);
+                            t.y = fma(-h, rv[l].y, t.y);
+                        } else {
+                            cfms(t, rv[l], HEL(l, j));
+                        }
                     }
                 }
                 double2 kv = make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
@@ -1042,7 +1056,15 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             v1.x += X.x;
             v1.y += X.y;
             *d1 = v1;
-            if (yused) {
+            if constexpr (SYM) {
+                if (row != cur_rr) {   // column update = conjugate of the row update
+                    double2* d2 = ksub + row * LD + cur_rr;
+                    double2 v2 = *d2;
+                    v2.x += X.x;
+                    v2.y -= X.y;
+                    *d2 = v2;
+                }
+            } else if (yused) {
                 double2* d2 = ksub + row * LD + cur_rr;
                 double2 v2 = *d2;
                 v2.x += Y.x;
@@ -1111,6 +1133,11 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                             X = make_double2(0.0, 0.0);
                             Y = make_double2(0.0, 0.0);
                             yused = false;
+                        }
+                        if constexpr (SYM) {
+                            const double2 c1 = cq_s[3 * heom::meta_kdir(meta) + (row == rr ? 1 : 0)];
+                            cfma(X, make_double2(c1.x * sq, c1.y * sq), Aj);
+                            continue;
                         }
                         const int ns = supp_s[m * (N + 1)];
                         if (ns == 1) {
@@ -1900,7 +1927,7 @@ static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     return post_launch(p, "stage_rows_kernel");
 }
 
-template <int N, bool TDEP, bool HREAL, bool PUSH>
+template <int N, bool TDEP, bool HREAL, bool PUSH, bool SYM>
 static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 2;
@@ -1921,7 +1948,7 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     const size_t smem = table_bytes + per_warp * warps;
     static bool attr_set = false;
     if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP, HREAL, PUSH>,
+        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP, HREAL, PUSH, SYM>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
         attr_set = true;
     }
@@ -1929,19 +1956,23 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     dim3 grid((unsigned)std::min<long long>(ctas, sm_count), p->B);
     HParam<N> hp;
     for (int e = 0; e < NN; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    stage_rows_async_kernel<N, TDEP, HREAL, PUSH><<<grid, warps * 32, smem, p->stream>>>(args, hp);
+    stage_rows_async_kernel<N, TDEP, HREAL, PUSH, SYM><<<grid, warps * 32, smem, p->stream>>>(args, hp);
     return post_launch(p, "stage_rows_async_kernel");
 }
 
-template <int N, bool PUSH>
+template <int N, bool PUSH, bool SYM>
 static int launch_async_p(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool hreal) {
-    if (tdep) return hreal ? launch_async<N, true, true, PUSH>(p, a, sm_count) : launch_async<N, true, false, PUSH>(p, a, sm_count);
-    return hreal ? launch_async<N, false, true, PUSH>(p, a, sm_count) : launch_async<N, false, false, PUSH>(p, a, sm_count);
+    if (tdep) return hreal ? launch_async<N, true, true, PUSH, SYM>(p, a, sm_count) : launch_async<N, true, false, PUSH, SYM>(p, a, sm_count);
+    return hreal ? launch_async<N, false, true, PUSH, SYM>(p, a, sm_count) : launch_async<N, false, false, PUSH, SYM>(p, a, sm_count);
 }
 template <int N>
 static int launch_async_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool hreal) {
-    return a.push_ptr ? launch_async_p<N, true>(p, a, sm_count, tdep, hreal)
-                      : launch_async_p<N, false>(p, a, sm_count, tdep, hreal);
+    const bool sym = a.herm && p->single_support && p->opt_sym != 0;
+    if (a.push_ptr)
+        return sym ? launch_async_p<N, true, true>(p, a, sm_count, tdep, hreal)
+                   : launch_async_p<N, true, false>(p, a, sm_count, tdep, hreal);
+    return sym ? launch_async_p<N, false, true>(p, a, sm_count, tdep, hreal)
+               : launch_async_p<N, false, false>(p, a, sm_count, tdep, hreal);
 }
 
 template <int N>
@@ -2366,6 +2397,7 @@ int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
     const std::string n(name);
     if (n == "qdiag") p->opt_qdiag = value;
     else if (n == "hermitian") p->opt_herm = value;
+    else if (n == "sym") p->opt_sym = value;
     else if (n == "real_h") p->opt_hreal = value;
     else if (n == "resident") p->opt_resident = value;
     else if (n == "rk13") p->opt_rk13 = value;
@@ -2381,6 +2413,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "q_diagonal") return p->q_diagonal;
     if (n == "hermitian") return p->herm_inputs && p->herm_state && p->opt_herm != 0;
     if (n == "hermitian_inputs") return p->herm_inputs && p->opt_herm != 0;
+    if (n == "sym") return p->herm_inputs && p->herm_state && p->opt_herm != 0 && p->single_support && p->opt_sym != 0;
     if (n == "real_h") return p->h_real && p->opt_hreal != 0;
     if (n == "resident_launches") return p->resident_launches;
     if (n == "resident_kind") return p->resident_kind;
@@ -2575,6 +2608,9 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
             }
             supp[(size_t)m * (N + 1)] = (unsigned char)c;
         }
+        p->single_support = diag;
+        for (int m = 0; m < p->M; ++m)
+            if (supp[(size_t)m * (N + 1)] != 1) p->single_support = false;
         p->r0mode.assign(p->M, 0);
         for (int m = 0; m < p->M; ++m) p->r0mode[m] = supp[(size_t)m * (N + 1)] ? supp[(size_t)m * (N + 1) + 1] : 0;
         p->h_real = true;

@@ -98,15 +98,21 @@ def test_warps_per_cta(warps, kernel):
 @pytest.mark.parametrize("kernel", [1, 3])
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L3", "deom_spin_boson_L10",
                                   "deom_aggregate_L3_T0"])
-@pytest.mark.parametrize("herm", [-1, 0])
-def test_row_kernels_on_diagonal_coupling(name, kernel, herm):
+@pytest.mark.parametrize("herm,sym", [(-1, -1), (-1, 0), (0, -1)])
+def test_row_kernels_on_diagonal_coupling(name, kernel, herm, sym):
     """Both row kernels (plain loads / cp.async staging), with and without
-    the Hermitian row fetch, on projector, sigma_z and occupation couplings."""
+    the Hermitian row fetch and the Hermitian-symmetric shortcuts of the async
+    kernel, on projector, sigma_z and occupation couplings."""
     g = golden(name)
     s = _solver_from(g)
     s.tuning = dict(kernel=kernel, warps_per_cta=0, use_graph=0)
-    s.options = {"hermitian": herm}
+    s.options = {"hermitian": herm, "sym": sym}
     _check_against_golden(g, s)
+    assert s._plan.info("resident_launches") == 0
+    if "fmo" in name:   # projector couplings: one support row per mode
+        assert s._plan.info("sym") == (1 if herm != 0 and sym != 0 else 0)
+    if "spin_boson" in name:   # sigma_z has two non-zero diagonal entries
+        assert s._plan.info("sym") == 0
 
 
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L2", "deom_spin_boson_L10",
