@@ -645,6 +645,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16_s(unsigned smem_dst_u32, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst_u32), "l"(gsrc) : "memory");
+}
 // same with an L2 eviction-priority hint (createpolicy): the stage input and the
 // neighbour rows are the only data with reuse (evict_last), y/acc are read once
 // per launch (evict_first)
@@ -746,8 +749,9 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     constexpr int EIT = (FLAT + 31) / 32;
     extern __shared__ double2 smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int b = blockIdx.y;
-    const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
+    // one launch per trajectory: the host passes array, operator and trajectory
+    // pointers of this batch entry, so no batch offset is carried (or rebuilt) here
+    const double2* __restrict__ ops = a.ops;
     const AsyncTables T = async_tables(N, a.nind, a.nmod, a.lmax, TDEP);
     double2* Hs = smem + T.H;
     double2* cb_s = smem + T.cb;
@@ -798,9 +802,9 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     }
     __syncthreads();
     const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
-    const long long boff = (long long)b * a.nmax * NN;
-    const double2* __restrict__ yin = a.yin + boff;
+    const double2* __restrict__ yin = a.yin;
     const int sub = lane / N, row = lane - sub * N;
+    // neighbour rows are addressed with 32-bit element offsets (host checks nmax N^2 < 2^32)
     const bool lane_ok = lane < APW * N;
     const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
     const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
@@ -809,9 +813,11 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     const unsigned long long pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 #define CP_KEEP(d_, s_) cp_async16_hint(d_, s_, pol_keep)
 #define CP_STREAM(d_, s_) cp_async16_hint(d_, s_, pol_stream)
+#define CP_ROW(t_, s_) cp_async16_hint(nbrow + (t_) * N, s_, pol_keep)
 #else
 #define CP_KEEP(d_, s_) cp_async16(d_, s_)
 #define CP_STREAM(d_, s_) cp_async16(d_, s_)
+#define CP_ROW(t_, s_) cp_async16_s(nbrow_u32 + (t_) * (N * 16), s_)
 #endif
     // flat element e = lane + 32 it  ->  offset in the (possibly padded) tile
     int pofs[EIT];
@@ -827,6 +833,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
     double2* const ksub = k_s + sub * N * LD;     // this ADO's k tile
     double2* const rsub = rho_s + sub * N * LD;
     double2* const nbrow = nb_s + sub * NN + row; // + t*N: row element of staged link t
+    const unsigned nbrow_u32 = smem_u32(nbrow);   // the same as a shared-window address for cp.async
 
     // Bookkeeping pipeline, carried in registers across iterations so that no
     // dependent global load sits on the critical path of a group:
@@ -893,7 +900,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
         const double2 d = nx_damp;
         const int pb = nx_pb, npush = on ? (nx_pe - nx_pb) : 0, pent = nx_pent;
         int2 rts[N];
-        const long long gbase = boff + base * NN;
+        const long long gbase = base * NN;
         // next group's records / damping (offsets arrived during the previous
         // iteration), and the offsets of the group after that
         nx_lbeg = nn_lbeg;
@@ -933,8 +940,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
             rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
             rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
             if (!BULK_ROWS && t < nl)
-                CP_KEEP(nbrow + t * N,
-                        yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
+                CP_ROW(t,
+                        yin + (((unsigned)rts[t].x * (unsigned)N + (unsigned)heom::meta_r0(rts[t].y)) * (unsigned)N + (unsigned)row));
         }
         cp_async_commit();
         if (!a.first) {
@@ -1093,8 +1100,8 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                     rts[t].x = __shfl_sync(0xffffffffu, rec.x, srcl);
                     rts[t].y = __shfl_sync(0xffffffffu, rec.y, srcl);
                     if (!BULK_ROWS && c0 + t < nl)
-                        CP_KEEP(nbrow + t * N,
-                                yin + ((long long)rts[t].x * NN + heom::meta_r0(rts[t].y) * N + row));
+                        CP_ROW(t,
+                                yin + (((unsigned)rts[t].x * (unsigned)N + (unsigned)heom::meta_r0(rts[t].y)) * (unsigned)N + (unsigned)row));
                 }
                 if (BULK_ROWS) {
                     const int mine = (on && row == 0) ? max(0, min(nl - c0, N)) : 0;
@@ -1222,7 +1229,7 @@ stage_rows_async_kernel(const StageArgs a, const __grid_constant__ HParam<N> hp)
                     outv = res;
                     st_stream(a.ydst + gi, res);
                     if (a.traj && base + e / NN == a.slot0)
-                        a.traj[b * a.traj_bstride + (step + 1) * NN + e % NN] = res;
+                        a.traj[(step + 1) * NN + e % NN] = res;
                 } else {
                     const double2 yv = a.first ? rho_s[pofs[it]] : y_s[e];
                     outv = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
@@ -1881,11 +1888,16 @@ __global__ void __launch_bounds__(1024) stage_generic_kernel(const StageArgs a) 
 // host side
 // ---------------------------------------------------------------------------
 // 13-pass difference form of RK4: only the async row kernel implements it
-static bool rk_scheme(const pyqed_heom_plan* p) {
-    const int kern = (p->kernel && p->kernel != 4) ? p->kernel
-                                                   : (p->N <= 8 ? ((p->use_qdiag && p->opt_rk13 != 0) ? 3 : 1) : 2);
-    return kern == 3;
+// Stage kernel of this plan: the explicit choice, else the async row kernel for
+// diagonal coupling (its neighbour rows use 32-bit element offsets, so only while
+// nmax N^2 < 2^32), the plain row kernel for other N <= 8, the generic kernel above.
+static int stage_kernel_of(const pyqed_heom_plan* p) {
+    if (p->kernel && p->kernel != 4) return p->kernel;
+    if (p->N > 8) return 2;
+    const bool fits32 = (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
+    return (p->use_qdiag && p->opt_rk13 != 0 && fits32) ? 3 : 1;
 }
+static bool rk_scheme(const pyqed_heom_plan* p) { return stage_kernel_of(p) == 3; }
 
 static int post_launch(pyqed_heom_plan* p, const char* what) {
     p->launches++;
@@ -1942,9 +1954,11 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     int warps = p->warps > 0 ? std::min(p->warps, maxw) : maxw;
     if (p->warps <= 0) {
         // small hierarchies: spread the groups over all SMs first
-        const long long per_sm = (args.ngroups * p->B + sm_count - 1) / sm_count;
+        const long long per_sm = (args.ngroups + sm_count - 1) / sm_count;
         warps = (int)std::max<long long>(1, std::min<long long>(maxw, per_sm));
     }
+    REQUIRE((unsigned long long)p->nmax * NN < (1ull << 32),
+            "hierarchy too large for the async row kernel's 32-bit element offsets (use kernel 1)");
     const size_t smem = table_bytes + per_warp * warps;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1953,11 +1967,26 @@ static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
         attr_set = true;
     }
     const long long ctas = (args.ngroups + warps - 1) / warps;
-    dim3 grid((unsigned)std::min<long long>(ctas, sm_count), p->B);
+    dim3 grid((unsigned)std::min<long long>(ctas, sm_count), 1);
     HParam<N> hp;
     for (int e = 0; e < NN; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    stage_rows_async_kernel<N, TDEP, HREAL, PUSH, SYM><<<grid, warps * 32, smem, p->stream>>>(args, hp);
-    return post_launch(p, "stage_rows_async_kernel");
+    // one launch per trajectory of the batch, each with its own array / operator /
+    // trajectory pointers: the kernel then carries no batch offset
+    const long long boff = p->nmax * NN;
+    for (int b = 0; b < p->B; ++b) {
+        stage_rows_async_kernel<N, TDEP, HREAL, PUSH, SYM><<<grid, warps * 32, smem, p->stream>>>(args, hp);
+        int rc = post_launch(p, "stage_rows_async_kernel");
+        if (rc) return rc;
+        args.yin += boff;
+        args.y += boff;
+        args.acc += boff;
+        args.yout += boff;
+        args.ydst += boff;
+        args.ops += args.ops_bstride;
+        if (args.traj) args.traj += args.traj_bstride;
+        args.out_elem_off += boff;
+    }
+    return 0;
 }
 
 template <int N, bool PUSH, bool SYM>
@@ -2188,8 +2217,7 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
         CU_TRY(cudaEventRecord(p->ev[p->ev_used].first, p->stream));
     }
     int rc = 0;
-    const int kern = (p->kernel && p->kernel != 4) ? p->kernel
-                                                   : (p->N <= 8 ? ((p->use_qdiag && p->opt_rk13 != 0) ? 3 : 1) : 2);
+    const int kern = stage_kernel_of(p);
     if (kern == 3 && a.first && a.last) {
         // single-stage (Euler) update: the async kernel only implements the difference-form
         // RK4 stages, so the plain-load row kernel takes it

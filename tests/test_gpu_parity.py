@@ -160,10 +160,15 @@ def test_chain_solver_matches_reference(tag):
     assert err < TOL, err
 
 
-def test_batch_of_waiting_times():
-    """Config 5 shape: trajectories that differ only in their field table."""
+@pytest.mark.parametrize("kernel", [0, 1, 3])
+def test_batch_of_waiting_times(kernel):
+    """Config 5 shape: trajectories that differ only in their field table
+    (kernel 0: one resident launch; 1, 3: per-stage row kernels - the async one
+    is launched once per trajectory with that trajectory's pointers)."""
     ga, gb = golden("deom_aggregate_L3_T0"), golden("deom_aggregate_L3_T37")
     s = _solver_from(ga)
+    if kernel:
+        s.tuning = dict(kernel=kernel, warps_per_cta=0, use_graph=0)
     dt, nt = float(ga["dt"]), int(ga["nt"])
     fa = pulse_from_samples(ga["pulse_system"], dt)
     fb = pulse_from_samples(gb["pulse_system"], dt)
