@@ -219,7 +219,68 @@ def save_generator():
     np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
 
 
+def _extract_class_member(path, cls, member, ns):
+    """Compile one method of a reference class as a plain function (``member`` None:
+    the whole class)."""
+    tree = ast.parse(open(path).read())
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            if member is None:
+                exec(compile(ast.Module([node], []), path, "exec"), ns)
+                return ns[cls]
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == member:
+                    exec(compile(ast.Module([sub], []), path, "exec"), ns)
+                    return ns[member]
+    raise KeyError((cls, member))
+
+
+def save_polariton():
+    """Hamiltonians of the reference's cavity-molecule model builder
+    (``Cavity``, ``Polariton.getH``; ``pyqed/polariton/cavity.py:404-678``) for a
+    two-level molecule and for a three-level ladder, RWA on and off."""
+    import warnings
+    from scipy.sparse import identity, kron, lil_matrix
+    path = f"{REF}/pyqed/polariton/cavity.py"
+    ns = dict(np=np, identity=identity, kron=kron, lil_matrix=lil_matrix, dag=ref_phys.dag,
+              ket2dm=ref_phys.ket2dm, Mol=object)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _extract(path, "ham_ho", ns)
+        Cavity = _extract_class_member(path, "Cavity", None, ns)
+        getH = _extract_class_member(path, "Polariton", "getH", ns)
+    out = {}
+    cases = {
+        "two_level": (np.diag([0.5, -0.5]).astype(complex), np.array([[0, 1], [1, 0]], dtype=complex),
+                      np.array([[0, 0], [1, 0]], dtype=complex), 1.0, 16, 0.1),
+        "ladder3": (np.diag([0.0, 0.9, 2.1]).astype(complex),
+                    np.array([[0, 1, 0.2], [1, 0, 0.7], [0.2, 0.7, 0]], dtype=complex),
+                    np.array([[0, 1, 0.2], [0, 0, 0.7], [0, 0, 0]], dtype=complex), 0.95, 5, 0.3),
+    }
+    for tag, (hmol, edip, lowering, wc, ncav, g) in cases.items():
+        mol = SimpleNamespace(getH=lambda h=hmol: h, edip=edip, idm=identity(hmol.shape[0]),
+                              lowering=lowering, raising=lowering.conj().T, dim=hmol.shape[0])
+        cav = Cavity(wc, ncav)
+        for rwa in (False, True):
+            me = SimpleNamespace(mol=mol, cav=cav, _g=g, gauge="length", H=None)
+            H = getH(me, RWA=rwa)
+            H = H.toarray() if hasattr(H, "toarray") else np.asarray(H)
+            out[f"{tag}_H_rwa{int(rwa)}"] = H
+        out[f"{tag}_hmol"], out[f"{tag}_edip"], out[f"{tag}_lowering"] = hmol, edip, lowering
+        out[f"{tag}_params"] = np.array([wc, ncav, g])
+        out[f"{tag}_create"] = cav.create().toarray()
+        out[f"{tag}_annihilate"] = cav.annihilate().toarray()
+        out[f"{tag}_num"] = cav.get_number_operator().toarray()
+        out[f"{tag}_hcav"] = np.asarray(cav.getH())
+        out[f"{tag}_vacuum_dm"] = np.asarray(cav.get_dm())
+    np.savez_compressed(os.path.join(HERE, "polariton.npz"), **out)
+    print("polariton.npz", sorted(out))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "polariton":
+        save_polariton()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "propagators":
         save_propagators()
         return
