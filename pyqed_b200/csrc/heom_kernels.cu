@@ -26,6 +26,8 @@
 
 #include "../../include/pyqed_heom.h"
 #include "heom_core.cuh"
+#include "heom_device.cuh"
+#include "heom_stage_sym.cuh"
 
 using heom::Pascal;
 
@@ -66,31 +68,11 @@ static int fail(const std::string& msg) {
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ---------------------------------------------------------------------------
-// complex helpers (double2 = re, im)
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void cfma(double2& acc, const double2 a, const double2 b) {
-    acc.x = fma(a.x, b.x, acc.x);
-    acc.x = fma(-a.y, b.y, acc.x);
-    acc.y = fma(a.x, b.y, acc.y);
-    acc.y = fma(a.y, b.x, acc.y);
-}
-__device__ __forceinline__ void cfms(double2& acc, const double2 a, const double2 b) {  // acc -= a*b
-    acc.x = fma(-a.x, b.x, acc.x);
-    acc.x = fma(a.y, b.y, acc.x);
-    acc.y = fma(-a.x, b.y, acc.y);
-    acc.y = fma(-a.y, b.x, acc.y);
-}
-__device__ __forceinline__ double2 cmul(const double2 a, const double2 b) {
-    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
-
-// ---------------------------------------------------------------------------
 // plan
 // ---------------------------------------------------------------------------
 struct TableLayout {
     size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
-        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, lex2slot, slot2lex, step_base, total;
+        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, lex2slot, slot2lex, step_base, links2, total;
 };
 
 struct pyqed_heom_plan {
@@ -113,6 +95,9 @@ struct pyqed_heom_plan {
     bool single_support = false; // every Q_m has exactly one non-zero diagonal entry
     int opt_rk13 = -1;  // difference-form RK4 in the async kernel (-1/1 on, 0 off)
     long long resident_launches = 0;
+    long long sym_launches = 0;  // stage launches that went to kernel 6
+    bool links2_built = false;
+    size_t bound_table_bytes = 0;
     int resident_kind = 0;  // 4 or 5: which resident kernel ran last
     TableLayout tl{};
     char* d_tables = nullptr;
@@ -178,6 +163,8 @@ static int compute_layout(pyqed_heom_plan* p) {
     t.lex2slot = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
     t.slot2lex = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
     t.step_base = take(sizeof(long long));
+    // second link table of kernel 6 (heom_stage_sym.cuh), only when that kernel was asked for
+    t.links2 = take(p->kernel == 6 ? sizeof(int2) * (size_t)std::max(1ll, p->nlinks) : 0);
     t.total = off;
     p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
     return 0;
@@ -361,52 +348,6 @@ __global__ void expectation_kernel(double2* out, const double2* rho, const doubl
 // ---------------------------------------------------------------------------
 // stage kernels
 // ---------------------------------------------------------------------------
-struct StageArgs {
-    const double2* yin;   // stage input (read-only in this launch)
-    const double2* y;     // state at the start of the step
-    double2* acc;         // running combination
-    double2* yout;        // next stage input (unused when last)
-    double2* ydst;        // end-of-step state (used when last)
-    const double2* damp;
-    const int* link_ptr;
-    const int2* links;
-    const double2* coef;  // [ci] -> (alphaL, alphaR)
-    const double2* ops;   // [b][1+M][N*N] operators at this stage time
-    long long ops_bstride;
-    const short* row_ptr;
-    const short* row_idx;
-    const short* col_ptr;
-    const short* col_idx;
-    const unsigned char* supp;  // diagonal-Q tables: [M][N+1] (count, rows) then [M][N] membership
-    double2* traj;        // may be null
-    const long long* step_base;
-    long long traj_bstride;
-    long long nmax, slot0, ngroups;
-    long long slot_lo, slot_hi;  // owned slot range of this rank (whole hierarchy on one GPU)
-    double a, w;
-    int local_step, first, last, N;
-    int scramble;  // rotate the visiting order inside runs of 16 groups (storage order 2)
-    int scheme;  // 0: running accumulator (16 passes/step); 1: difference form (13 passes/step, async kernel)
-    int herm, ncoef, nmod, nind, lmax;
-    const double2* cbase;  // [K][4]: minus (L,R) and plus (L,R) coefficients for n_eff = 1
-    const int* kmode;      // [K]: mode | first support row << 8
-    // fused multi-GPU halo (async kernel): rows of the stage output that other
-    // ranks need are stored into their arrays by the epilogue
-    const int* push_ptr;            // [owned+1] CSR over the owned slots, or null
-    const unsigned char* push_ent;  // entries: peer << 4 | row (15 = every row)
-    const unsigned long long* peer; // [world] base address of every rank's state buffer (device array)
-    long long out_elem_off;         // offset (double2) of this stage's output array in the state buffer
-};
-
-template <int N>
-struct HParam {
-    double2 v[N * N];
-};
-
-// streaming (evict-first) accesses for the arrays that are touched once per launch
-__device__ __forceinline__ double2 ld_stream(const double2* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(double2* p, const double2 v) { __stcs(p, v); }
-
 // Kernel 1 (N <= 8): a warp owns 32/N consecutive ADOs; lane (sub,row) owns one
 // matrix row in registers.  -i[H,rho] uses H from the constant bank (kernel
 // parameter) or, when H depends on time/trajectory, from shared memory.
@@ -641,69 +582,6 @@ __global__ void __launch_bounds__(256, HEOM_MINBLOCKS) stage_rows_kernel(const S
 // y' = -y/3 + S1/3 + 2 S2/3 + S3/3 + dt/6 k4, so no accumulator array is read or
 // written: 13 array passes per step instead of 16.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16_s(unsigned smem_dst_u32, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst_u32), "l"(gsrc) : "memory");
-}
-// same with an L2 eviction-priority hint (createpolicy): the stage input and the
-// neighbour rows are the only data with reuse (evict_last), y/acc are read once
-// per launch (evict_first)
-__device__ __forceinline__ void cp_async16_hint(void* smem_dst, const void* gsrc, unsigned long long pol) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-    unsigned long long p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
-    return p;
-}
-// ---- TMA bulk copies (cp.async.bulk, 1-D) completing on an mbarrier: the
-// contiguous tiles of a group (own y_in, y, stage buffers) are fetched with one
-// instruction each by one lane instead of 16 bytes per lane per LDGSTS
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int NWAIT>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(NWAIT) : "memory");
-}
-
 #ifndef HEOM_ASYNC_THREADS
 #define HEOM_ASYNC_THREADS 512
 #endif
@@ -1892,7 +1770,8 @@ __global__ void __launch_bounds__(1024) stage_generic_kernel(const StageArgs a) 
 // diagonal coupling (its neighbour rows use 32-bit element offsets, so only while
 // nmax N^2 < 2^32), the plain row kernel for other N <= 8, the generic kernel above.
 static int stage_kernel_of(const pyqed_heom_plan* p) {
-    if (p->kernel && p->kernel != 4) return p->kernel;
+    // 6 = kernel 3's scheme and buffers; launch_stage hands the eligible stages to kernel 6
+    if (p->kernel && p->kernel != 4 && p->kernel != 6) return p->kernel;
     if (p->N > 8) return 2;
     const bool fits32 = (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
     return (p->use_qdiag && p->opt_rk13 != 0 && fits32) ? 3 : 1;
@@ -2201,6 +2080,62 @@ static int try_resident(pyqed_heom_plan* p) {
     return rcode;
 }
 
+// kernel 6 (heom_stage_sym.cu) takes the difference-form RK4 stages of kernel 3 when every
+// ADO is Hermitian, every Q_m has one non-zero diagonal entry, H does not depend on time and
+// no fused halo push is requested; everything else stays with kernel 3
+static bool sym_eligible(const pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
+    return p->kernel == 6 && p->links2_built && !tdep && a.herm && p->single_support && p->opt_sym != 0 &&
+           !a.push_ptr && a.scheme == 1 && !(a.first && a.last);
+}
+static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
+    SymLaunch s{};
+    s.a.yin = a.yin;
+    s.a.y = a.y;
+    s.a.s1 = a.acc;    // last stage: first stage buffer
+    s.a.s2 = a.yout;   // last stage: second stage buffer
+    s.a.out = a.last ? a.ydst : a.yout;
+    s.a.damp = a.damp;
+    s.a.link_ptr = a.link_ptr;
+    s.a.links2 = p->tab<int2>(p->tl.links2);
+    s.a.cbase = a.cbase;
+    s.a.kmode = a.kmode;
+    s.a.ops = a.ops;
+    s.a.traj = a.last ? a.traj : nullptr;
+    s.a.step_base = a.step_base;
+    s.a.slot0 = a.slot0;
+    s.a.a = a.a;
+    s.a.w = a.w;
+    s.a.local_step = a.local_step;
+    s.a.scramble = a.scramble;
+    s.a.nind = a.nind;
+    s.a.nmod = a.nmod;
+    s.a.lmax = a.lmax;
+    s.H = reinterpret_cast<const double*>(p->H.data());
+    s.N = p->N;
+    s.K = p->K;
+    s.M = p->M;
+    s.L = p->L;
+    s.B = p->B;
+    s.stage = a.first ? 0 : (a.last ? 2 : 1);
+    s.hreal = (p->h_real && p->opt_hreal != 0) ? 1 : 0;
+    s.warps = p->warps;
+    s.sm_count = sm_count;
+    s.part_lo = p->part_lo;
+    s.part_hi = p->part_hi;
+    s.batch_elems = p->nmax * p->N * p->N;
+    s.traj_bstride = a.traj_bstride;
+    s.stream = p->stream;
+    const char* err = "";
+    if (heom_sym_launch(s, &err)) return fail(std::string("stage_rows_sym_kernel launch: ") + err);
+    p->launches += p->B;
+    p->sym_launches++;
+    if (p->debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) return fail(std::string("stage_rows_sym_kernel exec: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
 static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     if (p->part_hi <= p->part_lo) return 0;  // this rank owns nothing (tiny hierarchy, many ranks)
     static int sm_count = 0;
@@ -2218,7 +2153,9 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     }
     int rc = 0;
     const int kern = stage_kernel_of(p);
-    if (kern == 3 && a.first && a.last) {
+    if (kern == 3 && sym_eligible(p, a, tdep)) {
+        rc = launch_sym(p, a, sm_count);
+    } else if (kern == 3 && a.first && a.last) {
         // single-stage (Euler) update: the async kernel only implements the difference-form
         // RK4 stages, so the plain-load row kernel takes it
         switch (p->N) {
@@ -2412,7 +2349,7 @@ int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
 
 int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
     REQUIRE(p, "null plan");
-    REQUIRE(kernel >= 0 && kernel <= 4, "kernel must be 0..4");
+    REQUIRE((kernel >= 0 && kernel <= 4) || kernel == 6, "kernel must be 0..4 or 6");
     REQUIRE(warps >= 0 && warps <= 8, "warps_per_cta must be in [0, 8]");
     p->kernel = kernel;
     p->warps = warps;
@@ -2445,6 +2382,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "real_h") return p->h_real && p->opt_hreal != 0;
     if (n == "resident_launches") return p->resident_launches;
     if (n == "resident_kind") return p->resident_kind;
+    if (n == "sym_launches") return p->sym_launches;
     if (n == "rk_scheme") return rk_scheme(p) ? 1 : 0;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
@@ -2481,6 +2419,7 @@ int pyqed_heom_bind(pyqed_heom_plan* p, void* d_tables, size_t table_bytes, void
     REQUIRE(((uintptr_t)d_tables % 256) == 0 && ((uintptr_t)d_state % 256) == 0,
             "bind: buffers must be 256-byte aligned");
     p->d_tables = (char*)d_tables;
+    p->bound_table_bytes = table_bytes;
     p->d_state = (char*)d_state;
     p->stream = (cudaStream_t)stream;
     p->bound = true;
@@ -2712,6 +2651,19 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
                                           std::to_string(total_links) + " vs " +
                                           std::to_string(p->nlinks) + ")");
     p->slot0 = slot0;
+    p->links2_built = false;
+    if (p->kernel == 6 && N <= 8 && p->use_qdiag && p->single_support) {
+        const char* err = "";
+        if (heom_sym_supported(N, K, p->M, L, &err) == 0 &&
+            (unsigned long long)p->nmax * NN < (1ull << 32) &&
+            t.links2 + sizeof(int2) * (size_t)p->nlinks <= p->bound_table_bytes) {   // kernel chosen before bind
+            if (heom_sym_convert_links(h.links, p->tab<int2>(t.links2), p->nlinks, N, L, s, &err))
+                return fail(std::string("sym_convert_links_kernel launch: ") + err);
+            p->launches++;
+            CU_TRY(cudaStreamSynchronize(s));
+            p->links2_built = true;
+        }
+    }
     if (p->part_hi <= p->part_lo) {
         p->part_lo = 0;
         p->part_hi = p->nmax;

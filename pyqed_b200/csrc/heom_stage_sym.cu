@@ -1,0 +1,509 @@
+// heom_stage_sym.cu - kernel 6: Hermitian-symmetric RK4 stage kernel for N <= 8
+// with projector-like (diagonal, one non-zero entry) coupling operators.
+//
+// Evaluates, for every owned ADO n (generate_dot_element, pyqed/heom/deom.py:641-664),
+//     k_n = -(sum_k n_k gamma_k) rho_n - i[H, rho_n]
+//           - i sum_k sqrt(n_k)/sqrt(a_k) (eta_k Q_m rho_{n-e_k} - conj(eta_k) rho_{n-e_k} Q_m)
+//           - i sum_k sqrt(n_k+1) sqrt(a_k) [Q_m, rho_{n+e_k}]
+// and applies the stage update of the difference-form RK4 (rk4, deom.py:725-766;
+// DESIGN.md section 4) in the same pass.  See heom_stage_sym.cuh for what differs
+// from kernel 3; the arithmetic and its order are kernel 3's.
+//
+// Work split: persistent CTAs (one per SM); a warp owns APW = 32/N consecutive
+// ADOs ("group"), lane = (ADO sub, matrix row).  Per group:
+//   1. the group's link records (prefetched one group ahead into registers by a
+//      coalesced load) are published in the warp's shared-memory strip;
+//   2. own tile by one bulk copy (odd N) or cp.async, first chunk of neighbour
+//      rows by cp.async (16N bytes per link), y / stage buffers by bulk copies;
+//   3. -i[H,rho] with one product (rho H = (H rho)^dagger), damping;
+//   4. neighbour terms: (Q rho' - rho' Q) touches row r0 and column r0 only and the
+//      column update is the conjugate of the row update; contributions to one
+//      target row are summed in registers and flushed once;
+//   5. epilogue from shared memory with streaming stores.
+#ifndef HEOM_HOST_EMU
+#include <cuda_runtime.h>
+#endif
+
+#include <algorithm>
+
+#include "heom_core.cuh"
+#include "heom_stage_sym.cuh"
+
+#ifndef HEOM_SYM_THREADS
+#define HEOM_SYM_THREADS 512       // first / middle stage: 16 warps, 128 registers
+#endif
+#ifndef HEOM_SYM_LAST_THREADS
+#define HEOM_SYM_LAST_THREADS 448  // last stage stages one more tile per warp: 14 warps, 144 registers
+#endif
+
+namespace {
+
+constexpr int SYM_NCH = 4;   // link chunks (of N links) whose records are prefetched per ADO
+
+// per-warp shared memory in double2 units
+__host__ __device__ constexpr int sym_perwarp(int N, int stage) {
+    const int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD, FLAT = APW * NN;
+    // own tile, k tile, neighbour rows, [y], [first stage buffer], record strip, four mbarriers
+    return 2 * TILE + FLAT + (stage == 0 ? 0 : FLAT) + (stage == 2 ? FLAT : 0) + SYM_NCH * APW * N / 2 + 2;
+}
+__host__ __device__ constexpr int sym_max_threads(int stage) {
+    return stage == 2 ? HEOM_SYM_LAST_THREADS : HEOM_SYM_THREADS;
+}
+
+template <int N, bool HREAL, int STAGE>
+__global__ void __launch_bounds__(sym_max_threads(STAGE), 1)
+stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
+    constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
+    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
+    constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE), NCH = SYM_NCH;
+    constexpr bool BULK_TILE = (LD == N);   // padded tiles cannot be one bulk copy
+    constexpr int EIT = (FLAT + 31) / 32;
+    HEOM_DYN_SMEM(double2, smem);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int L1 = a.lmax + 1, ncq = 2 * a.nind * L1;
+    // coefficient pairs per (2k+dir, n_eff): [0] element off the diagonal, [1] the diagonal
+    // element (row == r0), both already times sqrt(n_eff)
+    double2* cq_s = smem;
+    double2* rho_s = smem + 2 * ncq + wid * PERWARP;
+    double2* k_s = rho_s + TILE;
+    double2* nb_s = k_s + TILE;
+    double2* y_s = nb_s + FLAT;                       // !FIRST
+    double2* acc_s = y_s + (FIRST ? 0 : FLAT);        // LAST
+    int2* strip = (int2*)(acc_s + (LAST ? FLAT : 0));
+    unsigned long long* barA = (unsigned long long*)(strip + NCH * APW * N);   // own tile
+    unsigned long long* barB = barA + 1;                                       // y / first stage buffer
+    unsigned long long* barD = barA + 2;                                       // second stage buffer
+    unsigned phA = 0, phB = 0, phD = 0;
+    if (lane == 0) {
+        mbar_init(barA, 1);
+        mbar_init(barB, 1);
+        mbar_init(barD, 1);
+        fence_proxy_async();
+    }
+    for (int e = threadIdx.x; e < ncq; e += blockDim.x) {
+        const int kd = e / L1, n = e - kd * L1;
+        const int k = kd >> 1, dir = kd & 1;
+        const int m = a.kmode[k] & 0xff, r0 = a.kmode[k] >> 8;
+        const double2 q = a.ops[(1 + m) * NN + r0 * N + r0];
+        const double2 bL = a.cbase[4 * k + 2 * dir], bR = a.cbase[4 * k + 2 * dir + 1];
+        const double2 c0 = cmul(bL, q);
+        const double2 c1 = cmul(make_double2(bL.x + bR.x, bL.y + bR.y), q);
+        const double sq = sqrt((double)n);
+        cq_s[2 * e] = make_double2(c0.x * sq, c0.y * sq);
+        cq_s[2 * e + 1] = make_double2(c1.x * sq, c1.y * sq);
+    }
+    __syncthreads();
+
+    const int sub = lane / N, row = lane - sub * N;
+    const bool lane_ok = lane < APW * N;
+    const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
+    const long long step = (LAST && a.traj) ? (*a.step_base + a.local_step) : 0;
+    const long long gstride = (long long)gridDim.x * nwarps;
+    // flat element e = lane + 32 it  ->  offset in the (possibly padded) tile
+    int pofs[EIT];
+#pragma unroll
+    for (int it = 0; it < EIT; ++it) {
+        const int e = lane + 32 * it;
+        if (LD == N) pofs[it] = e;
+        else {
+            const int s = e / NN, r = e - s * NN, i = r / N, j = r - i * N;
+            pofs[it] = (s * N + i) * LD + j;
+        }
+    }
+    double2* const ksub = k_s + sub * N * LD;     // this ADO's k tile
+    double2* const rsub = rho_s + sub * N * LD;
+    const double2* const nbrow = nb_s + sub * NN + row;   // + t*N: row element of staged link t
+    const unsigned nbrow_u32 = smem_u32(nbrow);
+    // + (c*APW*N + t): record t of chunk c (idle lanes stay inside the strip)
+    const int2* const strip_sub = strip + (lane_ok ? sub * N : 0);
+    const double2* const yin_row = a.yin + row;           // + links2.x: this lane's element of the neighbour row
+    const char* const cq_row = (const char*)cq_s;
+
+    // Bookkeeping pipeline carried in registers: link offsets two groups ahead,
+    // damping rate and the first NCH*N link records one group ahead.
+    long long g = (long long)blockIdx.x * nwarps + wid;
+    int nx_lbeg = 0, nx_lend = 0, nn_lbeg = 0, nn_lend = 0;
+    int2 nx_rec[NCH];
+    double2 nx_damp = make_double2(0.0, 0.0);
+    // visiting order: see stage_rows_async_kernel (rotation inside runs of 16 groups)
+    const long long gfull = a.scramble ? (a.ngroups & ~15ll) : 0;
+    auto gmap = [&](long long gg) {
+        const unsigned rot = ((unsigned)(gg >> 4) * 2654435761u) >> 28;
+        return gg < gfull ? ((gg & ~15ll) | ((gg + rot) & 15ll)) : gg;
+    };
+    auto fetch_ptr = [&](long long gg, int& lb, int& le) {
+        const long long slot = a.slot_lo + gmap(gg) * APW + sub;
+        lb = le = 0;
+        if (gg < a.ngroups && lane_ok && slot < a.slot_hi) {
+            lb = a.link_ptr[slot];
+            le = a.link_ptr[slot + 1];
+        }
+    };
+    auto fetch_rec = [&](long long gg, int lb, int le) {
+        const long long slot = a.slot_lo + gmap(gg) * APW + sub;
+        if (gg < a.ngroups && lane_ok && slot < a.slot_hi) nx_damp = a.damp[slot];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            nx_rec[c] = make_int2(0, 0);
+            if (lb + c * N + row < le) nx_rec[c] = __ldg(a.links2 + lb + c * N + row);
+        }
+    };
+    fetch_ptr(g, nx_lbeg, nx_lend);
+    fetch_rec(g, nx_lbeg, nx_lend);
+    fetch_ptr(g + gstride, nn_lbeg, nn_lend);
+
+    for (; g < a.ngroups; g += gstride) {
+        const long long base = a.slot_lo + gmap(g) * APW;
+        const int cnt = (int)min((long long)APW, a.slot_hi - base);
+        const int nelem = cnt * NN;
+        const bool on = lane_ok && sub < cnt;
+        const int lbeg = nx_lbeg, lend = nx_lend;
+        const int nl = on ? (lend - lbeg) : 0;
+        const double2 d = nx_damp;
+        const long long gbase = base * NN;
+        // publish this group's records, then start the prefetch of the next group's
+        if (lane_ok) {
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) strip[(c * APW + sub) * N + row] = nx_rec[c];
+        }
+        nx_lbeg = nn_lbeg;
+        nx_lend = nn_lend;
+        fetch_rec(g + gstride, nx_lbeg, nx_lend);
+        fetch_ptr(g + 2 * gstride, nn_lbeg, nn_lend);
+
+        // ---- issue: own tile + first chunk of neighbour rows (group A), y / stage buffer (group B)
+        if (BULK_TILE) {
+            if (lane == 0) {
+                fence_proxy_async();   // earlier generic-proxy reads of these buffers are done (warp sync)
+                mbar_expect_tx(barA, nelem * 16u);
+                bulk_g2s(rho_s, a.yin + gbase, nelem * 16u, barA);
+            }
+        } else {
+            const double2* src = a.yin + gbase + lane;
+#pragma unroll
+            for (int it = 0; it < EIT; ++it)
+                if (lane + 32 * it < nelem) cp_async16(&rho_s[pofs[it]], src + 32 * it);
+        }
+        __syncwarp();   // the strip is visible to the whole warp
+        int ry[N];      // coefficient offset | target row of the chunk's links
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+            const int2 r = strip_sub[t];
+            ry[t] = r.y;
+            if (t < nl) cp_async16_s(nbrow_u32 + t * (N * 16), yin_row + (unsigned)r.x);
+        }
+        cp_async_commit();
+        if (!FIRST) {
+            // y always; in the last stage also the first stage buffer - the second one
+            // follows into rho_s once the commutator has consumed the own tile
+            if (lane == 0) {
+                if (!BULK_TILE) fence_proxy_async();
+                mbar_expect_tx(barB, nelem * 16u * (LAST ? 2u : 1u));
+                bulk_g2s(y_s, a.y + gbase, nelem * 16u, barB);
+                if (LAST) bulk_g2s(acc_s, a.s1 + gbase, nelem * 16u, barB);
+            }
+        }
+        cp_async_wait<0>();
+        if (BULK_TILE) {
+            mbar_wait(barA, phA);
+            phA ^= 1u;
+        }
+        __syncwarp();
+
+        // ---- -i[H, rho] - damp rho
+#define HEL(r_, c_) (hp.v[(r_) * N + (c_)])
+        double2 ccol[N];   // (H rho)[rr][row], this lane's column
+        if (on) {
+            double2 col[N];
+#pragma unroll
+            for (int l = 0; l < N; ++l) col[l] = rsub[l * LD + row];
+#pragma unroll
+            for (int rr = 0; rr < N; ++rr) {
+                double2 c = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int l = 0; l < N; ++l) {
+                    if (HREAL) {
+                        const double h = HEL(rr, l).x;
+                        c.x = fma(h, col[l].x, c.x);
+                        c.y = fma(h, col[l].y, c.y);
+                    } else {
+                        cfma(c, HEL(rr, l), col[l]);
+                    }
+                }
+                ksub[rr * LD + row] = c;
+                ccol[rr] = c;
+            }
+        }
+#undef HEL
+        __syncwarp();
+        if (on) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const double2 rv = rsub[row * LD + j];
+                double2 t = ksub[row * LD + j];
+                // (rho H)[row][j] = conj((H rho)[j][row])
+                t.x -= ccol[j].x;
+                t.y += ccol[j].y;
+                double2 kv = make_double2(t.y - (d.x * rv.x - d.y * rv.y),
+                                          -t.x - (d.x * rv.y + d.y * rv.x));
+                if (LAST) {
+                    // fold the stage input's own weight into k: w (k + (2/dt) y_in) = w k + y_in / 3
+                    kv.x = fma(a.a, rv.x, kv.x);
+                    kv.y = fma(a.a, rv.y, kv.y);
+                }
+                ksub[row * LD + j] = kv;
+            }
+        }
+        __syncwarp();
+        if (LAST) {
+            // rho_s is free now: fetch the second stage buffer into it for the epilogue
+            if (BULK_TILE) {
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(barD, nelem * 16u);
+                    bulk_g2s(rho_s, a.s2 + gbase, nelem * 16u, barD);
+                }
+            } else {
+                const double2* sb = a.s2 + gbase + lane;
+#pragma unroll
+                for (int it = 0; it < EIT; ++it)
+                    if (lane + 32 * it < nelem) cp_async16(&rho_s[pofs[it]], sb + 32 * it);
+                cp_async_commit();
+            }
+        }
+
+        // ---- neighbour terms, N links per chunk; contributions to one target row
+        //      are summed in registers (X: element (cur_rr, row))
+        const int maxl = __reduce_max_sync(0xffffffffu, nl);
+        double2 X = make_double2(0.0, 0.0);
+        int cur_rr = -1;
+        auto flush = [&]() {
+            double2* d1 = ksub + cur_rr * LD + row;
+            double2 v1 = *d1;
+            v1.x += X.x;
+            v1.y += X.y;
+            *d1 = v1;
+            if (row != cur_rr) {   // column update = conjugate of the row update
+                double2* d2 = ksub + row * LD + cur_rr;
+                double2 v2 = *d2;
+                v2.x += X.x;
+                v2.y -= X.y;
+                *d2 = v2;
+            }
+        };
+        for (int c0 = 0, c = 0; c0 < maxl; c0 += N, ++c) {
+            if (c0 > 0) {
+                __syncwarp();  // every lane is done with the previous chunk's rows
+#pragma unroll
+                for (int t = 0; t < N; ++t) {
+                    int2 r = make_int2(0, 0);
+                    if (c < NCH) r = strip_sub[c * (APW * N) + t];
+                    else if (c0 + t < nl) r = __ldg(a.links2 + lbeg + c0 + t);
+                    ry[t] = r.y;
+                    if (c0 + t < nl) cp_async16_s(nbrow_u32 + t * (N * 16), yin_row + (unsigned)r.x);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+            }
+            if (c0 < nl) {
+#pragma unroll
+                for (int t = 0; t < N; ++t) {
+                    if (c0 + t < nl) {
+                        const int rr = ry[t] & 15;
+                        const double2 Aj = nbrow[t * N];
+                        if (rr != cur_rr) {
+                            if (cur_rr >= 0) {
+                                flush();
+                                __syncwarp(submask);
+                            }
+                            cur_rr = rr;
+                            X = make_double2(0.0, 0.0);
+                        }
+                        const double2 cf =
+                            *(const double2*)(cq_row + ((ry[t] & ~15) + (row == rr ? 16 : 0)));
+                        cfma(X, cf, Aj);
+                    }
+                }
+            }
+        }
+        if (cur_rr >= 0) flush();
+        cp_async_wait<0>();
+        if (!FIRST) {
+            mbar_wait(barB, phB);
+            phB ^= 1u;
+        }
+        if (BULK_TILE && LAST) {
+            mbar_wait(barD, phD);
+            phD ^= 1u;
+        }
+        __syncwarp();
+
+        // ---- epilogue from shared memory, streaming stores
+        int e0 = -1;   // LAST: flat offset of ADO 0 (rho_sys) inside this group, if it is here
+        if (LAST && a.traj) {
+            const long long d0 = a.slot0 - base;
+            if (d0 >= 0 && d0 < cnt) e0 = (int)d0 * NN;
+        }
+#pragma unroll
+        for (int it = 0; it < EIT; ++it) {
+            const int e = lane + 32 * it;
+            if (e < nelem) {
+                const double2 k = k_s[pofs[it]];
+                if (LAST) {
+                    // y' = -y/3 + S1/3 + 2 S2/3 + w (k4 + (2/dt) S3)   (S3's share is already in k)
+                    const double2 y0 = y_s[e], s1 = acc_s[e], s2 = rho_s[pofs[it]];
+                    const double third = 1.0 / 3.0;
+                    double2 res = make_double2(fma(a.w, k.x, third * (s1.x - y0.x)),
+                                               fma(a.w, k.y, third * (s1.y - y0.y)));
+                    res.x = fma(2.0 * third, s2.x, res.x);
+                    res.y = fma(2.0 * third, s2.y, res.y);
+                    st_stream(a.out + gbase + e, res);
+                    if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)NN)
+                        a.traj[(step + 1) * NN + (e - e0)] = res;
+                } else {
+                    const double2 yv = FIRST ? rho_s[pofs[it]] : y_s[e];
+                    st_stream(a.out + gbase + e, make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// links -> links2 (one thread per link)
+__global__ void sym_convert_links_kernel(const int2* links, int2* links2, long long nlinks, int N, int L) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= nlinks) return;
+    const int2 r = links[i];
+    const int r0 = heom::meta_r0(r.y);
+    const unsigned off = ((unsigned)r.x * (unsigned)N + (unsigned)r0) * (unsigned)N;
+    links2[i] = make_int2((int)off, sym_link_y(heom::meta_kdir(r.y), heom::meta_neff(r.y), L, r0));
+}
+
+thread_local const char* g_sym_err = "";
+
+size_t sym_table_bytes(int K, int L) { return sizeof(double2) * 2 * 2 * (size_t)K * (L + 1); }
+constexpr size_t SYM_SMEM_BUDGET = 227 * 1024;
+
+template <int N, bool HREAL, int STAGE>
+int sym_launch_t(const SymLaunch& s) {
+    constexpr int APW = 32 / N;
+    SymArgs args = s.a;
+    args.ngroups = (s.part_hi - s.part_lo + APW - 1) / APW;
+    args.slot_lo = s.part_lo;
+    args.slot_hi = s.part_hi;
+    const size_t table_bytes = sym_table_bytes(s.K, s.L);
+    const size_t per_warp = sizeof(double2) * sym_perwarp(N, STAGE);
+    if (table_bytes + per_warp > SYM_SMEM_BUDGET) {
+        g_sym_err = "shared-memory tables too large for kernel 6";
+        return 1;
+    }
+    const int maxw = (int)std::min<size_t>(sym_max_threads(STAGE) / 32, (SYM_SMEM_BUDGET - table_bytes) / per_warp);
+    int warps = s.warps > 0 ? std::min(s.warps, maxw) : maxw;
+    if (s.warps <= 0) {
+        // small hierarchies: spread the groups over all SMs first
+        const long long per_sm = (args.ngroups + s.sm_count - 1) / s.sm_count;
+        warps = (int)std::max<long long>(1, std::min<long long>(maxw, per_sm));
+    }
+    const size_t smem = table_bytes + per_warp * warps;
+    const long long ctas = (args.ngroups + warps - 1) / warps;
+    const unsigned grid = (unsigned)std::min<long long>(ctas, s.sm_count);
+    HParam<N> hp;
+    for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(s.H[2 * e], s.H[2 * e + 1]);
+    auto kern = stage_rows_sym_kernel<N, HREAL, STAGE>;
+#ifndef HEOM_HOST_EMU
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)SYM_SMEM_BUDGET);
+        if (e != cudaSuccess) {
+            g_sym_err = cudaGetErrorString(e);
+            return 1;
+        }
+        attr_set = true;
+    }
+#endif
+    // one launch per trajectory of the batch, each with its own array / trajectory pointers
+    for (int b = 0; b < s.B; ++b) {
+        HEOM_LAUNCH(kern, grid, warps * 32, smem, s.stream, args, hp);
+#ifndef HEOM_HOST_EMU
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            g_sym_err = cudaGetErrorString(e);
+            return 1;
+        }
+#endif
+        args.yin += s.batch_elems;
+        if (args.y) args.y += s.batch_elems;
+        if (args.s1) args.s1 += s.batch_elems;
+        if (args.s2) args.s2 += s.batch_elems;
+        args.out += s.batch_elems;
+        if (args.traj) args.traj += s.traj_bstride;
+    }
+    return 0;
+}
+
+template <int N>
+int sym_launch_n(const SymLaunch& s) {
+    if (s.hreal) {
+        switch (s.stage) {
+            case 0: return sym_launch_t<N, true, 0>(s);
+            case 1: return sym_launch_t<N, true, 1>(s);
+            default: return sym_launch_t<N, true, 2>(s);
+        }
+    }
+    switch (s.stage) {
+        case 0: return sym_launch_t<N, false, 0>(s);
+        case 1: return sym_launch_t<N, false, 1>(s);
+        default: return sym_launch_t<N, false, 2>(s);
+    }
+}
+
+}  // namespace
+
+int heom_sym_supported(int N, int K, int M, int L, const char** err) {
+    (void)M;
+    const char* why = nullptr;
+    if (N < 2 || N > 8) why = "kernel 6 needs 2 <= N <= 8";
+    else if (sym_table_bytes(K, L) + sizeof(double2) * sym_perwarp(N, 2) > SYM_SMEM_BUDGET)
+        why = "shared-memory tables too large for kernel 6";
+    else if ((((long long)2 * K) * (L + 1) + L) >= (1ll << 26))
+        why = "coefficient index does not fit the link record of kernel 6";
+    if (why && err) *err = why;
+    return why ? 1 : 0;
+}
+
+int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
+                           const char** err) {
+    if (nlinks <= 0) return 0;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((nlinks + threads - 1) / threads);
+    HEOM_LAUNCH(sym_convert_links_kernel, blocks, threads, 0, stream, links, links2, nlinks, N, L);
+#ifndef HEOM_HOST_EMU
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        if (err) *err = cudaGetErrorString(e);
+        return 1;
+    }
+#endif
+    (void)err;
+    return 0;
+}
+
+int heom_sym_launch(const SymLaunch& s, const char** err) {
+    int rc = 1;
+    g_sym_err = "kernel 6 needs 2 <= N <= 8";
+    switch (s.N) {
+        case 2: rc = sym_launch_n<2>(s); break;
+        case 3: rc = sym_launch_n<3>(s); break;
+        case 4: rc = sym_launch_n<4>(s); break;
+        case 5: rc = sym_launch_n<5>(s); break;
+        case 6: rc = sym_launch_n<6>(s); break;
+        case 7: rc = sym_launch_n<7>(s); break;
+        case 8: rc = sym_launch_n<8>(s); break;
+        default: break;
+    }
+    if (rc && err) *err = g_sym_err;
+    return rc;
+}

@@ -1,0 +1,62 @@
+// heom_stage_sym.cuh - interface of the Hermitian-symmetric stage kernel
+// (kernel 6, heom_stage_sym.cu) towards the plan code in heom_kernels.cu.
+//
+// Kernel 6 is the instruction-diet successor of the async row kernel's SYM path
+// (kernel 3): same work split (a warp owns 32/N consecutive ADOs, lane = (ADO,
+// row)), same difference-form RK4, same arithmetic in the same order - so its
+// results are bit-identical to kernel 3's - but
+//   * the RK stage kind (first / middle / last) is a template parameter,
+//   * links come from a second table ("links2") that already holds the element
+//     offset of the neighbour row and the byte offset of the link's coefficient
+//     pair in a shared-memory table pre-multiplied by sqrt(n_eff),
+//   * link records reach the lanes through a per-warp shared-memory strip
+//     (one coalesced load + broadcast reads) instead of warp shuffles,
+//   * only the pointers it needs are passed (fewer constant-bank reloads).
+// It applies when every Q_m is diagonal with one non-zero entry, every ADO is
+// Hermitian, H is time independent and no fused halo push is requested.
+#pragma once
+#include "heom_device.cuh"
+
+struct SymArgs {
+    const double2* yin;   // stage input
+    const double2* y;     // state at the start of the step (middle / last)
+    const double2* s1;    // first stage buffer (last stage)
+    const double2* s2;    // second stage buffer (last stage)
+    double2* out;         // next stage input, or the end-of-step state in the last stage
+    const double2* damp;
+    const int* link_ptr;
+    const int2* links2;   // x: element offset of the neighbour row, y: coefficient byte offset | row
+    const double2* cbase; // [K][4]
+    const int* kmode;     // [K]: mode | first support row << 8
+    const double2* ops;   // [1+M][N*N] (diagonal entries of Q_m are read)
+    double2* traj;        // may be null (last stage only)
+    const long long* step_base;
+    long long ngroups, slot_lo, slot_hi, slot0;
+    double a, w;
+    int local_step, scramble, nind, nmod, lmax;
+};
+
+// links2 record: x = (slot * N + r0) * N, y = ((2k+dir) * (L+1) + n_eff) << 5 | r0
+__host__ __device__ inline int sym_link_y(int kdir, int neff, int L, int r0) {
+    return ((kdir * (L + 1) + neff) << 5) | (r0 & 0xf);
+}
+
+struct SymLaunch {
+    SymArgs a;
+    const double* H;      // host, N*N interleaved complex (time-independent Hamiltonian)
+    int N, K, M, L, B;
+    int stage;            // 0 first, 1 middle, 2 last
+    int hreal;            // H has no imaginary part
+    int warps;            // 0 = automatic
+    int sm_count;
+    long long part_lo, part_hi;   // owned slot range
+    long long batch_elems;        // nmax * N * N: distance between trajectories in the ADO arrays
+    long long traj_bstride;
+    void* stream;
+};
+
+// All return 0 on success; on failure *err points to a static message.
+int heom_sym_supported(int N, int K, int M, int L, const char** err);
+int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
+                           const char** err);
+int heom_sym_launch(const SymLaunch& L, const char** err);

@@ -1,0 +1,181 @@
+// cuda_emu.h - a small host emulation of the CUDA execution model, for CPU tests.
+//
+// TEST INFRASTRUCTURE ONLY.  It lets `g++` compile a kernel translation unit of
+// pyqed_b200/csrc unchanged (the hardware wrappers of heom_device.cuh are
+// replaced below) and run it with one OS thread per CUDA thread:
+//   * a CTA = blockDim.x std::threads; CTAs of a grid run one after the other;
+//   * __syncthreads / __syncwarp(mask) / __reduce_*_sync / __shfl_sync are real
+//     barriers among the participating threads, so lanes run in arbitrary order
+//     between synchronisation points (more adversarial than the hardware: a
+//     missing __syncwarp shows up as a data race / wrong result);
+//   * dynamic shared memory is a per-CTA buffer filled with NaN bit patterns;
+//   * cp.async / cp.async.bulk copy immediately, mbarriers and fences are no-ops
+//     (asynchrony and proxy ordering are NOT modelled - those are checked on the
+//     GPU by the parity tests and compute-sanitizer).
+// What it checks is a kernel's indexing, table formats, stage algebra and
+// edge-case handling against the oracle, without a GPU.
+#pragma once
+#define HEOM_HOST_EMU 1
+
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+struct double2 { double x, y; };
+struct int2 { int x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __grid_constant__
+
+using std::max;
+using std::min;
+
+namespace emu {
+
+struct Dim { unsigned x = 1, y = 1, z = 1; };
+
+class Barrier {
+public:
+    void wait(int n) {
+        std::unique_lock<std::mutex> lk(m_);
+        const unsigned long g = gen_;
+        if (++count_ == n) {
+            count_ = 0;
+            ++gen_;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return gen_ != g; });
+        }
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int count_ = 0;
+    unsigned long gen_ = 0;
+};
+
+struct Warp {
+    std::mutex m;
+    std::map<unsigned, std::unique_ptr<Barrier>> bars;   // one barrier per participation mask
+    long long xchg[32];
+    Barrier& bar(unsigned mask) {
+        std::lock_guard<std::mutex> lk(m);
+        auto& b = bars[mask];
+        if (!b) b.reset(new Barrier);
+        return *b;
+    }
+};
+
+struct Cta {
+    std::vector<char> smem;
+    std::vector<Warp> warps;
+    Barrier all;
+    int nthreads = 0;
+};
+
+inline thread_local Dim t_threadIdx, t_blockIdx, t_blockDim, t_gridDim;
+inline thread_local Cta* t_cta = nullptr;
+
+inline Warp& my_warp() { return t_cta->warps[t_threadIdx.x >> 5]; }
+inline int popc(unsigned m) { return __builtin_popcount(m); }
+
+template <typename Kernel, typename... Args>
+void launch(Kernel kernel, unsigned grid, unsigned block, size_t smem_bytes, Args... args) {
+    for (unsigned b = 0; b < grid; ++b) {
+        Cta cta;
+        cta.smem.assign(smem_bytes + 64, (char)0xff);   // NaN patterns: stale reads poison the result
+        cta.warps = std::vector<Warp>((block + 31) / 32);
+        cta.nthreads = (int)block;
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; ++t)
+            th.emplace_back([&, t, b] {
+                t_threadIdx = Dim{t, 0, 0};
+                t_blockIdx = Dim{b, 0, 0};
+                t_blockDim = Dim{block, 1, 1};
+                t_gridDim = Dim{grid, 1, 1};
+                t_cta = &cta;
+                kernel(args...);
+            });
+        for (auto& x : th) x.join();
+    }
+}
+
+}  // namespace emu
+
+#define threadIdx (emu::t_threadIdx)
+#define blockIdx (emu::t_blockIdx)
+#define blockDim (emu::t_blockDim)
+#define gridDim (emu::t_gridDim)
+
+#define HEOM_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::t_cta->smem.data())
+#define HEOM_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu::launch(kernel, (unsigned)(grid), (unsigned)(block), (size_t)(smem), __VA_ARGS__)
+
+// ---- synchronisation and warp collectives ------------------------------------
+inline void __syncthreads() { emu::t_cta->all.wait(emu::t_cta->nthreads); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::my_warp().bar(mask).wait(emu::popc(mask)); }
+
+template <typename F>
+inline long long emu_collective(unsigned mask, long long mine, F combine) {
+    emu::Warp& w = emu::my_warp();
+    const int lane = threadIdx.x & 31;
+    w.xchg[lane] = mine;
+    __syncwarp(mask);
+    const long long r = combine(w.xchg);
+    __syncwarp(mask);
+    return r;
+}
+inline int __reduce_max_sync(unsigned mask, int v) {
+    return (int)emu_collective(mask, v, [&](const long long* x) {
+        long long r = INT32_MIN;
+        for (int l = 0; l < 32; ++l)
+            if (mask >> l & 1u) r = std::max(r, x[l]);
+        return r;
+    });
+}
+inline int __reduce_add_sync(unsigned mask, int v) {
+    return (int)emu_collective(mask, v, [&](const long long* x) {
+        long long r = 0;
+        for (int l = 0; l < 32; ++l)
+            if (mask >> l & 1u) r += x[l];
+        return r;
+    });
+}
+inline int __shfl_sync(unsigned mask, int v, int src) {
+    return (int)emu_collective(mask, v, [&](const long long* x) { return x[src & 31]; });
+}
+
+// ---- memory access wrappers ---------------------------------------------------
+template <typename T> inline T __ldg(const T* p) { return *p; }
+template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline void __stcs(T* p, const T v) { *p = v; }
+
+inline unsigned smem_u32(const void* p) {
+    return (unsigned)(reinterpret_cast<const char*>(p) - emu::t_cta->smem.data());
+}
+inline void cp_async16(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
+inline void cp_async16_s(unsigned smem_dst_u32, const void* gsrc) {
+    std::memcpy(emu::t_cta->smem.data() + smem_dst_u32, gsrc, 16);
+}
+inline void mbar_init(unsigned long long*, unsigned) {}
+inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
+inline void mbar_wait(unsigned long long*, unsigned) {}
+inline void fence_proxy_async() {}
+inline void cp_async_commit() {}
+template <int NWAIT> inline void cp_async_wait() {}

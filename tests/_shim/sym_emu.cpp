@@ -1,0 +1,77 @@
+// sym_emu.cpp - runs kernel 6 (pyqed_b200/csrc/heom_stage_sym.cu) on the CPU
+// through tests/_shim/cuda_emu.h.  TEST INFRASTRUCTURE ONLY: built and loaded by
+// tests/test_sym_kernel_emu.py, never by the product.
+#include "cuda_emu.h"
+
+#include "../../pyqed_b200/csrc/heom_stage_sym.cu"
+
+extern "C" {
+
+// One call = nt difference-form RK4 steps (the stage plan of run_stage in
+// heom_kernels.cu) on host arrays.  `state` holds the four ADO arrays Y, SA, SB,
+// ACC ([nmax][N][N] complex128 each, contiguous); `links` are the (slot, meta)
+// records of hier_links_kernel and are converted with the product's converter.
+// `parts` = [lo0, hi0, lo1, hi1, ...]: every stage is launched once per owned
+// range, like the ranks of a sharded run (all ranges read the same stage input).
+int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, const double* ops,
+                const double* cbase, const int* kmode, const double* damp, const int* link_ptr,
+                const int* links, long long nlinks, double* state, double dt, int nt, int hreal,
+                int sm_count, int warps, const long long* parts, int nparts, long long slot0,
+                int scramble, double* traj, const char** err) {
+    static const char* none = "";
+    *err = none;
+    if (heom_sym_supported(N, K, M, L, err)) return 1;
+    std::vector<int2> links2((size_t)std::max(1ll, nlinks));
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
+        return 1;
+    const long long NN = (long long)N * N, asz = nmax * NN;
+    double2* Y = reinterpret_cast<double2*>(state);
+    double2 *SA = Y + asz, *SB = SA + asz, *ACC = SB + asz;
+    long long step_base = 0;
+    if (traj) std::memcpy(traj, Y + slot0 * NN, sizeof(double2) * NN);
+    for (int step = 0; step < nt; ++step) {
+        for (int stage = 0; stage < 4; ++stage) {
+            SymLaunch s{};
+            s.a.damp = reinterpret_cast<const double2*>(damp);
+            s.a.link_ptr = link_ptr;
+            s.a.links2 = links2.data();
+            s.a.cbase = reinterpret_cast<const double2*>(cbase);
+            s.a.kmode = kmode;
+            s.a.ops = reinterpret_cast<const double2*>(ops);
+            s.a.step_base = &step_base;
+            s.a.local_step = step;
+            s.a.slot0 = slot0;
+            s.a.scramble = scramble;
+            s.a.nind = K;
+            s.a.nmod = M;
+            s.a.lmax = L;
+            s.a.y = Y;
+            switch (stage) {
+                case 0: s.a.yin = Y;  s.a.out = SA;  s.a.a = dt / 2; s.stage = 0; break;
+                case 1: s.a.yin = SA; s.a.out = SB;  s.a.a = dt / 2; s.stage = 1; break;
+                case 2: s.a.yin = SB; s.a.out = ACC; s.a.a = dt;     s.stage = 1; break;
+                default:
+                    s.a.yin = ACC; s.a.s1 = SA; s.a.s2 = SB; s.a.out = Y;
+                    s.a.a = 2.0 / dt; s.a.w = dt / 6; s.stage = 2;
+                    s.a.traj = reinterpret_cast<double2*>(traj);
+                    break;
+            }
+            s.H = H;
+            s.N = N; s.K = K; s.M = M; s.L = L; s.B = 1;
+            s.hreal = hreal;
+            s.warps = warps;
+            s.sm_count = sm_count;
+            s.batch_elems = asz;
+            s.traj_bstride = (long long)(nt + 1) * NN;
+            for (int p = 0; p < nparts; ++p) {
+                s.part_lo = parts[2 * p];
+                s.part_hi = parts[2 * p + 1];
+                if (s.part_hi <= s.part_lo) continue;
+                if (heom_sym_launch(s, err)) return 1;
+            }
+        }
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""Kernel 6 (``stage_rows_sym_kernel``, heom_stage_sym.cu) on the GPU.
+
+Kernel 6 was written after this round's GPU budget was spent: it is compiled,
+statically analysed and verified on the CPU through the emulation harness
+(``tests/test_sym_kernel_emu.py``) but has not run on hardware yet, so it is
+opt-in (``tuning = dict(kernel=6)``) and these tests only run with
+``PYQED_B200_TEST_KERNEL6=1``.  First thing to do with a GPU:
+
+    PYQED_B200_TEST_KERNEL6=1 python -m pytest tests/test_gpu_kernel6.py -m gpu -x -q
+    python bench.py --kernel 6
+
+The arithmetic and its order are kernel 3's, so besides the 1e-12 parity with
+the reference's outputs the results must be bit-identical to kernel 3's.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from test_gpu_parity import _solver_from, _check_against_golden, TOL
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PYQED_B200_TEST_KERNEL6") != "1",
+                                 reason="kernel 6 is opt-in until it has run on hardware "
+                                        "(set PYQED_B200_TEST_KERNEL6=1)")]
+
+K6 = dict(kernel=6, warps_per_cta=0, use_graph=0)
+K3 = dict(kernel=3, warps_per_cta=0, use_graph=0)
+
+
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L2", "deom_fmo_K21_L3"])
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_kernel6_matches_reference(name, order):
+    g = golden(name)
+    s = _solver_from(g, order=order)
+    s.tuning = dict(K6)
+    s.options = {"resident": 0}
+    _check_against_golden(g, s)
+    assert s._plan.info("sym_launches") == 4 * int(g["nt"])
+    assert s._plan.info("resident_launches") == 0
+
+
+@pytest.mark.parametrize("name", ["deom_spin_boson_L10", "deom_aggregate_L3_T37", "deom_random5_nonherm"])
+def test_kernel6_falls_back_where_it_does_not_apply(name):
+    """sigma_z / occupation couplings (several diagonal entries), time-dependent
+    fields and non-Hermitian problems stay with kernels 3 / 1."""
+    g = golden(name)
+    s = _solver_from(g)
+    s.tuning = dict(K6)
+    s.options = {"resident": 0}
+    _check_against_golden(g, s)
+    assert s._plan.info("sym_launches") == 0
+
+
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L3"])
+@pytest.mark.parametrize("warps", [0, 1, 3, 8])
+def test_kernel6_is_bit_identical_to_kernel3(name, warps):
+    g = golden(name)
+    out = []
+    for tuning in (dict(K3, warps_per_cta=warps), dict(K6, warps_per_cta=warps)):
+        s = _solver_from(g)
+        s.tuning = tuning
+        s.options = {"resident": 0}
+        _, traj = s.run(g["rho0"].copy(), float(g["dt"]), int(g["nt"]))
+        out.append((np.asarray(traj), np.array(s.ddos)))
+    assert s._plan.info("sym_launches") > 0
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("complex_h", [False, True])
+def test_kernel6_every_system_size(n, complex_h):
+    """All N = 2..8 instantiations, real and complex H, projector couplings whose
+    support rows are not in mode order, against the oracle and kernel 3."""
+    from oracle.deom_oracle import DeomOracle
+    from pyqed_b200.heom import DEOMSolver, Bath
+    from test_sym_kernel_emu import projector_problem
+    w = projector_problem(n, 2, 4, seed=10 * n + complex_h, complex_h=complex_h)
+    o = DeomOracle(w["system"], None, w["coupling"], None, w["expn"], w["etal"], w["etar"], w["etaa"],
+                   w["mode"], w["lmax"])
+    dt, nt = 0.004, 10
+    _, ref = o.run(w["rho0"], dt, nt)
+    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+    res = {}
+    for kern in (3, 6):
+        s = DEOMSolver(w["system"], None, bath, w["coupling"], None, lmax=w["lmax"])
+        s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
+        s.options = {"resident": 0}
+        _, got = s.run(w["rho0"].copy(), dt, nt)
+        assert np.max(np.abs(np.asarray(got) - np.asarray(ref))) < TOL
+        assert np.max(np.abs(s.ddos - o.ddos)) < TOL
+        assert (s._plan.info("sym_launches") > 0) == (kern == 6)
+        res[kern] = np.array(s.ddos)
+    assert np.array_equal(res[3], res[6])
+
+
+def test_kernel6_beyond_l2_invariants():
+    """65 780 ADOs (K=21, depth 5): the state no longer fits L2; trace, Hermiticity
+    and agreement with kernel 3 on every ADO."""
+    from pyqed_b200 import workloads as W
+    from pyqed_b200.heom import DEOMSolver, Bath
+    w = W.fmo(lmax=5, n_matsubara=2)
+    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+    res = {}
+    for kern in (3, 6):
+        s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
+                       lmax=w["lmax"])
+        s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
+        _, traj = s.run(w["rho0"].copy(), w["dt"], 6)
+        res[kern] = (np.asarray(traj), np.array(s.ddos))
+    traj = res[6][0]
+    assert np.max(np.abs(np.trace(traj, axis1=1, axis2=2) - 1)) < 1e-12
+    assert np.max(np.abs(traj - traj.conj().transpose(0, 2, 1))) < 1e-14
+    assert np.array_equal(res[3][0], res[6][0]) and np.array_equal(res[3][1], res[6][1])

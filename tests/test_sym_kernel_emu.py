@@ -1,0 +1,157 @@
+"""Kernel 6 (``pyqed_b200/csrc/heom_stage_sym.cu``) on the CPU.
+
+The kernel source is compiled unchanged with g++ against ``tests/_shim/cuda_emu.h``
+(one OS thread per CUDA thread, real barriers for the warp/CTA synchronisation;
+asynchronous copies complete immediately) and its RK4 trajectory and final ADOs
+are compared with the oracle.  This checks the link-record format (``links2``),
+the pre-scaled coefficient table, the compile-time stage kinds, the record
+strip, tail groups, owned ranges and the visiting-order rotation without a GPU.
+The asynchronous-copy / proxy ordering is what the GPU parity tests are for.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import deom_oracle as DO
+from pyqed_b200 import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+C128 = np.complex128
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emu") / "libsym_emu.so"
+    src = os.path.join(ROOT, "tests", "_shim", "sym_emu.cpp")
+    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++",
+                           "-o", str(out), src])
+    lib = ctypes.CDLL(str(out))
+    lib.emu_sym_run.restype = ctypes.c_int
+    return lib
+
+
+def link_meta(direction, k, neff, mode, r0):
+    """``heom::link_meta`` (pyqed_b200/csrc/heom_core.cuh)."""
+    return neff | (direction << 8) | (k << 9) | ((r0 & 0xf) << 16) | (mode << 24)
+
+
+def host_tables(w):
+    """The tables ``pyqed_heom_build_hierarchy`` builds on the device, in the
+    reference's id order (storage order 0), from the oracle's index tables."""
+    o = DO.DeomOracle(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"], w["expn"],
+                      w["etal"], w["etar"], w["etaa"], w["mode"], w["lmax"])
+    N, K, M = o.nsys, o.nind, o.Q0.shape[0]
+    r0 = []
+    for m in range(M):
+        nz = np.nonzero(np.diag(o.Q0[m]))[0]
+        assert len(nz) == 1 and np.count_nonzero(o.Q0[m]) == 1, "kernel 6 needs one-entry diagonal Q_m"
+        r0.append(int(nz[0]))
+    kmode = np.array([int(o.mode[k]) | (r0[int(o.mode[k])] << 8) for k in range(K)], dtype=np.int32)
+    sa = np.sqrt(o.etaa)
+    cbase = np.stack([-(1j / sa) * o.etal, (1j / sa) * o.etar, -1j * sa, 1j * sa], axis=1).astype(C128)
+    damp = (o.keys * o.expn[None, :]).sum(axis=1).astype(C128)
+    ptr = [0]
+    recs = []
+    for n in range(o.nmax):
+        for k in range(K):
+            m = int(o.mode[k])
+            if o.minus[n, k] >= 0:
+                recs.append((int(o.minus[n, k]), link_meta(0, k, int(o.keys[n, k]), m, r0[m])))
+            if o.plus[n, k] >= 0:
+                recs.append((int(o.plus[n, k]), link_meta(1, k, int(o.keys[n, k]) + 1, m, r0[m])))
+        ptr.append(len(recs))
+    links = np.array(recs, dtype=np.int32).reshape(-1, 2)
+    ops = np.concatenate([o.H0[None], o.Q0]).astype(C128)
+    return o, dict(N=N, K=K, M=M, kmode=kmode, cbase=np.ascontiguousarray(cbase), damp=damp,
+                   link_ptr=np.array(ptr, dtype=np.int32), links=np.ascontiguousarray(links), ops=ops)
+
+
+def run_emu(emu, w, nt, sm_count=3, warps=2, parts=None, scramble=0):
+    o, t = host_tables(w)
+    N, NN = t["N"], t["N"] ** 2
+    state = np.zeros((4, o.nmax, N, N), dtype=C128)
+    state[0, 0] = w["rho0"]
+    # the kernel must never depend on what the stage buffers held before
+    state[1:] = np.nan
+    traj = np.zeros((nt + 1, N, N), dtype=C128)
+    parts = np.array(parts if parts is not None else [0, o.nmax], dtype=np.int64)
+    H = np.ascontiguousarray(o.H0)
+    err = ctypes.c_char_p()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = emu.emu_sym_run(
+        ctypes.c_int(N), ctypes.c_int(t["K"]), ctypes.c_int(t["M"]), ctypes.c_int(o.lmax),
+        ctypes.c_longlong(o.nmax), p(H), p(t["ops"]), p(t["cbase"]), p(t["kmode"]), p(t["damp"]),
+        p(t["link_ptr"]), p(t["links"]), ctypes.c_longlong(len(t["links"])), p(state),
+        ctypes.c_double(w["dt"]), ctypes.c_int(nt), ctypes.c_int(int(np.all(H.imag == 0))),
+        ctypes.c_int(sm_count), ctypes.c_int(warps), p(parts), ctypes.c_int(len(parts) // 2),
+        ctypes.c_longlong(0), ctypes.c_int(scramble), p(traj), ctypes.byref(err))
+    assert rc == 0, err.value
+    _, ref = o.run(w["rho0"], w["dt"], nt)
+    return state[0], traj, o.ddos, np.array(ref)
+
+
+def check(emu, w, nt, **kw):
+    y, traj, ref_ados, ref_traj = run_emu(emu, w, nt, **kw)
+    scale = max(1.0, float(np.abs(ref_ados).max()))
+    assert np.isfinite(y).all()
+    assert np.abs(traj - ref_traj).max() < 1e-12
+    assert np.abs(y - ref_ados).max() < 1e-12 * scale
+
+
+def projector_problem(n, nind_per_mode, lmax, seed, complex_h):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(n, n)) + (1j * rng.normal(size=(n, n)) if complex_h else 0)
+    H = ((A + A.conj().T) / 2).astype(C128)
+    M = n
+    Q = np.zeros((M, n, n), C128)
+    for m in range(M):
+        Q[m, (m * 2 + 1) % n, (m * 2 + 1) % n] = 0.7 + 0.1 * m     # one diagonal entry, rows not in order
+    K = M * nind_per_mode
+    mode = np.repeat(np.arange(M), nind_per_mode)
+    expn = (0.5 + rng.random(K)).astype(C128)
+    etal = (rng.normal(size=K) * 0.3 + 1j * rng.normal(size=K) * 0.2).astype(C128)
+    etar = etal.conj()
+    etaa = np.abs(etal).astype(C128)
+    psi = rng.normal(size=n) + 1j * rng.normal(size=n)
+    rho0 = np.outer(psi, psi.conj()) / np.vdot(psi, psi)
+    return dict(system=H, system_dipole=np.zeros((n, n), C128), coupling=Q,
+                coupling_dipole=np.zeros_like(Q), expn=expn, etal=etal, etar=etar, etaa=etaa,
+                mode=mode, lmax=lmax, rho0=rho0.astype(C128), dt=0.01, nt=4)
+
+
+def test_fmo_n7_real_h(emu):
+    """The headline shape (N=7, projector couplings, real H) at depth 3: groups of
+    4 ADOs, 120 ADOs = 30 full groups; the odd-N bulk-tile path."""
+    check(emu, W.fmo(lmax=3, n_matsubara=0), nt=3)
+
+
+def test_fmo_matsubara_links_beyond_one_chunk(emu):
+    """K=21: up to 23 links per ADO at depth 2, i.e. four chunks of 7 from the strip."""
+    check(emu, W.fmo(lmax=2, n_matsubara=2), nt=2, sm_count=2, warps=3)
+
+
+@pytest.mark.parametrize("n,complex_h", [(2, False), (3, True), (4, True), (5, False), (6, True), (8, False)])
+def test_every_system_size(emu, n, complex_h):
+    """Even N (padded tiles, cp.async tile path), idle lanes (N=3,5,6,7), complex H."""
+    check(emu, projector_problem(n, 1, 3, seed=n, complex_h=complex_h), nt=2)
+
+
+def test_records_beyond_the_strip(emu):
+    """N=2 with K=12: 12 + 3 links per ADO > 4 chunks of 2 -> on-demand record loads."""
+    w = projector_problem(2, 6, 3, seed=11, complex_h=False)
+    check(emu, w, nt=2)
+
+
+def test_owned_ranges_and_rotation(emu):
+    """Two owned ranges (a sharded run's ranks) with a ragged boundary, the
+    visiting-order rotation of storage order 2, one warp per CTA."""
+    w = W.fmo(lmax=3, n_matsubara=0)
+    check(emu, w, nt=2, parts=[0, 57, 57, 120], scramble=1, sm_count=2, warps=1)
+
+
+def test_more_warps_than_groups(emu):
+    w = projector_problem(3, 1, 2, seed=5, complex_h=True)   # 10 ADOs = 1 group of 10
+    check(emu, w, nt=3, sm_count=4, warps=4)
