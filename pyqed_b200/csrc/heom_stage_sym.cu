@@ -6,8 +6,8 @@
 //           - i sum_k sqrt(n_k)/sqrt(a_k) (eta_k Q_m rho_{n-e_k} - conj(eta_k) rho_{n-e_k} Q_m)
 //           - i sum_k sqrt(n_k+1) sqrt(a_k) [Q_m, rho_{n+e_k}]
 // and applies the stage update of the difference-form RK4 (rk4, deom.py:725-766;
-// DESIGN.md section 4) in the same pass.  See heom_stage_sym.cuh for what differs
-// from kernel 3; the arithmetic and its order are kernel 3's.
+// DESIGN.md section 4) in the same pass.  heom_stage_sym.cuh says what differs
+// from kernel 3.
 //
 // Work split: persistent CTAs (one per SM); a warp owns APW = 32/N consecutive
 // ADOs ("group"), lane = (ADO sub, matrix row).  Per group:
@@ -15,11 +15,14 @@
 //      coalesced load) are published in the warp's shared-memory strip;
 //   2. own tile by one bulk copy (odd N) or cp.async, first chunk of neighbour
 //      rows by cp.async (16N bytes per link), y / stage buffers by bulk copies;
-//   3. -i[H,rho] with one product (rho H = (H rho)^dagger), damping;
-//   4. neighbour terms: (Q rho' - rho' Q) touches row r0 and column r0 only and the
-//      column update is the conjugate of the row update; contributions to one
-//      target row are summed in registers and flushed once;
-//   5. epilogue from shared memory with streaming stores.
+//   3. column `row` of P = -i H rho - (damp/2) rho into the k tile;
+//   4. neighbour terms: (Q rho' - rho' Q) touches row r0 and column r0 only; the
+//      lane's element of the row update is summed in registers per target row and
+//      added into the lane's own column of the tile;
+//   5. k = P' + P'^dagger (each lane finishes (N-1)/2 element pairs and its
+//      diagonal element) - this supplies both the rho H half of the commutator and
+//      the links' column updates;
+//   6. epilogue from shared memory with streaming stores.
 #ifndef HEOM_HOST_EMU
 #include <cuda_runtime.h>
 #endif
@@ -33,7 +36,7 @@
 #define HEOM_SYM_THREADS 512       // first / middle stage: 16 warps, 128 registers
 #endif
 #ifndef HEOM_SYM_LAST_THREADS
-#define HEOM_SYM_LAST_THREADS 448  // last stage stages one more tile per warp: 14 warps, 144 registers
+#define HEOM_SYM_LAST_THREADS 448  // last stage stages one more tile per warp: at most 14 warps, 144 registers
 #endif
 
 namespace {
@@ -90,15 +93,17 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
         const double2 c1 = cmul(make_double2(bL.x + bR.x, bL.y + bR.y), q);
         const double sq = sqrt((double)n);
         cq_s[2 * e] = make_double2(c0.x * sq, c0.y * sq);
-        cq_s[2 * e + 1] = make_double2(c1.x * sq, c1.y * sq);
+        // the diagonal element is counted twice by the P' + P'^dagger pass: halve it here
+        cq_s[2 * e + 1] = make_double2(0.5 * (c1.x * sq), 0.5 * (c1.y * sq));
     }
     __syncthreads();
 
     const int sub = lane / N, row = lane - sub * N;
     const bool lane_ok = lane < APW * N;
-    const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
     const long long step = (LAST && a.traj) ? (*a.step_base + a.local_step) : 0;
-    const long long gstride = (long long)gridDim.x * nwarps;
+    // slots, groups and element offsets are 32-bit here (the host checks nmax N^2 < 2^32)
+    const int ngroups = (int)a.ngroups, gstride = (int)gridDim.x * nwarps;
+    const int slot_lo = (int)a.slot_lo, slot_hi = (int)a.slot_hi;
     // flat element e = lane + 32 it  ->  offset in the (possibly padded) tile
     int pofs[EIT];
 #pragma unroll
@@ -111,7 +116,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
         }
     }
     double2* const ksub = k_s + sub * N * LD;     // this ADO's k tile
-    double2* const rsub = rho_s + sub * N * LD;
+    const double2* const rsub = rho_s + sub * N * LD;
     const double2* const nbrow = nb_s + sub * NN + row;   // + t*N: row element of staged link t
     const unsigned nbrow_u32 = smem_u32(nbrow);
     // + (c*APW*N + t): record t of chunk c (idle lanes stay inside the strip)
@@ -119,59 +124,64 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
     const double2* const yin_row = a.yin + row;           // + links2.x: this lane's element of the neighbour row
     const char* const cq_row = (const char*)cq_s;
 
-    // Bookkeeping pipeline carried in registers: link offsets two groups ahead,
-    // damping rate and the first NCH*N link records one group ahead.
-    long long g = (long long)blockIdx.x * nwarps + wid;
+    // Bookkeeping pipeline carried in registers: first slot and link offsets of the
+    // group two iterations ahead, damping rate and the first NCH*N link records of
+    // the next group.
+    // Visiting order: see stage_rows_async_kernel (rotation inside runs of 16 groups).
+    const int gfull = a.scramble ? (ngroups & ~15) : 0;
+    auto group_base = [&](int gg) {   // first slot of group gg, -1 past the end
+        const unsigned rot = ((unsigned)(gg >> 4) * 2654435761u) >> 28;
+        const int gm = gg < gfull ? ((gg & ~15) | ((gg + (int)rot) & 15)) : gg;
+        return gg < ngroups ? slot_lo + gm * APW : -1;
+    };
     int nx_lbeg = 0, nx_lend = 0, nn_lbeg = 0, nn_lend = 0;
     int2 nx_rec[NCH];
-    double2 nx_damp = make_double2(0.0, 0.0);
-    // visiting order: see stage_rows_async_kernel (rotation inside runs of 16 groups)
-    const long long gfull = a.scramble ? (a.ngroups & ~15ll) : 0;
-    auto gmap = [&](long long gg) {
-        const unsigned rot = ((unsigned)(gg >> 4) * 2654435761u) >> 28;
-        return gg < gfull ? ((gg & ~15ll) | ((gg + rot) & 15ll)) : gg;
-    };
-    auto fetch_ptr = [&](long long gg, int& lb, int& le) {
-        const long long slot = a.slot_lo + gmap(gg) * APW + sub;
+    double nx_damp = 0.0;
+    auto fetch_ptr = [&](int b0, int& lb, int& le) {
+        const int slot = b0 + sub;
         lb = le = 0;
-        if (gg < a.ngroups && lane_ok && slot < a.slot_hi) {
+        if (b0 >= 0 && lane_ok && slot < slot_hi) {
             lb = a.link_ptr[slot];
             le = a.link_ptr[slot + 1];
         }
     };
-    auto fetch_rec = [&](long long gg, int lb, int le) {
-        const long long slot = a.slot_lo + gmap(gg) * APW + sub;
-        if (gg < a.ngroups && lane_ok && slot < a.slot_hi) nx_damp = a.damp[slot];
+    auto fetch_rec = [&](int b0, int lb, int le) {
+        const int slot = b0 + sub;
+        if (b0 >= 0 && lane_ok && slot < slot_hi) nx_damp = a.damp[slot].x;   // real: Hermitian problem
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             nx_rec[c] = make_int2(0, 0);
             if (lb + c * N + row < le) nx_rec[c] = __ldg(a.links2 + lb + c * N + row);
         }
     };
-    fetch_ptr(g, nx_lbeg, nx_lend);
-    fetch_rec(g, nx_lbeg, nx_lend);
-    fetch_ptr(g + gstride, nn_lbeg, nn_lend);
+    int g = (int)blockIdx.x * nwarps + wid;
+    int cur_base = group_base(g), nx_base = group_base(g + gstride);
+    fetch_ptr(cur_base, nx_lbeg, nx_lend);
+    fetch_rec(cur_base, nx_lbeg, nx_lend);
+    fetch_ptr(nx_base, nn_lbeg, nn_lend);
 
-    for (; g < a.ngroups; g += gstride) {
-        const long long base = a.slot_lo + gmap(g) * APW;
-        const int cnt = (int)min((long long)APW, a.slot_hi - base);
+    for (; g < ngroups; g += gstride) {
+        const int base = cur_base;
+        const int cnt = min(APW, slot_hi - base);
         const int nelem = cnt * NN;
         const bool on = lane_ok && sub < cnt;
         const int lbeg = nx_lbeg, lend = nx_lend;
         const int nl = on ? (lend - lbeg) : 0;
-        const double2 d = nx_damp;
-        const long long gbase = base * NN;
+        const double dh = 0.5 * nx_damp;
+        const unsigned gbase = (unsigned)base * (unsigned)NN;
         // publish this group's records, then start the prefetch of the next group's
         if (lane_ok) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) strip[(c * APW + sub) * N + row] = nx_rec[c];
         }
+        cur_base = nx_base;
         nx_lbeg = nn_lbeg;
         nx_lend = nn_lend;
-        fetch_rec(g + gstride, nx_lbeg, nx_lend);
-        fetch_ptr(g + 2 * gstride, nn_lbeg, nn_lend);
+        fetch_rec(cur_base, nx_lbeg, nx_lend);
+        nx_base = group_base(g + 2 * gstride);
+        fetch_ptr(nx_base, nn_lbeg, nn_lend);
 
-        // ---- issue: own tile + first chunk of neighbour rows (group A), y / stage buffer (group B)
+        // ---- issue: own tile + first chunk of neighbour rows, y / first stage buffer
         if (BULK_TILE) {
             if (lane == 0) {
                 fence_proxy_async();   // earlier generic-proxy reads of these buffers are done (warp sync)
@@ -210,13 +220,16 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
         }
         __syncwarp();
 
-        // ---- -i[H, rho] - damp rho
+        // ---- P = -i H rho - (damp/2) rho, column `row` of this ADO.  The full
+        //      k = P' + P'^dagger (P' = P + row updates of the links) is formed after the
+        //      link loop: -i[H,rho] = -i H rho + (-i H rho)^dagger for Hermitian rho.
+        //      Last stage: the stage input's own weight, w (k + (2/dt) y_in), is folded in too.
 #define HEL(r_, c_) (hp.v[(r_) * N + (c_)])
-        double2 ccol[N];   // (H rho)[rr][row], this lane's column
         if (on) {
             double2 col[N];
 #pragma unroll
             for (int l = 0; l < N; ++l) col[l] = rsub[l * LD + row];
+            const double sh = LAST ? (0.5 * a.a - dh) : -dh;
 #pragma unroll
             for (int rr = 0; rr < N; ++rr) {
                 double2 c = make_double2(0.0, 0.0);
@@ -230,32 +243,12 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
                         cfma(c, HEL(rr, l), col[l]);
                     }
                 }
-                ksub[rr * LD + row] = c;
-                ccol[rr] = c;
+                ksub[rr * LD + row] = make_double2(fma(sh, col[rr].x, c.y), fma(sh, col[rr].y, -c.x));
             }
         }
 #undef HEL
-        __syncwarp();
-        if (on) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                const double2 rv = rsub[row * LD + j];
-                double2 t = ksub[row * LD + j];
-                // (rho H)[row][j] = conj((H rho)[j][row])
-                t.x -= ccol[j].x;
-                t.y += ccol[j].y;
-                double2 kv = make_double2(t.y - (d.x * rv.x - d.y * rv.y),
-                                          -t.x - (d.x * rv.y + d.y * rv.x));
-                if (LAST) {
-                    // fold the stage input's own weight into k: w (k + (2/dt) y_in) = w k + y_in / 3
-                    kv.x = fma(a.a, rv.x, kv.x);
-                    kv.y = fma(a.a, rv.y, kv.y);
-                }
-                ksub[row * LD + j] = kv;
-            }
-        }
-        __syncwarp();
         if (LAST) {
+            __syncwarp();   // every lane has read its column of the own tile
             // rho_s is free now: fetch the second stage buffer into it for the epilogue
             if (BULK_TILE) {
                 if (lane == 0) {
@@ -272,8 +265,11 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
             }
         }
 
-        // ---- neighbour terms, N links per chunk; contributions to one target row
-        //      are summed in registers (X: element (cur_rr, row))
+        // ---- neighbour terms, N links per chunk.  (Q rho' - rho' Q) touches row r0 and
+        //      column r0 only; a lane adds its element of the row update into its own column
+        //      of the tile (no other lane touches that column here) - the column update is
+        //      the conjugate and comes from the P' + P'^dagger pass below.  Contributions to
+        //      one target row are summed in registers (X: element (cur_rr, row)).
         const int maxl = __reduce_max_sync(0xffffffffu, nl);
         double2 X = make_double2(0.0, 0.0);
         int cur_rr = -1;
@@ -283,22 +279,26 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
             v1.x += X.x;
             v1.y += X.y;
             *d1 = v1;
-            if (row != cur_rr) {   // column update = conjugate of the row update
-                double2* d2 = ksub + row * LD + cur_rr;
-                double2 v2 = *d2;
-                v2.x += X.x;
-                v2.y -= X.y;
-                *d2 = v2;
-            }
         };
         for (int c0 = 0, c = 0; c0 < maxl; c0 += N, ++c) {
             if (c0 > 0) {
-                __syncwarp();  // every lane is done with the previous chunk's rows
+                __syncwarp();  // every lane is done with the previous chunk's rows (and records)
+                if ((c & (NCH - 1)) == 0) {
+                    // more than NCH chunks (rare): refill the strip with the next NCH chunks
+                    if (lane_ok) {
+#pragma unroll
+                        for (int cc = 0; cc < NCH; ++cc) {
+                            int2 r = make_int2(0, 0);
+                            if (lbeg + c0 + cc * N + row < lend) r = __ldg(a.links2 + lbeg + c0 + cc * N + row);
+                            strip[(cc * APW + sub) * N + row] = r;
+                        }
+                    }
+                    __syncwarp();
+                }
+                const int2* const recs = strip_sub + (c & (NCH - 1)) * (APW * N);
 #pragma unroll
                 for (int t = 0; t < N; ++t) {
-                    int2 r = make_int2(0, 0);
-                    if (c < NCH) r = strip_sub[c * (APW * N) + t];
-                    else if (c0 + t < nl) r = __ldg(a.links2 + lbeg + c0 + t);
+                    const int2 r = recs[t];
                     ry[t] = r.y;
                     if (c0 + t < nl) cp_async16_s(nbrow_u32 + t * (N * 16), yin_row + (unsigned)r.x);
                 }
@@ -313,10 +313,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
                         const int rr = ry[t] & 15;
                         const double2 Aj = nbrow[t * N];
                         if (rr != cur_rr) {
-                            if (cur_rr >= 0) {
-                                flush();
-                                __syncwarp(submask);
-                            }
+                            if (cur_rr >= 0) flush();
                             cur_rr = rr;
                             X = make_double2(0.0, 0.0);
                         }
@@ -328,6 +325,28 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
             }
         }
         if (cur_rr >= 0) flush();
+        __syncwarp();
+        // ---- k = P' + P'^dagger: this lane finishes its diagonal element and the pairs
+        //      (row, row+d), d = 1..(N-1)/2 (and d = N/2 from the lower half when N is even)
+        if (on) {
+            {
+                double2* pd = ksub + row * LD + row;
+                const double2 v = *pd;
+                *pd = make_double2(v.x + v.x, 0.0);
+            }
+#pragma unroll
+            for (int dd = 1; dd <= N / 2; ++dd) {
+                if (2 * dd == N && row >= N / 2) continue;
+                int j = row + dd;
+                if (j >= N) j -= N;
+                double2* pa = ksub + row * LD + j;
+                double2* pb = ksub + j * LD + row;
+                const double2 va = *pa, vb = *pb;
+                const double2 sum = make_double2(va.x + vb.x, va.y - vb.y);
+                *pa = sum;
+                *pb = make_double2(sum.x, -sum.y);
+            }
+        }
         cp_async_wait<0>();
         if (!FIRST) {
             mbar_wait(barB, phB);
@@ -358,12 +377,12 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
                                                fma(a.w, k.y, third * (s1.y - y0.y)));
                     res.x = fma(2.0 * third, s2.x, res.x);
                     res.y = fma(2.0 * third, s2.y, res.y);
-                    st_stream(a.out + gbase + e, res);
+                    st_stream(a.out + (gbase + e), res);
                     if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)NN)
                         a.traj[(step + 1) * NN + (e - e0)] = res;
                 } else {
                     const double2 yv = FIRST ? rho_s[pofs[it]] : y_s[e];
-                    st_stream(a.out + gbase + e, make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
+                    st_stream(a.out + (gbase + e), make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
                 }
             }
         }

@@ -3,17 +3,27 @@
 //
 // Kernel 6 is the instruction-diet successor of the async row kernel's SYM path
 // (kernel 3): same work split (a warp owns 32/N consecutive ADOs, lane = (ADO,
-// row)), same difference-form RK4, same arithmetic in the same order - so its
-// results are bit-identical to kernel 3's - but
-//   * the RK stage kind (first / middle / last) is a template parameter,
+// row)), same difference-form RK4 and the same staging of tiles and neighbour
+// rows, but
+//   * Hermiticity is used one step further: a lane computes column `row` of
+//     P = -i H rho - (damp/2) rho, adds the links' row updates into that same
+//     column (no other lane touches it, so the link loop needs no partial-warp
+//     barrier and no column read-modify-write), and one pass forms
+//     k = P' + P'^dagger at the end.  The second commutator pass of kernel 3
+//     (transposed reads of the tile) does not exist;
+//   * the RK stage kind (first / middle / last) is a template parameter;
 //   * links come from a second table ("links2") that already holds the element
 //     offset of the neighbour row and the byte offset of the link's coefficient
-//     pair in a shared-memory table pre-multiplied by sqrt(n_eff),
-//   * link records reach the lanes through a per-warp shared-memory strip
-//     (one coalesced load + broadcast reads) instead of warp shuffles,
-//   * only the pointers it needs are passed (fewer constant-bank reloads).
+//     pair in a shared-memory table pre-multiplied by sqrt(n_eff);
+//   * link records reach the lanes through a per-warp shared-memory strip (one
+//     coalesced load + broadcast reads) instead of warp shuffles;
+//   * slots, groups and element offsets are 32-bit, and only the pointers the
+//     kernel needs are passed (fewer constant-bank reloads).
+// Every stage output is Hermitian bit for bit.  Results differ from kernel 3's
+// by summation order only (~1e-16); both are held to 1e-12 of the reference.
 // It applies when every Q_m is diagonal with one non-zero entry, every ADO is
-// Hermitian, H is time independent and no fused halo push is requested.
+// Hermitian (so the damping rates are real), H is time independent and no
+// fused halo push is requested.
 #pragma once
 #include "heom_device.cuh"
 

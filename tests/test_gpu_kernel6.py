@@ -9,8 +9,9 @@ opt-in (``tuning = dict(kernel=6)``) and these tests only run with
     PYQED_B200_TEST_KERNEL6=1 python -m pytest tests/test_gpu_kernel6.py -m gpu -x -q
     python bench.py --kernel 6
 
-The arithmetic and its order are kernel 3's, so besides the 1e-12 parity with
-the reference's outputs the results must be bit-identical to kernel 3's.
+Kernel 6 differs from kernel 3 by summation order only, so besides the 1e-12
+parity with the reference's outputs it must agree with kernel 3 to ~1e-15 and
+keep every ADO Hermitian bit for bit.
 """
 import os
 
@@ -53,9 +54,15 @@ def test_kernel6_falls_back_where_it_does_not_apply(name):
     assert s._plan.info("sym_launches") == 0
 
 
+def _close_and_hermitian(a3, a6):
+    scale = max(1.0, float(np.abs(a3).max()))
+    assert np.max(np.abs(a3 - a6)) < 1e-13 * scale
+    assert np.array_equal(a6, a6.conj().swapaxes(-1, -2))
+
+
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L3"])
 @pytest.mark.parametrize("warps", [0, 1, 3, 8])
-def test_kernel6_is_bit_identical_to_kernel3(name, warps):
+def test_kernel6_agrees_with_kernel3(name, warps):
     g = golden(name)
     out = []
     for tuning in (dict(K3, warps_per_cta=warps), dict(K6, warps_per_cta=warps)):
@@ -65,8 +72,8 @@ def test_kernel6_is_bit_identical_to_kernel3(name, warps):
         _, traj = s.run(g["rho0"].copy(), float(g["dt"]), int(g["nt"]))
         out.append((np.asarray(traj), np.array(s.ddos)))
     assert s._plan.info("sym_launches") > 0
-    assert np.array_equal(out[0][0], out[1][0])
-    assert np.array_equal(out[0][1], out[1][1])
+    _close_and_hermitian(out[0][0], out[1][0])
+    _close_and_hermitian(out[0][1], out[1][1])
 
 
 @pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])
@@ -93,7 +100,7 @@ def test_kernel6_every_system_size(n, complex_h):
         assert np.max(np.abs(s.ddos - o.ddos)) < TOL
         assert (s._plan.info("sym_launches") > 0) == (kern == 6)
         res[kern] = np.array(s.ddos)
-    assert np.array_equal(res[3], res[6])
+    _close_and_hermitian(res[3], res[6])
 
 
 def test_kernel6_beyond_l2_invariants():
@@ -113,4 +120,5 @@ def test_kernel6_beyond_l2_invariants():
     traj = res[6][0]
     assert np.max(np.abs(np.trace(traj, axis1=1, axis2=2) - 1)) < 1e-12
     assert np.max(np.abs(traj - traj.conj().transpose(0, 2, 1))) < 1e-14
-    assert np.array_equal(res[3][0], res[6][0]) and np.array_equal(res[3][1], res[6][1])
+    _close_and_hermitian(res[3][0], res[6][0])
+    _close_and_hermitian(res[3][1], res[6][1])

@@ -99,6 +99,8 @@ def check(emu, w, nt, **kw):
     assert np.isfinite(y).all()
     assert np.abs(traj - ref_traj).max() < 1e-12
     assert np.abs(y - ref_ados).max() < 1e-12 * scale
+    # kernel 6 keeps every ADO Hermitian bit for bit
+    assert np.array_equal(y, y.conj().transpose(0, 2, 1))
 
 
 def projector_problem(n, nind_per_mode, lmax, seed, complex_h):
@@ -116,7 +118,8 @@ def projector_problem(n, nind_per_mode, lmax, seed, complex_h):
     etar = etal.conj()
     etaa = np.abs(etal).astype(C128)
     psi = rng.normal(size=n) + 1j * rng.normal(size=n)
-    rho0 = np.outer(psi, psi.conj()) / np.vdot(psi, psi)
+    rho0 = np.outer(psi, psi.conj())
+    rho0 = (rho0 + rho0.conj().T) / 2 / np.trace(rho0).real   # exactly Hermitian, as kernel 6 requires
     return dict(system=H, system_dipole=np.zeros((n, n), C128), coupling=Q,
                 coupling_dipole=np.zeros_like(Q), expn=expn, etal=etal, etar=etar, etaa=etaa,
                 mode=mode, lmax=lmax, rho0=rho0.astype(C128), dt=0.01, nt=4)
