@@ -9,18 +9,23 @@
 //     between synchronisation points (more adversarial than the hardware: a
 //     missing __syncwarp shows up as a data race / wrong result);
 //   * dynamic shared memory is a per-CTA buffer filled with NaN bit patterns;
-//   * cp.async / cp.async.bulk copy immediately, mbarriers and fences are no-ops
-//     (asynchrony and proxy ordering are NOT modelled - those are checked on the
-//     GPU by the parity tests and compute-sanitizer).
+//   * cp.async / cp.async.bulk + mbarrier are modelled at the two extremes of
+//     their legal timing (copies land at issue, or only when waited for - see
+//     "asynchronous copies" below); proxy fences are no-ops (cross-proxy ordering
+//     is NOT modelled - that is checked on the GPU by the parity tests and
+//     compute-sanitizer).
 // What it checks is a kernel's indexing, table formats, stage algebra and
 // edge-case handling against the oracle, without a GPU.
 #pragma once
 #define HEOM_HOST_EMU 1
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -168,14 +173,94 @@ template <typename T> inline void __stcs(T* p, const T v) { *p = v; }
 inline unsigned smem_u32(const void* p) {
     return (unsigned)(reinterpret_cast<const char*>(p) - emu::t_cta->smem.data());
 }
-inline void cp_async16(void* smem_dst, const void* gsrc) { std::memcpy(smem_dst, gsrc, 16); }
-inline void cp_async16_s(unsigned smem_dst_u32, const void* gsrc) {
-    std::memcpy(emu::t_cta->smem.data() + smem_dst_u32, gsrc, 16);
+
+// ---- asynchronous copies --------------------------------------------------------
+// Two timing models, chosen per launch with emu::g_async_late:
+//   0  a copy lands the moment it is issued (the earliest legal time: exposes
+//      write-after-read hazards on a buffer that is still being read);
+//   1  a cp.async copy lands when its group is waited for, a bulk copy when a
+//      thread waits on its mbarrier (the latest legal time: exposes reads before
+//      the wait, wrong wait counts, wrong expect_tx byte counts and phase-parity
+//      mistakes - a wait that can never complete aborts the process).
+namespace emu {
+inline int g_async_late = 0;
+struct Copy { void* dst; const void* src; unsigned bytes; };
+inline thread_local std::vector<std::vector<Copy>> t_groups;   // committed cp.async groups, oldest first
+inline thread_local std::vector<Copy> t_open;                  // copies of the group not yet committed
+struct MBar {
+    unsigned long completed = 0;   // phases completed so far
+    long long expected = 0, arrived = 0;
+    bool armed = false;
+    std::vector<Copy> copies;
+};
+struct MBars {
+    std::mutex m;
+    std::condition_variable cv;
+    std::map<const void*, MBar> bars;
+};
+inline MBars& mbars() {
+    static MBars all;   // keyed by shared-memory address; CTAs run one after the other
+    return all;
 }
-inline void mbar_init(unsigned long long*, unsigned) {}
-inline void mbar_expect_tx(unsigned long long*, unsigned) {}
-inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
-inline void mbar_wait(unsigned long long*, unsigned) {}
+inline void apply(const Copy& c) { std::memcpy(c.dst, c.src, c.bytes); }
+}  // namespace emu
+
+inline void cp_async16(void* smem_dst, const void* gsrc) {
+    if (emu::g_async_late) emu::t_open.push_back(emu::Copy{smem_dst, gsrc, 16});
+    else std::memcpy(smem_dst, gsrc, 16);
+}
+inline void cp_async16_s(unsigned smem_dst_u32, const void* gsrc) {
+    cp_async16(emu::t_cta->smem.data() + smem_dst_u32, gsrc);
+}
+inline void cp_async_commit() {
+    if (!emu::g_async_late) return;
+    emu::t_groups.push_back(std::move(emu::t_open));
+    emu::t_open.clear();
+}
+template <int NWAIT> inline void cp_async_wait() {
+    while ((int)emu::t_groups.size() > NWAIT) {
+        for (const auto& c : emu::t_groups.front()) emu::apply(c);
+        emu::t_groups.erase(emu::t_groups.begin());
+    }
+}
+inline void mbar_init(unsigned long long* bar, unsigned) {
+    std::lock_guard<std::mutex> lk(emu::mbars().m);
+    emu::mbars().bars[bar] = emu::MBar{};
+}
+inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    std::lock_guard<std::mutex> lk(emu::mbars().m);
+    emu::MBar& b = emu::mbars().bars[bar];
+    b.expected += bytes;
+    b.armed = true;
+    emu::mbars().cv.notify_all();
+}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    std::lock_guard<std::mutex> lk(emu::mbars().m);
+    emu::MBar& b = emu::mbars().bars[bar];
+    if (emu::g_async_late) b.copies.push_back(emu::Copy{dst, src, bytes});
+    else std::memcpy(dst, src, bytes);
+    b.arrived += bytes;
+    emu::mbars().cv.notify_all();
+}
+inline void mbar_wait(unsigned long long* bar, unsigned parity) {
+    std::unique_lock<std::mutex> lk(emu::mbars().m);
+    emu::MBar& b = emu::mbars().bars[bar];
+    for (;;) {
+        if ((b.completed & 1u) != parity) return;             // that phase is over
+        if (b.armed && b.arrived == b.expected) {              // every byte is in: the phase completes
+            for (const auto& c : b.copies) emu::apply(c);
+            b.copies.clear();
+            b.expected = b.arrived = 0;
+            b.armed = false;
+            ++b.completed;
+            emu::mbars().cv.notify_all();
+            return;
+        }
+        if (emu::mbars().cv.wait_for(lk, std::chrono::seconds(20)) == std::cv_status::timeout) {
+            std::fprintf(stderr, "cuda_emu: mbarrier wait cannot complete (expected %lld bytes, arrived %lld)\n",
+                         b.expected, b.arrived);
+            std::abort();
+        }
+    }
+}
 inline void fence_proxy_async() {}
-inline void cp_async_commit() {}
-template <int NWAIT> inline void cp_async_wait() {}

@@ -7,6 +7,9 @@
 
 extern "C" {
 
+// 0: asynchronous copies land when issued, 1: only when waited for (cuda_emu.h)
+void emu_set_async_late(int late) { emu::g_async_late = late; }
+
 // One call = nt difference-form RK4 steps (the stage plan of run_stage in
 // heom_kernels.cu) on host arrays.  `state` holds the four ADO arrays Y, SA, SB,
 // ACC ([nmax][N][N] complex128 each, contiguous); `links` are the (slot, meta)

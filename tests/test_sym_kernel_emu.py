@@ -2,11 +2,12 @@
 
 The kernel source is compiled unchanged with g++ against ``tests/_shim/cuda_emu.h``
 (one OS thread per CUDA thread, real barriers for the warp/CTA synchronisation;
-asynchronous copies complete immediately) and its RK4 trajectory and final ADOs
+asynchronous copies land either when issued or only when waited for) and its RK4 trajectory and final ADOs
 are compared with the oracle.  This checks the link-record format (``links2``),
 the pre-scaled coefficient table, the compile-time stage kinds, the record
 strip, tail groups, owned ranges and the visiting-order rotation without a GPU.
-The asynchronous-copy / proxy ordering is what the GPU parity tests are for.
+Cross-proxy fences are not modelled: that is what the GPU parity tests and
+compute-sanitizer are for.
 """
 import ctypes
 import os
@@ -23,7 +24,7 @@ C128 = np.complex128
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+def emu_lib(tmp_path_factory):
     out = tmp_path_factory.mktemp("emu") / "libsym_emu.so"
     src = os.path.join(ROOT, "tests", "_shim", "sym_emu.cpp")
     subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++",
@@ -31,6 +32,13 @@ def emu(tmp_path_factory):
     lib = ctypes.CDLL(str(out))
     lib.emu_sym_run.restype = ctypes.c_int
     return lib
+
+
+@pytest.fixture(params=["copies land at issue", "copies land at the wait"])
+def emu(request, emu_lib):
+    """Both extremes of the legal timing of cp.async / cp.async.bulk (cuda_emu.h)."""
+    emu_lib.emu_set_async_late(ctypes.c_int(int(request.param.endswith("wait"))))
+    return emu_lib
 
 
 def link_meta(direction, k, neff, mode, r0):
