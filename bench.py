@@ -273,6 +273,100 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------
+# kernel 6 (opt-in stage kernel, heom_stage_sym.cu): measured beside the headline
+# in a child process so that nothing it does can disturb the headline numbers
+# ---------------------------------------------------------------------------
+def kernel6_child(args):
+    """Runs in its own process: parity of kernel 6 against kernel 3 on a small
+    hierarchy, then the device-timed propagation of the workload with kernel 6.
+    Prints one JSON object."""
+    import torch
+    from pyqed_b200.heom import DEOMSolver, Bath
+    from pyqed_b200 import workloads as W
+    torch.cuda.set_device(0)
+    out = {}
+
+    def solver_for(w, kernel):
+        bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+        s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
+                       w["pulse_system_func"], w["pulse_coupling_func"], lmax=int(w["lmax"]), device=0,
+                       alias_rho0=False)
+        s.tuning = dict(kernel=kernel, warps_per_cta=0, use_graph=0)
+        s.options = {"resident": 0}
+        return s
+    # ---- parity first: K=21, depth 3 (2024 ADOs), 12 steps, every ADO
+    small = W.fmo(lmax=3, n_matsubara=2)
+    res = {}
+    for kern in (3, 6):
+        s = solver_for(small, kern)
+        _, traj = s.run(small["rho0"].copy(), small["dt"], 12)
+        res[kern] = (np.asarray(traj), np.array(s.ddos), int(s._plan.info("sym_launches")))
+    scale = max(1.0, float(np.abs(res[3][1]).max()))
+    out["parity_vs_kernel3"] = {
+        "workload": "fmo7 K=21 L=3 (2024 ADOs), 12 RK4 steps",
+        "max_abs_diff_trajectory": float(np.max(np.abs(res[3][0] - res[6][0]))),
+        "max_abs_diff_all_ados": float(np.max(np.abs(res[3][1] - res[6][1]))),
+        "ados_bitwise_hermitian": bool(np.array_equal(res[6][1], res[6][1].conj().transpose(0, 2, 1))),
+        "kernel6_stage_launches": res[6][2],
+    }
+    ok = (res[6][2] == 48 and out["parity_vs_kernel3"]["max_abs_diff_all_ados"] < 1e-12 * scale
+          and out["parity_vs_kernel3"]["max_abs_diff_trajectory"] < 1e-12)
+    out["parity_ok"] = bool(ok)
+    if ok:
+        # ---- timing, same recipe as the headline arm (CUDA events, inputs resident in HBM)
+        w = WORKLOADS[args.workload]()
+        K, Wm, dt = args.steps, args.warmup, w["dt"]
+        s = solver_for(w, 6)
+        s.run(w["rho0"].copy(), dt, 1)
+        plan = s._plan
+        plan.set_state(w["rho0"][None])
+        plan.propagate(dt, Wm, None, None, None, 0)
+        plan.synchronize()
+        sym0 = plan.info("sym_launches")
+        plan.stage_timing(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        plan.propagate(dt, K, None, None, None, 0)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        stage_ms, stage_n = plan.stage_timing(False)
+        n, nmax = int(w["system"].shape[0]), plan.nmax
+        peak, peak_src = peaks()
+        achieved = 64.0 * n * n * nmax / (stage_ms / max(stage_n, 1) * 1e-3) / 1e9
+        out.update({
+            "value": nmax * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K, "warmup": Wm,
+            "kernel": "stage_rows_sym_kernel", "stage_launches": int(plan.info("sym_launches") - sym0),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "avg_launch_ms": stage_ms / max(stage_n, 1), "launches_timed": stage_n},
+        })
+    print(json.dumps(out), flush=True)
+
+
+def kernel6_leg(args):
+    """Parent side: run ``kernel6_child`` in a child process with a time limit."""
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.abspath(__file__), "--kernel6-child", "--workload", args.workload,
+           "--steps", str(args.steps), "--warmup", str(args.warmup)]
+    note = ("opt-in stage kernel (tuning kernel=6), written after this round's GPU budget was spent; "
+            "measured here in a child process, not part of the headline value")
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"note": note, "error": (res.stderr or res.stdout)[-400:], "returncode": res.returncode}
+        out = json.loads(lines[-1])
+        out["note"] = note
+        return out
+    except subprocess.TimeoutExpired:
+        return {"note": note, "error": "child process exceeded 240 s"}
+    except Exception as exc:  # noqa: BLE001 - this leg must never take the bench line down
+        return {"note": note, "error": repr(exc)}
+
+
+# ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
 def run_gpu_arm(args):
@@ -454,6 +548,9 @@ def run_gpu_arm(args):
             line["cpu_baseline"] = cb
             line["cpu_baseline_python_loop"] = cpu_reference_leg(args.workload, budget_s=8.0)[0]
             line["cpu_baseline_batched"] = cpu_batched_leg(args.workload)
+        if (world == 1 and args.kernel == 0 and not args.no_cpu
+                and os.environ.get("PYQED_B200_BENCH_KERNEL6", "1") != "0"):
+            line["experimental"] = {"kernel6": kernel6_leg(args)}
         print(json.dumps(line), flush=True)
     if multi:
         dist.destroy_process_group()
@@ -477,12 +574,15 @@ def main():
     ap.add_argument("--resident", type=int, default=-1, help="0 off, 4 force kernel 4, default auto (kernel 5)")
     ap.add_argument("--fused", type=int, default=-1, help="multi-GPU: stage kernel stores halo rows itself")
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
+    ap.add_argument("--kernel6-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:
         args.steps = 20
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
-    if args.impl == "reference":
+    if args.kernel6_child:
+        kernel6_child(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)
