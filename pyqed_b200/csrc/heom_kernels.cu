@@ -2089,34 +2089,14 @@ static bool sym_eligible(const pyqed_heom_plan* p, const StageArgs& a, bool tdep
 }
 static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     SymLaunch s{};
-    s.a.yin = a.yin;
-    s.a.y = a.y;
-    s.a.s1 = a.acc;    // last stage: first stage buffer
-    s.a.s2 = a.yout;   // last stage: second stage buffer
-    s.a.out = a.last ? a.ydst : a.yout;
-    s.a.damp = a.damp;
-    s.a.link_ptr = a.link_ptr;
-    s.a.links2 = p->tab<int2>(p->tl.links2);
-    s.a.cbase = a.cbase;
-    s.a.kmode = a.kmode;
-    s.a.ops = a.ops;
-    s.a.traj = a.last ? a.traj : nullptr;
-    s.a.step_base = a.step_base;
-    s.a.slot0 = a.slot0;
-    s.a.a = a.a;
-    s.a.w = a.w;
-    s.a.local_step = a.local_step;
-    s.a.scramble = a.scramble;
-    s.a.nind = a.nind;
-    s.a.nmod = a.nmod;
-    s.a.lmax = a.lmax;
+    s.a = sym_args_from_stage(a, p->tab<int2>(p->tl.links2));
     s.H = reinterpret_cast<const double*>(p->H.data());
     s.N = p->N;
     s.K = p->K;
     s.M = p->M;
     s.L = p->L;
     s.B = p->B;
-    s.stage = a.first ? 0 : (a.last ? 2 : 1);
+    s.stage = sym_stage_kind(a);
     s.hreal = (p->h_real && p->opt_hreal != 0) ? 1 : 0;
     s.warps = p->warps;
     s.sm_count = sm_count;

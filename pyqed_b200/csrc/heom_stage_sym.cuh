@@ -51,6 +51,36 @@ __host__ __device__ inline int sym_link_y(int kdir, int neff, int L, int r0) {
     return ((kdir * (L + 1) + neff) << 5) | (r0 & 0xf);
 }
 
+// The kernel-6 view of a difference-form RK4 stage described by StageArgs (run_stage in
+// heom_kernels.cu): the last stage reads the first stage buffer from `acc` and the second
+// one from `yout` and writes the end-of-step state to `ydst`.
+inline SymArgs sym_args_from_stage(const StageArgs& a, const int2* links2) {
+    SymArgs s{};
+    s.yin = a.yin;
+    s.y = a.y;
+    s.s1 = a.acc;
+    s.s2 = a.yout;
+    s.out = a.last ? a.ydst : a.yout;
+    s.damp = a.damp;
+    s.link_ptr = a.link_ptr;
+    s.links2 = links2;
+    s.cbase = a.cbase;
+    s.kmode = a.kmode;
+    s.ops = a.ops;
+    s.traj = a.last ? a.traj : nullptr;
+    s.step_base = a.step_base;
+    s.slot0 = a.slot0;
+    s.a = a.a;
+    s.w = a.w;
+    s.local_step = a.local_step;
+    s.scramble = a.scramble;
+    s.nind = a.nind;
+    s.nmod = a.nmod;
+    s.lmax = a.lmax;
+    return s;
+}
+inline int sym_stage_kind(const StageArgs& a) { return a.first ? 0 : (a.last ? 2 : 1); }
+
 struct SymLaunch {
     SymArgs a;
     const double* H;      // host, N*N interleaved complex (time-independent Hamiltonian)

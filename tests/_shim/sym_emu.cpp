@@ -34,31 +34,37 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
     if (traj) std::memcpy(traj, Y + slot0 * NN, sizeof(double2) * NN);
     for (int step = 0; step < nt; ++step) {
         for (int stage = 0; stage < 4; ++stage) {
-            SymLaunch s{};
-            s.a.damp = reinterpret_cast<const double2*>(damp);
-            s.a.link_ptr = link_ptr;
-            s.a.links2 = links2.data();
-            s.a.cbase = reinterpret_cast<const double2*>(cbase);
-            s.a.kmode = kmode;
-            s.a.ops = reinterpret_cast<const double2*>(ops);
-            s.a.step_base = &step_base;
-            s.a.local_step = step;
-            s.a.slot0 = slot0;
-            s.a.scramble = scramble;
-            s.a.nind = K;
-            s.a.nmod = M;
-            s.a.lmax = L;
-            s.a.y = Y;
+            // the stage as run_stage (heom_kernels.cu) describes it ...
+            StageArgs st{};
+            st.damp = reinterpret_cast<const double2*>(damp);
+            st.link_ptr = link_ptr;
+            st.cbase = reinterpret_cast<const double2*>(cbase);
+            st.kmode = kmode;
+            st.ops = reinterpret_cast<const double2*>(ops);
+            st.step_base = &step_base;
+            st.local_step = step;
+            st.slot0 = slot0;
+            st.scramble = scramble;
+            st.nind = K;
+            st.nmod = M;
+            st.lmax = L;
+            st.traj = reinterpret_cast<double2*>(traj);
+            st.y = Y;
+            st.acc = ACC;
+            st.scheme = 1;
             switch (stage) {
-                case 0: s.a.yin = Y;  s.a.out = SA;  s.a.a = dt / 2; s.stage = 0; break;
-                case 1: s.a.yin = SA; s.a.out = SB;  s.a.a = dt / 2; s.stage = 1; break;
-                case 2: s.a.yin = SB; s.a.out = ACC; s.a.a = dt;     s.stage = 1; break;
+                case 0: st.yin = Y;  st.yout = SA;  st.a = dt / 2; st.first = 1; break;
+                case 1: st.yin = SA; st.yout = SB;  st.a = dt / 2; break;
+                case 2: st.yin = SB; st.yout = ACC; st.a = dt; break;
                 default:
-                    s.a.yin = ACC; s.a.s1 = SA; s.a.s2 = SB; s.a.out = Y;
-                    s.a.a = 2.0 / dt; s.a.w = dt / 6; s.stage = 2;
-                    s.a.traj = reinterpret_cast<double2*>(traj);
+                    st.yin = ACC; st.acc = SA; st.yout = SB; st.ydst = Y;
+                    st.a = 2.0 / dt; st.w = dt / 6; st.last = 1;
                     break;
             }
+            // ... and the product's mapping of it onto kernel 6
+            SymLaunch s{};
+            s.a = sym_args_from_stage(st, links2.data());
+            s.stage = sym_stage_kind(st);
             s.H = H;
             s.N = N; s.K = K; s.M = M; s.L = L; s.B = 1;
             s.hreal = hreal;
