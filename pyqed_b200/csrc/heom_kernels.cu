@@ -96,6 +96,7 @@ struct pyqed_heom_plan {
     int opt_rk13 = -1;  // difference-form RK4 in the async kernel (-1/1 on, 0 off)
     long long resident_launches = 0;
     long long sym_launches = 0;  // stage launches that went to kernel 6
+    long long packed_steps = 0;  // RK4 steps done by kernel 7 (packed Hermitian storage)
     bool links2_built = false;
     size_t bound_table_bytes = 0;
     int resident_kind = 0;  // 4 or 5: which resident kernel ran last
@@ -163,8 +164,8 @@ static int compute_layout(pyqed_heom_plan* p) {
     t.lex2slot = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
     t.slot2lex = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
     t.step_base = take(sizeof(long long));
-    // second link table of kernel 6 (heom_stage_sym.cuh), only when that kernel was asked for
-    t.links2 = take(p->kernel == 6 ? sizeof(int2) * (size_t)std::max(1ll, p->nlinks) : 0);
+    // second link table of kernels 6 / 7 (heom_stage_sym.cuh), only when one of them was asked for
+    t.links2 = take((p->kernel == 6 || p->kernel == 7) ? sizeof(int2) * (size_t)std::max(1ll, p->nlinks) : 0);
     t.total = off;
     p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
     return 0;
@@ -1770,8 +1771,10 @@ __global__ void __launch_bounds__(1024) stage_generic_kernel(const StageArgs a) 
 // diagonal coupling (its neighbour rows use 32-bit element offsets, so only while
 // nmax N^2 < 2^32), the plain row kernel for other N <= 8, the generic kernel above.
 static int stage_kernel_of(const pyqed_heom_plan* p) {
-    // 6 = kernel 3's scheme and buffers; launch_stage hands the eligible stages to kernel 6
-    if (p->kernel && p->kernel != 4 && p->kernel != 6) return p->kernel;
+    // 6 = kernel 3's scheme and buffers; launch_stage hands the eligible stages to kernel 6.
+    // 7 = whole propagations on packed Hermitian storage where eligible (pyqed_heom_propagate),
+    //     kernel 3 otherwise
+    if (p->kernel && p->kernel != 4 && p->kernel != 6 && p->kernel != 7) return p->kernel;
     if (p->N > 8) return 2;
     const bool fits32 = (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
     return (p->use_qdiag && p->opt_rk13 != 0 && fits32) ? 3 : 1;
@@ -2329,7 +2332,7 @@ int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
 
 int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
     REQUIRE(p, "null plan");
-    REQUIRE((kernel >= 0 && kernel <= 4) || kernel == 6, "kernel must be 0..4 or 6");
+    REQUIRE((kernel >= 0 && kernel <= 4) || kernel == 6 || kernel == 7, "kernel must be 0..4, 6 or 7");
     REQUIRE(warps >= 0 && warps <= 8, "warps_per_cta must be in [0, 8]");
     p->kernel = kernel;
     p->warps = warps;
@@ -2363,6 +2366,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "resident_launches") return p->resident_launches;
     if (n == "resident_kind") return p->resident_kind;
     if (n == "sym_launches") return p->sym_launches;
+    if (n == "packed_steps") return p->packed_steps;
     if (n == "rk_scheme") return rk_scheme(p) ? 1 : 0;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
@@ -2632,12 +2636,12 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
                                           std::to_string(p->nlinks) + ")");
     p->slot0 = slot0;
     p->links2_built = false;
-    if (p->kernel == 6 && N <= 8 && p->use_qdiag && p->single_support) {
+    if ((p->kernel == 6 || p->kernel == 7) && N <= 8 && p->use_qdiag && p->single_support) {
         const char* err = "";
         if (heom_sym_supported(N, K, p->M, L, &err) == 0 &&
             (unsigned long long)p->nmax * NN < (1ull << 32) &&
             t.links2 + sizeof(int2) * (size_t)p->nlinks <= p->bound_table_bytes) {   // kernel chosen before bind
-            if (heom_sym_convert_links(h.links, p->tab<int2>(t.links2), p->nlinks, N, L, s, &err))
+            if (heom_sym_convert_links(h.links, p->tab<int2>(t.links2), p->nlinks, N, L, p->kernel == 7 ? 1 : 0, s, &err))
                 return fail(std::string("sym_convert_links_kernel launch: ") + err);
             p->launches++;
             CU_TRY(cudaStreamSynchronize(s));
@@ -2862,6 +2866,58 @@ int pyqed_heom_propagate_begin(pyqed_heom_plan* p, double dt, int64_t nt, const 
     return 0;
 }
 
+// kernel 7 (heom_stage_sym.cu, heom_packed_propagate): the whole propagation on packed
+// Hermitian storage.  Same eligibility as kernel 6, plus one trajectory and the whole
+// hierarchy on this GPU (the halo exchange works on full matrices).
+static bool packed_eligible(const pyqed_heom_plan* p) {
+    return p->kernel == 7 && p->links2_built && !p->ctx_tdep && p->herm_inputs && p->herm_state &&
+           p->opt_herm != 0 && p->single_support && p->opt_sym != 0 && !p->push_ptr && p->B == 1 &&
+           p->part_lo == 0 && p->part_hi == p->nmax && rk_scheme(p);
+}
+static int run_packed(pyqed_heom_plan* p, double dt, int64_t nt) {
+    static int sm_count = 0;
+    if (!sm_count) CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    const TableLayout& t = p->tl;
+    PackedRun r{};
+    r.Y = p->arr(ARR_Y);
+    r.work = p->arr(ARR_SA);   // the three stage arrays hold the four triangle arrays
+    r.work_bytes = 3 * p->array_bytes;
+    r.tables.damp = p->tab<double2>(t.damp);
+    r.tables.link_ptr = p->tab<int>(t.link_ptr);
+    r.tables.links2 = p->tab<int2>(t.links2);
+    r.tables.cbase = p->tab<double2>(t.cbase);
+    r.tables.kmode = p->tab<int>(t.kmode);
+    r.tables.ops = p->tab<double2>(t.ops_base);
+    r.tables.traj = p->ctx_traj;
+    r.tables.step_base = p->tab<long long>(t.step_base);
+    r.tables.slot0 = p->slot0;
+    r.tables.scramble = p->order == 2;
+    r.tables.nind = p->K;
+    r.tables.nmod = p->M;
+    r.tables.lmax = p->L;
+    r.H = reinterpret_cast<const double*>(p->H.data());
+    r.N = p->N;
+    r.K = p->K;
+    r.M = p->M;
+    r.L = p->L;
+    r.nmax = p->nmax;
+    r.nt = nt;
+    r.dt = dt;
+    r.hreal = (p->h_real && p->opt_hreal != 0) ? 1 : 0;
+    r.warps = p->warps;
+    r.sm_count = sm_count;
+    r.stream = p->stream;
+    const char* err = "";
+    if (heom_packed_propagate(r, &err)) return fail(std::string("packed propagation (kernel 7): ") + err);
+    p->launches += 4 * nt + 2;
+    p->packed_steps += nt;
+    if (p->debug_sync) {
+        cudaError_t e = cudaStreamSynchronize(p->stream);
+        if (e != cudaSuccess) return fail(std::string("packed propagation (kernel 7) exec: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
 int pyqed_heom_propagate_stage(pyqed_heom_plan* p, int64_t step, int stage) {
     REQUIRE(p && p->built && p->ctx_valid, "propagate_stage: call propagate_begin first");
     REQUIRE(stage >= 0 && stage <= 3 && step >= 0 && step < p->ctx_nt, "propagate_stage: bad step/stage");
@@ -2878,6 +2934,7 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
         if (rr == 0) return 0;
         if (rr > 0) return 1;
         REQUIRE(p->kernel != 4, "kernel 4 (cluster-resident) is not applicable to this problem");
+        if (packed_eligible(p)) return run_packed(p, dt, nt);
         for (int64_t i = 0; i < nt; ++i)
             for (int st = 0; st < 4; ++st)
                 if (run_stage(p, i, st)) return 1;

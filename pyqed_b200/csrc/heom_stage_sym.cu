@@ -43,36 +43,50 @@ namespace {
 
 constexpr int SYM_NCH = 4;   // link chunks (of N links) whose records are prefetched per ADO
 
-// per-warp shared memory in double2 units
-__host__ __device__ constexpr int sym_perwarp(int N, int stage) {
+constexpr int SYM_TOFS = 16;  // double2 units reserved for the packed-row offset table (N*N ints)
+
+// per-warp shared memory in double2 units.  `packed`: the ADO arrays hold the upper
+// triangle only (N(N+1)/2 elements per ADO, row-major), see stage_rows_sym_kernel.
+__host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed) {
     const int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD, FLAT = APW * NN;
+    const int FE = APW * (packed ? N * (N + 1) / 2 : NN);   // a group's elements in the global arrays
+    const int RT = packed ? FE : TILE;                       // own tile as staged
     // own tile, k tile, neighbour rows, [y], [first stage buffer], record strip, four mbarriers
-    return 2 * TILE + FLAT + (stage == 0 ? 0 : FLAT) + (stage == 2 ? FLAT : 0) + SYM_NCH * APW * N / 2 + 2;
+    return RT + TILE + FLAT + (stage == 0 ? 0 : FE) + (stage == 2 ? FE : 0) + SYM_NCH * APW * N / 2 + 2;
 }
 __host__ __device__ constexpr int sym_max_threads(int stage) {
     return stage == 2 ? HEOM_SYM_LAST_THREADS : HEOM_SYM_THREADS;
 }
 
-template <int N, bool HREAL, int STAGE>
+// PACKED (kernel 7): every ADO is Hermitian, so the global arrays hold only the upper
+// triangle, N(N+1)/2 elements per ADO in row-major order (element (i,j), i <= j, at
+// i N - i(i-1)/2 + j - i) - 448 instead of 784 bytes for N = 7.  The k tile in shared memory
+// stays a full N x N matrix; the own tile is read through the triangle (conjugating below
+// the diagonal), a neighbour-row element (r0, j) comes from (min, max) of the pair, and the
+// epilogue writes the upper triangle of the stage output.
+template <int N, bool HREAL, int STAGE, bool PACKED>
 __global__ void __launch_bounds__(sym_max_threads(STAGE), 1)
 stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
     constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE), NCH = SYM_NCH;
-    constexpr bool BULK_TILE = (LD == N);   // padded tiles cannot be one bulk copy
-    constexpr int EIT = (FLAT + 31) / 32;
+    constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE, PACKED), NCH = SYM_NCH;
+    constexpr int PK = N * (N + 1) / 2, EL = PACKED ? PK : NN;   // elements per ADO in the global arrays
+    constexpr int FE = APW * EL, RT = PACKED ? FE : TILE;
+    constexpr bool BULK_TILE = PACKED || (LD == N);   // padded tiles cannot be one bulk copy
+    constexpr int EIT = (FE + 31) / 32;
     HEOM_DYN_SMEM(double2, smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int L1 = a.lmax + 1, ncq = 2 * a.nind * L1;
     // coefficient pairs per (2k+dir, n_eff): [0] element off the diagonal, [1] the diagonal
     // element (row == r0), both already times sqrt(n_eff)
     double2* cq_s = smem;
-    double2* rho_s = smem + 2 * ncq + wid * PERWARP;
-    double2* k_s = rho_s + TILE;
+    int* tofs_s = (int*)(smem + 2 * ncq);   // PACKED: [r0][j] -> offset of element (r0, j) in the triangle
+    double2* rho_s = smem + 2 * ncq + SYM_TOFS + wid * PERWARP;
+    double2* k_s = rho_s + RT;
     double2* nb_s = k_s + TILE;
-    double2* y_s = nb_s + FLAT;                       // !FIRST
-    double2* acc_s = y_s + (FIRST ? 0 : FLAT);        // LAST
-    int2* strip = (int2*)(acc_s + (LAST ? FLAT : 0));
+    double2* y_s = nb_s + FLAT;                     // !FIRST
+    double2* acc_s = y_s + (FIRST ? 0 : FE);        // LAST
+    int2* strip = (int2*)(acc_s + (LAST ? FE : 0));
     unsigned long long* barA = (unsigned long long*)(strip + NCH * APW * N);   // own tile
     unsigned long long* barB = barA + 1;                                       // y / first stage buffer
     unsigned long long* barD = barA + 2;                                       // second stage buffer
@@ -96,6 +110,12 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
         // the diagonal element is counted twice by the P' + P'^dagger pass: halve it here
         cq_s[2 * e + 1] = make_double2(0.5 * (c1.x * sq), 0.5 * (c1.y * sq));
     }
+    if (PACKED) {
+        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+            const int r0 = e / N, j = e - r0 * N, lo = min(r0, j), hi = max(r0, j);
+            tofs_s[e] = lo * N - lo * (lo - 1) / 2 + (hi - lo);
+        }
+    }
     __syncthreads();
 
     const int sub = lane / N, row = lane - sub * N;
@@ -104,19 +124,31 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
     // slots, groups and element offsets are 32-bit here (the host checks nmax N^2 < 2^32)
     const int ngroups = (int)a.ngroups, gstride = (int)gridDim.x * nwarps;
     const int slot_lo = (int)a.slot_lo, slot_hi = (int)a.slot_hi;
-    // flat element e = lane + 32 it  ->  offset in the (possibly padded) tile
-    int pofs[EIT];
+    // flat element e = lane + 32 it of the group in the global arrays  ->  offset in the
+    // staged own tile (rofs) and in the full, possibly padded, k tile (kofs)
+    int kofs[EIT];
 #pragma unroll
     for (int it = 0; it < EIT; ++it) {
         const int e = lane + 32 * it;
-        if (LD == N) pofs[it] = e;
-        else {
-            const int s = e / NN, r = e - s * NN, i = r / N, j = r - i * N;
-            pofs[it] = (s * N + i) * LD + j;
+        const int s = e / EL;
+        int i = 0, j = e - s * EL;
+        if (PACKED) {
+            while (i < N - 1 && j >= N - i) {   // row i of the triangle holds N - i elements
+                j -= N - i;
+                ++i;
+            }
+            j += i;
+        } else {
+            i = j / N;
+            j -= i * N;
         }
+        kofs[it] = (s * N + i) * LD + j;
     }
+    auto rofs = [&](int it) { return PACKED ? lane + 32 * it : kofs[it]; };
     double2* const ksub = k_s + sub * N * LD;     // this ADO's k tile
-    const double2* const rsub = rho_s + sub * N * LD;
+    const double2* const rsub = rho_s + sub * (PACKED ? PK : N * LD);
+    const int frow = row * N - row * (row - 1) / 2 - row;   // PACKED: element (row, l), l >= row, at frow + l
+    const int* const trow = tofs_s + row;                   // PACKED: + r0*N: offset of element (r0, row)
     const double2* const nbrow = nb_s + sub * NN + row;   // + t*N: row element of staged link t
     const unsigned nbrow_u32 = smem_u32(nbrow);
     // + (c*APW*N + t): record t of chunk c (idle lanes stay inside the strip)
@@ -163,12 +195,12 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
     for (; g < ngroups; g += gstride) {
         const int base = cur_base;
         const int cnt = min(APW, slot_hi - base);
-        const int nelem = cnt * NN;
+        const int nelem = cnt * EL;
         const bool on = lane_ok && sub < cnt;
         const int lbeg = nx_lbeg, lend = nx_lend;
         const int nl = on ? (lend - lbeg) : 0;
         const double dh = 0.5 * nx_damp;
-        const unsigned gbase = (unsigned)base * (unsigned)NN;
+        const unsigned gbase = (unsigned)base * (unsigned)EL;
         // publish this group's records, then start the prefetch of the next group's
         if (lane_ok) {
 #pragma unroll
@@ -192,7 +224,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
             const double2* src = a.yin + gbase + lane;
 #pragma unroll
             for (int it = 0; it < EIT; ++it)
-                if (lane + 32 * it < nelem) cp_async16(&rho_s[pofs[it]], src + 32 * it);
+                if (lane + 32 * it < nelem) cp_async16(&rho_s[rofs(it)], src + 32 * it);
         }
         __syncwarp();   // the strip is visible to the whole warp
         int ry[N];      // coefficient offset | target row of the chunk's links
@@ -200,7 +232,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
         for (int t = 0; t < N; ++t) {
             const int2 r = strip_sub[t];
             ry[t] = r.y;
-            if (t < nl) cp_async16_s(nbrow_u32 + t * (N * 16), yin_row + (unsigned)r.x);
+            if (t < nl)
+                cp_async16_s(nbrow_u32 + t * (N * 16),
+                             PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
+                                    : yin_row + (unsigned)r.x);
         }
         cp_async_commit();
         if (!FIRST) {
@@ -228,7 +263,16 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
         if (on) {
             double2 col[N];
 #pragma unroll
-            for (int l = 0; l < N; ++l) col[l] = rsub[l * LD + row];
+            for (int l = 0; l < N; ++l) {
+                if (PACKED) {
+                    // element (l, row) of the Hermitian tile from its upper triangle
+                    const int cl = l * N - l * (l - 1) / 2 - l;   // (l, j), j >= l, at cl + j
+                    const double2 v = rsub[l <= row ? cl + row : frow + l];
+                    col[l] = make_double2(v.x, l <= row ? v.y : -v.y);
+                } else {
+                    col[l] = rsub[l * LD + row];
+                }
+            }
             const double sh = LAST ? (0.5 * a.a - dh) : -dh;
 #pragma unroll
             for (int rr = 0; rr < N; ++rr) {
@@ -260,7 +304,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
                 const double2* sb = a.s2 + gbase + lane;
 #pragma unroll
                 for (int it = 0; it < EIT; ++it)
-                    if (lane + 32 * it < nelem) cp_async16(&rho_s[pofs[it]], sb + 32 * it);
+                    if (lane + 32 * it < nelem) cp_async16(&rho_s[rofs(it)], sb + 32 * it);
                 cp_async_commit();
             }
         }
@@ -300,7 +344,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
                 for (int t = 0; t < N; ++t) {
                     const int2 r = recs[t];
                     ry[t] = r.y;
-                    if (c0 + t < nl) cp_async16_s(nbrow_u32 + t * (N * 16), yin_row + (unsigned)r.x);
+                    if (c0 + t < nl)
+                        cp_async16_s(nbrow_u32 + t * (N * 16),
+                                     PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
+                                            : yin_row + (unsigned)r.x);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
@@ -311,7 +358,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
                 for (int t = 0; t < N; ++t) {
                     if (c0 + t < nl) {
                         const int rr = ry[t] & 15;
-                        const double2 Aj = nbrow[t * N];
+                        double2 Aj = nbrow[t * N];
+                        if (PACKED && row < rr) Aj.y = -Aj.y;   // fetched (row, r0): conjugate
                         if (rr != cur_rr) {
                             if (cur_rr >= 0) flush();
                             cur_rr = rr;
@@ -362,26 +410,33 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
         int e0 = -1;   // LAST: flat offset of ADO 0 (rho_sys) inside this group, if it is here
         if (LAST && a.traj) {
             const long long d0 = a.slot0 - base;
-            if (d0 >= 0 && d0 < cnt) e0 = (int)d0 * NN;
+            if (d0 >= 0 && d0 < cnt) e0 = (int)d0 * EL;
         }
 #pragma unroll
         for (int it = 0; it < EIT; ++it) {
             const int e = lane + 32 * it;
             if (e < nelem) {
-                const double2 k = k_s[pofs[it]];
+                const double2 k = k_s[kofs[it]];
                 if (LAST) {
                     // y' = -y/3 + S1/3 + 2 S2/3 + w (k4 + (2/dt) S3)   (S3's share is already in k)
-                    const double2 y0 = y_s[e], s1 = acc_s[e], s2 = rho_s[pofs[it]];
+                    const double2 y0 = y_s[e], s1 = acc_s[e], s2 = rho_s[rofs(it)];
                     const double third = 1.0 / 3.0;
                     double2 res = make_double2(fma(a.w, k.x, third * (s1.x - y0.x)),
                                                fma(a.w, k.y, third * (s1.y - y0.y)));
                     res.x = fma(2.0 * third, s2.x, res.x);
                     res.y = fma(2.0 * third, s2.y, res.y);
                     st_stream(a.out + (gbase + e), res);
-                    if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)NN)
-                        a.traj[(step + 1) * NN + (e - e0)] = res;
+                    if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)EL) {
+                        if (PACKED) {   // the trajectory holds full matrices
+                            const int kk = kofs[it] - (e0 / EL) * (N * LD), i = kk / LD, j = kk - i * LD;
+                            a.traj[(step + 1) * NN + i * N + j] = res;
+                            if (i != j) a.traj[(step + 1) * NN + j * N + i] = make_double2(res.x, -res.y);
+                        } else {
+                            a.traj[(step + 1) * NN + (e - e0)] = res;
+                        }
+                    }
                 } else {
-                    const double2 yv = FIRST ? rho_s[pofs[it]] : y_s[e];
+                    const double2 yv = FIRST ? rho_s[rofs(it)] : y_s[e];
                     st_stream(a.out + (gbase + e), make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
                 }
             }
@@ -390,22 +445,54 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
     }
 }
 
-// links -> links2 (one thread per link)
-__global__ void sym_convert_links_kernel(const int2* links, int2* links2, long long nlinks, int N, int L) {
+// links -> links2 (one thread per link).  packed: x = first element of the neighbour's triangle
+__global__ void sym_convert_links_kernel(const int2* links, int2* links2, long long nlinks, int N, int L,
+                                         int packed) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nlinks) return;
     const int2 r = links[i];
     const int r0 = heom::meta_r0(r.y);
-    const unsigned off = ((unsigned)r.x * (unsigned)N + (unsigned)r0) * (unsigned)N;
+    const unsigned off = packed ? (unsigned)r.x * (unsigned)(N * (N + 1) / 2)
+                                : ((unsigned)r.x * (unsigned)N + (unsigned)r0) * (unsigned)N;
     links2[i] = make_int2((int)off, sym_link_y(heom::meta_kdir(r.y), heom::meta_neff(r.y), L, r0));
 }
 
 thread_local const char* g_sym_err = "";
 
-size_t sym_table_bytes(int K, int L) { return sizeof(double2) * 2 * 2 * (size_t)K * (L + 1); }
+size_t sym_table_bytes(int K, int L) { return sizeof(double2) * (2 * 2 * (size_t)K * (L + 1) + SYM_TOFS); }
+
+// full [nmax][N][N] <-> upper triangle [nmax][N(N+1)/2] (one thread per triangle element)
+__global__ void sym_pack_kernel(double2* tri, const double2* full, long long nmax, int N) {
+    const int PK = N * (N + 1) / 2;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= nmax * PK) return;
+    const long long slot = e / PK;
+    int i = 0, j = (int)(e - slot * PK);
+    while (i < N - 1 && j >= N - i) {
+        j -= N - i;
+        ++i;
+    }
+    j += i;
+    tri[e] = full[slot * N * N + i * N + j];
+}
+__global__ void sym_unpack_kernel(double2* full, const double2* tri, long long nmax, int N) {
+    const int PK = N * (N + 1) / 2;
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= nmax * PK) return;
+    const long long slot = e / PK;
+    int i = 0, j = (int)(e - slot * PK);
+    while (i < N - 1 && j >= N - i) {
+        j -= N - i;
+        ++i;
+    }
+    j += i;
+    const double2 v = tri[e];
+    full[slot * N * N + i * N + j] = v;
+    if (i != j) full[slot * N * N + j * N + i] = make_double2(v.x, -v.y);
+}
 constexpr size_t SYM_SMEM_BUDGET = 227 * 1024;
 
-template <int N, bool HREAL, int STAGE>
+template <int N, bool HREAL, int STAGE, bool PACKED>
 int sym_launch_t(const SymLaunch& s) {
     constexpr int APW = 32 / N;
     SymArgs args = s.a;
@@ -413,7 +500,7 @@ int sym_launch_t(const SymLaunch& s) {
     args.slot_lo = s.part_lo;
     args.slot_hi = s.part_hi;
     const size_t table_bytes = sym_table_bytes(s.K, s.L);
-    const size_t per_warp = sizeof(double2) * sym_perwarp(N, STAGE);
+    const size_t per_warp = sizeof(double2) * sym_perwarp(N, STAGE, PACKED);
     if (table_bytes + per_warp > SYM_SMEM_BUDGET) {
         g_sym_err = "shared-memory tables too large for kernel 6";
         return 1;
@@ -430,7 +517,7 @@ int sym_launch_t(const SymLaunch& s) {
     const unsigned grid = (unsigned)std::min<long long>(ctas, s.sm_count);
     HParam<N> hp;
     for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(s.H[2 * e], s.H[2 * e + 1]);
-    auto kern = stage_rows_sym_kernel<N, HREAL, STAGE>;
+    auto kern = stage_rows_sym_kernel<N, HREAL, STAGE, PACKED>;
 #ifndef HEOM_HOST_EMU
     static bool attr_set = false;
     if (!attr_set) {
@@ -463,20 +550,24 @@ int sym_launch_t(const SymLaunch& s) {
     return 0;
 }
 
-template <int N>
-int sym_launch_n(const SymLaunch& s) {
+template <int N, bool PACKED>
+int sym_launch_p(const SymLaunch& s) {
     if (s.hreal) {
         switch (s.stage) {
-            case 0: return sym_launch_t<N, true, 0>(s);
-            case 1: return sym_launch_t<N, true, 1>(s);
-            default: return sym_launch_t<N, true, 2>(s);
+            case 0: return sym_launch_t<N, true, 0, PACKED>(s);
+            case 1: return sym_launch_t<N, true, 1, PACKED>(s);
+            default: return sym_launch_t<N, true, 2, PACKED>(s);
         }
     }
     switch (s.stage) {
-        case 0: return sym_launch_t<N, false, 0>(s);
-        case 1: return sym_launch_t<N, false, 1>(s);
-        default: return sym_launch_t<N, false, 2>(s);
+        case 0: return sym_launch_t<N, false, 0, PACKED>(s);
+        case 1: return sym_launch_t<N, false, 1, PACKED>(s);
+        default: return sym_launch_t<N, false, 2, PACKED>(s);
     }
+}
+template <int N>
+int sym_launch_n(const SymLaunch& s) {
+    return s.packed ? sym_launch_p<N, true>(s) : sym_launch_p<N, false>(s);
 }
 
 }  // namespace
@@ -485,7 +576,7 @@ int heom_sym_supported(int N, int K, int M, int L, const char** err) {
     (void)M;
     const char* why = nullptr;
     if (N < 2 || N > 8) why = "kernel 6 needs 2 <= N <= 8";
-    else if (sym_table_bytes(K, L) + sizeof(double2) * sym_perwarp(N, 2) > SYM_SMEM_BUDGET)
+    else if (sym_table_bytes(K, L) + sizeof(double2) * sym_perwarp(N, 2, false) > SYM_SMEM_BUDGET)
         why = "shared-memory tables too large for kernel 6";
     else if ((((long long)2 * K) * (L + 1) + L) >= (1ll << 26))
         why = "coefficient index does not fit the link record of kernel 6";
@@ -493,12 +584,12 @@ int heom_sym_supported(int N, int K, int M, int L, const char** err) {
     return why ? 1 : 0;
 }
 
-int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
-                           const char** err) {
+int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, int packed,
+                           void* stream, const char** err) {
     if (nlinks <= 0) return 0;
     const int threads = 256;
     const unsigned blocks = (unsigned)((nlinks + threads - 1) / threads);
-    HEOM_LAUNCH(sym_convert_links_kernel, blocks, threads, 0, stream, links, links2, nlinks, N, L);
+    HEOM_LAUNCH(sym_convert_links_kernel, blocks, threads, 0, stream, links, links2, nlinks, N, L, packed);
 #ifndef HEOM_HOST_EMU
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -525,4 +616,63 @@ int heom_sym_launch(const SymLaunch& s, const char** err) {
     }
     if (rc && err) *err = g_sym_err;
     return rc;
+}
+
+// ---------------------------------------------------------------------------
+// kernel 7: nt RK4 steps on upper-triangle arrays.  Y (full matrices) is packed into the
+// work region, propagated there by the PACKED instantiations - the four triangle arrays play
+// the roles of Y, SA, SB, ACC in run_stage's difference-form plan (heom_kernels.cu) - and
+// unpacked back into Y at the end.
+// ---------------------------------------------------------------------------
+int heom_packed_propagate(const PackedRun& r, const char** err) {
+    const int N = r.N, PK = N * (N + 1) / 2;
+    const long long tri = r.nmax * PK;
+    const size_t arr = ((size_t)tri * sizeof(double2) + 255) / 256 * 256 / sizeof(double2);   // aligned stride
+    if (4 * arr * sizeof(double2) > r.work_bytes) {
+        if (err) *err = "kernel 7: work region too small for four triangle arrays";
+        return 1;
+    }
+    double2 *P0 = r.work, *P1 = P0 + arr, *P2 = P1 + arr, *P3 = P2 + arr;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((tri + threads - 1) / threads);
+    HEOM_LAUNCH(sym_pack_kernel, blocks, threads, 0, r.stream, P0, (const double2*)r.Y, r.nmax, N);
+    for (long long step = 0; step < r.nt; ++step) {
+        for (int stage = 0; stage < 4; ++stage) {
+            SymLaunch s{};
+            s.a = r.tables;   // damp, link_ptr, links2 (packed form), cbase, kmode, ops, step_base, slot0, ...
+            s.a.local_step = (int)step;
+            s.a.y = P0;
+            switch (stage) {
+                case 0: s.a.yin = P0; s.a.out = P1; s.a.a = r.dt / 2; s.stage = 0; break;
+                case 1: s.a.yin = P1; s.a.out = P2; s.a.a = r.dt / 2; s.stage = 1; break;
+                case 2: s.a.yin = P2; s.a.out = P3; s.a.a = r.dt;     s.stage = 1; break;
+                default:
+                    s.a.yin = P3; s.a.s1 = P1; s.a.s2 = P2; s.a.out = P0;
+                    s.a.a = 2.0 / r.dt; s.a.w = r.dt / 6; s.stage = 2;
+                    break;
+            }
+            if (stage != 3) s.a.traj = nullptr;
+            s.H = r.H;
+            s.N = N; s.K = r.K; s.M = r.M; s.L = r.L; s.B = 1;
+            s.hreal = r.hreal;
+            s.packed = 1;
+            s.warps = r.warps;
+            s.sm_count = r.sm_count;
+            s.part_lo = 0;
+            s.part_hi = r.nmax;
+            s.batch_elems = tri;
+            s.traj_bstride = 0;
+            s.stream = r.stream;
+            if (heom_sym_launch(s, err)) return 1;
+        }
+    }
+    HEOM_LAUNCH(sym_unpack_kernel, blocks, threads, 0, r.stream, r.Y, (const double2*)P0, r.nmax, N);
+#ifndef HEOM_HOST_EMU
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        if (err) *err = cudaGetErrorString(e);
+        return 1;
+    }
+#endif
+    return 0;
 }

@@ -25,7 +25,7 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
     *err = none;
     if (heom_sym_supported(N, K, M, L, err)) return 1;
     std::vector<int2> links2((size_t)std::max(1ll, nlinks));
-    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 0, nullptr, err))
         return 1;
     const long long NN = (long long)N * N, asz = nmax * NN;
     double2* Y = reinterpret_cast<double2*>(state);
@@ -81,6 +81,52 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
         }
     }
     return 0;
+}
+
+// Kernel 7: the product's packed-storage driver (heom_packed_propagate) on host arrays.
+// `Y` is the full state [nmax][N][N]; the work region is filled with NaNs first.
+int emu_packed_run(int N, int K, int M, int L, long long nmax, const double* H, const double* ops,
+                   const double* cbase, const int* kmode, const double* damp, const int* link_ptr,
+                   const int* links, long long nlinks, double* Y, double dt, int nt, int hreal,
+                   int sm_count, int warps, long long slot0, int scramble, double* traj, const char** err) {
+    static const char* none = "";
+    *err = none;
+    if (heom_sym_supported(N, K, M, L, err)) return 1;
+    std::vector<int2> links2((size_t)std::max(1ll, nlinks));
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 1, nullptr, err))
+        return 1;
+    const long long NN = (long long)N * N, PK = (long long)N * (N + 1) / 2;
+    const size_t arr = ((size_t)(nmax * PK) * sizeof(double2) + 255) / 256 * 256;
+    std::vector<char> work(4 * arr, (char)0xff);
+    long long step_base = 0;
+    if (traj) std::memcpy(traj, reinterpret_cast<double2*>(Y) + slot0 * NN, sizeof(double2) * NN);
+    PackedRun r{};
+    r.Y = reinterpret_cast<double2*>(Y);
+    r.work = reinterpret_cast<double2*>(work.data());
+    r.work_bytes = work.size();
+    r.tables.damp = reinterpret_cast<const double2*>(damp);
+    r.tables.link_ptr = link_ptr;
+    r.tables.links2 = links2.data();
+    r.tables.cbase = reinterpret_cast<const double2*>(cbase);
+    r.tables.kmode = kmode;
+    r.tables.ops = reinterpret_cast<const double2*>(ops);
+    r.tables.traj = reinterpret_cast<double2*>(traj);
+    r.tables.step_base = &step_base;
+    r.tables.slot0 = slot0;
+    r.tables.scramble = scramble;
+    r.tables.nind = K;
+    r.tables.nmod = M;
+    r.tables.lmax = L;
+    r.H = H;
+    r.N = N; r.K = K; r.M = M; r.L = L;
+    r.nmax = nmax;
+    r.nt = nt;
+    r.dt = dt;
+    r.hreal = hreal;
+    r.warps = warps;
+    r.sm_count = sm_count;
+    r.stream = nullptr;
+    return heom_packed_propagate(r, err);
 }
 
 }  // extern "C"

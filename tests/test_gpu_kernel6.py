@@ -1,10 +1,11 @@
-"""Kernel 6 (``stage_rows_sym_kernel``, heom_stage_sym.cu) on the GPU.
+"""Kernels 6 and 7 (``stage_rows_sym_kernel``, heom_stage_sym.cu) on the GPU.
 
-Kernel 6 was written after this round's GPU budget was spent: it is compiled,
-statically analysed and verified on the CPU through the emulation harness
-(``tests/test_sym_kernel_emu.py``) but has not run on hardware yet, so it is
-opt-in (``tuning = dict(kernel=6)``) and these tests only run with
-``PYQED_B200_TEST_KERNEL6=1``.  First thing to do with a GPU:
+Kernel 6 and its packed-storage variant kernel 7 were written after this round's
+GPU budget was spent: they are compiled, statically analysed and verified on the
+CPU through the emulation harness (``tests/test_sym_kernel_emu.py``) but have not
+run on hardware yet, so they are opt-in (``tuning = dict(kernel=6)`` / ``7``) and
+these tests only run with ``PYQED_B200_TEST_KERNEL6=1``.  First thing to do with
+a GPU (``tools/kernel6_gpu_check.sh`` does all of it):
 
     PYQED_B200_TEST_KERNEL6=1 python -m pytest tests/test_gpu_kernel6.py -m gpu -x -q
     python bench.py --kernel 6
@@ -30,28 +31,41 @@ K6 = dict(kernel=6, warps_per_cta=0, use_graph=0)
 K3 = dict(kernel=3, warps_per_cta=0, use_graph=0)
 
 
+def _tuning(kernel, warps=0):
+    return dict(kernel=kernel, warps_per_cta=warps, use_graph=0)
+
+
+def _ran(plan, kernel, nt):
+    """Did the propagation really go through the kernel under test?"""
+    if kernel == 6:
+        return plan.info("sym_launches") == 4 * nt and plan.info("packed_steps") == 0
+    return plan.info("packed_steps") == nt and plan.info("sym_launches") == 0
+
+
+@pytest.mark.parametrize("kernel", [6, 7])
 @pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L2", "deom_fmo_K21_L3"])
 @pytest.mark.parametrize("order", [0, 1, 2])
-def test_kernel6_matches_reference(name, order):
+def test_kernel6_matches_reference(name, order, kernel):
     g = golden(name)
     s = _solver_from(g, order=order)
-    s.tuning = dict(K6)
+    s.tuning = _tuning(kernel)
     s.options = {"resident": 0}
     _check_against_golden(g, s)
-    assert s._plan.info("sym_launches") == 4 * int(g["nt"])
+    assert _ran(s._plan, kernel, int(g["nt"]))
     assert s._plan.info("resident_launches") == 0
 
 
+@pytest.mark.parametrize("kernel", [6, 7])
 @pytest.mark.parametrize("name", ["deom_spin_boson_L10", "deom_aggregate_L3_T37", "deom_random5_nonherm"])
-def test_kernel6_falls_back_where_it_does_not_apply(name):
+def test_kernel6_falls_back_where_it_does_not_apply(name, kernel):
     """sigma_z / occupation couplings (several diagonal entries), time-dependent
     fields and non-Hermitian problems stay with kernels 3 / 1."""
     g = golden(name)
     s = _solver_from(g)
-    s.tuning = dict(K6)
+    s.tuning = _tuning(kernel)
     s.options = {"resident": 0}
     _check_against_golden(g, s)
-    assert s._plan.info("sym_launches") == 0
+    assert s._plan.info("sym_launches") == 0 and s._plan.info("packed_steps") == 0
 
 
 def _close_and_hermitian(a3, a6):
@@ -64,16 +78,19 @@ def _close_and_hermitian(a3, a6):
 @pytest.mark.parametrize("warps", [0, 1, 3, 8])
 def test_kernel6_agrees_with_kernel3(name, warps):
     g = golden(name)
-    out = []
-    for tuning in (dict(K3, warps_per_cta=warps), dict(K6, warps_per_cta=warps)):
+    out = {}
+    for kernel in (3, 6, 7):
         s = _solver_from(g)
-        s.tuning = tuning
+        s.tuning = _tuning(kernel, warps)
         s.options = {"resident": 0}
         _, traj = s.run(g["rho0"].copy(), float(g["dt"]), int(g["nt"]))
-        out.append((np.asarray(traj), np.array(s.ddos)))
-    assert s._plan.info("sym_launches") > 0
-    _close_and_hermitian(out[0][0], out[1][0])
-    _close_and_hermitian(out[0][1], out[1][1])
+        out[kernel] = (np.asarray(traj), np.array(s.ddos))
+        assert kernel == 3 or _ran(s._plan, kernel, int(g["nt"]))
+    for kernel in (6, 7):
+        _close_and_hermitian(out[3][0], out[kernel][0])
+        _close_and_hermitian(out[3][1], out[kernel][1])
+    # kernel 7 does kernel 6's arithmetic on the same values: identical bits
+    assert np.array_equal(out[6][0], out[7][0]) and np.array_equal(out[6][1], out[7][1])
 
 
 @pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8])
@@ -91,16 +108,17 @@ def test_kernel6_every_system_size(n, complex_h):
     _, ref = o.run(w["rho0"], dt, nt)
     bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
     res = {}
-    for kern in (3, 6):
+    for kern in (3, 6, 7):
         s = DEOMSolver(w["system"], None, bath, w["coupling"], None, lmax=w["lmax"])
-        s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
+        s.tuning = _tuning(kern)
         s.options = {"resident": 0}
         _, got = s.run(w["rho0"].copy(), dt, nt)
         assert np.max(np.abs(np.asarray(got) - np.asarray(ref))) < TOL
         assert np.max(np.abs(s.ddos - o.ddos)) < TOL
-        assert (s._plan.info("sym_launches") > 0) == (kern == 6)
+        assert kern == 3 or _ran(s._plan, kern, nt)
         res[kern] = np.array(s.ddos)
     _close_and_hermitian(res[3], res[6])
+    _close_and_hermitian(res[3], res[7])
 
 
 def test_kernel6_beyond_l2_invariants():
@@ -111,14 +129,40 @@ def test_kernel6_beyond_l2_invariants():
     w = W.fmo(lmax=5, n_matsubara=2)
     bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
     res = {}
-    for kern in (3, 6):
+    for kern in (3, 6, 7):
         s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
                        lmax=w["lmax"])
-        s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
+        s.tuning = _tuning(kern)
         _, traj = s.run(w["rho0"].copy(), w["dt"], 6)
         res[kern] = (np.asarray(traj), np.array(s.ddos))
-    traj = res[6][0]
-    assert np.max(np.abs(np.trace(traj, axis1=1, axis2=2) - 1)) < 1e-12
-    assert np.max(np.abs(traj - traj.conj().transpose(0, 2, 1))) < 1e-14
-    _close_and_hermitian(res[3][0], res[6][0])
-    _close_and_hermitian(res[3][1], res[6][1])
+        assert kern == 3 or _ran(s._plan, kern, 6)
+    for kern in (6, 7):
+        traj = res[kern][0]
+        assert np.max(np.abs(np.trace(traj, axis1=1, axis2=2) - 1)) < 1e-12
+        assert np.max(np.abs(traj - traj.conj().transpose(0, 2, 1))) < 1e-14
+        _close_and_hermitian(res[3][0], res[kern][0])
+        _close_and_hermitian(res[3][1], res[kern][1])
+
+
+def test_kernel7_two_runs_and_restart():
+    """Kernel 7 packs the state on entry and unpacks it on exit: two consecutive
+    propagations must equal one long one, and the ADOs read back in between must
+    be the full matrices."""
+    g = golden("deom_fmo_K21_L2")
+    dt, nt = float(g["dt"]), int(g["nt"])
+    a = _solver_from(g)
+    a.tuning = _tuning(7)
+    a.options = {"resident": 0}
+    _, full = a.run(g["rho0"].copy(), dt, nt)
+    b = _solver_from(g)
+    b.tuning = _tuning(7)
+    b.options = {"resident": 0}
+    h = nt // 2
+    b.prepare(g["rho0"].copy(), dt, h)
+    mid = np.array(b.ddos)
+    assert np.array_equal(mid, mid.conj().transpose(0, 2, 1))
+    b._plan.propagate(dt, nt - h, None, None, None, method=0)
+    end = b._plan.get_ados()[0]
+    assert np.array_equal(end, np.array(a.ddos))
+    assert np.array_equal(np.asarray(full)[-1], end[0])
+    assert b._plan.info("packed_steps") == nt

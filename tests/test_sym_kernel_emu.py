@@ -101,6 +101,29 @@ def run_emu(emu, w, nt, sm_count=3, warps=2, parts=None, scramble=0):
     return state[0], traj, o.ddos, np.array(ref)
 
 
+def run_emu_packed(emu, w, nt, sm_count=3, warps=2, scramble=0):
+    """Kernel 7: ``heom_packed_propagate`` (pack, nt steps on upper triangles, unpack)."""
+    o, t = host_tables(w)
+    N = t["N"]
+    y = np.zeros((o.nmax, N, N), dtype=C128)
+    y[0] = w["rho0"]
+    traj = np.zeros((nt + 1, N, N), dtype=C128)
+    H = np.ascontiguousarray(o.H0)
+    err = ctypes.c_char_p()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    emu.emu_packed_run.restype = ctypes.c_int
+    rc = emu.emu_packed_run(
+        ctypes.c_int(N), ctypes.c_int(t["K"]), ctypes.c_int(t["M"]), ctypes.c_int(o.lmax),
+        ctypes.c_longlong(o.nmax), p(H), p(t["ops"]), p(t["cbase"]), p(t["kmode"]), p(t["damp"]),
+        p(t["link_ptr"]), p(t["links"]), ctypes.c_longlong(len(t["links"])), p(y),
+        ctypes.c_double(w["dt"]), ctypes.c_int(nt), ctypes.c_int(int(np.all(H.imag == 0))),
+        ctypes.c_int(sm_count), ctypes.c_int(warps), ctypes.c_longlong(0), ctypes.c_int(scramble),
+        p(traj), ctypes.byref(err))
+    assert rc == 0, err.value
+    _, ref = o.run(w["rho0"], w["dt"], nt)
+    return y, traj, o.ddos, np.array(ref)
+
+
 def check(emu, w, nt, **kw):
     y, traj, ref_ados, ref_traj = run_emu(emu, w, nt, **kw)
     scale = max(1.0, float(np.abs(ref_ados).max()))
@@ -109,6 +132,14 @@ def check(emu, w, nt, **kw):
     assert np.abs(y - ref_ados).max() < 1e-12 * scale
     # kernel 6 keeps every ADO Hermitian bit for bit
     assert np.array_equal(y, y.conj().transpose(0, 2, 1))
+    if "parts" not in kw:   # kernel 7 (packed storage) owns the whole hierarchy
+        kw.pop("parts", None)
+        y7, traj7, _, _ = run_emu_packed(emu, w, nt, **kw)
+        assert np.abs(traj7 - ref_traj).max() < 1e-12
+        assert np.abs(y7 - ref_ados).max() < 1e-12 * scale
+        assert np.array_equal(y7, y7.conj().transpose(0, 2, 1))
+        # same arithmetic on the same values as kernel 6: identical bits
+        assert np.array_equal(y7, y) and np.array_equal(traj7, traj)
 
 
 def projector_problem(n, nind_per_mode, lmax, seed, complex_h):
@@ -161,6 +192,7 @@ def test_owned_ranges_and_rotation(emu):
     visiting-order rotation of storage order 2, one warp per CTA."""
     w = W.fmo(lmax=3, n_matsubara=0)
     check(emu, w, nt=2, parts=[0, 57, 57, 120], scramble=1, sm_count=2, warps=1)
+    check(emu, w, nt=2, scramble=1, sm_count=2, warps=1)   # whole hierarchy: kernel 7 too
 
 
 def test_more_warps_than_groups(emu):
