@@ -490,6 +490,10 @@ def run_gpu_arm(args):
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else {}
     stage_ms, stage_n = plan.stage_timing(False)
+    if stage_n == 0 and plan.info("packed_steps") > 0:
+        # kernel 7 runs the whole propagation in one call (no per-stage events): its stage time
+        # is the step time / 4, pack and unpack passes included
+        stage_ms, stage_n = ms, 4 * K
     launches = plan.launch_count() - launches0
     per_rank = None
     if multi:
@@ -517,10 +521,12 @@ def run_gpu_arm(args):
         achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
         state_mb = nmax * n * n * 16 / 1e6
         kname = {1: "stage_rows_kernel", 2: "stage_generic_kernel", 3: "stage_rows_async_kernel",
-                 4: "resident_cluster_kernel", 5: "resident_elem_kernel", 6: "stage_rows_async_kernel"}[
+                 4: "resident_cluster_kernel", 5: "resident_elem_kernel", 6: "stage_rows_async_kernel",
+                 7: "stage_rows_async_kernel"}[
             plan.info("resident_kind") if plan.info("resident_launches") > 0 else
             (args.kernel or (2 if n > 8 else (3 if plan.info("qdiag") else 1)))] \
-            if not plan.info("sym_launches") > 0 else "stage_rows_sym_kernel"
+            if not (plan.info("sym_launches") > 0 or plan.info("packed_steps") > 0) else \
+            ("stage_rows_sym_kernel<PACKED>" if plan.info("packed_steps") > 0 else "stage_rows_sym_kernel")
         order_name = ["reference", "lexicographic", "blocked lexicographic"][order]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
