@@ -197,7 +197,13 @@ int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
  * (N <= 8), 2 generic one-CTA-per-ADO kernel, 3 row-per-lane kernel with
  * cp.async staging (N <= 8, diagonal Q_m), 4 cluster-resident propagation
  * (whole hierarchy in distributed shared memory, small hierarchies only;
- * chosen automatically when it fits); warps per CTA for kernels 1 and 3;
+ * chosen automatically when it fits), 6 Hermitian-symmetric stage kernel and
+ * 7 the same on packed (upper-triangle) storage for whole propagate calls -
+ * both opt-in, both fall back to kernel 3 where they do not apply (they need
+ * Hermitian ADOs, one-entry diagonal Q_m and a time-independent H; 7 also one
+ * trajectory and the whole hierarchy on this GPU).  Choose the kernel before
+ * pyqed_heom_table_bytes: kernels 6 / 7 add a second link table to the table
+ * buffer.  warps per CTA for kernels 1, 3, 6 and 7;
  * use_graph: reserved (ignored): small hierarchies are propagated by a single
  * cluster-resident launch instead of a graph. */
 int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
