@@ -28,6 +28,7 @@
 #endif
 
 #include <algorithm>
+#include <type_traits>
 
 #include "heom_core.cuh"
 #include "heom_stage_sym.cuh"
@@ -64,9 +65,18 @@ __host__ __device__ constexpr int sym_max_threads(int stage) {
 // stays a full N x N matrix; the own tile is read through the triangle (conjugating below
 // the diagonal), a neighbour-row element (r0, j) comes from (min, max) of the pair, and the
 // epilogue writes the upper triangle of the stage output.
+// H as a kernel parameter (constant bank): complex entries, or the real parts only when H
+// is real - two of those come with one 128-bit constant load
+template <int N>
+struct HParamReal {
+    double v[N * N + (N * N & 1)];
+};
+template <int N, bool HREAL>
+using HParamOf = typename std::conditional<HREAL, HParamReal<N>, HParam<N>>::type;
+
 template <int N, bool HREAL, int STAGE, bool PACKED>
 __global__ void __launch_bounds__(sym_max_threads(STAGE), 1)
-stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
+stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL> hp) {
     constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE, PACKED), NCH = SYM_NCH;
@@ -279,8 +289,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParam<N> hp) {
                 double2 c = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int l = 0; l < N; ++l) {
-                    if (HREAL) {
-                        const double h = HEL(rr, l).x;
+                    if constexpr (HREAL) {
+                        const double h = HEL(rr, l);
                         c.x = fma(h, col[l].x, c.x);
                         c.y = fma(h, col[l].y, c.y);
                     } else {
@@ -515,8 +525,11 @@ int sym_launch_t(const SymLaunch& s) {
     const size_t smem = table_bytes + per_warp * warps;
     const long long ctas = (args.ngroups + warps - 1) / warps;
     const unsigned grid = (unsigned)std::min<long long>(ctas, s.sm_count);
-    HParam<N> hp;
-    for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(s.H[2 * e], s.H[2 * e + 1]);
+    HParamOf<N, HREAL> hp{};
+    for (int e = 0; e < N * N; ++e) {
+        if constexpr (HREAL) hp.v[e] = s.H[2 * e];
+        else hp.v[e] = make_double2(s.H[2 * e], s.H[2 * e + 1]);
+    }
     auto kern = stage_rows_sym_kernel<N, HREAL, STAGE, PACKED>;
 #ifndef HEOM_HOST_EMU
     static bool attr_set = false;
