@@ -264,3 +264,4 @@ inline void mbar_wait(unsigned long long* bar, unsigned parity) {
     }
 }
 inline void fence_proxy_async() {}
+inline void __threadfence_system() {}

@@ -46,17 +46,24 @@ def link_meta(direction, k, neff, mode, r0):
     return neff | (direction << 8) | (k << 9) | ((r0 & 0xf) << 16) | (mode << 24)
 
 
-def host_tables(w):
+def host_tables(w, single_support=True):
     """The tables ``pyqed_heom_build_hierarchy`` builds on the device, in the
     reference's id order (storage order 0), from the oracle's index tables."""
     o = DO.DeomOracle(w["system"], w["system_dipole"], w["coupling"], w["coupling_dipole"], w["expn"],
                       w["etal"], w["etar"], w["etaa"], w["mode"], w["lmax"])
     N, K, M = o.nsys, o.nind, o.Q0.shape[0]
     r0 = []
+    # diagonal-Q support tables: [M][N+1] (count, rows) then [M][N] membership
+    supp = np.zeros(M * (2 * N + 1), dtype=np.uint8)
     for m in range(M):
         nz = np.nonzero(np.diag(o.Q0[m]))[0]
-        assert len(nz) == 1 and np.count_nonzero(o.Q0[m]) == 1, "kernel 6 needs one-entry diagonal Q_m"
+        assert np.count_nonzero(o.Q0[m]) == len(nz) >= 1, "diagonal coupling operators only"
+        if single_support:
+            assert len(nz) == 1, "kernels 6 / 7 need one-entry diagonal Q_m"
         r0.append(int(nz[0]))
+        supp[m * (N + 1)] = len(nz)
+        supp[m * (N + 1) + 1:m * (N + 1) + 1 + len(nz)] = nz
+        supp[M * (N + 1) + m * N + nz] = 1
     kmode = np.array([int(o.mode[k]) | (r0[int(o.mode[k])] << 8) for k in range(K)], dtype=np.int32)
     sa = np.sqrt(o.etaa)
     cbase = np.stack([-(1j / sa) * o.etal, (1j / sa) * o.etar, -1j * sa, 1j * sa], axis=1).astype(C128)
@@ -73,7 +80,7 @@ def host_tables(w):
         ptr.append(len(recs))
     links = np.array(recs, dtype=np.int32).reshape(-1, 2)
     ops = np.concatenate([o.H0[None], o.Q0]).astype(C128)
-    return o, dict(N=N, K=K, M=M, kmode=kmode, cbase=np.ascontiguousarray(cbase), damp=damp,
+    return o, dict(N=N, K=K, M=M, kmode=kmode, supp=supp, cbase=np.ascontiguousarray(cbase), damp=damp,
                    link_ptr=np.array(ptr, dtype=np.int32), links=np.ascontiguousarray(links), ops=ops)
 
 
