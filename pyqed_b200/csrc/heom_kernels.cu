@@ -2295,9 +2295,11 @@ int pyqed_heom_propagate_begin(pyqed_heom_plan* p, double dt, int64_t nt, const 
 // Hermitian storage.  Same eligibility as kernel 6, plus one trajectory and the whole
 // hierarchy on this GPU (the halo exchange works on full matrices).
 static bool packed_eligible(const pyqed_heom_plan* p) {
+    // four triangle arrays (256-byte aligned) must fit into the three stage arrays
+    const size_t tri = align_up(sizeof(double2) * (size_t)p->nmax * (p->N * (p->N + 1) / 2));
     return p->kernel == 7 && p->links2_built && !p->ctx_tdep && p->herm_inputs && p->herm_state &&
            p->opt_herm != 0 && p->single_support && p->opt_sym != 0 && !p->push_ptr && p->B == 1 &&
-           p->part_lo == 0 && p->part_hi == p->nmax && rk_scheme(p);
+           p->part_lo == 0 && p->part_hi == p->nmax && rk_scheme(p) && 4 * tri <= 3 * p->array_bytes;
 }
 static int run_packed(pyqed_heom_plan* p, double dt, int64_t nt) {
     static int sm_count = 0;

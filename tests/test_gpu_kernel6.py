@@ -115,7 +115,9 @@ def test_kernel6_every_system_size(n, complex_h):
         _, got = s.run(w["rho0"].copy(), dt, nt)
         assert np.max(np.abs(np.asarray(got) - np.asarray(ref))) < TOL
         assert np.max(np.abs(s.ddos - o.ddos)) < TOL
-        assert kern == 3 or _ran(s._plan, kern, nt)
+        # N = 2: four triangle arrays (3/4 of a full one each) do not fit into the three stage
+        # arrays once aligned, so kernel 7 declines and kernel 3 runs
+        assert kern == 3 or (kern == 7 and n == 2) or _ran(s._plan, kern, nt)
         res[kern] = np.array(s.ddos)
     _close_and_hermitian(res[3], res[6])
     _close_and_hermitian(res[3], res[7])
