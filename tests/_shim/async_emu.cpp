@@ -43,7 +43,9 @@ void launch_n(const StageArgs& a, const double* H, int K, int M, int L, int warp
 
 extern "C" {
 
+#ifndef EMU_ONE_SETTER
 void emu_set_async_late(int late) { emu::g_async_late = late; }
+#endif
 
 // nt difference-form RK4 steps with the stage plan of run_stage (heom_kernels.cu, scheme 1)
 // on host arrays; `state` = Y, SA, SB, ACC.  `parts`: owned slot ranges, one launch each.

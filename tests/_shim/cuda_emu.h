@@ -102,7 +102,7 @@ template <typename Kernel, typename... Args>
 void launch(Kernel kernel, unsigned grid, unsigned block, size_t smem_bytes, Args... args) {
     for (unsigned b = 0; b < grid; ++b) {
         Cta cta;
-        cta.smem.assign(smem_bytes + 64, (char)0xff);   // NaN patterns: stale reads poison the result
+        cta.smem.assign(smem_bytes, (char)0xff);   // NaN patterns: stale reads poison the result
         cta.warps = std::vector<Warp>((block + 31) / 32);
         cta.nthreads = (int)block;
         std::vector<std::thread> th;

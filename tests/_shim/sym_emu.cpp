@@ -8,7 +8,9 @@
 extern "C" {
 
 // 0: asynchronous copies land when issued, 1: only when waited for (cuda_emu.h)
+#ifndef EMU_ONE_SETTER
 void emu_set_async_late(int late) { emu::g_async_late = late; }
+#endif
 
 // One call = nt difference-form RK4 steps (the stage plan of run_stage in
 // heom_kernels.cu) on host arrays.  `state` holds the four ADO arrays Y, SA, SB,
