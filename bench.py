@@ -568,15 +568,21 @@ def run_gpu_arm(args):
         }
         if per_rank:
             line["ranks"] = per_rank
+        def aux(key, leg):
+            """Auxiliary legs are reported beside the headline; a failure in one of them is
+            recorded, never allowed to take the measured line down."""
+            try:
+                line[key] = leg()
+            except Exception as exc:  # noqa: BLE001
+                line[key] = {"error": repr(exc)[-300:]}
         if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_cpu:
             # BASELINE.json configs[1] (330 ADOs, cache resident) measured beside the
             # headline workload so that both readings of "the configuration" are on record
-            line["other_workloads"] = {"fmo7_K7_L4": small_workload_leg("fmo7_K7_L4", local)}
+            aux("other_workloads", lambda: {"fmo7_K7_L4": small_workload_leg("fmo7_K7_L4", local)})
         if world == 1 and not args.no_cpu:
-            cb, _, _ = cpu_native_leg(args.workload)
-            line["cpu_baseline"] = cb
-            line["cpu_baseline_python_loop"] = cpu_reference_leg(args.workload, budget_s=8.0)[0]
-            line["cpu_baseline_batched"] = cpu_batched_leg(args.workload)
+            aux("cpu_baseline", lambda: cpu_native_leg(args.workload)[0])
+            aux("cpu_baseline_python_loop", lambda: cpu_reference_leg(args.workload, budget_s=8.0)[0])
+            aux("cpu_baseline_batched", lambda: cpu_batched_leg(args.workload))
         if (world == 1 and args.kernel == 0 and not args.no_cpu
                 and os.environ.get("PYQED_B200_BENCH_KERNEL6", "1") != "0"):
             line["experimental"] = kernel6_leg(args)
