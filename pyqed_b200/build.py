@@ -16,7 +16,8 @@ SOURCES = [os.path.join(CSRC, "heom_kernels.cu"), os.path.join(CSRC, "heom_stage
 SRC = SOURCES[0]
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpyqed_heom.so")
-DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("heom_core.cuh", "heom_device.cuh", "heom_stage_async.cuh", "heom_stage_sym.cuh")] + \
+DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("heom_core.cuh", "heom_device.cuh", "heom_hierarchy.cuh", "heom_stage_rows.cuh", "heom_stage_async.cuh",
+                                                 "heom_resident.cuh", "heom_stage_generic.cuh", "heom_stage_sym.cuh")] + \
     [os.path.join(os.path.dirname(HERE), "include", "pyqed_heom.h")]
 
 

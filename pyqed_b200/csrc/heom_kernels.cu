@@ -32,13 +32,6 @@
 
 using heom::Pascal;
 
-// build-time tuning knobs (see pyqed_b200/build.py)
-#ifndef HEOM_U
-#define HEOM_U 4          // links fetched per batch in the diagonal-Q path
-#endif
-#ifndef HEOM_MINBLOCKS
-#define HEOM_MINBLOCKS 2  // __launch_bounds__ min blocks per SM for the row kernel
-#endif
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -166,1027 +159,10 @@ static int compute_layout(pyqed_heom_plan* p) {
     return 0;
 }
 
-// ---------------------------------------------------------------------------
-// hierarchy builder kernels
-// ---------------------------------------------------------------------------
-struct HierArgs {
-    const long long* pascal;
-    int side, K, L, order;
-    long long nmax;
-    uint8_t* keys;
-    int* id_of_slot;
-    int* slot_of_id;
-    double2* damp;
-    int* link_ptr;
-    int2* links;
-    const double2* expn;  // [K] device copy (stored at the head of coef scratch)
-    const int* mode;      // [K]: mode | first support row << 8
-    int* lex2slot;        // order 2 only: lexicographic rank <-> storage slot
-    int* slot2lex;
-};
-
-// Storage order 2 = lexicographic order with a stable partition inside every
-// aligned block of ORDER2_BLOCK ranks: ADOs below the top tier (which carry the
-// K extra n+e_k links) first, top-tier ADOs after them.  Consecutive slots then
-// have similar link counts (warps stay balanced) while the locality and the
-// small rank-boundary halos of the lexicographic order are kept.
-constexpr int ORDER2_BLOCK = 64;
-__global__ void hier_blockperm_kernel(HierArgs h) {
-    const long long blk = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const long long r0 = blk * ORDER2_BLOCK;
-    if (r0 >= h.nmax) return;
-    Pascal P{h.pascal, h.side};
-    const int cnt = (int)min((long long)ORDER2_BLOCK, h.nmax - r0);
-    unsigned long long top = 0ull;
-    uint8_t key[heom::MAX_NIND];
-    for (int i = 0; i < cnt; ++i) {
-        heom::unrank_lex(r0 + i, h.K, h.L, P, key);
-        int tier = 0;
-        for (int k = 0; k < h.K; ++k) tier += key[k];
-        if (tier == h.L) top |= 1ull << i;
-    }
-    const int nlow = cnt - __popcll(top);
-    int a = 0, b = nlow;
-    for (int i = 0; i < cnt; ++i) {
-        const int pos = ((top >> i) & 1ull) ? b++ : a++;
-        h.lex2slot[r0 + i] = (int)(r0 + pos);
-        h.slot2lex[r0 + pos] = (int)(r0 + i);
-    }
-}
-__device__ __forceinline__ void unrank_any(const HierArgs& h, long long slot, const Pascal& P, uint8_t* key) {
-    if (h.order == 2) heom::unrank_lex(h.slot2lex[slot], h.K, h.L, P, key);
-    else heom::unrank_slot(h.order, slot, h.K, h.L, P, key);
-}
-__device__ __forceinline__ long long rank_any(const HierArgs& h, const uint8_t* key, const Pascal& P) {
-    if (h.order == 2) return h.lex2slot[heom::rank_lex(key, h.K, h.L, P)];
-    return heom::rank_slot(h.order, key, h.K, h.L, P);
-}
-
-// pass 1: one thread per storage slot - multi-index, damping rate, link count
-__global__ void hier_keys_kernel(HierArgs h) {
-    const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (slot >= h.nmax) return;
-    Pascal P{h.pascal, h.side};
-    uint8_t key[heom::MAX_NIND];
-    unrank_any(h, slot, P, key);
-    int tier = 0, nz = 0;
-    double dr = 0.0, di = 0.0;
-    for (int k = 0; k < h.K; ++k) {
-        h.keys[slot * h.K + k] = key[k];
-        tier += key[k];
-        nz += key[k] > 0;
-        const double2 g = h.expn[k];
-        dr += key[k] * g.x;
-        di += key[k] * g.y;
-    }
-    h.damp[slot] = make_double2(dr, di);
-    const long long id = heom::rank_ref(key, h.K, P);
-    h.id_of_slot[slot] = (int)id;
-    h.slot_of_id[id] = (int)slot;
-    h.link_ptr[slot] = nz + (tier < h.L ? h.K : 0);
-    if (slot == 0) h.link_ptr[h.nmax] = 0;
-}
-
-// pass 2: fill links in the reference's summation order (k ascending; for each
-// k the n-e_k term, then the n+e_k term; deom.py:651-664)
-__global__ void hier_links_kernel(HierArgs h) {
-    const long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (slot >= h.nmax) return;
-    Pascal P{h.pascal, h.side};
-    uint8_t key[heom::MAX_NIND];
-    int tier = 0;
-    for (int k = 0; k < h.K; ++k) {
-        key[k] = h.keys[slot * h.K + k];
-        tier += key[k];
-    }
-    int w = h.link_ptr[slot];
-    for (int k = 0; k < h.K; ++k) {
-        const int nk = key[k];
-        if (nk > 0) {
-            key[k] = (uint8_t)(nk - 1);
-            const long long nb = rank_any(h, key, P);
-            key[k] = (uint8_t)nk;
-            h.links[w++] = make_int2((int)nb, heom::link_meta(0, k, nk, h.mode[k] & 0xff, h.mode[k] >> 8));
-        }
-        if (tier < h.L) {
-            key[k] = (uint8_t)(nk + 1);
-            const long long nb = rank_any(h, key, P);
-            key[k] = (uint8_t)nk;
-            h.links[w++] = make_int2((int)nb, heom::link_meta(1, k, nk + 1, h.mode[k] & 0xff, h.mode[k] >> 8));
-        }
-    }
-}
-
-// gather / scatter between storage-slot order and reference id order
-__global__ void permute_kernel(double2* dst, const double2* src, const int* map, long long nmax,
-                               int NN, int dst_is_mapped) {
-    // dst_is_mapped: dst[map[i]] = src[i]   else   dst[i] = src[map[i]]
-    const long long total = nmax * NN;
-    const long long boff = blockIdx.y * total;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const long long i = e / NN;
-        const int r = (int)(e - i * NN);
-        const long long j = map[i];
-        if (dst_is_mapped) dst[boff + j * NN + r] = src[boff + e];
-        else dst[boff + e] = src[boff + j * NN + r];
-    }
-}
-
-// ---------------------------------------------------------------------------
-// time-dependent operators: ops_t[b][o] = base[o] + dip[o] * field_o[b][step][tidx]
-// (generate_time, deom.py:676-687).  Single block; the tables are tiny.
-// ---------------------------------------------------------------------------
-__global__ void prep_ops_kernel(double2* ops_t, const double2* base, const double2* dip,
-                                const double* fsys, const double* fcoup, const long long* step_base,
-                                int local_step, int tidx, long long nt, int B, int M1, int NN) {
-    const long long step = *step_base + local_step;
-    const int per = M1 * NN;
-    for (int e = threadIdx.x; e < B * per; e += blockDim.x) {
-        const int b = e / per, r = e - b * per, o = r / NN;
-        const double* f = (o == 0) ? fsys : fcoup;
-        const double s = f ? f[((long long)b * nt + step) * 3 + tidx] : 0.0;
-        const double2 v = base[r], d = dip[r];
-        ops_t[e] = make_double2(fma(d.x, s, v.x), fma(d.y, s, v.y));
-    }
-}
-
-__global__ void advance_kernel(long long* step_base, long long by) { *step_base += by; }
-
-// rho_sys of every trajectory -> traj[b][index]
-__global__ void record_kernel(double2* traj, const double2* y, long long nmax, long long slot0,
-                              int NN, long long traj_bstride, long long index) {
-    const int b = blockIdx.x;
-    for (int e = threadIdx.x; e < NN; e += blockDim.x)
-        traj[b * traj_bstride + index * NN + e] = y[(b * nmax + slot0) * NN + e];
-}
-
-// out[b][o][p] = Tr(op_o rho[b][p])
-__global__ void expectation_kernel(double2* out, const double2* rho, const double2* ops,
-                                   long long npts, int n_ops, int N) {
-    const long long total = (long long)gridDim.y * n_ops * npts;
-    const int NN = N * N;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_ops * npts;
-         t += (long long)gridDim.x * blockDim.x) {
-        (void)total;
-        const int b = blockIdx.y;
-        const int o = (int)(t / npts);
-        const long long pt = t - (long long)o * npts;
-        const double2* r = rho + ((long long)b * npts + pt) * NN;
-        const double2* a = ops + (long long)o * NN;
-        double2 s = make_double2(0.0, 0.0);
-        for (int i = 0; i < N; ++i)
-            for (int j = 0; j < N; ++j) cfma(s, a[i * N + j], r[j * N + i]);
-        out[((long long)b * n_ops + o) * npts + pt] = s;
-    }
-}
-
-// ---------------------------------------------------------------------------
-// stage kernels
-// ---------------------------------------------------------------------------
-// Kernel 1 (N <= 8): a warp owns 32/N consecutive ADOs; lane (sub,row) owns one
-// matrix row in registers.  -i[H,rho] uses H from the constant bank (kernel
-// parameter) or, when H depends on time/trajectory, from shared memory.
-//
-// Neighbour terms, two variants:
-//  QDIAG (every Q_m diagonal: projectors, sigma_z, occupation numbers): the
-//    coupling is element-wise, (Q rho' - rho' Q)_ij = (q_i - q_j) rho'_ij, so a
-//    link only needs the rows r of rho' with q_r != 0 (plus, for non-Hermitian
-//    ADOs, the matching column entries).  The N lanes of an ADO fetch such a row
-//    with one coalesced 16N-byte request and accumulate into the shared k tile;
-//    U links are fetched per batch to keep U independent loads in flight per lane.
-//  general Q: per-lane sparse row/column products in registers.
-template <int N, bool TDEP, bool QDIAG>
-__global__ void __launch_bounds__(256, HEOM_MINBLOCKS) stage_rows_kernel(const StageArgs a,
-                                                         const __grid_constant__ HParam<N> hp) {
-    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int U = HEOM_U;
-    extern __shared__ double2 smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int b = blockIdx.y;
-    const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
-    double2* Hs = smem;
-    double2* coef_s = Hs + (TDEP ? NN : 0);
-    double2* qd_s = coef_s + (QDIAG ? 2 * a.ncoef : 0);
-    double2* tiles = qd_s + (QDIAG ? a.nmod * N : 0);
-    double2* rho_s = tiles + wid * 2 * TILE;
-    double2* k_s = rho_s + TILE;
-    unsigned char* supp_s = (unsigned char*)(tiles + nwarps * 2 * TILE);
-    if (TDEP) {
-        for (int e = threadIdx.x; e < NN; e += blockDim.x) Hs[e] = ops[e];
-    }
-    if (QDIAG) {
-        for (int e = threadIdx.x; e < 2 * a.ncoef; e += blockDim.x) coef_s[e] = a.coef[e];
-        for (int e = threadIdx.x; e < a.nmod * N; e += blockDim.x) {
-            const int m = e / N, j = e - m * N;
-            qd_s[e] = ops[(1 + m) * NN + j * N + j];
-        }
-        for (int e = threadIdx.x; e < a.nmod * (2 * N + 1); e += blockDim.x) supp_s[e] = a.supp[e];
-    }
-    if (TDEP || QDIAG) __syncthreads();
-#define HEL(r_, c_) (TDEP ? Hs[(r_) * N + (c_)] : hp.v[(r_) * N + (c_)])
-    const long long boff = (long long)b * a.nmax * NN;
-    const double2* __restrict__ yin = a.yin + boff;
-    const int sub = lane / N, row = lane - sub * N;
-    const bool lane_ok = lane < APW * N;
-    const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
-    const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
-    const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
-
-    for (long long g = (long long)blockIdx.x * nwarps + wid; g < a.ngroups;
-         g += (long long)gridDim.x * nwarps) {
-        const long long gm = (a.scramble && g < (a.ngroups & ~15ll))
-                                 ? ((g & ~15ll) | ((g + (((unsigned)(g >> 4) * 2654435761u) >> 28)) & 15ll))
-                                 : g;
-        const long long base = a.slot_lo + gm * APW;
-        const int cnt = (int)min((long long)APW, a.slot_hi - base);
-        const int nelem = cnt * NN;
-        const double2* src = yin + base * NN;
-        for (int e = lane; e < nelem; e += 32) {
-            const int s = e / NN, r = e - s * NN, i = r / N, j = r - i * N;
-            rho_s[(s * N + i) * LD + j] = ldg2(src + e);
-        }
-        __syncwarp();
-        const bool on = lane_ok && sub < cnt;
-        if (on) {  // column pass: (H rho)[:, row]
-            double2 col[N];
-#pragma unroll
-            for (int l = 0; l < N; ++l) col[l] = rho_s[(sub * N + l) * LD + row];
-#pragma unroll
-            for (int rr = 0; rr < N; ++rr) {
-                double2 c = make_double2(0.0, 0.0);
-#pragma unroll
-                for (int l = 0; l < N; ++l) cfma(c, HEL(rr, l), col[l]);
-                k_s[(sub * N + rr) * LD + row] = c;
-            }
-        }
-        __syncwarp();
-        if (on) {
-            const long long slot = base + sub;
-            double2 r[N];
-            {
-                double2 rv[N];
-#pragma unroll
-                for (int l = 0; l < N; ++l) rv[l] = rho_s[(sub * N + row) * LD + l];
-                const double2 d = a.damp[slot];
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    double2 t = k_s[(sub * N + row) * LD + j];
-#pragma unroll
-                    for (int l = 0; l < N; ++l) cfms(t, rv[l], HEL(l, j));
-                    // -i t - damp * rho
-                    r[j] = make_double2(t.y - (d.x * rv[j].x - d.y * rv[j].y),
-                                        -t.x - (d.x * rv[j].y + d.y * rv[j].x));
-                }
-            }
-            const int lbeg = a.link_ptr[slot], lend = a.link_ptr[slot + 1];
-            if (QDIAG) {
-#pragma unroll
-                for (int j = 0; j < N; ++j) k_s[(sub * N + row) * LD + j] = r[j];
-                __syncwarp(submask);
-                for (int lp = lbeg; lp < lend; lp += U) {
-                    int2 lk[U];
-                    double2 A[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        lk[u] = (lp + u < lend) ? __ldg(a.links + lp + u) : make_int2((int)slot, 0);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int m = heom::meta_mode(lk[u].y);
-                        const int r0 = supp_s[m * (N + 1) + 1];
-                        A[u] = ldg2(yin + (long long)lk[u].x * NN + r0 * N + row);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int ci = heom::meta_ci(lk[u].y, a.nind, a.lmax), m = heom::meta_mode(lk[u].y);
-                        const double2 aL = coef_s[2 * ci], aR = coef_s[2 * ci + 1];
-                        const double2* __restrict__ pn = yin + (long long)lk[u].x * NN;
-                        const int ns = supp_s[m * (N + 1)];
-                        const double2 qj = qd_s[m * N + row];
-                        const bool outside = insupp_s[m * N + row] == 0;
-                        for (int t = 0; t < ns; ++t) {
-                            const int rr = supp_s[m * (N + 1) + 1 + t];
-                            const double2 Aj = (t == 0) ? A[u] : ldg2(pn + rr * N + row);
-                            const double2 qr = qd_s[m * N + rr];
-                            double2 c = cmul(aL, qr);
-                            cfma(c, aR, qj);
-                            double2* d1 = &k_s[(sub * N + rr) * LD + row];
-                            double2 v1 = *d1;
-                            cfma(v1, c, Aj);
-                            *d1 = v1;
-                            if (outside) {  // element (row, rr): only the right product survives
-                                const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y)
-                                                          : ldg2(pn + row * N + rr);
-                                double2* d2 = &k_s[(sub * N + row) * LD + rr];
-                                double2 v2 = *d2;
-                                cfma(v2, cmul(aR, qr), Bj);
-                                *d2 = v2;
-                            }
-                        }
-                        __syncwarp(submask);
-                    }
-                }
-            } else {
-                for (int lp = lbeg; lp < lend; ++lp) {
-                    const int2 lk = a.links[lp];
-                    const double2* __restrict__ pn = yin + (long long)lk.x * NN;
-                    const int ci = heom::meta_ci(lk.y, a.nind, a.lmax), m1 = 1 + heom::meta_mode(lk.y);
-                    const double2 aL = a.coef[2 * ci], aR = a.coef[2 * ci + 1];
-                    const double2* __restrict__ Qm = ops + m1 * NN;
-                    const short* rp = a.row_ptr + m1 * (N + 1);
-                    const short* ri = a.row_idx + m1 * NN;
-                    for (int t = rp[row]; t < rp[row + 1]; ++t) {
-                        const int l = ri[t];
-                        const double2 q = cmul(aL, Qm[row * N + l]);
-#pragma unroll
-                        for (int j = 0; j < N; ++j) cfma(r[j], q, ldg2(pn + l * N + j));
-                    }
-                    const short* cp = a.col_ptr + m1 * (N + 1);
-                    const short* cidx = a.col_idx + m1 * NN;
-#pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        for (int t = cp[j]; t < cp[j + 1]; ++t) {
-                            const int l = cidx[t];
-                            const double2 q = cmul(aR, Qm[l * N + j]);
-                            cfma(r[j], q, ldg2(pn + row * N + l));
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < N; ++j) k_s[(sub * N + row) * LD + j] = r[j];
-            }
-        }
-        __syncwarp();
-        // flat epilogue: coalesced 128-bit streaming traffic on y / acc / outputs.
-        // All loads of the group are issued before the first store so that they
-        // overlap (the compiler cannot prove the outputs do not alias the inputs).
-        const long long gbase = boff + base * NN;
-        constexpr int EIT = (APW * NN + 31) / 32;
-        double2 yv[EIT], bs[EIT];
-#pragma unroll
-        for (int it = 0; it < EIT; ++it) {
-            const int e = lane + 32 * it;
-            if (e < nelem) {
-                const long long gi = gbase + e;
-                if (!a.first) {
-                    bs[it] = ld_stream(a.acc + gi);
-                    if (!a.last) yv[it] = ld_stream(a.y + gi);
-                }
-            }
-        }
-#pragma unroll
-        for (int it = 0; it < EIT; ++it) {
-            const int e = lane + 32 * it;
-            if (e < nelem) {
-                const int s = e / NN, rr = e - s * NN, i = rr / N, j = rr - i * N;
-                const int si = (s * N + i) * LD + j;
-                const double2 k = k_s[si];
-                const long long gi = gbase + e;
-                if (a.first) {
-                    yv[it] = rho_s[si];
-                    bs[it] = yv[it];
-                }
-                const double2 res = make_double2(fma(a.w, k.x, bs[it].x), fma(a.w, k.y, bs[it].y));
-                if (a.last) {
-                    st_stream(a.ydst + gi, res);
-                    if (a.traj && base + s == a.slot0)
-                        a.traj[b * a.traj_bstride + (step + 1) * NN + rr] = res;
-                } else {
-                    st_stream(a.acc + gi, res);
-                    st_stream(a.yout + gi,
-                              make_double2(fma(a.a, k.x, yv[it].x), fma(a.a, k.y, yv[it].y)));
-                }
-            }
-        }
-        __syncwarp();
-    }
-#undef HEL
-}
-
-// ---------------------------------------------------------------------------
-// Kernel 4: cluster-resident propagation for small hierarchies (N <= 8, diagonal
-// Q_m).  One thread-block cluster per trajectory keeps the whole hierarchy - y,
-// acc and both stage buffers - in distributed shared memory for all nt steps;
-// neighbour rows are read from the owning CTA's shared memory (DSMEM) and the
-// only synchronisation per RK stage is a hardware cluster barrier.  Hierarchies
-// of a few hundred ADOs (BASELINE configs 1, 2, 5) are otherwise bound by
-// launch and L2 latency, not bandwidth.
-// ---------------------------------------------------------------------------
-struct ResidentArgs {
-    StageArgs s;          // tables, traj, herm, ...; array pointers: s.y = state (global)
-    const double* fsys;   // [B][nt][3] or null
-    const double* fcoup;
-    const double2* ops_base;  // [1+M][NN]
-    const double2* ops_dip;
-    double dt;
-    long long nt;
-    int apc;              // ADOs per CTA (multiple of 32/N)
-    int tdep;
-    int maxlinks;         // links per ADO, upper bound (sizes the per-warp link cache)
-};
-
-template <int N, bool HREAL>
-__global__ void __launch_bounds__(512, 1)
-resident_cluster_kernel(const ResidentArgs ra, const __grid_constant__ HParam<N> hp) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const StageArgs& a = ra.s;
-    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, ADO = N * LD;
-    constexpr int FLAT = APW * NN, EIT = (FLAT + 31) / 32;
-    extern __shared__ double2 smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
-    const int b = blockIdx.x / csize;       // trajectory
-    const int apc = ra.apc;
-    const AsyncTables T = async_tables(N, a.nind, a.nmod, a.lmax, true);
-    double2* Hs = smem + T.H;
-    double2* cb_s = smem + T.cb;
-    double2* cq_s = smem + T.cq;
-    double2* qd_s = smem + T.qd;
-    double* sq_s = (double*)(smem + T.sq);
-    double2* arr0 = smem + T.warp0;          // 4 arrays of apc ADOs each
-    double2* Yb = arr0;
-    double2* ACCb = Yb + (size_t)apc * ADO;
-    double2* SAb = ACCb + (size_t)apc * ADO;
-    double2* SBb = SAb + (size_t)apc * ADO;
-    // per-ADO link cache: (generic pointer to the neighbour's row in its CTA's Y array, meta)
-    struct LinkEnt { const double2* rowp; int meta; int pad; };
-    LinkEnt* lk_s = (LinkEnt*)(SBb + (size_t)apc * ADO);
-    unsigned char* supp_s = (unsigned char*)(lk_s + (size_t)apc * ra.maxlinks);
-    const unsigned char* insupp_s = supp_s + a.nmod * (N + 1);
-
-    // ---- static tables
-    for (int e = threadIdx.x; e < 4 * a.nind; e += blockDim.x) cb_s[e] = a.cbase[e];
-    for (int e = threadIdx.x; e <= a.lmax; e += blockDim.x) sq_s[e] = sqrt((double)e);
-    for (int e = threadIdx.x; e < a.nmod * (2 * N + 1); e += blockDim.x) supp_s[e] = a.supp[e];
-    auto load_ops = [&](long long step, int tidx) {
-        // H(t), diag Q_m(t) and the single-row coefficient table (generate_time, deom.py:676-687)
-        const double fs = (ra.tdep && ra.fsys) ? ra.fsys[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
-        const double fc = (ra.tdep && ra.fcoup) ? ra.fcoup[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
-        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
-            const double2 v = ra.ops_base[e], d = ra.ops_dip[e];
-            Hs[e] = make_double2(fma(d.x, fs, v.x), fma(d.y, fs, v.y));
-        }
-        for (int e = threadIdx.x; e < a.nmod * N; e += blockDim.x) {
-            const int m = e / N, j = e - m * N, o = (1 + m) * NN + j * N + j;
-            const double2 v = ra.ops_base[o], d = ra.ops_dip[o];
-            qd_s[e] = make_double2(fma(d.x, fc, v.x), fma(d.y, fc, v.y));
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < 2 * a.nind; e += blockDim.x) {
-            const int k = e >> 1, dir = e & 1;
-            const int m = a.kmode[k] & 0xff, r0 = a.kmode[k] >> 8;
-            const double2 q = qd_s[m * N + r0];
-            const double2 bL = cb_s[4 * k + 2 * dir], bR = cb_s[4 * k + 2 * dir + 1];
-            cq_s[3 * e + 0] = cmul(bL, q);
-            cq_s[3 * e + 1] = cmul(make_double2(bL.x + bR.x, bL.y + bR.y), q);
-            cq_s[3 * e + 2] = cmul(bR, q);
-        }
-        __syncthreads();
-    };
-    __syncthreads();
-    load_ops(0, 0);
-
-    // ---- this warp's ADOs
-    const int sub = lane / N, row = lane - sub * N;
-    const bool lane_ok = lane < APW * N;
-    const unsigned submask = lane_ok ? (((1u << N) - 1u) << (sub * N)) : 0u;
-    const int li0 = wid * APW;                                   // first local ADO of the warp
-    // groups of APW consecutive slots are dealt round-robin to the CTAs of the
-    // cluster, so the link-heavy low tiers (which are contiguous in the reference
-    // order) do not all land in one CTA: group g lives in CTA g % csize
-    const long long slot_w = ((long long)wid * csize + crank) * APW;   // its global slot
-    const long long slot = slot_w + sub;
-    const int cnt = (int)max(0ll, min((long long)APW, a.nmax - slot_w));
-    const bool on = lane_ok && sub < cnt;
-    const int nelem = cnt * NN;
-    const long long boff = (long long)b * a.nmax * NN;
-    int pofs[EIT];   // flat element -> offset inside the warp's (padded) tile
-#pragma unroll
-    for (int it = 0; it < EIT; ++it) {
-        const int e = lane + 32 * it;
-        const int s2 = e / NN, r = e - s2 * NN, i = r / N, j = r - i * N;
-        pofs[it] = (s2 * N + i) * LD + j;
-    }
-    const int woff = li0 * ADO;                                   // warp tile offset in each array
-    double2 damp = make_double2(0.0, 0.0);
-    int lbeg = 0, lend = 0;
-    if (on) {
-        damp = a.damp[slot];
-        lbeg = a.link_ptr[slot];
-        lend = a.link_ptr[slot + 1];
-    }
-    const int nl = lend - lbeg;
-    LinkEnt* const mylk = lk_s + (size_t)(li0 + sub) * ra.maxlinks;
-    if (on) {
-        for (int t = row; t < nl; t += N) {
-            const int2 lk = __ldg(a.links + lbeg + t);
-            const int og = lk.x / APW;                       // owner group of the neighbour
-            const int orank = og % csize, oli = (og / csize) * APW + (lk.x - og * APW);
-            LinkEnt en;
-            en.rowp = cluster.map_shared_rank(Yb, orank) + (size_t)oli * ADO + heom::meta_r0(lk.y) * LD;
-            en.meta = lk.y;
-            en.pad = 0;
-            mylk[t] = en;
-        }
-    }
-    // initial state from global memory; the other arrays start at zero
-#pragma unroll
-    for (int it = 0; it < EIT; ++it) {
-        const int e = lane + 32 * it;
-        if (e < FLAT) {
-            const double2 z = make_double2(0.0, 0.0);
-            Yb[woff + pofs[it]] = e < nelem ? a.y[boff + slot_w * NN + e] : z;
-            ACCb[woff + pofs[it]] = z;
-            SAb[woff + pofs[it]] = z;
-            SBb[woff + pofs[it]] = z;
-        }
-    }
-    cluster.sync();
-
-#define HEL(r_, c_) (Hs[(r_) * N + (c_)])
-    for (long long step = 0; step < ra.nt; ++step) {
-        for (int st = 0; st < 4; ++st) {
-            double2* inb = st == 0 ? Yb : (st == 2 ? SBb : SAb);
-            double2* outb = st == 0 ? SAb : (st == 1 ? SBb : (st == 2 ? SAb : Yb));
-            const double ac = st == 2 ? ra.dt : ra.dt * 0.5;
-            const double wc = (st == 0 || st == 3) ? ra.dt / 6.0 : ra.dt / 3.0;
-            if (ra.tdep && st != 2 && !(step == 0 && st == 0)) load_ops(step, st == 0 ? 0 : (st == 3 ? 2 : 1));
-            // stage 3 writes y in place: its k tile lives in SB (free at that point)
-            double2* kt = (st == 3 ? SBb : outb) + woff;
-            const double2* rsub = inb + woff + sub * ADO;
-            double2* ksub = kt + sub * ADO;
-            if (on) {
-                double2 col[N];
-#pragma unroll
-                for (int l = 0; l < N; ++l) col[l] = rsub[l * LD + row];
-#pragma unroll
-                for (int rr = 0; rr < N; ++rr) {
-                    double2 c = make_double2(0.0, 0.0);
-#pragma unroll
-                    for (int l = 0; l < N; ++l) {
-                        if (HREAL) {
-                            const double h = HEL(rr, l).x;
-                            c.x = fma(h, col[l].x, c.x);
-                            c.y = fma(h, col[l].y, c.y);
-                        } else {
-                            cfma(c, HEL(rr, l), col[l]);
-                        }
-                    }
-                    ksub[rr * LD + row] = c;
-                }
-            }
-            __syncwarp();
-            if (on) {
-                double2 rv[N];
-#pragma unroll
-                for (int l = 0; l < N; ++l) rv[l] = rsub[row * LD + l];
-#pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    double2 t = ksub[row * LD + j];
-#pragma unroll
-                    for (int l = 0; l < N; ++l) {
-                        if (HREAL) {
-                            const double h = HEL(l, j).x;
-                            t.x = fma(-h, rv[l].x, t.x);
-                            t.y = fma(-h, rv[l].y, t.y);
-                        } else {
-                            cfms(t, rv[l], HEL(l, j));
-                        }
-                    }
-                    ksub[row * LD + j] = make_double2(t.y - (damp.x * rv[j].x - damp.y * rv[j].y),
-                                                      -t.x - (damp.x * rv[j].y + damp.y * rv[j].x));
-                }
-            }
-            __syncwarp();
-            // ---- neighbour terms: rows read through distributed shared memory
-            if (on) {
-                double2 X = make_double2(0.0, 0.0), Y = make_double2(0.0, 0.0);
-                int cur_rr = -1;
-                bool yused = false;
-                auto flush = [&]() {
-                    double2* d1 = ksub + cur_rr * LD + row;
-                    double2 v1 = *d1;
-                    v1.x += X.x;
-                    v1.y += X.y;
-                    *d1 = v1;
-                    if (yused) {
-                        double2* d2 = ksub + row * LD + cur_rr;
-                        double2 v2 = *d2;
-                        v2.x += Y.x;
-                        v2.y += Y.y;
-                        *d2 = v2;
-                    }
-                };
-                const ptrdiff_t boffs = inb - Yb;   // same layout in every CTA of the cluster
-                constexpr int U = 4;
-                for (int c0 = 0; c0 < nl; c0 += U) {
-                    LinkEnt en[U];
-                    double2 A[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        en[u] = mylk[min(c0 + u, nl - 1)];
-                        A[u] = en[u].rowp[boffs + row];   // first support row, element `row`
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (c0 + u < nl) {
-                            const int meta = en[u].meta;
-                            const int m = heom::meta_mode(meta);
-                            const int r0 = heom::meta_r0(meta);
-                            const double2* rin = en[u].rowp + boffs - r0 * LD;   // neighbour ADO base
-                            const double sq = sq_s[heom::meta_neff(meta)];
-                            const int ns = supp_s[m * (N + 1)];
-                            const int kd = heom::meta_kdir(meta);
-                            const double2 qj = qd_s[m * N + row];
-                            const bool outside = insupp_s[m * N + row] == 0;
-                            for (int t2 = 0; t2 < ns; ++t2) {
-                                const int rr = supp_s[m * (N + 1) + 1 + t2];
-                                const double2 Aj = (t2 == 0) ? A[u] : rin[rr * LD + row];
-                                if (rr != cur_rr) {
-                                    if (cur_rr >= 0) {
-                                        flush();
-                                        __syncwarp(submask);
-                                    }
-                                    cur_rr = rr;
-                                    X = make_double2(0.0, 0.0);
-                                    Y = make_double2(0.0, 0.0);
-                                    yused = false;
-                                }
-                                double2 c;
-                                if (ns == 1) {
-                                    const double2 c1 = cq_s[3 * kd + (row == rr ? 1 : 0)];
-                                    c = make_double2(c1.x * sq, c1.y * sq);
-                                } else {
-                                    const double2 bL = cb_s[2 * kd], bR = cb_s[2 * kd + 1];
-                                    c = cmul(make_double2(bL.x * sq, bL.y * sq), qd_s[m * N + rr]);
-                                    cfma(c, make_double2(bR.x * sq, bR.y * sq), qj);
-                                }
-                                cfma(X, c, Aj);
-                                if (outside) {
-                                    const double2 bR = cb_s[2 * kd + 1];
-                                    const double2 cr =
-                                        cmul(make_double2(bR.x * sq, bR.y * sq), qd_s[m * N + rr]);
-                                    const double2 Bj = a.herm ? make_double2(Aj.x, -Aj.y) : rin[row * LD + rr];
-                                    cfma(Y, cr, Bj);
-                                    yused = true;
-                                }
-                            }
-                        }
-                    }
-                }
-                if (cur_rr >= 0) flush();
-            }
-            __syncwarp();
-            // ---- stage update in shared memory
-#pragma unroll
-            for (int it = 0; it < EIT; ++it) {
-                const int e = lane + 32 * it;
-                if (e < nelem) {
-                    const int o = woff + pofs[it];
-                    const double2 k = kt[pofs[it]];
-                    if (st == 3) {
-                        const double2 bs = ACCb[o];
-                        const double2 res = make_double2(fma(wc, k.x, bs.x), fma(wc, k.y, bs.y));
-                        Yb[o] = res;
-                        if (a.traj && slot_w + e / NN == a.slot0)
-                            a.traj[b * a.traj_bstride + (step + 1) * NN + e % NN] = res;
-                    } else {
-                        const double2 yv = Yb[o];
-                        const double2 bs = st == 0 ? yv : ACCb[o];
-                        ACCb[o] = make_double2(fma(wc, k.x, bs.x), fma(wc, k.y, bs.y));
-                        outb[o] = make_double2(fma(ac, k.x, yv.x), fma(ac, k.y, yv.y));
-                    }
-                }
-            }
-            cluster.sync();
-        }
-    }
-#undef HEL
-    // ---- final state back to global memory
-#pragma unroll
-    for (int it = 0; it < EIT; ++it) {
-        const int e = lane + 32 * it;
-        if (e < nelem) const_cast<double2*>(a.y)[boff + slot_w * NN + e] = Yb[woff + pofs[it]];
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Kernel 5: cluster-resident propagation, element-parallel.  Same residency as
-// kernel 4 (whole hierarchy in distributed shared memory, one cluster per
-// trajectory, one hardware cluster barrier per RK stage) but a whole warp works
-// on one ADO, one or two matrix elements per lane: the dependent chain per lane
-// is 2N complex FMAs instead of 2N^2, which is what bounds tiny hierarchies.
-// For diagonal Q_m the coupling is element-wise, so a lane reads exactly its own
-// element of each neighbour through DSMEM - no Hermiticity assumption needed.
-// ADOs are dealt round-robin to the CTAs of the cluster (slot s -> CTA s % C).
-// ---------------------------------------------------------------------------
-template <int N>
-__global__ void __launch_bounds__(512, 1)
-resident_elem_kernel(const ResidentArgs ra) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const StageArgs& a = ra.s;
-    constexpr int NN = N * N, EPL = (NN + 31) / 32;
-    extern __shared__ double2 smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
-    const int b = blockIdx.x / csize;
-    const int apc = ra.apc;
-    struct LinkEnt { const double2* tile; int meta; int pad; };
-    struct AdoMeta { double2 damp; int nl; int pad; };
-    // shared-memory carve-up
-    double2* Hs = smem;
-    double2* qd_s = Hs + NN;
-    double2* cb_s = qd_s + a.nmod * N;
-    double* sq_s = (double*)(cb_s + 4 * a.nind);
-    double2* Yb = (double2*)(sq_s + ((a.lmax + 2) & ~1));
-    double2* ACCb = Yb + (size_t)apc * NN;
-    double2* SAb = ACCb + (size_t)apc * NN;
-    double2* SBb = SAb + (size_t)apc * NN;
-    LinkEnt* lk_s = (LinkEnt*)(SBb + (size_t)apc * NN);
-    AdoMeta* am_s = (AdoMeta*)(lk_s + (size_t)apc * ra.maxlinks);
-
-    for (int e = threadIdx.x; e < 4 * a.nind; e += blockDim.x) cb_s[e] = a.cbase[e];
-    for (int e = threadIdx.x; e <= a.lmax; e += blockDim.x) sq_s[e] = sqrt((double)e);
-    auto load_ops = [&](long long step, int tidx) {
-        const double fs = (ra.tdep && ra.fsys) ? ra.fsys[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
-        const double fc = (ra.tdep && ra.fcoup) ? ra.fcoup[((long long)b * ra.nt + step) * 3 + tidx] : 0.0;
-        __syncthreads();
-        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
-            const double2 v = ra.ops_base[e], d = ra.ops_dip[e];
-            Hs[e] = make_double2(fma(d.x, fs, v.x), fma(d.y, fs, v.y));
-        }
-        for (int e = threadIdx.x; e < a.nmod * N; e += blockDim.x) {
-            const int m = e / N, j = e - m * N, o = (1 + m) * NN + j * N + j;
-            const double2 v = ra.ops_base[o], d = ra.ops_dip[o];
-            qd_s[e] = make_double2(fma(d.x, fc, v.x), fma(d.y, fc, v.y));
-        }
-        __syncthreads();
-    };
-    load_ops(0, 0);
-
-    int ei[EPL], ej[EPL];
-    bool ev[EPL];
-#pragma unroll
-    for (int t = 0; t < EPL; ++t) {
-        const int e = lane + 32 * t;
-        ev[t] = e < NN;
-        ei[t] = ev[t] ? e / N : 0;
-        ej[t] = ev[t] ? e - (e / N) * N : 0;
-    }
-    const long long boff = (long long)b * a.nmax * NN;
-    // ---- per-ADO setup: state from global memory, link cache, damping
-    for (int li = wid; li < apc; li += nwarps) {
-        const long long slot = (long long)li * csize + crank;
-        const bool on = slot < a.nmax;
-        int lbeg = 0, nl = 0;
-        double2 damp = make_double2(0.0, 0.0);
-        if (on) {
-            lbeg = a.link_ptr[slot];
-            nl = a.link_ptr[slot + 1] - lbeg;
-            damp = a.damp[slot];
-        }
-        if (lane == 0) {
-            AdoMeta m;
-            m.damp = damp;
-            m.nl = nl;
-            m.pad = 0;
-            am_s[li] = m;
-        }
-        for (int t = lane; t < nl; t += 32) {
-            const int2 lk = __ldg(a.links + lbeg + t);
-            LinkEnt en;
-            en.tile = cluster.map_shared_rank(Yb, lk.x % csize) + (size_t)(lk.x / csize) * NN;
-            en.meta = lk.y;
-            en.pad = 0;
-            lk_s[(size_t)li * ra.maxlinks + t] = en;
-        }
-#pragma unroll
-        for (int t = 0; t < EPL; ++t)
-            if (ev[t]) {
-                const int e = lane + 32 * t;
-                const double2 z = make_double2(0.0, 0.0);
-                Yb[li * NN + e] = on ? a.y[boff + slot * NN + e] : z;
-                ACCb[li * NN + e] = z;
-                SAb[li * NN + e] = z;
-                SBb[li * NN + e] = z;
-            }
-    }
-    cluster.sync();
-
-    for (long long step = 0; step < ra.nt; ++step) {
-        for (int st = 0; st < 4; ++st) {
-            double2* inb = st == 0 ? Yb : (st == 2 ? SBb : SAb);
-            double2* outb = st == 0 ? SAb : (st == 1 ? SBb : (st == 2 ? SAb : Yb));
-            const double ac = st == 2 ? ra.dt : ra.dt * 0.5;
-            const double wc = (st == 0 || st == 3) ? ra.dt / 6.0 : ra.dt / 3.0;
-            if (ra.tdep && st != 2 && !(step == 0 && st == 0)) load_ops(step, st == 0 ? 0 : (st == 3 ? 2 : 1));
-            const ptrdiff_t boffs = inb - Yb;
-            for (int li = wid; li < apc; li += nwarps) {
-                const long long slot = (long long)li * csize + crank;
-                if (slot >= a.nmax) continue;   // warp-uniform
-                const double2* in = inb + (size_t)li * NN;
-                const AdoMeta am = am_s[li];
-                const LinkEnt* mylk = lk_s + (size_t)li * ra.maxlinks;
-                double2 k[EPL];
-#pragma unroll
-                for (int t = 0; t < EPL; ++t) {
-                    k[t] = make_double2(0.0, 0.0);
-                    if (ev[t]) {
-                        double2 c = make_double2(0.0, 0.0);
-#pragma unroll
-                        for (int l = 0; l < N; ++l) {
-                            cfma(c, Hs[ei[t] * N + l], in[l * N + ej[t]]);
-                            cfms(c, in[ei[t] * N + l], Hs[l * N + ej[t]]);
-                        }
-                        const double2 own = in[lane + 32 * t];
-                        k[t] = make_double2(c.y - (am.damp.x * own.x - am.damp.y * own.y),
-                                            -c.x - (am.damp.x * own.y + am.damp.y * own.x));
-                    }
-                }
-                constexpr int U = 4;
-                for (int c0 = 0; c0 < am.nl; c0 += U) {
-                    LinkEnt en[U];
-                    double2 A[U][EPL];
-                    double2 cf[U][EPL];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const bool live = c0 + u < am.nl;
-                        en[u] = mylk[min(c0 + u, am.nl - 1)];
-                        const int meta = en[u].meta;
-                        const int m = heom::meta_mode(meta), kd = heom::meta_kdir(meta);
-                        const double sq = live ? sq_s[heom::meta_neff(meta)] : 0.0;
-                        const double2 bL = cb_s[2 * kd], bR = cb_s[2 * kd + 1];
-#pragma unroll
-                        for (int t = 0; t < EPL; ++t) {
-                            const double2 qi = qd_s[m * N + ei[t]], qj = qd_s[m * N + ej[t]];
-                            double2 c = cmul(make_double2(bL.x * sq, bL.y * sq), qi);
-                            cfma(c, make_double2(bR.x * sq, bR.y * sq), qj);
-                            cf[u][t] = c;
-                            const bool need = ev[t] && live && (c.x != 0.0 || c.y != 0.0);
-                            A[u][t] = need ? en[u].tile[boffs + lane + 32 * t] : make_double2(0.0, 0.0);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-#pragma unroll
-                        for (int t = 0; t < EPL; ++t) cfma(k[t], cf[u][t], A[u][t]);
-                }
-                // stage update in shared memory (each lane owns its elements)
-#pragma unroll
-                for (int t = 0; t < EPL; ++t)
-                    if (ev[t]) {
-                        const int o = li * NN + lane + 32 * t;
-                        if (st == 3) {
-                            const double2 bs = ACCb[o];
-                            const double2 res = make_double2(fma(wc, k[t].x, bs.x), fma(wc, k[t].y, bs.y));
-                            Yb[o] = res;
-                            if (a.traj && slot == a.slot0)
-                                a.traj[b * a.traj_bstride + (step + 1) * NN + lane + 32 * t] = res;
-                        } else {
-                            const double2 yv = Yb[o];
-                            const double2 bs = st == 0 ? yv : ACCb[o];
-                            ACCb[o] = make_double2(fma(wc, k[t].x, bs.x), fma(wc, k[t].y, bs.y));
-                            outb[o] = make_double2(fma(ac, k[t].x, yv.x), fma(ac, k[t].y, yv.y));
-                        }
-                    }
-            }
-            cluster.sync();
-        }
-    }
-    for (int li = wid; li < apc; li += nwarps) {
-        const long long slot = (long long)li * csize + crank;
-        if (slot >= a.nmax) continue;
-#pragma unroll
-        for (int t = 0; t < EPL; ++t)
-            if (ev[t]) const_cast<double2*>(a.y)[boff + slot * NN + lane + 32 * t] = Yb[li * NN + lane + 32 * t];
-    }
-}
-
-// Kernel 2 (any N): one CTA per ADO, one thread per matrix element (strided);
-// all operators (H and Q_m) go through their sparsity lists, so cost scales
-// with nnz.  rho_n is staged in shared memory; neighbours are read through L2.
-__global__ void __launch_bounds__(1024) stage_generic_kernel(const StageArgs a) {
-    extern __shared__ double2 smem[];
-    const int N = a.N, NN = N * N, M1 = 1 + a.nmod;
-    // shared memory: rho_n | operator values [1+M][NN] | links of this ADO (slot, alphaL, alphaR)
-    //                | sparsity lists (row_ptr, row_idx, col_ptr, col_idx as shorts)
-    double2* rho_s = smem;
-    double2* ops_s = rho_s + NN;
-    double2* lcf_s = ops_s + (size_t)M1 * NN;          // [maxl][2]
-    const int maxl = 2 * a.nind;
-    int2* lk_s = (int2*)(lcf_s + 2 * maxl);            // [maxl]
-    short* rp_s = (short*)(lk_s + maxl);
-    short* ri_s = rp_s + M1 * (N + 1);
-    short* cp_s = ri_s + M1 * NN;
-    short* ci_s = cp_s + M1 * (N + 1);
-    const int b = blockIdx.y;
-    const double2* __restrict__ ops = a.ops + (long long)b * a.ops_bstride;
-    for (int e = threadIdx.x; e < M1 * NN; e += blockDim.x) {
-        ops_s[e] = ops[e];
-        ri_s[e] = a.row_idx[e];
-        ci_s[e] = a.col_idx[e];
-    }
-    for (int e = threadIdx.x; e < M1 * (N + 1); e += blockDim.x) {
-        rp_s[e] = a.row_ptr[e];
-        cp_s[e] = a.col_ptr[e];
-    }
-    const long long boff = (long long)b * a.nmax * NN;
-    const double2* __restrict__ yin = a.yin + boff;
-    const long long step = a.traj ? (*a.step_base + a.local_step) : 0;
-    for (long long slot = a.slot_lo + blockIdx.x; slot < a.slot_hi; slot += gridDim.x) {
-        const int lbeg = a.link_ptr[slot], nl = a.link_ptr[slot + 1] - lbeg;
-        __syncthreads();   // previous ADO fully consumed (and tables loaded on the first pass)
-        for (int e = threadIdx.x; e < NN; e += blockDim.x) rho_s[e] = ldg2(yin + slot * NN + e);
-        for (int t = threadIdx.x; t < nl; t += blockDim.x) {
-            const int2 lk = __ldg(a.links + lbeg + t);
-            const int ci = heom::meta_ci(lk.y, a.nind, a.lmax);
-            lk_s[t] = lk;
-            lcf_s[2 * t] = a.coef[2 * ci];
-            lcf_s[2 * t + 1] = a.coef[2 * ci + 1];
-        }
-        const double2 d = a.damp[slot];
-        __syncthreads();
-        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
-            const int i = e / N, j = e - i * N;
-            const long long gi = boff + slot * NN + e;
-            // the epilogue's operands are fetched now so that they are in flight
-            // while the right-hand side is evaluated
-            double2 yv = make_double2(0.0, 0.0), bs = make_double2(0.0, 0.0);
-            if (!a.first) {
-                bs = ld_stream(a.acc + gi);
-                if (!a.last) yv = ld_stream(a.y + gi);
-            }
-            const double2 own = rho_s[e];
-            double2 v = make_double2(-(d.x * own.x - d.y * own.y), -(d.x * own.y + d.y * own.x));
-            for (int t = rp_s[i]; t < rp_s[i + 1]; ++t) {   // -i H rho
-                const int l = ri_s[t];
-                const double2 h = ops_s[i * N + l];
-                cfma(v, make_double2(h.y, -h.x), rho_s[l * N + j]);
-            }
-            for (int t = cp_s[j]; t < cp_s[j + 1]; ++t) {   // +i rho H
-                const int l = ci_s[t];
-                const double2 h = ops_s[l * N + j];
-                cfma(v, make_double2(-h.y, h.x), rho_s[i * N + l]);
-            }
-            for (int lp = 0; lp < nl; ++lp) {
-                const int2 lk = lk_s[lp];
-                const double2* __restrict__ pn = yin + (long long)lk.x * NN;
-                const int m1 = 1 + heom::meta_mode(lk.y);
-                const double2* Qm = ops_s + m1 * NN;
-                const short* rp = rp_s + m1 * (N + 1);
-                const short* ri = ri_s + m1 * NN;
-                const short* cp = cp_s + m1 * (N + 1);
-                const short* cx = ci_s + m1 * NN;
-                const int r0 = rp[i], r1 = rp[i + 1], c0 = cp[j], c1 = cp[j + 1];
-                double2 sl = make_double2(0.0, 0.0), sr = make_double2(0.0, 0.0);
-                if (r1 - r0 <= 2 && c1 - c0 <= 2) {
-                    // sparse coupling operator: issue the (at most four) neighbour loads together
-                    double2 q[4], x[4];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const bool lv = r0 + u < r1, rv = c0 + u < c1;
-                        const int ll = lv ? ri[r0 + u] : 0, lr = rv ? cx[c0 + u] : 0;
-                        q[u] = lv ? Qm[i * N + ll] : make_double2(0.0, 0.0);
-                        q[2 + u] = rv ? Qm[lr * N + j] : make_double2(0.0, 0.0);
-                        x[u] = lv ? ldg2(pn + ll * N + j) : make_double2(0.0, 0.0);
-                        x[2 + u] = rv ? ldg2(pn + i * N + lr) : make_double2(0.0, 0.0);
-                    }
-                    cfma(sl, q[0], x[0]);
-                    cfma(sl, q[1], x[1]);
-                    cfma(sr, q[2], x[2]);
-                    cfma(sr, q[3], x[3]);
-                } else {
-                    for (int t = r0; t < r1; ++t) {
-                        const int l = ri[t];
-                        cfma(sl, Qm[i * N + l], ldg2(pn + l * N + j));
-                    }
-                    for (int t = c0; t < c1; ++t) {
-                        const int l = cx[t];
-                        cfma(sr, Qm[l * N + j], ldg2(pn + i * N + l));
-                    }
-                }
-                cfma(v, lcf_s[2 * lp], sl);
-                cfma(v, lcf_s[2 * lp + 1], sr);
-            }
-            if (a.last) {
-                if (a.first) bs = own;
-                const double2 res = make_double2(fma(a.w, v.x, bs.x), fma(a.w, v.y, bs.y));
-                a.ydst[gi] = res;
-                if (a.traj && slot == a.slot0)
-                    a.traj[b * a.traj_bstride + (step + 1) * NN + e] = res;
-            } else {
-                if (a.first) {
-                    yv = own;
-                    bs = own;
-                }
-                a.acc[gi] = make_double2(fma(a.w, v.x, bs.x), fma(a.w, v.y, bs.y));
-                a.yout[gi] = make_double2(fma(a.a, v.x, yv.x), fma(a.a, v.y, yv.y));
-            }
-        }
-    }
-}
+#include "heom_hierarchy.cuh"
+#include "heom_stage_rows.cuh"
+#include "heom_resident.cuh"
+#include "heom_stage_generic.cuh"
 
 // ---------------------------------------------------------------------------
 // host side
