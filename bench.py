@@ -285,13 +285,13 @@ def kernel6_child(args):
     from pyqed_b200 import workloads as W
     torch.cuda.set_device(0)
 
-    def solver_for(w, kernel):
+    def solver_for(w, kernel, prefetch=0):
         bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
         s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
                        w["pulse_system_func"], w["pulse_coupling_func"], lmax=int(w["lmax"]), device=0,
                        alias_rho0=False)
         s.tuning = dict(kernel=kernel, warps_per_cta=0, use_graph=0)
-        s.options = {"resident": 0}
+        s.options = {"resident": 0, "prefetch": prefetch}
         return s
 
     def ran(plan, kernel, nt):
@@ -307,11 +307,12 @@ def kernel6_child(args):
     scale = max(1.0, float(np.abs(ados3).max()))
     peak, peak_src = peaks()
     out = {}
-    for kernel, label in ((6, "kernel6"), (7, "kernel7_packed")):
+    for kernel, prefetch, label in ((6, 0, "kernel6"), (7, 0, "kernel7_packed"),
+                                    (7, 1, "kernel7_packed_prefetch")):
         o = {}
         out[label] = o
         try:
-            s = solver_for(small, kernel)
+            s = solver_for(small, kernel, prefetch)
             _, traj = s.run(small["rho0"].copy(), small["dt"], nt_small)
             traj, ados = np.asarray(traj), np.array(s.ddos)
             o["parity_vs_kernel3"] = {
@@ -330,7 +331,7 @@ def kernel6_child(args):
             # ---- timing, same recipe as the headline arm (CUDA events, inputs resident in HBM)
             w = WORKLOADS[args.workload]()
             K, Wm, dt = args.steps, args.warmup, w["dt"]
-            s = solver_for(w, kernel)
+            s = solver_for(w, kernel, prefetch)
             _, tr1 = s.run(w["rho0"].copy(), dt, 1)
             plan = s._plan
             plan.set_state(w["rho0"][None])
@@ -351,7 +352,8 @@ def kernel6_child(args):
             achieved = 64.0 * n * n * nmax / (avg_launch_ms * 1e-3) / 1e9
             o.update({
                 "value": nmax * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
-                "warmup": Wm, "kernel": "stage_rows_sym_kernel" + ("<PACKED>" if kernel == 7 else ""),
+                "warmup": Wm, "kernel": "stage_rows_sym_kernel" + ("<PACKED>" if kernel == 7 else "")
+                                                    + (" double-buffered tiles" if prefetch else ""),
                 "trace_rho_sys_after_1_step": float(np.trace(np.asarray(tr1)[-1]).real),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "peak_source": peak_src,
@@ -376,7 +378,7 @@ def kernel6_leg(args):
     note = ("opt-in stage kernels (tuning kernel=6 / 7), written after this round's GPU budget was spent; "
             "measured here in a child process, not part of the headline value")
     try:
-        res = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=540)
         lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
         if res.returncode != 0 or not lines:
             return {"note": note, "error": (res.stderr or res.stdout)[-400:], "returncode": res.returncode}
@@ -384,7 +386,7 @@ def kernel6_leg(args):
         out["note"] = note
         return out
     except subprocess.TimeoutExpired:
-        return {"note": note, "error": "child process exceeded 420 s"}
+        return {"note": note, "error": "child process exceeded 540 s"}
     except Exception as exc:  # noqa: BLE001 - this leg must never take the bench line down
         return {"note": note, "error": repr(exc)}
 
@@ -410,7 +412,8 @@ def run_gpu_arm(args):
     n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
     K, Wm, dt = args.steps, args.warmup, w["dt"]
     tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
-    options = {"qdiag": args.qdiag, "hermitian": args.herm, "resident": args.resident, "rk13": args.rk13}
+    options = {"qdiag": args.qdiag, "hermitian": args.herm, "resident": args.resident, "rk13": args.rk13,
+               "prefetch": args.prefetch}
     in_bytes = sum(np.asarray(w[k]).nbytes for k in
                    ("rho0", "system", "system_dipole", "coupling", "coupling_dipole", "expn", "etal",
                     "etar", "etaa", "mode"))
@@ -610,6 +613,7 @@ def main():
     ap.add_argument("--fused", type=int, default=-1, help="multi-GPU: stage kernel stores halo rows itself")
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
     ap.add_argument("--kernel6-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--prefetch", type=int, default=0, help="kernel 7: double-buffered tiles fetched one group ahead")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:

@@ -227,9 +227,12 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *   "resident"   allow the cluster-resident kernels for small hierarchies
  *                (4 = prefer the row-per-lane variant, kernel 4, over the
  *                element-parallel kernel 5)
+ *   "prefetch"   1 = kernel 7 keeps the streamed tiles in two buffer sets and fetches
+ *                them one group ahead (default 0)
  *   "debug_sync" synchronise and check after every launch
  * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "sym", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
- * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes"); -1 for an unknown name. */
+ * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes", "sym_launches" (stage launches done by
+ * kernel 6), "packed_steps" (RK4 steps done by kernel 7)); -1 for an unknown name. */
 int pyqed_heom_set_option(pyqed_heom_plan* plan, const char* name, int value);
 int64_t pyqed_heom_get_info(pyqed_heom_plan* plan, const char* name);
 

@@ -82,6 +82,7 @@ struct pyqed_heom_plan {
     int opt_sym = -1;            // async kernel: Hermitian-symmetric shortcuts (0 off)
     bool single_support = false; // every Q_m has exactly one non-zero diagonal entry
     int opt_rk13 = -1;  // difference-form RK4 in the async kernel (-1/1 on, 0 off)
+    int opt_prefetch = 0;  // kernel 7: double-buffered streamed tiles, fetched one group ahead (1 on)
     long long resident_launches = 0;
     long long sym_launches = 0;  // stage launches that went to kernel 6
     long long packed_steps = 0;  // RK4 steps done by kernel 7 (packed Hermitian storage)
@@ -750,6 +751,7 @@ int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
     else if (n == "real_h") p->opt_hreal = value;
     else if (n == "resident") p->opt_resident = value;
     else if (n == "rk13") p->opt_rk13 = value;
+    else if (n == "prefetch") p->opt_prefetch = value;
     else if (n == "debug_sync") p->debug_sync = value != 0;
     else return fail("unknown option '" + n + "'");
     return 0;
@@ -1309,6 +1311,7 @@ static int run_packed(pyqed_heom_plan* p, double dt, int64_t nt) {
     r.hreal = (p->h_real && p->opt_hreal != 0) ? 1 : 0;
     r.warps = p->warps;
     r.sm_count = sm_count;
+    r.prefetch = p->opt_prefetch > 0 ? 1 : 0;
     r.stream = p->stream;
     const char* err = "";
     if (heom_packed_propagate(r, &err)) return fail(std::string("packed propagation (kernel 7): ") + err);

@@ -48,12 +48,16 @@ constexpr int SYM_TOFS = 16;  // double2 units reserved for the packed-row offse
 
 // per-warp shared memory in double2 units.  `packed`: the ADO arrays hold the upper
 // triangle only (N(N+1)/2 elements per ADO, row-major), see stage_rows_sym_kernel.
-__host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed) {
+// `db`: the streamed tiles (own tile, y, first stage buffer) are double-buffered and fetched
+// one group ahead.
+__host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed, bool db = false) {
     const int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD, FLAT = APW * NN;
     const int FE = APW * (packed ? N * (N + 1) / 2 : NN);   // a group's elements in the global arrays
     const int RT = packed ? FE : TILE;                       // own tile as staged
-    // own tile, k tile, neighbour rows, [y], [first stage buffer], record strip, four mbarriers
-    return RT + TILE + FLAT + (stage == 0 ? 0 : FE) + (stage == 2 ? FE : 0) + SYM_NCH * APW * N / 2 + 2;
+    const int nb = db ? 2 : 1;
+    // own tile, k tile, neighbour rows, [y], [first stage buffer], record strip, mbarriers
+    return nb * RT + TILE + FLAT + (stage == 0 ? 0 : nb * FE) + (stage == 2 ? nb * FE : 0) +
+           SYM_NCH * APW * N / 2 + 3;
 }
 __host__ __device__ constexpr int sym_max_threads(int stage) {
     return stage == 2 ? HEOM_SYM_LAST_THREADS : HEOM_SYM_THREADS;
@@ -74,15 +78,20 @@ struct HParamReal {
 template <int N, bool HREAL>
 using HParamOf = typename std::conditional<HREAL, HParamReal<N>, HParam<N>>::type;
 
-template <int N, bool HREAL, int STAGE, bool PACKED>
+// DB: the bulk-copied tiles of a group (own tile, y, first stage buffer) live in two buffer
+// sets; the copies for the next group are issued before the current group is processed, so
+// they are in flight during the whole group instead of being waited for right after issue.
+template <int N, bool HREAL, int STAGE, bool PACKED, bool DB>
 __global__ void __launch_bounds__(sym_max_threads(STAGE), 1)
 stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL> hp) {
     constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE, PACKED), NCH = SYM_NCH;
+    constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE, PACKED, DB), NCH = SYM_NCH;
+    constexpr int NBUF = DB ? 2 : 1;
     constexpr int PK = N * (N + 1) / 2, EL = PACKED ? PK : NN;   // elements per ADO in the global arrays
     constexpr int FE = APW * EL, RT = PACKED ? FE : TILE;
     constexpr bool BULK_TILE = PACKED || (LD == N);   // padded tiles cannot be one bulk copy
+    static_assert(!DB || BULK_TILE, "double buffering needs bulk-copied tiles");
     constexpr int EIT = (FE + 31) / 32;
     HEOM_DYN_SMEM(double2, smem);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -91,19 +100,23 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     // element (row == r0), both already times sqrt(n_eff)
     double2* cq_s = smem;
     int* tofs_s = (int*)(smem + 2 * ncq);   // PACKED: [r0][j] -> offset of element (r0, j) in the triangle
-    double2* rho_s = smem + 2 * ncq + SYM_TOFS + wid * PERWARP;
-    double2* k_s = rho_s + RT;
+    // buffer set b of the streamed tiles: rho0 + b*RT, y0 + b*FE, acc0 + b*FE
+    double2* const rho0 = smem + 2 * ncq + SYM_TOFS + wid * PERWARP;
+    double2* k_s = rho0 + NBUF * RT;
     double2* nb_s = k_s + TILE;
-    double2* y_s = nb_s + FLAT;                     // !FIRST
-    double2* acc_s = y_s + (FIRST ? 0 : FE);        // LAST
-    int2* strip = (int2*)(acc_s + (LAST ? FE : 0));
-    unsigned long long* barA = (unsigned long long*)(strip + NCH * APW * N);   // own tile
-    unsigned long long* barB = barA + 1;                                       // y / first stage buffer
-    unsigned long long* barD = barA + 2;                                       // second stage buffer
-    unsigned phA = 0, phB = 0, phD = 0;
+    double2* const y0 = nb_s + FLAT;                            // !FIRST
+    double2* const acc0 = y0 + (FIRST ? 0 : NBUF * FE);         // LAST
+    int2* strip = (int2*)(acc0 + (LAST ? NBUF * FE : 0));
+    unsigned long long* barA0 = (unsigned long long*)(strip + NCH * APW * N);   // own tile, per buffer set
+    unsigned long long* barB0 = barA0 + NBUF;                                   // y / first stage buffer
+    unsigned long long* barD = barA0 + 2 * NBUF;                                // second stage buffer
+    unsigned phA = 0, phB = 0, phD = 0;   // phA / phB: one phase bit per buffer set
     if (lane == 0) {
-        mbar_init(barA, 1);
-        mbar_init(barB, 1);
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(barA0 + b, 1);
+            mbar_init(barB0 + b, 1);
+        }
         mbar_init(barD, 1);
         fence_proxy_async();
     }
@@ -156,7 +169,6 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     }
     auto rofs = [&](int it) { return PACKED ? lane + 32 * it : kofs[it]; };
     double2* const ksub = k_s + sub * N * LD;     // this ADO's k tile
-    const double2* const rsub = rho_s + sub * (PACKED ? PK : N * LD);
     const int frow = row * N - row * (row - 1) / 2 - row;   // PACKED: element (row, l), l >= row, at frow + l
     const int* const trow = tofs_s + row;                   // PACKED: + r0*N: offset of element (r0, row)
     const double2* const nbrow = nb_s + sub * NN + row;   // + t*N: row element of staged link t
@@ -201,9 +213,31 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     fetch_ptr(cur_base, nx_lbeg, nx_lend);
     fetch_rec(cur_base, nx_lbeg, nx_lend);
     fetch_ptr(nx_base, nn_lbeg, nn_lend);
+    // DB: bulk copies of the streamed tiles of the group that starts at slot b0 into buffer set b
+    // (one lane; the warp has synchronised after its last generic-proxy access to that set)
+    auto issue_streamed = [&](int b0, int b) {
+        const unsigned ne = (unsigned)(min(APW, slot_hi - b0) * EL) * 16u;
+        const unsigned gb = (unsigned)b0 * (unsigned)EL;
+        fence_proxy_async();
+        mbar_expect_tx(barA0 + b, ne);
+        bulk_g2s(rho0 + b * RT, a.yin + gb, ne, barA0 + b);
+        if (!FIRST) {
+            mbar_expect_tx(barB0 + b, ne * (LAST ? 2u : 1u));
+            bulk_g2s(y0 + b * FE, a.y + gb, ne, barB0 + b);
+            if (LAST) bulk_g2s(acc0 + b * FE, a.s1 + gb, ne, barB0 + b);
+        }
+    };
+    int buf = 0;
+    if (DB && lane == 0 && cur_base >= 0) issue_streamed(cur_base, 0);
 
     for (; g < ngroups; g += gstride) {
         const int base = cur_base;
+        double2* const rho_s = rho0 + buf * RT;
+        double2* const y_s = y0 + buf * FE;
+        double2* const acc_s = acc0 + buf * FE;
+        unsigned long long* const barA = barA0 + buf;
+        unsigned long long* const barB = barB0 + buf;
+        const double2* const rsub = rho_s + sub * (PACKED ? PK : N * LD);
         const int cnt = min(APW, slot_hi - base);
         const int nelem = cnt * EL;
         const bool on = lane_ok && sub < cnt;
@@ -224,7 +258,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         fetch_ptr(nx_base, nn_lbeg, nn_lend);
 
         // ---- issue: own tile + first chunk of neighbour rows, y / first stage buffer
-        if (BULK_TILE) {
+        if (DB) {
+            // this group's tiles were issued one iteration ago; now the next group's
+            if (lane == 0 && cur_base >= 0) issue_streamed(cur_base, buf ^ 1);
+        } else if (BULK_TILE) {
             if (lane == 0) {
                 fence_proxy_async();   // earlier generic-proxy reads of these buffers are done (warp sync)
                 mbar_expect_tx(barA, nelem * 16u);
@@ -248,7 +285,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                                     : yin_row + (unsigned)r.x);
         }
         cp_async_commit();
-        if (!FIRST) {
+        if (!FIRST && !DB) {
             // y always; in the last stage also the first stage buffer - the second one
             // follows into rho_s once the commutator has consumed the own tile
             if (lane == 0) {
@@ -260,8 +297,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         }
         cp_async_wait<0>();
         if (BULK_TILE) {
-            mbar_wait(barA, phA);
-            phA ^= 1u;
+            mbar_wait(barA, (phA >> buf) & 1u);
+            phA ^= 1u << buf;
         }
         __syncwarp();
 
@@ -407,8 +444,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         }
         cp_async_wait<0>();
         if (!FIRST) {
-            mbar_wait(barB, phB);
-            phB ^= 1u;
+            mbar_wait(barB, (phB >> buf) & 1u);
+            phB ^= 1u << buf;
         }
         if (BULK_TILE && LAST) {
             mbar_wait(barD, phD);
@@ -452,6 +489,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             }
         }
         __syncwarp();
+        if (DB) buf ^= 1;
     }
 }
 
@@ -502,7 +540,7 @@ __global__ void sym_unpack_kernel(double2* full, const double2* tri, long long n
 }
 constexpr size_t SYM_SMEM_BUDGET = 227 * 1024;
 
-template <int N, bool HREAL, int STAGE, bool PACKED>
+template <int N, bool HREAL, int STAGE, bool PACKED, bool DB>
 int sym_launch_t(const SymLaunch& s) {
     constexpr int APW = 32 / N;
     SymArgs args = s.a;
@@ -510,7 +548,7 @@ int sym_launch_t(const SymLaunch& s) {
     args.slot_lo = s.part_lo;
     args.slot_hi = s.part_hi;
     const size_t table_bytes = sym_table_bytes(s.K, s.L);
-    const size_t per_warp = sizeof(double2) * sym_perwarp(N, STAGE, PACKED);
+    const size_t per_warp = sizeof(double2) * sym_perwarp(N, STAGE, PACKED, DB);
     if (table_bytes + per_warp > SYM_SMEM_BUDGET) {
         g_sym_err = "shared-memory tables too large for kernel 6";
         return 1;
@@ -530,7 +568,7 @@ int sym_launch_t(const SymLaunch& s) {
         if constexpr (HREAL) hp.v[e] = s.H[2 * e];
         else hp.v[e] = make_double2(s.H[2 * e], s.H[2 * e + 1]);
     }
-    auto kern = stage_rows_sym_kernel<N, HREAL, STAGE, PACKED>;
+    auto kern = stage_rows_sym_kernel<N, HREAL, STAGE, PACKED, DB>;
 #ifndef HEOM_HOST_EMU
     static bool attr_set = false;
     if (!attr_set) {
@@ -563,24 +601,27 @@ int sym_launch_t(const SymLaunch& s) {
     return 0;
 }
 
-template <int N, bool PACKED>
+template <int N, bool PACKED, bool DB>
 int sym_launch_p(const SymLaunch& s) {
     if (s.hreal) {
         switch (s.stage) {
-            case 0: return sym_launch_t<N, true, 0, PACKED>(s);
-            case 1: return sym_launch_t<N, true, 1, PACKED>(s);
-            default: return sym_launch_t<N, true, 2, PACKED>(s);
+            case 0: return sym_launch_t<N, true, 0, PACKED, DB>(s);
+            case 1: return sym_launch_t<N, true, 1, PACKED, DB>(s);
+            default: return sym_launch_t<N, true, 2, PACKED, DB>(s);
         }
     }
     switch (s.stage) {
-        case 0: return sym_launch_t<N, false, 0, PACKED>(s);
-        case 1: return sym_launch_t<N, false, 1, PACKED>(s);
-        default: return sym_launch_t<N, false, 2, PACKED>(s);
+        case 0: return sym_launch_t<N, false, 0, PACKED, DB>(s);
+        case 1: return sym_launch_t<N, false, 1, PACKED, DB>(s);
+        default: return sym_launch_t<N, false, 2, PACKED, DB>(s);
     }
 }
 template <int N>
 int sym_launch_n(const SymLaunch& s) {
-    return s.packed ? sym_launch_p<N, true>(s) : sym_launch_p<N, false>(s);
+    // the double-buffered variant exists for packed storage only (its tiles are small enough
+    // to keep nearly all warps)
+    if (s.packed) return s.prefetch ? sym_launch_p<N, true, true>(s) : sym_launch_p<N, true, false>(s);
+    return sym_launch_p<N, false, false>(s);
 }
 
 }  // namespace
@@ -669,6 +710,7 @@ int heom_packed_propagate(const PackedRun& r, const char** err) {
             s.N = N; s.K = r.K; s.M = r.M; s.L = r.L; s.B = 1;
             s.hreal = r.hreal;
             s.packed = 1;
+            s.prefetch = r.prefetch;
             s.warps = r.warps;
             s.sm_count = r.sm_count;
             s.part_lo = 0;

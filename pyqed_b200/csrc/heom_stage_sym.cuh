@@ -88,6 +88,7 @@ struct SymLaunch {
     int stage;            // 0 first, 1 middle, 2 last
     int hreal;            // H has no imaginary part
     int packed;           // kernel 7: the ADO arrays hold upper triangles (N(N+1)/2 elements per ADO)
+    int prefetch;         // packed only: double-buffered tiles, fetched one group ahead
     int warps;            // 0 = automatic
     int sm_count;
     long long part_lo, part_hi;   // owned slot range
@@ -116,6 +117,7 @@ struct PackedRun {
     long long nmax, nt;
     double dt;
     int hreal, warps, sm_count;
+    int prefetch;         // 1: double-buffered streamed tiles (stage_rows_sym_kernel<..., DB>)
     void* stream;
 };
 int heom_packed_propagate(const PackedRun& r, const char** err);

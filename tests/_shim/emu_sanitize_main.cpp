@@ -52,10 +52,10 @@ int main(int argc, char** argv) {
     int bad = 0;
     for (int late = 0; late < 2; ++late) {
         emu::g_async_late = late;
-        std::vector<double> s6(4 * asz, 0.0), s3(4 * asz, 0.0), s3g(4 * asz, 0.0), y7(asz, 0.0);
+        std::vector<double> s6(4 * asz, 0.0), s3(4 * asz, 0.0), s3g(4 * asz, 0.0), y7(asz, 0.0), y7p(asz, 0.0);
         for (auto* v : {&s6, &s3, &s3g})
             for (size_t i = asz; i < 4 * asz; ++i) (*v)[i] = std::nan("");
-        for (size_t i = 0; i < 2 * NN; ++i) s6[i] = s3[i] = s3g[i] = y7[i] = rho0[i];
+        for (size_t i = 0; i < 2 * NN; ++i) s6[i] = s3[i] = s3g[i] = y7[i] = y7p[i] = rho0[i];
         std::vector<double> t6(2 * NN * (nt + 1)), t7(t6.size()), t3(t6.size());
         const char* err = "";
         if (emu_sym_run(N, K, M, L, nmax, H.data(), ops.data(), cbase.data(), kmode.data(), damp.data(),
@@ -63,7 +63,10 @@ int main(int argc, char** argv) {
                         t6.data(), &err) ||
             emu_packed_run(N, K, M, L, nmax, H.data(), ops.data(), cbase.data(), kmode.data(), damp.data(),
                            link_ptr.data(), links.data(), nlinks, y7.data(), dtv[0], nt, hreal, 3, 2, 0, 1,
-                           t7.data(), &err)) {
+                           t7.data(), 0, &err) ||
+            emu_packed_run(N, K, M, L, nmax, H.data(), ops.data(), cbase.data(), kmode.data(), damp.data(),
+                           link_ptr.data(), links.data(), nlinks, y7p.data(), dtv[0], nt, hreal, 3, 2, 0, 1,
+                           nullptr, 1, &err)) {
             std::cerr << "kernel 6/7 failed: " << err << "\n";
             return 1;
         }
@@ -76,7 +79,8 @@ int main(int argc, char** argv) {
         s6.resize(asz);
         s3.resize(asz);
         s3g.resize(asz);
-        const double d67 = max_abs_diff(s6, y7), d36 = max_abs_diff(s3, s6), d33 = max_abs_diff(s3, s3g);
+        const double d67 = std::max(max_abs_diff(s6, y7), max_abs_diff(y7, y7p));   // incl. the prefetching variant
+        const double d36 = max_abs_diff(s3, s6), d33 = max_abs_diff(s3, s3g);
         std::cout << "late=" << late << " |k6-k7|=" << d67 << " |k3-k6|=" << d36 << " |k3sym-k3general|=" << d33
                   << " |traj6-traj7|=" << max_abs_diff(t6, t7) << "\n";
         if (!(d67 == 0.0) || !(d36 < 1e-12) || !(d33 < 1e-12) || !(max_abs_diff(t6, t3) < 1e-12)) bad = 1;

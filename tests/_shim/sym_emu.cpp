@@ -90,7 +90,8 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
 int emu_packed_run(int N, int K, int M, int L, long long nmax, const double* H, const double* ops,
                    const double* cbase, const int* kmode, const double* damp, const int* link_ptr,
                    const int* links, long long nlinks, double* Y, double dt, int nt, int hreal,
-                   int sm_count, int warps, long long slot0, int scramble, double* traj, const char** err) {
+                   int sm_count, int warps, long long slot0, int scramble, double* traj, int prefetch,
+                   const char** err) {
     static const char* none = "";
     *err = none;
     if (heom_sym_supported(N, K, M, L, err)) return 1;
@@ -127,6 +128,7 @@ int emu_packed_run(int N, int K, int M, int L, long long nmax, const double* H, 
     r.hreal = hreal;
     r.warps = warps;
     r.sm_count = sm_count;
+    r.prefetch = prefetch;
     r.stream = nullptr;
     return heom_packed_propagate(r, err);
 }

@@ -146,6 +146,23 @@ def test_kernel6_beyond_l2_invariants():
         _close_and_hermitian(res[3][1], res[kern][1])
 
 
+@pytest.mark.parametrize("name", ["deom_fmo_K7_L4", "deom_fmo_K21_L3"])
+@pytest.mark.parametrize("warps", [0, 1, 5])
+def test_kernel7_with_double_buffered_tiles(name, warps):
+    """``prefetch`` = the streamed tiles of the next group are in flight while the
+    current one is processed; same arithmetic, identical bits."""
+    g = golden(name)
+    out = []
+    for prefetch in (0, 1):
+        s = _solver_from(g)
+        s.tuning = _tuning(7, warps)
+        s.options = {"resident": 0, "prefetch": prefetch}
+        _check_against_golden(g, s)
+        assert _ran(s._plan, 7, int(g["nt"]))
+        out.append(np.array(s.ddos))
+    assert np.array_equal(out[0], out[1])
+
+
 def test_kernel7_two_runs_and_restart():
     """Kernel 7 packs the state on entry and unpacks it on exit: two consecutive
     propagations must equal one long one, and the ADOs read back in between must

@@ -108,7 +108,7 @@ def run_emu(emu, w, nt, sm_count=3, warps=2, parts=None, scramble=0):
     return state[0], traj, o.ddos, np.array(ref)
 
 
-def run_emu_packed(emu, w, nt, sm_count=3, warps=2, scramble=0):
+def run_emu_packed(emu, w, nt, sm_count=3, warps=2, scramble=0, prefetch=0):
     """Kernel 7: ``heom_packed_propagate`` (pack, nt steps on upper triangles, unpack)."""
     o, t = host_tables(w)
     N = t["N"]
@@ -125,7 +125,7 @@ def run_emu_packed(emu, w, nt, sm_count=3, warps=2, scramble=0):
         p(t["link_ptr"]), p(t["links"]), ctypes.c_longlong(len(t["links"])), p(y),
         ctypes.c_double(w["dt"]), ctypes.c_int(nt), ctypes.c_int(int(np.all(H.imag == 0))),
         ctypes.c_int(sm_count), ctypes.c_int(warps), ctypes.c_longlong(0), ctypes.c_int(scramble),
-        p(traj), ctypes.byref(err))
+        p(traj), ctypes.c_int(prefetch), ctypes.byref(err))
     assert rc == 0, err.value
     _, ref = o.run(w["rho0"], w["dt"], nt)
     return y, traj, o.ddos, np.array(ref)
@@ -147,6 +147,9 @@ def check(emu, w, nt, **kw):
         assert np.array_equal(y7, y7.conj().transpose(0, 2, 1))
         # same arithmetic on the same values as kernel 6: identical bits
         assert np.array_equal(y7, y) and np.array_equal(traj7, traj)
+        # ... and with the streamed tiles double-buffered and fetched one group ahead
+        y7p, traj7p, _, _ = run_emu_packed(emu, w, nt, prefetch=1, **kw)
+        assert np.array_equal(y7p, y) and np.array_equal(traj7p, traj)
 
 
 def projector_problem(n, nind_per_mode, lmax, seed, complex_h):

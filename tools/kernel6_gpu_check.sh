@@ -19,6 +19,8 @@ tail -c 1200 "$out/bench_default.json"; echo
 tail -c 1200 "$out/bench_kernel6.json"; echo
 timeout 600 python bench.py --no-cpu --kernel 7 --steps 20 --warmup 3 > "$out/bench_kernel7.json" 2> "$out/bench_kernel7.err"
 tail -c 1200 "$out/bench_kernel7.json"; echo
+timeout 600 python bench.py --no-cpu --kernel 7 --prefetch 1 --steps 20 --warmup 3 > "$out/bench_kernel7_prefetch.json" 2> "$out/bench_kernel7_prefetch.err"
+tail -c 1200 "$out/bench_kernel7_prefetch.json"; echo
 
 echo "== launch list of kernel 6 (per-launch times are cold-cache and serialised)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
