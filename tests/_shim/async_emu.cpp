@@ -95,13 +95,15 @@ int emu_async_run(int N, int K, int M, int L, long long nmax, const double* H, c
                 s.slot_hi = parts[2 * p + 1];
                 if (s.slot_hi <= s.slot_lo) continue;
                 switch (N) {
+#ifndef HEOM_EMU_FEW_N
                     case 2: launch_n<2>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
                     case 3: launch_n<3>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
-                    case 4: launch_n<4>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
                     case 5: launch_n<5>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
                     case 6: launch_n<6>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
-                    case 7: launch_n<7>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
                     case 8: launch_n<8>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
+#endif
+                    case 4: launch_n<4>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
+                    case 7: launch_n<7>(s, H, K, M, L, warps, sm_count, hreal, sym); break;
                     default: return 1;
                 }
             }

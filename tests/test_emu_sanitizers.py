@@ -34,8 +34,8 @@ def dump(w, nt, path):
 @pytest.fixture(scope="module")
 def problems(tmp_path_factory):
     out = []
-    for i, (w, nt) in enumerate([(W.fmo(lmax=2, n_matsubara=1), 2),            # N=7, K=14, 120 ADOs, 3 chunks
-                                 (projector_problem(4, 2, 3, seed=3, complex_h=True), 2)]):  # even N, padded tiles
+    for i, (w, nt) in enumerate([(W.fmo(lmax=2, n_matsubara=1), 1),            # N=7, K=14, 120 ADOs, 3 chunks
+                                 (projector_problem(4, 2, 3, seed=3, complex_h=True), 1)]):  # even N, padded tiles
         d = tmp_path_factory.mktemp(f"problem{i}")
         dump(w, nt, str(d))
         out.append(str(d))
@@ -52,7 +52,7 @@ def binaries(tmp_path_factory):
     def build(sanitizer):
         exe = str(d / f"emu_{sanitizer}")
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-pthread", f"-fsanitize={sanitizer}",
-                               "-fno-omit-frame-pointer", "-o", exe, src])
+                               "-fno-omit-frame-pointer", "-DHEOM_EMU_FEW_N", "-o", exe, src])
         return exe
     with ThreadPoolExecutor(2) as pool:
         return dict(zip(("address", "thread"), pool.map(build, ("address", "thread"))))
