@@ -99,6 +99,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async16_s(unsigned smem_dst_u32, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst_u32), "l"(gsrc) : "memory");
 }
+// predicated form: one instruction under a predicate instead of a branch around the copy
+__device__ __forceinline__ void cp_async16_s_if(unsigned smem_dst_u32, const void* gsrc, bool pred) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "@p cp.async.cg.shared.global [%0], [%1], 16;\n"
+        "}\n" ::"r"(smem_dst_u32),
+        "l"(gsrc), "r"((int)pred)
+        : "memory");
+}
 // same with an L2 eviction-priority hint (createpolicy): the stage input and the
 // neighbour rows are the only data with reuse (evict_last), y/acc are read once
 // per launch (evict_first)

@@ -279,10 +279,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         for (int t = 0; t < N; ++t) {
             const int2 r = strip_sub[t];
             ry[t] = r.y;
-            if (t < nl)
-                cp_async16_s(nbrow_u32 + t * (N * 16),
-                             PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
-                                    : yin_row + (unsigned)r.x);
+            cp_async16_s_if(nbrow_u32 + t * (N * 16),
+                            PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
+                                   : yin_row + (unsigned)r.x,
+                            t < nl);
         }
         cp_async_commit();
         if (!FIRST && !DB) {
@@ -391,10 +391,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                 for (int t = 0; t < N; ++t) {
                     const int2 r = recs[t];
                     ry[t] = r.y;
-                    if (c0 + t < nl)
-                        cp_async16_s(nbrow_u32 + t * (N * 16),
-                                     PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
-                                            : yin_row + (unsigned)r.x);
+                    cp_async16_s_if(nbrow_u32 + t * (N * 16),
+                                    PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
+                                           : yin_row + (unsigned)r.x,
+                                    c0 + t < nl);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();

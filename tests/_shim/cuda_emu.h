@@ -212,6 +212,9 @@ inline void cp_async16(void* smem_dst, const void* gsrc) {
 inline void cp_async16_s(unsigned smem_dst_u32, const void* gsrc) {
     cp_async16(emu::t_cta->smem.data() + smem_dst_u32, gsrc);
 }
+inline void cp_async16_s_if(unsigned smem_dst_u32, const void* gsrc, bool pred) {
+    if (pred) cp_async16_s(smem_dst_u32, gsrc);
+}
 inline void cp_async_commit() {
     if (!emu::g_async_late) return;
     emu::t_groups.push_back(std::move(emu::t_open));
