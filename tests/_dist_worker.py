@@ -143,6 +143,7 @@ def gpu_mode(args):
         sh = S.ShardedDEOM(g["system"], g["system_dipole"], g["coupling"], g["coupling_dipole"],
                            g["expn"], g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]),
                            tr, device=dev, order=args.order,
+                           tuning=dict(kernel=args.kernel, warps_per_cta=0, use_graph=0),
                            peer_push={-1: None, 0: False, 1: True}[args.push],
                            fused_push={-1: None, 0: False, 1: True}[args.fused])
         nt = int(g["nt"])
@@ -158,6 +159,8 @@ def gpu_mode(args):
             assert e2 < 1e-12, (name, e2)
         if 0 < sh.hi - sh.lo < sh.nmax:
             assert sum(sh.halo.recv_counts) > 0   # a proper sub-range always has foreign neighbours
+        if args.kernel == 6:   # did the stages really go through kernel 6 where it applies?
+            print(f"rank {tr.rank}: {name} kernel6 stage launches {sh.plan.info('sym_launches')} of {4 * nt}", flush=True)
         print(f"rank {tr.rank}: {name} push={sh.symm is not None} fused={sh.fused} ok (owned {sh.hi - sh.lo} of {sh.nmax}, halo items "
               f"{sh.need32.numel()}, row items {sh.row_items}, err {err:.1e})", flush=True)
 
@@ -170,6 +173,7 @@ if __name__ == "__main__":
     ap.add_argument("--order", type=int, default=1)
     ap.add_argument("--push", type=int, default=-1)
     ap.add_argument("--fused", type=int, default=-1)
+    ap.add_argument("--kernel", type=int, default=0, help="stage kernel (tuning), e.g. 6")
     a = ap.parse_args()
     dist.init_process_group(a.backend)
     try:

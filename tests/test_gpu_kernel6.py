@@ -185,3 +185,19 @@ def test_kernel7_two_runs_and_restart():
     assert np.array_equal(end, np.array(a.ddos))
     assert np.array_equal(np.asarray(full)[-1], end[0])
     assert b._plan.info("packed_steps") == nt
+
+
+@pytest.mark.parametrize("world,order", [(2, 2), (3, 1)])
+def test_kernel6_sharded_ranks_sharing_one_device(world, order):
+    """Kernel 6 as the stage kernel of a sharded run (owned slot ranges, halo rows
+    exchanged on full matrices; gloo transport staged through the host).  Projector
+    couplings go through kernel 6, sigma_z and dense ones fall back."""
+    from test_sharded import _launch
+    out = _launch(world, ["gpu", "--backend", "gloo", "--order", str(order), "--kernel", "6", "--cases",
+                          "deom_fmo_K21_L2,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
+    assert out.count(" ok (owned") == 4 * world
+    import re
+    done = {(m.group(1), int(m.group(2)), int(m.group(3)))
+            for m in re.finditer(r"rank \d+: (\S+) kernel6 stage launches (\d+) of (\d+)", out)}
+    for name, launched, total in done:
+        assert launched == (total if "fmo" in name else 0), (name, launched, total)
