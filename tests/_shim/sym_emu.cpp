@@ -85,6 +85,49 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
     return 0;
 }
 
+// One stage of one rank: kernel 6 over the owned range [lo, hi) of the arrays given (a sharded
+// run in miniature - the caller moves the halo rows between the ranks' arrays).
+int emu_sym_stage(int N, int K, int M, int L, const double* H, const double* ops, const double* cbase,
+                  const int* kmode, const double* damp, const int* link_ptr, const int* links, long long nlinks,
+                  const double* yin, const double* y, const double* s1, const double* s2, double* out, double a,
+                  double w, int stage_kind, int hreal, int sm_count, int warps, long long lo, long long hi,
+                  long long nmax, const char** err) {
+    static const char* none = "";
+    *err = none;
+    std::vector<int2> links2((size_t)std::max(1ll, nlinks));
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 0, nullptr, err))
+        return 1;
+    long long step_base = 0;
+    SymLaunch s{};
+    s.a.yin = reinterpret_cast<const double2*>(yin);
+    s.a.y = reinterpret_cast<const double2*>(y);
+    s.a.s1 = reinterpret_cast<const double2*>(s1);
+    s.a.s2 = reinterpret_cast<const double2*>(s2);
+    s.a.out = reinterpret_cast<double2*>(out);
+    s.a.damp = reinterpret_cast<const double2*>(damp);
+    s.a.link_ptr = link_ptr;
+    s.a.links2 = links2.data();
+    s.a.cbase = reinterpret_cast<const double2*>(cbase);
+    s.a.kmode = kmode;
+    s.a.ops = reinterpret_cast<const double2*>(ops);
+    s.a.step_base = &step_base;
+    s.a.a = a;
+    s.a.w = w;
+    s.a.nind = K;
+    s.a.nmod = M;
+    s.a.lmax = L;
+    s.H = H;
+    s.N = N; s.K = K; s.M = M; s.L = L; s.B = 1;
+    s.stage = stage_kind;
+    s.hreal = hreal;
+    s.warps = warps;
+    s.sm_count = sm_count;
+    s.part_lo = lo;
+    s.part_hi = hi;
+    s.batch_elems = nmax * N * N;
+    return heom_sym_launch(s, err);
+}
+
 // Kernel 7: the product's packed-storage driver (heom_packed_propagate) on host arrays.
 // `Y` is the full state [nmax][N][N]; the work region is filled with NaNs first.
 int emu_packed_run(int N, int K, int M, int L, long long nmax, const double* H, const double* ops,

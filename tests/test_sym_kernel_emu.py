@@ -208,3 +208,58 @@ def test_owned_ranges_and_rotation(emu):
 def test_more_warps_than_groups(emu):
     w = projector_problem(3, 1, 2, seed=5, complex_h=True)   # 10 ADOs = 1 group of 10
     check(emu, w, nt=3, sm_count=4, warps=4)
+
+
+def test_sharded_ranks_read_only_their_halo_rows(emu):
+    """Two ranks with separate arrays: everything a rank does not own is NaN except
+    the rows its links point at (the halo rows ``sharded.needed_items`` exchanges).
+    Kernel 6 must reproduce the oracle from that alone - one NaN read would poison
+    the result."""
+    w = W.fmo(lmax=3, n_matsubara=0)
+    o, t = host_tables(w)
+    N, nmax, dt, nt = t["N"], o.nmax, w["dt"], 2
+    bounds = [0, 53, nmax]
+    ptr, links = t["link_ptr"], t["links"]
+    need = []   # per rank: (slot, row) pairs of foreign rows its owned ADOs read
+    for r in range(2):
+        lo, hi = bounds[r], bounds[r + 1]
+        rec = links[ptr[lo]:ptr[hi]]
+        foreign = (rec[:, 0] < lo) | (rec[:, 0] >= hi)
+        need.append(sorted({(int(s_), int((m_ >> 16) & 0xf)) for s_, m_ in rec[foreign]}))
+        assert need[-1]
+    state = np.full((2, 4, nmax, N, N), np.nan, dtype=C128)   # rank, (Y, SA, SB, ACC)
+    y0 = np.zeros((nmax, N, N), C128)
+    y0[0] = w["rho0"]
+    for r in range(2):
+        state[r, 0, bounds[r]:bounds[r + 1]] = y0[bounds[r]:bounds[r + 1]]
+
+    def exchange(arr):
+        for r in range(2):
+            for slot, row in need[r]:
+                state[r, arr, slot, row] = state[1 - r, arr, slot, row]
+    exchange(0)
+    H = np.ascontiguousarray(o.H0)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    emu.emu_sym_stage.restype = ctypes.c_int
+    plan = [(0, 1, 0, dt / 2, 0.0), (1, 2, 1, dt / 2, 0.0), (2, 3, 1, dt, 0.0), (3, 0, 2, 2.0 / dt, dt / 6)]
+    for _ in range(nt):
+        for yin, out, kind, a, wgt in plan:
+            for r in range(2):
+                err = ctypes.c_char_p()
+                st = state[r]
+                rc = emu.emu_sym_stage(
+                    ctypes.c_int(N), ctypes.c_int(t["K"]), ctypes.c_int(t["M"]), ctypes.c_int(o.lmax), p(H),
+                    p(t["ops"]), p(t["cbase"]), p(t["kmode"]), p(t["damp"]), p(ptr), p(links),
+                    ctypes.c_longlong(len(links)), p(st[yin]), p(st[0]), p(st[1]), p(st[2]), p(st[out]),
+                    ctypes.c_double(a), ctypes.c_double(wgt), ctypes.c_int(kind),
+                    ctypes.c_int(int(np.all(H.imag == 0))), ctypes.c_int(2), ctypes.c_int(2),
+                    ctypes.c_longlong(bounds[r]), ctypes.c_longlong(bounds[r + 1]), ctypes.c_longlong(nmax),
+                    ctypes.byref(err))
+                assert rc == 0, err.value
+            exchange(out)
+    o.run(w["rho0"], dt, nt)
+    got = np.concatenate([state[0, 0, :bounds[1]], state[1, 0, bounds[1]:]])
+    assert np.isfinite(got).all()
+    assert np.abs(got - o.ddos).max() < 1e-12
+    # what a rank does not own and does not need was never written
+    assert np.isnan(state[0, 0, bounds[1]:]).any() and np.isnan(state[1, 0, :bounds[1]]).any()
