@@ -158,6 +158,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "r"(parity)
         : "memory");
 }
+// shared -> global bulk stores (TMA, 1-D), tracked per thread in bulk async-groups.  Used for
+// the fused halo push: a row staged in shared memory goes to a peer's array with one
+// instruction.  wait_read: the sources may be overwritten; wait_all: the stores are complete.
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }

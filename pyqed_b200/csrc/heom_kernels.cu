@@ -486,11 +486,12 @@ static int try_resident(pyqed_heom_plan* p) {
 }
 
 // kernel 6 (heom_stage_sym.cu) takes the difference-form RK4 stages of kernel 3 when every
-// ADO is Hermitian, every Q_m has one non-zero diagonal entry, H does not depend on time and
-// no fused halo push is requested; everything else stays with kernel 3
+// ADO is Hermitian, every Q_m has one non-zero diagonal entry and H does not depend on time
+// (with push tables its PUSH instantiation stores the halo rows into the peers' arrays);
+// everything else stays with kernel 3
 static bool sym_eligible(const pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     return p->kernel == 6 && p->links2_built && !tdep && a.herm && p->single_support && p->opt_sym != 0 &&
-           !a.push_ptr && a.scheme == 1 && !(a.first && a.last);
+           (!a.push_ptr || p->B == 1) && a.scheme == 1 && !(a.first && a.last);
 }
 static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     SymLaunch s{};

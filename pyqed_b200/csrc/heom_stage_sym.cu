@@ -81,9 +81,14 @@ using HParamOf = typename std::conditional<HREAL, HParamReal<N>, HParam<N>>::typ
 // DB: the bulk-copied tiles of a group (own tile, y, first stage buffer) live in two buffer
 // sets; the copies for the next group are issued before the current group is processed, so
 // they are in flight during the whole group instead of being waited for right after issue.
-template <int N, bool HREAL, int STAGE, bool PACKED, bool DB>
+// PUSH: fused multi-GPU halo.  The epilogue also leaves the stage output in the k tile, and
+// the rows other ranks need (push tables, as for kernel 3's fused push) go from there into
+// the peers' arrays as bulk shared->global stores over NVLink - one instruction per row, in
+// flight while the warp loads its next group.
+template <int N, bool HREAL, int STAGE, bool PACKED, bool DB, bool PUSH>
 __global__ void __launch_bounds__(sym_max_threads(STAGE), 1)
 stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL> hp) {
+    static_assert(!PUSH || (!PACKED && !DB), "the fused push works on full matrices");
     constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
     constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE, PACKED, DB), NCH = SYM_NCH;
@@ -189,14 +194,19 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         return gg < ngroups ? slot_lo + gm * APW : -1;
     };
     int nx_lbeg = 0, nx_lend = 0, nn_lbeg = 0, nn_lend = 0;
+    int nx_pb = 0, nx_pe = 0, nn_pb = 0, nn_pe = 0;   // PUSH: entry range of this lane's ADO
     int2 nx_rec[NCH];
     double nx_damp = 0.0;
-    auto fetch_ptr = [&](int b0, int& lb, int& le) {
+    auto fetch_ptr = [&](int b0, int& lb, int& le, int& pb, int& pe) {
         const int slot = b0 + sub;
-        lb = le = 0;
+        lb = le = pb = pe = 0;
         if (b0 >= 0 && lane_ok && slot < slot_hi) {
             lb = a.link_ptr[slot];
             le = a.link_ptr[slot + 1];
+            if (PUSH) {
+                pb = a.push_ptr[slot - slot_lo];
+                pe = a.push_ptr[slot - slot_lo + 1];
+            }
         }
     };
     auto fetch_rec = [&](int b0, int lb, int le) {
@@ -210,9 +220,9 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     };
     int g = (int)blockIdx.x * nwarps + wid;
     int cur_base = group_base(g), nx_base = group_base(g + gstride);
-    fetch_ptr(cur_base, nx_lbeg, nx_lend);
+    fetch_ptr(cur_base, nx_lbeg, nx_lend, nx_pb, nx_pe);
     fetch_rec(cur_base, nx_lbeg, nx_lend);
-    fetch_ptr(nx_base, nn_lbeg, nn_lend);
+    fetch_ptr(nx_base, nn_lbeg, nn_lend, nn_pb, nn_pe);
     // DB: bulk copies of the streamed tiles of the group that starts at slot b0 into buffer set b
     // (one lane; the warp has synchronised after its last generic-proxy access to that set)
     auto issue_streamed = [&](int b0, int b) {
@@ -243,6 +253,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         const bool on = lane_ok && sub < cnt;
         const int lbeg = nx_lbeg, lend = nx_lend;
         const int nl = on ? (lend - lbeg) : 0;
+        const int pb = nx_pb, pe = on ? nx_pe : nx_pb;
         const double dh = 0.5 * nx_damp;
         const unsigned gbase = (unsigned)base * (unsigned)EL;
         // publish this group's records, then start the prefetch of the next group's
@@ -253,9 +264,11 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         cur_base = nx_base;
         nx_lbeg = nn_lbeg;
         nx_lend = nn_lend;
+        nx_pb = nn_pb;
+        nx_pe = nn_pe;
         fetch_rec(cur_base, nx_lbeg, nx_lend);
         nx_base = group_base(g + 2 * gstride);
-        fetch_ptr(nx_base, nn_lbeg, nn_lend);
+        fetch_ptr(nx_base, nn_lbeg, nn_lend, nn_pb, nn_pe);
 
         // ---- issue: own tile + first chunk of neighbour rows, y / first stage buffer
         if (DB) {
@@ -300,6 +313,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             mbar_wait(barA, (phA >> buf) & 1u);
             phA ^= 1u << buf;
         }
+        if (PUSH) bulk_wait_read();   // the previous group's rows have left the k tile
         __syncwarp();
 
         // ---- P = -i H rho - (damp/2) rho, column `row` of this ADO.  The full
@@ -473,6 +487,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     res.x = fma(2.0 * third, s2.x, res.x);
                     res.y = fma(2.0 * third, s2.y, res.y);
                     st_stream(a.out + (gbase + e), res);
+                    if (PUSH) k_s[kofs[it]] = res;
                     if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)EL) {
                         if (PACKED) {   // the trajectory holds full matrices
                             const int kk = kofs[it] - (e0 / EL) * (N * LD), i = kk / LD, j = kk - i * LD;
@@ -484,12 +499,40 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     }
                 } else {
                     const double2 yv = FIRST ? rho_s[rofs(it)] : y_s[e];
-                    st_stream(a.out + (gbase + e), make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y)));
+                    const double2 res = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
+                    st_stream(a.out + (gbase + e), res);
+                    if (PUSH) k_s[kofs[it]] = res;
                 }
+            }
+        }
+        if (PUSH) {
+            // rows of this group's output that other ranks read: from the k tile straight into
+            // their arrays.  The N lanes of an ADO share its entries.
+            const bool any = __reduce_max_sync(0xffffffffu, pe - pb) > 0;
+            if (any) {
+                fence_proxy_async();   // this lane's tile writes are ordered before the bulk stores
+                __syncwarp();
+                for (int q = pb + row; q < pe; q += N) {
+                    const int ent = a.push_ent[q], r = ent & 15;
+                    double2* dst = reinterpret_cast<double2*>(__ldg(a.peer + (ent >> 4))) + a.out_elem_off +
+                                   (gbase + (unsigned)(sub * NN));
+                    if (r == 15) {
+#pragma unroll
+                        for (int rr = 0; rr < N; ++rr) bulk_s2g(dst + rr * N, ksub + rr * LD, N * 16u);
+                    } else {
+                        bulk_s2g(dst + r * N, ksub + r * LD, N * 16u);
+                    }
+                }
+                bulk_commit();
             }
         }
         __syncwarp();
         if (DB) buf ^= 1;
+    }
+    if (PUSH) {
+        // remote rows must have landed before the stream-ordered barrier that follows the kernel
+        bulk_wait_all();
+        __threadfence_system();
     }
 }
 
@@ -540,7 +583,7 @@ __global__ void sym_unpack_kernel(double2* full, const double2* tri, long long n
 }
 constexpr size_t SYM_SMEM_BUDGET = 227 * 1024;
 
-template <int N, bool HREAL, int STAGE, bool PACKED, bool DB>
+template <int N, bool HREAL, int STAGE, bool PACKED, bool DB, bool PUSH>
 int sym_launch_t(const SymLaunch& s) {
     constexpr int APW = 32 / N;
     SymArgs args = s.a;
@@ -568,7 +611,7 @@ int sym_launch_t(const SymLaunch& s) {
         if constexpr (HREAL) hp.v[e] = s.H[2 * e];
         else hp.v[e] = make_double2(s.H[2 * e], s.H[2 * e + 1]);
     }
-    auto kern = stage_rows_sym_kernel<N, HREAL, STAGE, PACKED, DB>;
+    auto kern = stage_rows_sym_kernel<N, HREAL, STAGE, PACKED, DB, PUSH>;
 #ifndef HEOM_HOST_EMU
     static bool attr_set = false;
     if (!attr_set) {
@@ -596,24 +639,25 @@ int sym_launch_t(const SymLaunch& s) {
         if (args.s1) args.s1 += s.batch_elems;
         if (args.s2) args.s2 += s.batch_elems;
         args.out += s.batch_elems;
+        args.out_elem_off += s.batch_elems;
         if (args.traj) args.traj += s.traj_bstride;
     }
     return 0;
 }
 
-template <int N, bool PACKED, bool DB>
+template <int N, bool PACKED, bool DB, bool PUSH = false>
 int sym_launch_p(const SymLaunch& s) {
     if (s.hreal) {
         switch (s.stage) {
-            case 0: return sym_launch_t<N, true, 0, PACKED, DB>(s);
-            case 1: return sym_launch_t<N, true, 1, PACKED, DB>(s);
-            default: return sym_launch_t<N, true, 2, PACKED, DB>(s);
+            case 0: return sym_launch_t<N, true, 0, PACKED, DB, PUSH>(s);
+            case 1: return sym_launch_t<N, true, 1, PACKED, DB, PUSH>(s);
+            default: return sym_launch_t<N, true, 2, PACKED, DB, PUSH>(s);
         }
     }
     switch (s.stage) {
-        case 0: return sym_launch_t<N, false, 0, PACKED, DB>(s);
-        case 1: return sym_launch_t<N, false, 1, PACKED, DB>(s);
-        default: return sym_launch_t<N, false, 2, PACKED, DB>(s);
+        case 0: return sym_launch_t<N, false, 0, PACKED, DB, PUSH>(s);
+        case 1: return sym_launch_t<N, false, 1, PACKED, DB, PUSH>(s);
+        default: return sym_launch_t<N, false, 2, PACKED, DB, PUSH>(s);
     }
 }
 template <int N>
@@ -621,7 +665,8 @@ int sym_launch_n(const SymLaunch& s) {
     // the double-buffered variant exists for packed storage only (its tiles are small enough
     // to keep nearly all warps)
     if (s.packed) return s.prefetch ? sym_launch_p<N, true, true>(s) : sym_launch_p<N, true, false>(s);
-    return sym_launch_p<N, false, false>(s);
+    // full matrices: with push tables the epilogue stores the halo rows into the peers' arrays
+    return s.a.push_ptr ? sym_launch_p<N, false, false, true>(s) : sym_launch_p<N, false, false>(s);
 }
 
 }  // namespace

@@ -22,8 +22,12 @@
 // Every stage output is Hermitian bit for bit.  Results differ from kernel 3's
 // by summation order only (~1e-16); both are held to 1e-12 of the reference.
 // It applies when every Q_m is diagonal with one non-zero entry, every ADO is
-// Hermitian (so the damping rates are real), H is time independent and no
-// fused halo push is requested.
+// Hermitian (so the damping rates are real) and H is time independent.  With push
+// tables (sharded runs, ShardedDEOM(fused_push=True)) the PUSH instantiation also
+// performs the halo exchange: the epilogue leaves the stage output in shared
+// memory and the rows other ranks read go from there into their arrays as bulk
+// shared->global stores (cp.async.bulk, one instruction per 16N-byte row) over
+// NVLink, in flight while the warp loads its next group.
 #pragma once
 #include "heom_device.cuh"
 
@@ -44,6 +48,12 @@ struct SymArgs {
     long long ngroups, slot_lo, slot_hi, slot0;
     double a, w;
     int local_step, scramble, nind, nmod, lmax;
+    // fused multi-GPU halo (PUSH instantiations): rows of the stage output that other ranks
+    // need are stored into their arrays by the epilogue (same tables as kernel 3's fused push)
+    const int* push_ptr;            // [owned+1] CSR over the owned slots, or null
+    const unsigned char* push_ent;  // entries: peer << 4 | row (15 = every row)
+    const unsigned long long* peer; // [world] base address of every rank's state buffer
+    long long out_elem_off;         // offset (double2) of this stage's output array in the state buffer
 };
 
 // links2 record: x = (slot * N + r0) * N, y = ((2k+dir) * (L+1) + n_eff) << 5 | r0
@@ -77,6 +87,10 @@ inline SymArgs sym_args_from_stage(const StageArgs& a, const int2* links2) {
     s.nind = a.nind;
     s.nmod = a.nmod;
     s.lmax = a.lmax;
+    s.push_ptr = a.push_ptr;
+    s.push_ent = a.push_ent;
+    s.peer = a.peer;
+    s.out_elem_off = a.out_elem_off;
     return s;
 }
 inline int sym_stage_kind(const StageArgs& a) { return a.first ? 0 : (a.last ? 2 : 1); }

@@ -267,4 +267,19 @@ inline void mbar_wait(unsigned long long* bar, unsigned parity) {
     }
 }
 inline void fence_proxy_async() {}
+// shared -> global bulk stores: performed at issue, or (late model) when the issuing thread
+// waits for its bulk groups - the source must stay intact until then
+namespace emu {
+inline thread_local std::vector<std::pair<Copy, std::vector<char>>> t_bulk_stores;
+}
+inline void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+    if (emu::g_async_late) emu::t_bulk_stores.push_back({emu::Copy{gdst, smem_src, bytes}, {}});
+    else std::memcpy(gdst, smem_src, bytes);
+}
+inline void bulk_commit() {}
+inline void bulk_wait_read() {
+    for (auto& c : emu::t_bulk_stores) emu::apply(c.first);   // reads the source as late as allowed
+    emu::t_bulk_stores.clear();
+}
+inline void bulk_wait_all() { bulk_wait_read(); }
 inline void __threadfence_system() {}

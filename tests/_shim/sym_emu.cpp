@@ -91,7 +91,8 @@ int emu_sym_stage(int N, int K, int M, int L, const double* H, const double* ops
                   const int* kmode, const double* damp, const int* link_ptr, const int* links, long long nlinks,
                   const double* yin, const double* y, const double* s1, const double* s2, double* out, double a,
                   double w, int stage_kind, int hreal, int sm_count, int warps, long long lo, long long hi,
-                  long long nmax, const char** err) {
+                  long long nmax, const int* push_ptr, const unsigned char* push_ent,
+                  const unsigned long long* peer, long long out_elem_off, const char** err) {
     static const char* none = "";
     *err = none;
     std::vector<int2> links2((size_t)std::max(1ll, nlinks));
@@ -116,6 +117,10 @@ int emu_sym_stage(int N, int K, int M, int L, const double* H, const double* ops
     s.a.nind = K;
     s.a.nmod = M;
     s.a.lmax = L;
+    s.a.push_ptr = push_ptr;     // null: no fused push
+    s.a.push_ent = push_ent;
+    s.a.peer = peer;
+    s.a.out_elem_off = out_elem_off;
     s.H = H;
     s.N = N; s.K = K; s.M = M; s.L = L; s.B = 1;
     s.stage = stage_kind;

@@ -201,3 +201,20 @@ def test_kernel6_sharded_ranks_sharing_one_device(world, order):
             for m in re.finditer(r"rank \d+: (\S+) kernel6 stage launches (\d+) of (\d+)", out)}
     for name, launched, total in done:
         assert launched == (total if "fmo" in name else 0), (name, launched, total)
+
+
+def test_kernel6_fused_push_two_gpus():
+    """Kernel 6's PUSH instantiation: the stage kernel's epilogue stores the halo rows into
+    the peer's arrays as bulk shared->global stores over NVLink (symmetric memory), no
+    separate push kernel."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from test_sharded import _launch
+    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", "1", "--fused", "1", "--kernel", "6",
+                      "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_spin_boson_L10"])
+    assert out.count(" ok (owned") == 6
+    assert out.count("fused=True") == 6
+    import re
+    for m in re.finditer(r"rank \d+: (\S+) kernel6 stage launches (\d+) of (\d+)", out):
+        assert int(m.group(2)) == (int(m.group(3)) if "fmo" in m.group(1) else 0), m.group(0)

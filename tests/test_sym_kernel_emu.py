@@ -210,12 +210,17 @@ def test_more_warps_than_groups(emu):
     check(emu, w, nt=3, sm_count=4, warps=4)
 
 
-def test_sharded_ranks_read_only_their_halo_rows(emu):
+@pytest.mark.parametrize("shape", ["fmo N=7", "even N=4"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_sharded_ranks_read_only_their_halo_rows(emu, fused, shape):
     """Two ranks with separate arrays: everything a rank does not own is NaN except
     the rows its links point at (the halo rows ``sharded.needed_items`` exchanges).
     Kernel 6 must reproduce the oracle from that alone - one NaN read would poison
-    the result."""
-    w = W.fmo(lmax=3, n_matsubara=0)
+    the result.  ``fused``: no exchange by the test at all - the PUSH instantiation's
+    epilogue stores the rows the other rank needs into that rank's arrays itself
+    (bulk shared->global stores, push tables as ``ShardedDEOM`` builds them)."""
+    # odd N: unpadded tiles; even N: padded k tile (row stride N + 1)
+    w = W.fmo(lmax=3, n_matsubara=0) if "fmo" in shape else projector_problem(4, 2, 3, seed=31, complex_h=True)
     o, t = host_tables(w)
     N, nmax, dt, nt = t["N"], o.nmax, w["dt"], 2
     bounds = [0, 53, nmax]
@@ -238,6 +243,16 @@ def test_sharded_ranks_read_only_their_halo_rows(emu):
             for slot, row in need[r]:
                 state[r, arr, slot, row] = state[1 - r, arr, slot, row]
     exchange(0)
+    # push tables of rank r: CSR over its owned slots, entry = peer << 4 | row
+    push_ptr, push_ent = [], []
+    for r in range(2):
+        lo, hi = bounds[r], bounds[r + 1]
+        per_slot = [[] for _ in range(hi - lo)]
+        for slot, row in need[1 - r]:          # what the other rank reads from this one
+            per_slot[slot - lo].append(((1 - r) << 4) | row)
+        push_ptr.append(np.concatenate([[0], np.cumsum([len(x) for x in per_slot])]).astype(np.int32))
+        push_ent.append(np.array([e for x in per_slot for e in x] or [0], dtype=np.uint8))
+    peers = np.array([state[0].ctypes.data, state[1].ctypes.data], dtype=np.uint64)
     H = np.ascontiguousarray(o.H0)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     emu.emu_sym_stage.restype = ctypes.c_int
@@ -254,9 +269,11 @@ def test_sharded_ranks_read_only_their_halo_rows(emu):
                     ctypes.c_double(a), ctypes.c_double(wgt), ctypes.c_int(kind),
                     ctypes.c_int(int(np.all(H.imag == 0))), ctypes.c_int(2), ctypes.c_int(2),
                     ctypes.c_longlong(bounds[r]), ctypes.c_longlong(bounds[r + 1]), ctypes.c_longlong(nmax),
-                    ctypes.byref(err))
+                    p(push_ptr[r]) if fused else None, p(push_ent[r]) if fused else None,
+                    p(peers) if fused else None, ctypes.c_longlong(out * nmax * N * N), ctypes.byref(err))
                 assert rc == 0, err.value
-            exchange(out)
+            if not fused:
+                exchange(out)
     o.run(w["rho0"], dt, nt)
     got = np.concatenate([state[0, 0, :bounds[1]], state[1, 0, bounds[1]:]])
     assert np.isfinite(got).all()
