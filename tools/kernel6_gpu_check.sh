@@ -5,6 +5,12 @@
 #   gpurun --timeout 1500 -- 'bash tools/kernel6_gpu_check.sh'
 #
 # Everything lands under gpurun_out/k6/; copy what is worth keeping into profiles/.
+#
+# Two GPUs (fused bulk-store halo push of kernel 6, and kernel 6 as the stage kernel of a sharded run):
+#   gpurun --gpus 2 --timeout 900 -- 'PYQED_B200_TEST_KERNEL6=1 python -m pytest tests/test_gpu_kernel6.py -m gpu -q -k "fused or sharded";
+#     for f in 0 1; do python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+#       bench.py --gpus 2 --kernel 6 --fused $f --steps 10 --warmup 3 > gpurun_out/k6/bench_n2_kernel6_fused$f.json; done'
+
 set -u
 out=gpurun_out/k6
 mkdir -p "$out"
