@@ -76,6 +76,63 @@ int main(int argc, char** argv) {
         emu_async_run(N, K, M, L, nmax, H.data(), ops.data(), cbase.data(), kmode.data(), supp.data(), damp.data(),
                       link_ptr.data(), links.data(), s3g.data(), dtv[0], nt, hreal, 0, 0, 3, 2, parts, 2, 0, 0,
                       nullptr);
+        // two ranks with their own state buffers and kernel 6's fused push (no exchange by the
+        // host): every rank must end up with kernel 6's single-rank result on the slots it owns
+        {
+            const long long lo[2] = {0, nmax / 2 + 1}, hi[2] = {nmax / 2 + 1, nmax};
+            std::vector<std::vector<double>> st(2, std::vector<double>(4 * asz, std::nan("")));
+            for (int r = 0; r < 2; ++r) {
+                for (size_t i = 0; i < asz; ++i) st[r][i] = 0.0;           // Y: every rank starts from the full state
+                for (size_t i = 0; i < 2 * NN; ++i) st[r][i] = rho0[i];
+            }
+            std::vector<std::vector<int>> pptr(2);
+            std::vector<std::vector<unsigned char>> pent(2);
+            for (int r = 0; r < 2; ++r) {   // rows of rank r's slots that the other rank's links read
+                std::vector<std::vector<unsigned char>> per((size_t)(hi[r] - lo[r]));
+                const int q = 1 - r;
+                for (long long n = lo[q]; n < hi[q]; ++n)
+                    for (int l = link_ptr[n]; l < link_ptr[n + 1]; ++l) {
+                        const long long nb = links[2 * l];
+                        const unsigned char ent = (unsigned char)((q << 4) | ((links[2 * l + 1] >> 16) & 0xf));
+                        if (nb >= lo[r] && nb < hi[r]) {
+                            auto& v = per[(size_t)(nb - lo[r])];
+                            if (std::find(v.begin(), v.end(), ent) == v.end()) v.push_back(ent);
+                        }
+                    }
+                pptr[r].push_back(0);
+                for (auto& v : per) {
+                    pent[r].insert(pent[r].end(), v.begin(), v.end());
+                    pptr[r].push_back((int)pent[r].size());
+                }
+                if (pent[r].empty()) pent[r].push_back(0);
+            }
+            const unsigned long long peers[2] = {(unsigned long long)(uintptr_t)st[0].data(),
+                                                 (unsigned long long)(uintptr_t)st[1].data()};
+            const double dt = dtv[0];
+            const struct { int yin, out, kind; double a, w; } plan[4] = {
+                {0, 1, 0, dt / 2, 0.0}, {1, 2, 1, dt / 2, 0.0}, {2, 3, 1, dt, 0.0}, {3, 0, 2, 2.0 / dt, dt / 6}};
+            for (int step = 0; step < nt; ++step)
+                for (const auto& p : plan)
+                    for (int r = 0; r < 2; ++r) {
+                        double* b = st[r].data();
+                        if (emu_sym_stage(N, K, M, L, H.data(), ops.data(), cbase.data(), kmode.data(), damp.data(),
+                                          link_ptr.data(), links.data(), nlinks, b + p.yin * asz, b, b + asz,
+                                          b + 2 * asz, b + p.out * asz, p.a, p.w, p.kind, hreal, 2, 2, lo[r], hi[r],
+                                          nmax, pptr[r].data(), pent[r].data(), peers, (long long)p.out * nmax * NN,
+                                          &err)) {
+                            std::cerr << "fused push failed: " << err << "\n";
+                            return 1;
+                        }
+                    }
+            double dpush = 0.0;
+            for (int r = 0; r < 2; ++r)
+                for (size_t i = 2 * NN * (size_t)lo[r]; i < 2 * NN * (size_t)hi[r]; ++i) {
+                    const double d = std::fabs(st[r][i] - s6[i]);
+                    if (!(d <= dpush)) dpush = d;
+                }
+            std::cout << "late=" << late << " |fused-push ranks - k6|=" << dpush << "\n";
+            if (!(dpush == 0.0)) bad = 1;
+        }
         s6.resize(asz);
         s3.resize(asz);
         s3g.resize(asz);
