@@ -283,3 +283,4 @@ inline void bulk_wait_read() {
 }
 inline void bulk_wait_all() { bulk_wait_read(); }
 inline void __threadfence_system() {}
+inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
