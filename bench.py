@@ -378,7 +378,7 @@ def kernel6_leg(args):
     note = ("opt-in stage kernels (tuning kernel=6 / 7), written after this round's GPU budget was spent; "
             "measured here in a child process, not part of the headline value")
     try:
-        res = subprocess.run(cmd, capture_output=True, text=True, timeout=540)
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
         lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
         if res.returncode != 0 or not lines:
             return {"note": note, "error": (res.stderr or res.stdout)[-400:], "returncode": res.returncode}
@@ -386,7 +386,7 @@ def kernel6_leg(args):
         out["note"] = note
         return out
     except subprocess.TimeoutExpired:
-        return {"note": note, "error": "child process exceeded 540 s"}
+        return {"note": note, "error": "child process exceeded 180 s"}
     except Exception as exc:  # noqa: BLE001 - this leg must never take the bench line down
         return {"note": note, "error": repr(exc)}
 
