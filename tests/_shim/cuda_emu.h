@@ -100,6 +100,10 @@ inline int popc(unsigned m) { return __builtin_popcount(m); }
 
 template <typename Kernel, typename... Args>
 void launch(Kernel kernel, unsigned grid, unsigned block, size_t smem_bytes, Args... args) {
+    if (block == 0 || block > 1024 || smem_bytes > 232448) {   // sm_100a: 1024 threads, 227 KB per CTA
+        std::fprintf(stderr, "cuda_emu: illegal launch (%u threads, %zu bytes of shared memory)\n", block, smem_bytes);
+        std::abort();
+    }
     for (unsigned b = 0; b < grid; ++b) {
         Cta cta;
         cta.smem.assign(smem_bytes, (char)0xff);   // NaN patterns: stale reads poison the result
@@ -203,9 +207,29 @@ inline MBars& mbars() {
     return all;
 }
 inline void apply(const Copy& c) { std::memcpy(c.dst, c.src, c.bytes); }
+// Operand rules of the hardware copies that a memcpy would silently forgive: cp.async ..., 16
+// needs both addresses 16-byte aligned; cp.async.bulk needs 16-byte aligned addresses and a
+// size that is a non-zero multiple of 16; the shared-memory side must lie inside the CTA's
+// dynamic shared memory; an mbarrier is 8-byte aligned and its tx-count is below 2^20.
+inline void require(bool ok, const char* what) {
+    if (ok) return;
+    std::fprintf(stderr, "cuda_emu: illegal operand: %s\n", what);
+    std::abort();
+}
+inline bool in_smem(const void* p, size_t bytes) {
+    const char* b = t_cta->smem.data();
+    const char* q = reinterpret_cast<const char*>(p);
+    return q >= b && q + bytes <= b + t_cta->smem.size();
+}
+inline bool smem_aligned(const void* p, size_t a) {
+    return (size_t)(reinterpret_cast<const char*>(p) - t_cta->smem.data()) % a == 0;
+}
+inline bool gmem_aligned(const void* p, size_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; }
 }  // namespace emu
 
 inline void cp_async16(void* smem_dst, const void* gsrc) {
+    emu::require(emu::in_smem(smem_dst, 16) && emu::smem_aligned(smem_dst, 16), "cp.async 16: shared destination");
+    emu::require(emu::gmem_aligned(gsrc, 16), "cp.async 16: global source not 16-byte aligned");
     if (emu::g_async_late) emu::t_open.push_back(emu::Copy{smem_dst, gsrc, 16});
     else std::memcpy(smem_dst, gsrc, 16);
 }
@@ -227,10 +251,12 @@ template <int NWAIT> inline void cp_async_wait() {
     }
 }
 inline void mbar_init(unsigned long long* bar, unsigned) {
+    emu::require(emu::in_smem(bar, 8) && emu::smem_aligned(bar, 8), "mbarrier.init: address");
     std::lock_guard<std::mutex> lk(emu::mbars().m);
     emu::mbars().bars[bar] = emu::MBar{};
 }
 inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    emu::require(bytes < (1u << 20), "mbarrier expect_tx: tx-count out of range");
     std::lock_guard<std::mutex> lk(emu::mbars().m);
     emu::MBar& b = emu::mbars().bars[bar];
     b.expected += bytes;
@@ -238,6 +264,9 @@ inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     emu::mbars().cv.notify_all();
 }
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    emu::require(bytes > 0 && bytes % 16 == 0, "cp.async.bulk global->shared: size not a non-zero multiple of 16");
+    emu::require(emu::in_smem(dst, bytes) && emu::smem_aligned(dst, 16), "cp.async.bulk global->shared: shared destination");
+    emu::require(emu::gmem_aligned(src, 16), "cp.async.bulk global->shared: global source not 16-byte aligned");
     std::lock_guard<std::mutex> lk(emu::mbars().m);
     emu::MBar& b = emu::mbars().bars[bar];
     if (emu::g_async_late) b.copies.push_back(emu::Copy{dst, src, bytes});
@@ -273,6 +302,9 @@ namespace emu {
 inline thread_local std::vector<std::pair<Copy, std::vector<char>>> t_bulk_stores;
 }
 inline void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+    emu::require(bytes > 0 && bytes % 16 == 0, "cp.async.bulk shared->global: size not a non-zero multiple of 16");
+    emu::require(emu::in_smem(smem_src, bytes) && emu::smem_aligned(smem_src, 16), "cp.async.bulk shared->global: shared source");
+    emu::require(emu::gmem_aligned(gdst, 16), "cp.async.bulk shared->global: global destination not 16-byte aligned");
     if (emu::g_async_late) emu::t_bulk_stores.push_back({emu::Copy{gdst, smem_src, bytes}, {}});
     else std::memcpy(gdst, smem_src, bytes);
 }

@@ -58,11 +58,23 @@ def binaries(tmp_path_factory):
         return dict(zip(("address", "thread"), pool.map(build, ("address", "thread"))))
 
 
-@pytest.mark.parametrize("sanitizer", ["address", "thread"])
-def test_emulated_kernels_under_sanitizer(sanitizer, problems, binaries):
+def run_sanitized(exe, problems):
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0", TSAN_OPTIONS="halt_on_error=1")
-    for d in problems:
-        res = subprocess.run([binaries[sanitizer], d], capture_output=True, text=True, timeout=900, env=env)
+    return [subprocess.run([exe, d], capture_output=True, text=True, timeout=900, env=env) for d in problems]
+
+
+@pytest.fixture(scope="module")
+def runs(problems, binaries):
+    """Both instrumented programs run side by side (they are independent processes)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as pool:
+        futures = {s: pool.submit(run_sanitized, binaries[s], problems) for s in ("address", "thread")}
+        return {s: f.result() for s, f in futures.items()}
+
+
+@pytest.mark.parametrize("sanitizer", ["address", "thread"])
+def test_emulated_kernels_under_sanitizer(sanitizer, runs):
+    for res in runs[sanitizer]:
         assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
         assert "emulated kernels agree" in res.stdout
         assert "Sanitizer" not in res.stderr, res.stderr[-4000:]
