@@ -12,116 +12,11 @@
 // Layout: ADO arrays are [batch][slot][N][N] complex128, interleaved re/im, so
 // one matrix element is one 128-bit access.  "slot" is the storage order
 // (heom_core.cuh); links hold neighbour slots.
-#include <cuda_runtime.h>
-#include <cooperative_groups.h>
+#include "heom_plan.cuh"
 #include <cub/device/device_scan.cuh>
 
-#include <algorithm>
-#include <complex>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
+thread_local std::string g_heom_err;
 
-#include "../../include/pyqed_heom.h"
-#include "heom_core.cuh"
-#include "heom_device.cuh"
-#include "heom_stage_async.cuh"
-#include "heom_stage_sym.cuh"
-
-using heom::Pascal;
-
-
-// ---------------------------------------------------------------------------
-// error plumbing
-// ---------------------------------------------------------------------------
-static thread_local std::string g_err;
-static int fail(const std::string& msg) {
-    g_err = msg;
-    return 1;
-}
-#define CU_TRY(expr)                                                                    \
-    do {                                                                                \
-        cudaError_t _e = (expr);                                                        \
-        if (_e != cudaSuccess)                                                          \
-            return fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +     \
-                        __FILE__ + ":" + std::to_string(__LINE__) + ")");               \
-    } while (0)
-#define REQUIRE(cond, msg)               \
-    do {                                 \
-        if (!(cond)) return fail(msg);   \
-    } while (0)
-
-static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-
-// ---------------------------------------------------------------------------
-// plan
-// ---------------------------------------------------------------------------
-struct TableLayout {
-    size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
-        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, lex2slot, slot2lex, step_base, links2, total;
-};
-
-struct pyqed_heom_plan {
-    int device = 0, N = 0, K = 0, M = 0, L = 0, B = 1, order = 0;
-    long long nmax = 0, nlinks = 0;
-    int side = 0;
-    std::vector<long long> pascal;
-    std::vector<std::complex<double>> H, mu, Q, Qd, expn, etal, etar, etaa;
-    std::vector<long long> mode;
-    bool have_sys = false, have_coup = false, have_bath = false, bound = false, built = false;
-    bool mu_nonzero = false, qd_nonzero = false;
-    bool q_diagonal = false;     // every Q_m (and its dipole) is diagonal
-    bool herm_inputs = false;    // operators/bath keep every ADO Hermitian
-    bool herm_state = false;     // ... and so is the state that was loaded
-    bool use_qdiag = false;      // resolved at build time from the options below
-    bool h_real = false;         // H and mu have no imaginary part
-    std::vector<int> r0mode;     // first row with a non-zero diagonal entry, per mode
-    int opt_qdiag = -1, opt_herm = -1, opt_hreal = -1, opt_resident = -1;  // -1 auto, 0 off, 1 on
-    int opt_sym = -1;            // async kernel: Hermitian-symmetric shortcuts (0 off)
-    bool single_support = false; // every Q_m has exactly one non-zero diagonal entry
-    int opt_rk13 = -1;  // difference-form RK4 in the async kernel (-1/1 on, 0 off)
-    int opt_prefetch = 0;  // kernel 7: double-buffered streamed tiles, fetched one group ahead (1 on)
-    long long resident_launches = 0;
-    long long sym_launches = 0;  // stage launches that went to kernel 6
-    long long packed_steps = 0;  // RK4 steps done by kernel 7 (packed Hermitian storage)
-    bool links2_built = false;
-    size_t bound_table_bytes = 0;
-    int resident_kind = 0;  // 4 or 5: which resident kernel ran last
-    TableLayout tl{};
-    char* d_tables = nullptr;
-    char* d_state = nullptr;
-    size_t array_bytes = 0;  // one [B][nmax][N][N] array, aligned
-    cudaStream_t stream = nullptr;
-    long long slot0 = 0;  // storage slot of ADO id 0
-    long long part_lo = 0, part_hi = 0;  // owned slot range (multi-GPU); [0, nmax) by default
-    // tuning
-    int kernel = 0, warps = 0, use_graph = 0;
-    // accounting
-    long long launches = 0;
-    bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
-    size_t ev_used = 0;
-    // internal small device buffers for the field tables of one propagate call
-    double* d_fsys = nullptr;
-    double* d_fcoup = nullptr;
-    size_t field_cap = 0;
-    bool debug_sync = false;
-    // fused peer push (multi-GPU)
-    const int* push_ptr = nullptr;
-    const unsigned char* push_ent = nullptr;
-    unsigned long long* d_peer = nullptr;
-    // context of the propagation in progress (propagate_begin)
-    bool ctx_valid = false, ctx_tdep = false, ctx_use_fs = false, ctx_use_fc = false;
-    double ctx_dt = 0.0;
-    long long ctx_nt = 0;
-    double2* ctx_traj = nullptr;
-
-    double2* arr(int which) const { return (double2*)(d_state + (size_t)which * array_bytes); }
-    template <typename T> T* tab(size_t off) const { return (T*)(d_tables + off); }
-};
-enum { ARR_Y = 0, ARR_SA = 1, ARR_SB = 2, ARR_ACC = 3 };
 
 static int compute_layout(pyqed_heom_plan* p) {
     const size_t NN = (size_t)p->N * p->N, M1 = 1 + p->M;
@@ -161,265 +56,12 @@ static int compute_layout(pyqed_heom_plan* p) {
 }
 
 #include "heom_hierarchy.cuh"
-#include "heom_stage_rows.cuh"
-#include "heom_resident.cuh"
+#include "heom_stage_async.cuh"   // AsyncTables (shared-memory layout, also used by the resident kernels)
+#include "heom_resident.cuh"      // ResidentArgs; the kernels are instantiated in heom_inst.cu
 #include "heom_stage_generic.cuh"
-
-// ---------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------
-// 13-pass difference form of RK4: only the async row kernel implements it
-// Stage kernel of this plan: the explicit choice, else the async row kernel for
-// diagonal coupling (its neighbour rows use 32-bit element offsets, so only while
-// nmax N^2 < 2^32), the plain row kernel for other N <= 8, the generic kernel above.
-static int stage_kernel_of(const pyqed_heom_plan* p) {
-    // 6 = kernel 3's scheme and buffers; launch_stage hands the eligible stages to kernel 6.
-    // 7 = whole propagations on packed Hermitian storage where eligible (pyqed_heom_propagate),
-    //     kernel 3 otherwise
-    if (p->kernel && p->kernel != 4 && p->kernel != 6 && p->kernel != 7) return p->kernel;
-    if (p->N > 8) return 2;
-    const bool fits32 = (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
-    return (p->use_qdiag && p->opt_rk13 != 0 && fits32) ? 3 : 1;
-}
-static bool rk_scheme(const pyqed_heom_plan* p) { return stage_kernel_of(p) == 3; }
-
-static int post_launch(pyqed_heom_plan* p, const char* what) {
-    p->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(std::string(what) + " launch: " + cudaGetErrorString(e));
-    if (p->debug_sync) {
-        e = cudaStreamSynchronize(p->stream);
-        if (e != cudaSuccess) return fail(std::string(what) + " exec: " + cudaGetErrorString(e));
-    }
-    return 0;
-}
-
-template <int N, bool TDEP, bool QDIAG>
-static int launch_rows(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
-    constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    StageArgs args = a;
-    args.ngroups = (p->part_hi - p->part_lo + APW - 1) / APW;
-    int warps = p->warps > 0 ? std::min(p->warps, 8) : 8;
-    if (p->warps <= 0) {
-        // small hierarchies: prefer more CTAs over fuller CTAs
-        while (warps > 1 && args.ngroups * p->B < (long long)warps * sm_count * 2) warps >>= 1;
-    }
-    size_t smem = sizeof(double2) * ((TDEP ? N * N : 0) + (size_t)warps * 2 * TILE);
-    if (QDIAG) smem += sizeof(double2) * (2 * (size_t)args.ncoef + (size_t)p->M * N) +
-                       align_up((size_t)p->M * (2 * N + 1), 16);
-    REQUIRE(smem <= 200 * 1024, "shared-memory tables too large for the row kernel");
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(stage_rows_kernel<N, TDEP, QDIAG>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
-    long long ctas = (args.ngroups + warps - 1) / warps;
-    const long long cap = (long long)sm_count * 16;
-    dim3 grid((unsigned)std::min(ctas, cap), p->B);
-    HParam<N> hp;
-    for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    stage_rows_kernel<N, TDEP, QDIAG><<<grid, warps * 32, smem, p->stream>>>(args, hp);
-    return post_launch(p, "stage_rows_kernel");
-}
-
-template <int N, bool TDEP, bool HREAL, bool PUSH, bool SYM>
-static int launch_async(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
-    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = 2 * TILE + 3 * FLAT + 2;
-    StageArgs args = a;
-    args.ngroups = (p->part_hi - p->part_lo + APW - 1) / APW;
-    const AsyncTables T = async_tables(N, p->K, p->M, p->L, TDEP);
-    const size_t table_bytes = sizeof(double2) * T.warp0 + T.bytes_tail;
-    const size_t per_warp = sizeof(double2) * (a.last ? PERWARP : PERWARP - FLAT);
-    const size_t budget = 227 * 1024;
-    REQUIRE(table_bytes + per_warp <= budget, "shared-memory tables too large for the async row kernel");
-    int maxw = (int)std::min<size_t>(ASYNC_MAX_THREADS / 32, (budget - table_bytes) / per_warp);
-    int warps = p->warps > 0 ? std::min(p->warps, maxw) : maxw;
-    if (p->warps <= 0) {
-        // small hierarchies: spread the groups over all SMs first
-        const long long per_sm = (args.ngroups + sm_count - 1) / sm_count;
-        warps = (int)std::max<long long>(1, std::min<long long>(maxw, per_sm));
-    }
-    REQUIRE((unsigned long long)p->nmax * NN < (1ull << 32),
-            "hierarchy too large for the async row kernel's 32-bit element offsets (use kernel 1)");
-    const size_t smem = table_bytes + per_warp * warps;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU_TRY(cudaFuncSetAttribute(stage_rows_async_kernel<N, TDEP, HREAL, PUSH, SYM>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        attr_set = true;
-    }
-    const long long ctas = (args.ngroups + warps - 1) / warps;
-    dim3 grid((unsigned)std::min<long long>(ctas, sm_count), 1);
-    HParam<N> hp;
-    for (int e = 0; e < NN; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    // one launch per trajectory of the batch, each with its own array / operator /
-    // trajectory pointers: the kernel then carries no batch offset
-    const long long boff = p->nmax * NN;
-    for (int b = 0; b < p->B; ++b) {
-        stage_rows_async_kernel<N, TDEP, HREAL, PUSH, SYM><<<grid, warps * 32, smem, p->stream>>>(args, hp);
-        int rc = post_launch(p, "stage_rows_async_kernel");
-        if (rc) return rc;
-        args.yin += boff;
-        args.y += boff;
-        args.acc += boff;
-        args.yout += boff;
-        args.ydst += boff;
-        args.ops += args.ops_bstride;
-        if (args.traj) args.traj += args.traj_bstride;
-        args.out_elem_off += boff;
-    }
-    return 0;
-}
-
-template <int N, bool PUSH, bool SYM>
-static int launch_async_p(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool hreal) {
-    if (tdep) return hreal ? launch_async<N, true, true, PUSH, SYM>(p, a, sm_count) : launch_async<N, true, false, PUSH, SYM>(p, a, sm_count);
-    return hreal ? launch_async<N, false, true, PUSH, SYM>(p, a, sm_count) : launch_async<N, false, false, PUSH, SYM>(p, a, sm_count);
-}
-template <int N>
-static int launch_async_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool hreal) {
-    const bool sym = a.herm && p->single_support && p->opt_sym != 0;
-    if (a.push_ptr)
-        return sym ? launch_async_p<N, true, true>(p, a, sm_count, tdep, hreal)
-                   : launch_async_p<N, true, false>(p, a, sm_count, tdep, hreal);
-    return sym ? launch_async_p<N, false, true>(p, a, sm_count, tdep, hreal)
-               : launch_async_p<N, false, false>(p, a, sm_count, tdep, hreal);
-}
-
-template <int N>
-static int launch_rows_n(pyqed_heom_plan* p, const StageArgs& a, int sm_count, bool tdep, bool qdiag) {
-    if (tdep) return qdiag ? launch_rows<N, true, true>(p, a, sm_count) : launch_rows<N, true, false>(p, a, sm_count);
-    return qdiag ? launch_rows<N, false, true>(p, a, sm_count) : launch_rows<N, false, false>(p, a, sm_count);
-}
 
 extern "C" {
 static void fill_stage_args(pyqed_heom_plan* p, StageArgs& a);
-}
-
-// ---- cluster-resident propagation (kernel 4) -----------------------------------
-struct ResidentConfig {
-    int cluster = 0, warps = 0, apc = 0;
-    size_t smem = 0;
-};
-
-template <int N>
-static bool resident_fits(const pyqed_heom_plan* p, ResidentConfig& rc) {
-    constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N;
-    const AsyncTables T = async_tables(N, p->K, p->M, p->L, true);
-    const size_t table_bytes = sizeof(double2) * T.warp0 + T.bytes_tail;
-    const int maxlinks = std::max(1, std::min(p->L, p->K) + p->K);
-    const size_t per_warp = sizeof(double2) * 4 * APW * N * LD + (size_t)16 * APW * maxlinks;
-    const size_t budget = 227 * 1024;
-    if (table_bytes + per_warp > budget) return false;
-    const int maxw = (int)std::min<size_t>(16, (budget - table_bytes) / per_warp);
-    const long long groups = (p->nmax + APW - 1) / APW;
-    int cs_min = 1;
-    while (cs_min <= 16 && (groups + cs_min - 1) / cs_min > maxw) cs_min <<= 1;
-    if (cs_min > 16) return false;
-    int cs = cs_min;
-    if (p->B <= 8)  // few trajectories: spread one hierarchy over as many SMs as a cluster allows
-        while (cs < 16 && cs < groups) cs <<= 1;
-    rc.cluster = cs;
-    rc.warps = (int)((groups + cs - 1) / cs);
-    rc.apc = rc.warps * APW;
-    rc.smem = table_bytes + per_warp * rc.warps;
-    return true;
-}
-
-template <int N, bool HREAL>
-static int launch_resident_t(pyqed_heom_plan* p, const ResidentArgs& ra_in, ResidentConfig rc) {
-    auto kern = resident_cluster_kernel<N, HREAL>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    HParam<N> hp;
-    for (int e = 0; e < N * N; ++e) hp.v[e] = make_double2(p->H[e].real(), p->H[e].imag());
-    for (;;) {
-        ResidentArgs ra = ra_in;
-        ra.apc = rc.apc;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(rc.cluster * p->B));
-        cfg.blockDim = dim3((unsigned)(rc.warps * 32));
-        cfg.dynamicSmemBytes = rc.smem;
-        cfg.stream = p->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)rc.cluster;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        int nclusters = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
-        if (e == cudaSuccess && nclusters >= 1) {
-            CU_TRY(cudaLaunchKernelEx(&cfg, kern, ra, hp));
-            return post_launch(p, "resident_cluster_kernel");
-        }
-        cudaGetLastError();
-        // this cluster shape cannot be co-scheduled: halve the cluster if the
-        // hierarchy still fits, otherwise report that kernel 4 is unavailable
-        constexpr int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N;
-        const long long groups = (p->nmax + APW - 1) / APW;
-        const int cs = rc.cluster / 2;
-        if (cs < 1) return -1;
-        const int warps = (int)((groups + cs - 1) / cs);
-        const int maxlinks = std::max(1, std::min(p->L, p->K) + p->K);
-        const size_t per_warp = sizeof(double2) * 4 * APW * N * LD + (size_t)16 * APW * maxlinks;
-        const size_t smem = rc.smem - per_warp * rc.warps + per_warp * warps;
-        if (warps > 16 || smem > 227 * 1024) return -1;
-        rc.cluster = cs;
-        rc.warps = warps;
-        rc.apc = warps * APW;
-        rc.smem = smem;
-    }
-}
-
-template <int N>
-static int launch_resident_elem(pyqed_heom_plan* p, const ResidentArgs& ra_in) {
-    constexpr int NN = N * N;
-    const int maxlinks = ra_in.maxlinks;
-    const size_t table_bytes = sizeof(double2) * (NN + (size_t)p->M * N + 4 * (size_t)p->K) +
-                               sizeof(double) * ((p->L + 2) & ~1);
-    const size_t per_ado = sizeof(double2) * 4 * NN + (size_t)16 * maxlinks + 32;
-    const size_t budget = 227 * 1024;
-    if (table_bytes + per_ado > budget) return -1;
-    const long long cap = (long long)((budget - table_bytes) / per_ado);   // ADOs per CTA
-    int cs = 1;
-    while (cs <= 16 && (p->nmax + cs - 1) / cs > cap) cs <<= 1;
-    if (cs > 16) return -1;
-    if (p->B <= 8)
-        while (cs < 16 && cs < p->nmax) cs <<= 1;
-    auto kern = resident_elem_kernel<N>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    for (; cs >= 1; cs >>= 1) {
-        const long long apc = (p->nmax + cs - 1) / cs;
-        if (apc > cap) return -1;
-        ResidentArgs ra = ra_in;
-        ra.apc = (int)apc;
-        const int warps = (int)std::min<long long>(16, apc);
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(cs * p->B));
-        cfg.blockDim = dim3((unsigned)(warps * 32));
-        cfg.dynamicSmemBytes = table_bytes + per_ado * apc;
-        cfg.stream = p->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)cs;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        int nclusters = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
-        if (e == cudaSuccess && nclusters >= 1) {
-            CU_TRY(cudaLaunchKernelEx(&cfg, kern, ra));
-            return post_launch(p, "resident_elem_kernel");
-        }
-        cudaGetLastError();
-    }
-    return -1;
 }
 
 // returns 0 = done, -1 = not applicable (caller falls back to per-stage launches), 1 = error
@@ -430,13 +72,9 @@ static int try_resident(pyqed_heom_plan* p) {
     ResidentConfig rc;
     bool fits = false;
     switch (p->N) {
-        case 2: fits = resident_fits<2>(p, rc); break;
-        case 3: fits = resident_fits<3>(p, rc); break;
-        case 4: fits = resident_fits<4>(p, rc); break;
-        case 5: fits = resident_fits<5>(p, rc); break;
-        case 6: fits = resident_fits<6>(p, rc); break;
-        case 7: fits = resident_fits<7>(p, rc); break;
-        case 8: fits = resident_fits<8>(p, rc); break;
+#define FITS_CASE(n) case n: fits = heom_resident_fits_##n(p, rc); break;
+        FITS_CASE(2) FITS_CASE(3) FITS_CASE(4) FITS_CASE(5) FITS_CASE(6) FITS_CASE(7) FITS_CASE(8)
+#undef FITS_CASE
     }
     if (!fits && p->opt_resident == 4) return -1;
     ResidentArgs ra;
@@ -464,7 +102,7 @@ static int try_resident(pyqed_heom_plan* p) {
     int rcode = -1;
     if (p->opt_resident != 4) {   // default: element-parallel kernel 5; "resident" = 4 forces kernel 4
 #define RESE_CASE(n) \
-    case n: rcode = launch_resident_elem<n>(p, ra); break;
+    case n: rcode = heom_launch_resident_elem_##n(p, ra); break;
         switch (p->N) { RESE_CASE(2) RESE_CASE(3) RESE_CASE(4) RESE_CASE(5) RESE_CASE(6) RESE_CASE(7) RESE_CASE(8) }
 #undef RESE_CASE
         if (rcode > 0) return rcode;
@@ -472,7 +110,7 @@ static int try_resident(pyqed_heom_plan* p) {
     }
     if (rcode != 0 && fits) {
 #define RES_CASE(n) \
-    case n: rcode = hr ? launch_resident_t<n, true>(p, ra, rc) : launch_resident_t<n, false>(p, ra, rc); break;
+    case n: rcode = heom_launch_resident_##n(p, ra, rc, hr); break;
         switch (p->N) { RES_CASE(2) RES_CASE(3) RES_CASE(4) RES_CASE(5) RES_CASE(6) RES_CASE(7) RES_CASE(8) }
 #undef RES_CASE
         if (rcode == 0) p->resident_kind = 4;
@@ -524,10 +162,7 @@ static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
 
 static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     if (p->part_hi <= p->part_lo) return 0;  // this rank owns nothing (tiny hierarchy, many ranks)
-    static int sm_count = 0;
-    if (!sm_count) {
-        CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, p->device));
-    }
+    const int sm_count = sm_count_of(p->device);
     if (p->timing) {
         if (p->ev_used == p->ev.size()) {
             cudaEvent_t e0, e1;
@@ -545,7 +180,7 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
         // single-stage (Euler) update: the async kernel only implements the difference-form
         // RK4 stages, so the plain-load row kernel takes it
         switch (p->N) {
-#define ROWS_EULER_CASE(n) case n: rc = launch_rows_n<n>(p, a, sm_count, tdep, p->use_qdiag); break;
+#define ROWS_EULER_CASE(n) case n: rc = heom_launch_rows_##n(p, a, sm_count, tdep, p->use_qdiag); break;
             ROWS_EULER_CASE(2) ROWS_EULER_CASE(3) ROWS_EULER_CASE(4) ROWS_EULER_CASE(5) ROWS_EULER_CASE(6)
             ROWS_EULER_CASE(7) ROWS_EULER_CASE(8)
 #undef ROWS_EULER_CASE
@@ -555,7 +190,7 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
                 "kernel 3 needs 2 <= N <= 8 and diagonal coupling operators");
 #define ASYNC_CASE(n)                                                                  \
     case n:                                                                            \
-        rc = launch_async_n<n>(p, a, sm_count, tdep, p->h_real && p->opt_hreal != 0); \
+        rc = heom_launch_async_##n(p, a, sm_count, tdep, p->h_real && p->opt_hreal != 0); \
         break;
         switch (p->N) {
             ASYNC_CASE(2) ASYNC_CASE(3) ASYNC_CASE(4) ASYNC_CASE(5) ASYNC_CASE(6) ASYNC_CASE(7) ASYNC_CASE(8)
@@ -565,7 +200,7 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
         REQUIRE(p->N >= 2 && p->N <= 8, "kernel 1 needs 2 <= N <= 8");
 #define ROWS_CASE(n)                                              \
     case n:                                                       \
-        rc = launch_rows_n<n>(p, a, sm_count, tdep, p->use_qdiag); \
+        rc = heom_launch_rows_##n(p, a, sm_count, tdep, p->use_qdiag); \
         break;
         switch (p->N) {
             ROWS_CASE(2) ROWS_CASE(3) ROWS_CASE(4) ROWS_CASE(5) ROWS_CASE(6) ROWS_CASE(7) ROWS_CASE(8)
@@ -580,11 +215,9 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
         const size_t smem = sizeof(double2) * (NN + M1 * NN + 2 * 2 * (size_t)p->K) + sizeof(int2) * 2 * (size_t)p->K +
                             sizeof(short) * 2 * (M1 * NN + M1 * (p->N + 1)) + 16;
         REQUIRE(smem <= 200 * 1024, "operators too large for the generic kernel's shared memory");
-        static bool gen_attr = false;
-        if (!gen_attr) {
+        static PerDeviceOnce gen_attr;
+        if (gen_attr.need(p->device))
             CU_TRY(cudaFuncSetAttribute(stage_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            gen_attr = true;
-        }
         dim3 grid((unsigned)std::max(1ll, std::min(p->part_hi - p->part_lo, (long long)sm_count * 32)), p->B);
         stage_generic_kernel<<<grid, threads, smem, p->stream>>>(a);
         rc = post_launch(p, "stage_generic_kernel");
@@ -603,7 +236,7 @@ static int launch_stage(pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
 extern "C" {
 
 int pyqed_heom_version(void) { return 1; }
-const char* pyqed_heom_last_error(void) { return g_err.c_str(); }
+const char* pyqed_heom_last_error(void) { return g_heom_err.c_str(); }
 
 static bool build_pascal(int side, std::vector<long long>& tab) {
     tab.assign((size_t)side * side, 0);
@@ -1281,8 +914,7 @@ static bool packed_eligible(const pyqed_heom_plan* p) {
            p->part_lo == 0 && p->part_hi == p->nmax && rk_scheme(p) && 4 * tri <= 3 * p->array_bytes;
 }
 static int run_packed(pyqed_heom_plan* p, double dt, int64_t nt) {
-    static int sm_count = 0;
-    if (!sm_count) CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    const int sm_count = sm_count_of(p->device);
     const TableLayout& t = p->tl;
     PackedRun r{};
     r.Y = p->arr(ARR_Y);

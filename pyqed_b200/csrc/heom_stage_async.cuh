@@ -38,7 +38,7 @@ constexpr int ASYNC_MAX_THREADS = HEOM_ASYNC_THREADS;
 // Column entry (row, rr) of a neighbour, needed only when the ADOs are not
 // Hermitian.  Kept out of line so that the address arithmetic is not hoisted
 // into the common (Hermitian) path of the link loop.
-__device__ __noinline__ double2 load_neighbour_entry(const double2* yin, int nbr, int NN, int off) {
+static __device__ __noinline__ double2 load_neighbour_entry(const double2* yin, int nbr, int NN, int off) {
     return __ldg(yin + ((long long)nbr * NN + off));
 }
 

@@ -671,6 +671,19 @@ int sym_launch_n(const SymLaunch& s) {
 
 }  // namespace
 
+// One object file per system size (build.py: -DHEOM_SYM_INST_N=n): heom_sym_launch_n<n> is the
+// only thing such an object defines.  Without the macro (the common object, and the
+// single-translation-unit build of the CPU emulation tests) everything else is compiled.
+#if defined(HEOM_SYM_INST_N)
+#define HEOM_SYM_CAT2(a, b) a##b
+#define HEOM_SYM_CAT(a, b) HEOM_SYM_CAT2(a, b)
+int HEOM_SYM_CAT(heom_sym_launch_n, HEOM_SYM_INST_N)(const SymLaunch& s, const char** err) {
+    g_sym_err = "";
+    const int rc = sym_launch_n<HEOM_SYM_INST_N>(s);
+    if (rc && err) *err = g_sym_err;
+    return rc;
+}
+#else
 int heom_sym_supported(int N, int K, int M, int L, const char** err) {
     (void)M;
     const char* why = nullptr;
@@ -700,23 +713,38 @@ int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, in
     return 0;
 }
 
-int heom_sym_launch(const SymLaunch& s, const char** err) {
-    int rc = 1;
-    g_sym_err = "kernel 6 needs 2 <= N <= 8";
-    switch (s.N) {
-#ifndef HEOM_EMU_FEW_N   // (the sanitizer builds of the CPU tests instantiate N = 4 and 7 only)
-        case 2: rc = sym_launch_n<2>(s); break;
-        case 3: rc = sym_launch_n<3>(s); break;
-        case 5: rc = sym_launch_n<5>(s); break;
-        case 6: rc = sym_launch_n<6>(s); break;
-        case 8: rc = sym_launch_n<8>(s); break;
-#endif
-        case 4: rc = sym_launch_n<4>(s); break;
-        case 7: rc = sym_launch_n<7>(s); break;
-        default: break;
-    }
+#if defined(HEOM_SYM_SPLIT)
+#define HEOM_SYM_DECL(n) int heom_sym_launch_n##n(const SymLaunch& s, const char** err);
+HEOM_SYM_DECL(2) HEOM_SYM_DECL(3) HEOM_SYM_DECL(4) HEOM_SYM_DECL(5) HEOM_SYM_DECL(6) HEOM_SYM_DECL(7) HEOM_SYM_DECL(8)
+#undef HEOM_SYM_DECL
+#define HEOM_SYM_CALL(n) heom_sym_launch_n##n(s, err)
+#else
+#define HEOM_SYM_CALL(n) sym_launch_one<n>(s, err)
+namespace {
+template <int N>
+int sym_launch_one(const SymLaunch& s, const char** err) {
+    const int rc = sym_launch_n<N>(s);
     if (rc && err) *err = g_sym_err;
     return rc;
+}
+}  // namespace
+#endif
+
+int heom_sym_launch(const SymLaunch& s, const char** err) {
+    switch (s.N) {
+#ifndef HEOM_EMU_FEW_N   // (the sanitizer builds of the CPU tests instantiate N = 4 and 7 only)
+        case 2: return HEOM_SYM_CALL(2);
+        case 3: return HEOM_SYM_CALL(3);
+        case 5: return HEOM_SYM_CALL(5);
+        case 6: return HEOM_SYM_CALL(6);
+        case 8: return HEOM_SYM_CALL(8);
+#endif
+        case 4: return HEOM_SYM_CALL(4);
+        case 7: return HEOM_SYM_CALL(7);
+        default: break;
+    }
+    if (err) *err = "kernel 6 needs 2 <= N <= 8";
+    return 1;
 }
 
 // ---------------------------------------------------------------------------
@@ -778,3 +806,4 @@ int heom_packed_propagate(const PackedRun& r, const char** err) {
 #endif
     return 0;
 }
+#endif  // !HEOM_SYM_INST_N
