@@ -413,7 +413,7 @@ def run_gpu_arm(args):
     K, Wm, dt = args.steps, args.warmup, w["dt"]
     tuning = dict(kernel=args.kernel, warps_per_cta=args.warps, use_graph=args.graph)
     options = {"qdiag": args.qdiag, "hermitian": args.herm, "resident": args.resident, "rk13": args.rk13,
-               "prefetch": args.prefetch}
+               "prefetch": args.prefetch, "dynsched": args.dynsched, "packed": args.packed}
     in_bytes = sum(np.asarray(w[k]).nbytes for k in
                    ("rho0", "system", "system_dipole", "coupling", "coupling_dipole", "expn", "etal",
                     "etar", "etaa", "mode"))
@@ -614,6 +614,8 @@ def main():
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
     ap.add_argument("--kernel6-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--prefetch", type=int, default=0, help="kernel 7: double-buffered tiles fetched one group ahead")
+    ap.add_argument("--dynsched", type=int, default=-1, help="kernels 6/7: 0 = static group stride, default: global work counter")
+    ap.add_argument("--packed", type=int, default=-1, help="0: never use packed Hermitian storage (kernel 7)")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:

@@ -145,6 +145,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy value)
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                              unsigned long long pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async16_s_if_hint(unsigned smem_dst_u32, const void* gsrc, bool pred,
+                                                     unsigned long long pol) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %2, 0;\n"
+        "@p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %3;\n"
+        "}\n" ::"r"(smem_dst_u32),
+        "l"(gsrc), "r"((int)pred), "l"(pol)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
         "{\n"

@@ -18,6 +18,69 @@
 thread_local std::string g_heom_err;
 
 
+// Structure of the problem (host): diagonal / single-entry coupling operators, Hermiticity of
+// operators and bath, real H.  `supp`: [M][N+1] (count, rows) then [M][N] membership of the
+// diagonal supports.
+static void analyse_structure(pyqed_heom_plan* p, std::vector<unsigned char>& supp) {
+    const int N = p->N, NN = N * N, K = p->K;
+    const std::complex<double> Z(0, 0);
+    bool diag = true, herm = true;
+    for (int m = 0; m < p->M && diag; ++m)
+        for (int i = 0; i < N && diag; ++i)
+            for (int j = 0; j < N; ++j)
+                if (i != j && (p->Q[(size_t)m * NN + i * N + j] != Z || p->Qd[(size_t)m * NN + i * N + j] != Z)) {
+                    diag = false;
+                    break;
+                }
+    auto is_herm = [&](const std::complex<double>* A) {
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j)
+                if (A[i * N + j] != std::conj(A[j * N + i])) return false;
+        return true;
+    };
+    herm = is_herm(p->H.data()) && is_herm(p->mu.data());
+    for (int m = 0; m < p->M && herm; ++m)
+        herm = is_herm(p->Q.data() + (size_t)m * NN) && is_herm(p->Qd.data() + (size_t)m * NN);
+    for (int k = 0; k < K && herm; ++k)
+        herm = p->expn[k].imag() == 0.0 && p->etaa[k].imag() == 0.0 && p->etaa[k].real() > 0.0 &&
+               p->etar[k] == std::conj(p->etal[k]);
+    p->q_diagonal = diag;
+    p->herm_inputs = herm;
+    p->use_qdiag = diag && p->opt_qdiag != 0 && N <= 8;
+    supp.assign((size_t)p->M * (2 * N + 1), 0);
+    unsigned char* ins = supp.data() + (size_t)p->M * (N + 1);
+    for (int m = 0; m < p->M; ++m) {
+        int c = 0;
+        for (int j = 0; j < N; ++j) {
+            const bool nzd = p->Q[(size_t)m * NN + j * N + j] != Z || p->Qd[(size_t)m * NN + j * N + j] != Z;
+            if (nzd) {
+                supp[(size_t)m * (N + 1) + 1 + c++] = (unsigned char)j;
+                ins[(size_t)m * N + j] = 1;
+            }
+        }
+        supp[(size_t)m * (N + 1)] = (unsigned char)c;
+    }
+    p->single_support = diag;
+    for (int m = 0; m < p->M; ++m)
+        if (supp[(size_t)m * (N + 1)] != 1) p->single_support = false;
+    p->r0mode.assign(p->M, 0);
+    for (int m = 0; m < p->M; ++m) p->r0mode[m] = supp[(size_t)m * (N + 1)] ? supp[(size_t)m * (N + 1) + 1] : 0;
+    p->h_real = true;
+    for (int e = 0; e < NN; ++e)
+        if (p->H[e].imag() != 0.0 || p->mu[e].imag() != 0.0) p->h_real = false;
+}
+
+// kernels 6 / 7 (heom_stage_sym.cu) can take this problem: chosen automatically (kernel 0) or
+// asked for (6, 7); the state must be Hermitian too, which is checked per propagation
+static bool sym_wanted(const pyqed_heom_plan* p) {
+    if (!(p->kernel == 0 || p->kernel == 6 || p->kernel == 7)) return false;
+    if (p->N < 2 || p->N > 8 || !p->use_qdiag || !p->single_support || !p->herm_inputs) return false;
+    if (p->opt_herm == 0 || p->opt_sym == 0 || p->opt_rk13 == 0) return false;
+    const char* err = "";
+    return heom_sym_supported(p->N, p->K, p->M, p->L, &err) == 0 &&
+           (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
+}
+
 static int compute_layout(pyqed_heom_plan* p) {
     const size_t NN = (size_t)p->N * p->N, M1 = 1 + p->M;
     TableLayout& t = p->tl;
@@ -48,8 +111,15 @@ static int compute_layout(pyqed_heom_plan* p) {
     t.lex2slot = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
     t.slot2lex = take(sizeof(int) * (p->order == 2 ? p->nmax : 1));
     t.step_base = take(sizeof(long long));
-    // second link table of kernels 6 / 7 (heom_stage_sym.cuh), only when one of them was asked for
-    t.links2 = take((p->kernel == 6 || p->kernel == 7) ? sizeof(int2) * (size_t)std::max(1ll, p->nlinks) : 0);
+    t.sched = take(sizeof(unsigned) * 4);
+    // second link table of kernels 6 / 7 (heom_stage_sym.cuh), only when they can take the problem
+    bool sym = false;
+    if (p->have_sys && p->have_coup && p->have_bath) {
+        std::vector<unsigned char> supp;
+        analyse_structure(p, supp);
+        sym = sym_wanted(p);
+    }
+    t.links2 = take(sym ? sizeof(int2) * (size_t)std::max(1ll, p->nlinks) : 0);
     t.total = off;
     p->array_bytes = align_up(sizeof(double2) * (size_t)p->B * p->nmax * NN);
     return 0;
@@ -128,7 +198,8 @@ static int try_resident(pyqed_heom_plan* p) {
 // (with push tables its PUSH instantiation stores the halo rows into the peers' arrays);
 // everything else stays with kernel 3
 static bool sym_eligible(const pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
-    return p->kernel == 6 && p->links2_built && !tdep && a.herm && p->single_support && p->opt_sym != 0 &&
+    return (p->kernel == 0 || p->kernel == 6 || p->kernel == 7) && p->links2_built && !tdep && a.herm &&
+           p->single_support && p->opt_sym != 0 &&
            (!a.push_ptr || p->B == 1) && a.scheme == 1 && !(a.first && a.last);
 }
 static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
@@ -149,6 +220,8 @@ static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     s.batch_elems = p->nmax * p->N * p->N;
     s.traj_bstride = a.traj_bstride;
     s.stream = p->stream;
+    s.sched = p->opt_dynsched != 0 ? p->tab<unsigned>(p->tl.sched) : nullptr;
+    s.sched_total = &p->sched_total;
     const char* err = "";
     if (heom_sym_launch(s, &err)) return fail(std::string("stage_rows_sym_kernel launch: ") + err);
     p->launches += p->B;
@@ -386,6 +459,8 @@ int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
     else if (n == "resident") p->opt_resident = value;
     else if (n == "rk13") p->opt_rk13 = value;
     else if (n == "prefetch") p->opt_prefetch = value;
+    else if (n == "dynsched") p->opt_dynsched = value;
+    else if (n == "packed") p->opt_packed = value;
     else if (n == "debug_sync") p->debug_sync = value != 0;
     else return fail("unknown option '" + n + "'");
     return 0;
@@ -558,52 +633,9 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
                            cudaMemcpyHostToDevice, s));
     CU_TRY(cudaMemcpyAsync(p->d_tables + t.col_idx, cidx.data(), sizeof(short) * cidx.size(),
                            cudaMemcpyHostToDevice, s));
-    {   // structure of the coupling operators and of the whole problem
-        const std::complex<double> Z(0, 0);
-        bool diag = true, herm = true;
-        for (int m = 0; m < p->M && diag; ++m)
-            for (int i = 0; i < N && diag; ++i)
-                for (int j = 0; j < N; ++j)
-                    if (i != j && (p->Q[(size_t)m * NN + i * N + j] != Z || p->Qd[(size_t)m * NN + i * N + j] != Z)) {
-                        diag = false;
-                        break;
-                    }
-        auto is_herm = [&](const std::complex<double>* A) {
-            for (int i = 0; i < N; ++i)
-                for (int j = 0; j < N; ++j)
-                    if (A[i * N + j] != std::conj(A[j * N + i])) return false;
-            return true;
-        };
-        herm = is_herm(p->H.data()) && is_herm(p->mu.data());
-        for (int m = 0; m < p->M && herm; ++m)
-            herm = is_herm(p->Q.data() + (size_t)m * NN) && is_herm(p->Qd.data() + (size_t)m * NN);
-        for (int k = 0; k < K && herm; ++k)
-            herm = p->expn[k].imag() == 0.0 && p->etaa[k].imag() == 0.0 && p->etaa[k].real() > 0.0 &&
-                   p->etar[k] == std::conj(p->etal[k]);
-        p->q_diagonal = diag;
-        p->herm_inputs = herm;
-        p->use_qdiag = diag && p->opt_qdiag != 0 && N <= 8;
-        std::vector<unsigned char> supp((size_t)p->M * (2 * N + 1), 0);
-        unsigned char* ins = supp.data() + (size_t)p->M * (N + 1);
-        for (int m = 0; m < p->M; ++m) {
-            int c = 0;
-            for (int j = 0; j < N; ++j) {
-                const bool nzd = p->Q[(size_t)m * NN + j * N + j] != Z || p->Qd[(size_t)m * NN + j * N + j] != Z;
-                if (nzd) {
-                    supp[(size_t)m * (N + 1) + 1 + c++] = (unsigned char)j;
-                    ins[(size_t)m * N + j] = 1;
-                }
-            }
-            supp[(size_t)m * (N + 1)] = (unsigned char)c;
-        }
-        p->single_support = diag;
-        for (int m = 0; m < p->M; ++m)
-            if (supp[(size_t)m * (N + 1)] != 1) p->single_support = false;
-        p->r0mode.assign(p->M, 0);
-        for (int m = 0; m < p->M; ++m) p->r0mode[m] = supp[(size_t)m * (N + 1)] ? supp[(size_t)m * (N + 1) + 1] : 0;
-        p->h_real = true;
-        for (int e = 0; e < NN; ++e)
-            if (p->H[e].imag() != 0.0 || p->mu[e].imag() != 0.0) p->h_real = false;
+    {
+        std::vector<unsigned char> supp;
+        analyse_structure(p, supp);
         CU_TRY(cudaMemcpyAsync(p->d_tables + t.supp, supp.data(), supp.size(), cudaMemcpyHostToDevice, s));
         CU_TRY(cudaStreamSynchronize(s));
     }
@@ -673,12 +705,10 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
                                           std::to_string(p->nlinks) + ")");
     p->slot0 = slot0;
     p->links2_built = false;
-    if ((p->kernel == 6 || p->kernel == 7) && N <= 8 && p->use_qdiag && p->single_support) {
+    if (sym_wanted(p)) {
         const char* err = "";
-        if (heom_sym_supported(N, K, p->M, L, &err) == 0 &&
-            (unsigned long long)p->nmax * NN < (1ull << 32) &&
-            t.links2 + sizeof(int2) * (size_t)p->nlinks <= p->bound_table_bytes) {   // kernel chosen before bind
-            if (heom_sym_convert_links(h.links, p->tab<int2>(t.links2), p->nlinks, N, L, p->kernel == 7 ? 1 : 0, s, &err))
+        if (t.links2 + sizeof(int2) * (size_t)p->nlinks <= p->bound_table_bytes) {   // (options changed after bind)
+            if (heom_sym_convert_links(h.links, p->tab<int2>(t.links2), p->nlinks, N, L, s, &err))
                 return fail(std::string("sym_convert_links_kernel launch: ") + err);
             p->launches++;
             CU_TRY(cudaStreamSynchronize(s));
@@ -894,6 +924,8 @@ int pyqed_heom_propagate_begin(pyqed_heom_plan* p, double dt, int64_t nt, const 
         if (upload_fields(p, p->ctx_use_fs ? fsys : nullptr, p->ctx_use_fc ? fcoup : nullptr, nt)) return 1;
     }
     CU_TRY(cudaMemsetAsync(p->d_tables + p->tl.step_base, 0, sizeof(long long), p->stream));
+    CU_TRY(cudaMemsetAsync(p->d_tables + p->tl.sched, 0, sizeof(unsigned) * 4, p->stream));
+    p->sched_total = 0;
     if (p->ctx_traj) {
         record_kernel<<<p->B, 64, 0, p->stream>>>(p->ctx_traj, p->arr(ARR_Y), p->nmax, p->slot0, NN,
                                                   (long long)(nt + 1) * NN, 0);
@@ -909,7 +941,8 @@ int pyqed_heom_propagate_begin(pyqed_heom_plan* p, double dt, int64_t nt, const 
 static bool packed_eligible(const pyqed_heom_plan* p) {
     // four triangle arrays (256-byte aligned) must fit into the three stage arrays
     const size_t tri = align_up(sizeof(double2) * (size_t)p->nmax * (p->N * (p->N + 1) / 2));
-    return p->kernel == 7 && p->links2_built && !p->ctx_tdep && p->herm_inputs && p->herm_state &&
+    return (p->kernel == 0 || p->kernel == 7) && p->opt_packed != 0 && p->links2_built && !p->ctx_tdep &&
+           p->herm_inputs && p->herm_state &&
            p->opt_herm != 0 && p->single_support && p->opt_sym != 0 && !p->push_ptr && p->B == 1 &&
            p->part_lo == 0 && p->part_hi == p->nmax && rk_scheme(p) && 4 * tri <= 3 * p->array_bytes;
 }
@@ -946,6 +979,8 @@ static int run_packed(pyqed_heom_plan* p, double dt, int64_t nt) {
     r.sm_count = sm_count;
     r.prefetch = p->opt_prefetch > 0 ? 1 : 0;
     r.stream = p->stream;
+    r.sched = p->opt_dynsched != 0 ? p->tab<unsigned>(p->tl.sched) : nullptr;
+    r.sched_total = &p->sched_total;
     const char* err = "";
     if (heom_packed_propagate(r, &err)) return fail(std::string("packed propagation (kernel 7): ") + err);
     p->launches += 4 * nt + 2;

@@ -50,7 +50,7 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 // ---------------------------------------------------------------------------
 struct TableLayout {
     size_t pascal, keys, id_of_slot, slot_of_id, damp, link_ptr, links, coef, ops_base, ops_dip,
-        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, lex2slot, slot2lex, step_base, links2, total;
+        ops_t, row_ptr, row_idx, col_ptr, col_idx, supp, cbase, kmode, lex2slot, slot2lex, step_base, sched, links2, total;
 };
 
 struct pyqed_heom_plan {
@@ -73,6 +73,9 @@ struct pyqed_heom_plan {
     bool single_support = false; // every Q_m has exactly one non-zero diagonal entry
     int opt_rk13 = -1;  // difference-form RK4 in the async kernel (-1/1 on, 0 off)
     int opt_prefetch = 0;  // kernel 7: double-buffered streamed tiles, fetched one group ahead (1 on)
+    int opt_packed = -1;   // packed Hermitian storage (kernel 7) where eligible (-1/1 on, 0 off)
+    int opt_dynsched = -1;  // kernels 6 / 7: groups handed out by a global counter (-1/1 on, 0 static stride)
+    unsigned sched_total = 0;  // host copy of the schedule counter (tl.sched), see SymArgs::sched_base
     long long resident_launches = 0;
     long long sym_launches = 0;  // stage launches that went to kernel 6
     long long packed_steps = 0;  // RK4 steps done by kernel 7 (packed Hermitian storage)

@@ -42,6 +42,14 @@
 
 namespace {
 
+// L2 eviction-priority hints (build-time, pyqed_b200/build.py defines=...): 1 = the arrays that are
+// only streamed (y, stage buffers of the last stage) are fetched evict_first, so that L2 is left
+// to the stage input, the only array with reuse (own tile + neighbour rows); 2 = the stage input
+// is fetched evict_last as well
+#ifndef HEOM_SYM_L2HINT
+#define HEOM_SYM_L2HINT 0
+#endif
+
 constexpr int SYM_NCH = 4;   // link chunks (of N links) whose records are prefetched per ADO
 
 constexpr int SYM_TOFS = 16;  // double2 units reserved for the packed-row offset table (N*N ints)
@@ -50,10 +58,22 @@ constexpr int SYM_TOFS = 16;  // double2 units reserved for the packed-row offse
 // triangle only (N(N+1)/2 elements per ADO, row-major), see stage_rows_sym_kernel.
 // `db`: the streamed tiles (own tile, y, first stage buffer) are double-buffered and fetched
 // one group ahead.
+// Shared-memory layouts chosen for the banks (a 128-bit access is served per quarter warp, eight
+// 16-byte slots wide): with lane = sub N + row,
+//   k tile:         element (i, j) of ADO `sub` at sub KSUB + 8 i + j, KSUB = 9N - 8 (= N mod 8):
+//                   column accesses (fixed i), the diagonal, the (row, row+d) diagonals and their
+//                   transposes all land in slot lane + const (mod 8) - no conflicts;
+//   neighbour rows: element `row` of link t at sub NBSUB + t N + row, NBSUB = N mod 8.
+// (The staged own tile keeps the layout of the global array, it arrives by bulk copy.)
+__host__ __device__ constexpr int sym_kld() { return 8; }
+__host__ __device__ constexpr int sym_ksub(int N) { return 9 * N - 8; }
+__host__ __device__ constexpr int sym_nbsub(int N) { return N * N + ((N - N * N) % 8 + 8) % 8; }
+
 __host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed, bool db = false) {
-    const int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD, FLAT = APW * NN;
-    const int FE = APW * (packed ? N * (N + 1) / 2 : NN);   // a group's elements in the global arrays
-    const int RT = packed ? FE : TILE;                       // own tile as staged
+    const int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE_R = APW * N * LD;
+    const int TILE = APW * sym_ksub(N), FLAT = APW * sym_nbsub(N);
+    const int FE = APW * (packed ? N * (N + 1) / 2 : N * N);   // a group's elements in the global arrays
+    const int RT = packed ? FE : TILE_R;                     // own tile as staged
     const int nb = db ? 2 : 1;
     // own tile, k tile, neighbour rows, [y], [first stage buffer], record strip, mbarriers
     return nb * RT + TILE + FLAT + (stage == 0 ? 0 : nb * FE) + (stage == 2 ? nb * FE : 0) +
@@ -90,11 +110,13 @@ __global__ void __launch_bounds__(sym_max_threads(STAGE), 1)
 stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL> hp) {
     static_assert(!PUSH || (!PACKED && !DB), "the fused push works on full matrices");
     constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
-    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE = APW * N * LD;
-    constexpr int FLAT = APW * NN, PERWARP = sym_perwarp(N, STAGE, PACKED, DB), NCH = SYM_NCH;
+    constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE_R = APW * N * LD;
+    constexpr int KLD = sym_kld(), KSUB = sym_ksub(N), NBSUB = sym_nbsub(N);
+    constexpr int TILE = APW * KSUB, FLAT = APW * NBSUB;   // k tile, neighbour rows
+    constexpr int PERWARP = sym_perwarp(N, STAGE, PACKED, DB), NCH = SYM_NCH;
     constexpr int NBUF = DB ? 2 : 1;
     constexpr int PK = N * (N + 1) / 2, EL = PACKED ? PK : NN;   // elements per ADO in the global arrays
-    constexpr int FE = APW * EL, RT = PACKED ? FE : TILE;
+    constexpr int FE = APW * EL, RT = PACKED ? FE : TILE_R;
     constexpr bool BULK_TILE = PACKED || (LD == N);   // padded tiles cannot be one bulk copy
     static_assert(!DB || BULK_TILE, "double buffering needs bulk-copied tiles");
     constexpr int EIT = (FE + 31) / 32;
@@ -148,13 +170,28 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
 
     const int sub = lane / N, row = lane - sub * N;
     const bool lane_ok = lane < APW * N;
+    constexpr int L2H = HEOM_SYM_L2HINT;
+    const unsigned long long pol_stream = L2H >= 1 ? l2_policy_evict_first() : 0ull;
+    const unsigned long long pol_keep = L2H >= 2 ? l2_policy_evict_last() : 0ull;
+    auto g2s_stream = [&](void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+        if (L2H >= 1) bulk_g2s_hint(dst, src, bytes, bar, pol_stream);
+        else bulk_g2s(dst, src, bytes, bar);
+    };
+    auto g2s_yin = [&](void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+        if (L2H >= 2) bulk_g2s_hint(dst, src, bytes, bar, pol_keep);
+        else bulk_g2s(dst, src, bytes, bar);
+    };
+    auto row_copy = [&](unsigned dst_u32, const void* src, bool pred) {
+        if (L2H >= 2) cp_async16_s_if_hint(dst_u32, src, pred, pol_keep);
+        else cp_async16_s_if(dst_u32, src, pred);
+    };
     const long long step = (LAST && a.traj) ? (*a.step_base + a.local_step) : 0;
     // slots, groups and element offsets are 32-bit here (the host checks nmax N^2 < 2^32)
     const int ngroups = (int)a.ngroups, gstride = (int)gridDim.x * nwarps;
     const int slot_lo = (int)a.slot_lo, slot_hi = (int)a.slot_hi;
     // flat element e = lane + 32 it of the group in the global arrays  ->  offset in the
-    // staged own tile (rofs) and in the full, possibly padded, k tile (kofs)
-    int kofs[EIT];
+    // staged own tile (rofs) and in the k tile (kofs)
+    int kofs[EIT], rofs_[PACKED || BULK_TILE ? 1 : EIT];
 #pragma unroll
     for (int it = 0; it < EIT; ++it) {
         const int e = lane + 32 * it;
@@ -170,28 +207,61 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             i = j / N;
             j -= i * N;
         }
-        kofs[it] = (s * N + i) * LD + j;
+        kofs[it] = s * KSUB + i * KLD + j;
+        if (!(PACKED || BULK_TILE)) rofs_[it] = (s * N + i) * LD + j;   // padded rows (even N)
     }
-    auto rofs = [&](int it) { return PACKED ? lane + 32 * it : kofs[it]; };
-    double2* const ksub = k_s + sub * N * LD;     // this ADO's k tile
+    // bulk-copied tiles (packed, or odd N) keep the flat layout of the global array
+    auto rofs = [&](int it) { return (PACKED || BULK_TILE) ? lane + 32 * it : rofs_[it]; };
+    double2* const ksub = k_s + sub * KSUB;     // this ADO's k tile
     const int frow = row * N - row * (row - 1) / 2 - row;   // PACKED: element (row, l), l >= row, at frow + l
     const int* const trow = tofs_s + row;                   // PACKED: + r0*N: offset of element (r0, row)
-    const double2* const nbrow = nb_s + sub * NN + row;   // + t*N: row element of staged link t
+    const double2* const nbrow = nb_s + sub * NBSUB + row;   // + t*N: row element of staged link t
     const unsigned nbrow_u32 = smem_u32(nbrow);
     // + (c*APW*N + t): record t of chunk c (idle lanes stay inside the strip)
     const int2* const strip_sub = strip + (lane_ok ? sub * N : 0);
-    const double2* const yin_row = a.yin + row;           // + links2.x: this lane's element of the neighbour row
+    // this lane's element of the neighbour row of link record r (links2): the neighbour's slot and
+    // the row r0 = r.y & 15, or - SYM_LINK_POOL set - the element offset of a row that lies
+    // outside the ADOs of this rank (halo row pool of a sharded run, rows stored as N elements)
+    auto row_src = [&](const int2 r) -> const double2* {
+        const unsigned r0 = (unsigned)r.y & 15u;
+        unsigned off = PACKED ? (unsigned)r.x * (unsigned)PK + (unsigned)trow[r0 * N]
+                              : ((unsigned)r.x * (unsigned)N + r0) * (unsigned)N + (unsigned)row;
+        if (r.y & SYM_LINK_POOL) off = (unsigned)r.x + (unsigned)row;
+        return a.yin + off;
+    };
     const char* const cq_row = (const char*)cq_s;
 
     // Bookkeeping pipeline carried in registers: first slot and link offsets of the
     // group two iterations ahead, damping rate and the first NCH*N link records of
     // the next group.
     // Visiting order: see stage_rows_async_kernel (rotation inside runs of 16 groups).
-    const int gfull = a.scramble ? (ngroups & ~15) : 0;
+    // Dynamic schedule (a.sched): groups are handed out in storage order by a global counter, so
+    // the groups in flight on the whole chip always form one short window of consecutive slots
+    // whatever the speed of the individual warps.  With a static stride the CTAs drift apart by
+    // several sweeps (a sweep of the whole grid moves ~40 MB through L2), and the temporal
+    // locality of the lexicographic storage order - half of all links point less than 1024
+    // slots away - never reaches L2.  The counter is not reset between launches: the host passes
+    // its value at launch (a.sched_base); every warp draws exactly one index past the end.
+    const bool dyn = a.sched != nullptr;
+    const int gfull = (a.scramble && !dyn) ? (ngroups & ~15) : 0;
     auto group_base = [&](int gg) {   // first slot of group gg, -1 past the end
         const unsigned rot = ((unsigned)(gg >> 4) * 2654435761u) >> 28;
         const int gm = gg < gfull ? ((gg & ~15) | ((gg + (int)rot) & 15)) : gg;
         return gg < ngroups ? slot_lo + gm * APW : -1;
+    };
+    int glast = dyn ? -1 : (int)blockIdx.x * nwarps + wid - gstride;
+    auto next_group = [&]() {
+        if (dyn) {
+            if (glast < ngroups) {
+                unsigned v = 0;
+                if (lane == 0) v = atomicAdd(a.sched, 1u) - a.sched_base;
+                v = (unsigned)__shfl_sync(0xffffffffu, (int)v, 0);
+                glast = (int)(v < (unsigned)ngroups ? v : (unsigned)ngroups);
+            }
+        } else {
+            glast += gstride;
+        }
+        return glast;
     };
     int nx_lbeg = 0, nx_lend = 0, nn_lbeg = 0, nn_lend = 0;
     int nx_pb = 0, nx_pe = 0, nn_pb = 0, nn_pe = 0;   // PUSH: entry range of this lane's ADO
@@ -218,8 +288,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             if (lb + c * N + row < le) nx_rec[c] = __ldg(a.links2 + lb + c * N + row);
         }
     };
-    int g = (int)blockIdx.x * nwarps + wid;
-    int cur_base = group_base(g), nx_base = group_base(g + gstride);
+    int cur_base = group_base(next_group());
+    int nx_base = group_base(next_group());
     fetch_ptr(cur_base, nx_lbeg, nx_lend, nx_pb, nx_pe);
     fetch_rec(cur_base, nx_lbeg, nx_lend);
     fetch_ptr(nx_base, nn_lbeg, nn_lend, nn_pb, nn_pe);
@@ -230,17 +300,17 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         const unsigned gb = (unsigned)b0 * (unsigned)EL;
         fence_proxy_async();
         mbar_expect_tx(barA0 + b, ne);
-        bulk_g2s(rho0 + b * RT, a.yin + gb, ne, barA0 + b);
+        g2s_yin(rho0 + b * RT, a.yin + gb, ne, barA0 + b);
         if (!FIRST) {
             mbar_expect_tx(barB0 + b, ne * (LAST ? 2u : 1u));
-            bulk_g2s(y0 + b * FE, a.y + gb, ne, barB0 + b);
-            if (LAST) bulk_g2s(acc0 + b * FE, a.s1 + gb, ne, barB0 + b);
+            g2s_stream(y0 + b * FE, a.y + gb, ne, barB0 + b);
+            if (LAST) g2s_stream(acc0 + b * FE, a.s1 + gb, ne, barB0 + b);
         }
     };
     int buf = 0;
     if (DB && lane == 0 && cur_base >= 0) issue_streamed(cur_base, 0);
 
-    for (; g < ngroups; g += gstride) {
+    while (cur_base >= 0) {
         const int base = cur_base;
         double2* const rho_s = rho0 + buf * RT;
         double2* const y_s = y0 + buf * FE;
@@ -267,7 +337,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         nx_pb = nn_pb;
         nx_pe = nn_pe;
         fetch_rec(cur_base, nx_lbeg, nx_lend);
-        nx_base = group_base(g + 2 * gstride);
+        nx_base = group_base(next_group());
         fetch_ptr(nx_base, nn_lbeg, nn_lend, nn_pb, nn_pe);
 
         // ---- issue: own tile + first chunk of neighbour rows, y / first stage buffer
@@ -278,7 +348,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             if (lane == 0) {
                 fence_proxy_async();   // earlier generic-proxy reads of these buffers are done (warp sync)
                 mbar_expect_tx(barA, nelem * 16u);
-                bulk_g2s(rho_s, a.yin + gbase, nelem * 16u, barA);
+                g2s_yin(rho_s, a.yin + gbase, nelem * 16u, barA);
             }
         } else {
             const double2* src = a.yin + gbase + lane;
@@ -292,10 +362,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         for (int t = 0; t < N; ++t) {
             const int2 r = strip_sub[t];
             ry[t] = r.y;
-            cp_async16_s_if(nbrow_u32 + t * (N * 16),
-                            PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
-                                   : yin_row + (unsigned)r.x,
-                            t < nl);
+            row_copy(nbrow_u32 + t * (N * 16), row_src(r), t < nl);
         }
         cp_async_commit();
         if (!FIRST && !DB) {
@@ -304,8 +371,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             if (lane == 0) {
                 if (!BULK_TILE) fence_proxy_async();
                 mbar_expect_tx(barB, nelem * 16u * (LAST ? 2u : 1u));
-                bulk_g2s(y_s, a.y + gbase, nelem * 16u, barB);
-                if (LAST) bulk_g2s(acc_s, a.s1 + gbase, nelem * 16u, barB);
+                g2s_stream(y_s, a.y + gbase, nelem * 16u, barB);
+                if (LAST) g2s_stream(acc_s, a.s1 + gbase, nelem * 16u, barB);
             }
         }
         cp_async_wait<0>();
@@ -348,7 +415,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                         cfma(c, HEL(rr, l), col[l]);
                     }
                 }
-                ksub[rr * LD + row] = make_double2(fma(sh, col[rr].x, c.y), fma(sh, col[rr].y, -c.x));
+                ksub[rr * KLD + row] = make_double2(fma(sh, col[rr].x, c.y), fma(sh, col[rr].y, -c.x));
             }
         }
 #undef HEL
@@ -359,7 +426,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                 if (lane == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(barD, nelem * 16u);
-                    bulk_g2s(rho_s, a.s2 + gbase, nelem * 16u, barD);
+                    g2s_stream(rho_s, a.s2 + gbase, nelem * 16u, barD);
                 }
             } else {
                 const double2* sb = a.s2 + gbase + lane;
@@ -379,7 +446,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         double2 X = make_double2(0.0, 0.0);
         int cur_rr = -1;
         auto flush = [&]() {
-            double2* d1 = ksub + cur_rr * LD + row;
+            double2* d1 = ksub + cur_rr * KLD + row;
             double2 v1 = *d1;
             v1.x += X.x;
             v1.y += X.y;
@@ -405,10 +472,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                 for (int t = 0; t < N; ++t) {
                     const int2 r = recs[t];
                     ry[t] = r.y;
-                    cp_async16_s_if(nbrow_u32 + t * (N * 16),
-                                    PACKED ? a.yin + ((unsigned)r.x + (unsigned)trow[(r.y & 15) * N])
-                                           : yin_row + (unsigned)r.x,
-                                    c0 + t < nl);
+                    row_copy(nbrow_u32 + t * (N * 16), row_src(r), c0 + t < nl);
                 }
                 cp_async_commit();
                 cp_async_wait<0>();
@@ -420,14 +484,15 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     if (c0 + t < nl) {
                         const int rr = ry[t] & 15;
                         double2 Aj = nbrow[t * N];
-                        if (PACKED && row < rr) Aj.y = -Aj.y;   // fetched (row, r0): conjugate
+                        // read through the triangle as (row, r0): conjugate (pool rows are plain rows)
+                        if (PACKED && row < rr && !(ry[t] & SYM_LINK_POOL)) Aj.y = -Aj.y;
                         if (rr != cur_rr) {
                             if (cur_rr >= 0) flush();
                             cur_rr = rr;
                             X = make_double2(0.0, 0.0);
                         }
                         const double2 cf =
-                            *(const double2*)(cq_row + ((ry[t] & ~15) + (row == rr ? 16 : 0)));
+                            *(const double2*)(cq_row + ((ry[t] & ~31) + (row == rr ? 16 : 0)));
                         cfma(X, cf, Aj);
                     }
                 }
@@ -439,7 +504,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         //      (row, row+d), d = 1..(N-1)/2 (and d = N/2 from the lower half when N is even)
         if (on) {
             {
-                double2* pd = ksub + row * LD + row;
+                double2* pd = ksub + row * KLD + row;
                 const double2 v = *pd;
                 *pd = make_double2(v.x + v.x, 0.0);
             }
@@ -448,8 +513,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                 if (2 * dd == N && row >= N / 2) continue;
                 int j = row + dd;
                 if (j >= N) j -= N;
-                double2* pa = ksub + row * LD + j;
-                double2* pb = ksub + j * LD + row;
+                double2* pa = ksub + row * KLD + j;
+                double2* pb = ksub + j * KLD + row;
                 const double2 va = *pa, vb = *pb;
                 const double2 sum = make_double2(va.x + vb.x, va.y - vb.y);
                 *pa = sum;
@@ -490,7 +555,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     if (PUSH) k_s[kofs[it]] = res;
                     if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)EL) {
                         if (PACKED) {   // the trajectory holds full matrices
-                            const int kk = kofs[it] - (e0 / EL) * (N * LD), i = kk / LD, j = kk - i * LD;
+                            const int kk = kofs[it] - (e0 / EL) * KSUB, i = kk / KLD, j = kk - i * KLD;
                             a.traj[(step + 1) * NN + i * N + j] = res;
                             if (i != j) a.traj[(step + 1) * NN + j * N + i] = make_double2(res.x, -res.y);
                         } else {
@@ -518,9 +583,9 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                                    (gbase + (unsigned)(sub * NN));
                     if (r == 15) {
 #pragma unroll
-                        for (int rr = 0; rr < N; ++rr) bulk_s2g(dst + rr * N, ksub + rr * LD, N * 16u);
+                        for (int rr = 0; rr < N; ++rr) bulk_s2g(dst + rr * N, ksub + rr * KLD, N * 16u);
                     } else {
-                        bulk_s2g(dst + r * N, ksub + r * LD, N * 16u);
+                        bulk_s2g(dst + r * N, ksub + r * KLD, N * 16u);
                     }
                 }
                 bulk_commit();
@@ -536,16 +601,12 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     }
 }
 
-// links -> links2 (one thread per link).  packed: x = first element of the neighbour's triangle
-__global__ void sym_convert_links_kernel(const int2* links, int2* links2, long long nlinks, int N, int L,
-                                         int packed) {
+// links -> links2 (one thread per link): x = neighbour slot, y = coefficient byte offset | row
+__global__ void sym_convert_links_kernel(const int2* links, int2* links2, long long nlinks, int L) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nlinks) return;
     const int2 r = links[i];
-    const int r0 = heom::meta_r0(r.y);
-    const unsigned off = packed ? (unsigned)r.x * (unsigned)(N * (N + 1) / 2)
-                                : ((unsigned)r.x * (unsigned)N + (unsigned)r0) * (unsigned)N;
-    links2[i] = make_int2((int)off, sym_link_y(heom::meta_kdir(r.y), heom::meta_neff(r.y), L, r0));
+    links2[i] = make_int2(r.x, sym_link_y(heom::meta_kdir(r.y), heom::meta_neff(r.y), L, heom::meta_r0(r.y)));
 }
 
 thread_local const char* g_sym_err = "";
@@ -624,8 +685,15 @@ int sym_launch_t(const SymLaunch& s) {
         attr_set = true;
     }
 #endif
+    // dynamic schedule only where a warp processes several groups (otherwise the order is moot)
+    const bool dyn = s.sched && s.sched_total && args.ngroups > 2ll * grid * warps;
+    args.sched = dyn ? s.sched : nullptr;
     // one launch per trajectory of the batch, each with its own array / trajectory pointers
     for (int b = 0; b < s.B; ++b) {
+        if (dyn) {
+            args.sched_base = *s.sched_total;
+            *s.sched_total += (unsigned)args.ngroups + grid * (unsigned)warps;
+        }
         HEOM_LAUNCH(kern, grid, warps * 32, smem, s.stream, args, hp);
 #ifndef HEOM_HOST_EMU
         cudaError_t e = cudaGetLastError();
@@ -696,12 +764,13 @@ int heom_sym_supported(int N, int K, int M, int L, const char** err) {
     return why ? 1 : 0;
 }
 
-int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, int packed,
-                           void* stream, const char** err) {
+int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
+                           const char** err) {
+    (void)N;
     if (nlinks <= 0) return 0;
     const int threads = 256;
     const unsigned blocks = (unsigned)((nlinks + threads - 1) / threads);
-    HEOM_LAUNCH(sym_convert_links_kernel, blocks, threads, 0, stream, links, links2, nlinks, N, L, packed);
+    HEOM_LAUNCH(sym_convert_links_kernel, blocks, threads, 0, stream, links, links2, nlinks, L);
 #ifndef HEOM_HOST_EMU
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -793,6 +862,8 @@ int heom_packed_propagate(const PackedRun& r, const char** err) {
             s.batch_elems = tri;
             s.traj_bstride = 0;
             s.stream = r.stream;
+            s.sched = r.sched;
+            s.sched_total = r.sched_total;
             if (heom_sym_launch(s, err)) return 1;
         }
     }

@@ -39,7 +39,7 @@ struct SymArgs {
     double2* out;         // next stage input, or the end-of-step state in the last stage
     const double2* damp;
     const int* link_ptr;
-    const int2* links2;   // x: element offset of the neighbour row, y: coefficient byte offset | row
+    const int2* links2;   // x: neighbour slot (or pool element offset), y: coefficient byte offset | flags | row
     const double2* cbase; // [K][4]
     const int* kmode;     // [K]: mode | first support row << 8
     const double2* ops;   // [1+M][N*N] (diagonal entries of Q_m are read)
@@ -54,9 +54,16 @@ struct SymArgs {
     const unsigned char* push_ent;  // entries: peer << 4 | row (15 = every row)
     const unsigned long long* peer; // [world] base address of every rank's state buffer
     long long out_elem_off;         // offset (double2) of this stage's output array in the state buffer
+    // dynamic group schedule: global counter (never reset; sched_base = its value at launch), or null
+    unsigned* sched;
+    unsigned sched_base;
 };
 
-// links2 record: x = (slot * N + r0) * N, y = ((2k+dir) * (L+1) + n_eff) << 5 | r0
+// links2 record: x = neighbour slot, y = ((2k+dir) * (L+1) + n_eff) << 5 | r0.  One table serves
+// full and packed (kernel 7) storage.  With SYM_LINK_POOL set in y, x is instead the element
+// offset (double2 units from the array base) of a plain N-element row: the halo rows a sharded
+// rank receives from its peers live in a row pool behind its own ADOs.
+constexpr int SYM_LINK_POOL = 16;
 __host__ __device__ inline int sym_link_y(int kdir, int neff, int L, int r0) {
     return ((kdir * (L + 1) + neff) << 5) | (r0 & 0xf);
 }
@@ -109,12 +116,16 @@ struct SymLaunch {
     long long batch_elems;        // nmax * N * N: distance between trajectories in the ADO arrays
     long long traj_bstride;
     void* stream;
+    // dynamic group schedule (large hierarchies): device counter and the host's running copy of its
+    // value (advanced by groups + warps per launch); null = static stride
+    unsigned* sched;
+    unsigned* sched_total;
 };
 
 // All return 0 on success; on failure *err points to a static message.
 int heom_sym_supported(int N, int K, int M, int L, const char** err);
-int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, int packed,
-                           void* stream, const char** err);
+int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
+                           const char** err);
 int heom_sym_launch(const SymLaunch& L, const char** err);
 
 // Kernel 7 = kernel 6 on packed Hermitian storage.  Every ADO is Hermitian, so only the
@@ -133,5 +144,7 @@ struct PackedRun {
     int hreal, warps, sm_count;
     int prefetch;         // 1: double-buffered streamed tiles (stage_rows_sym_kernel<..., DB>)
     void* stream;
+    unsigned* sched;        // as in SymLaunch
+    unsigned* sched_total;
 };
 int heom_packed_propagate(const PackedRun& r, const char** err);

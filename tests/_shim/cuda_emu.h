@@ -315,4 +315,15 @@ inline void bulk_wait_read() {
 }
 inline void bulk_wait_all() { bulk_wait_read(); }
 inline void __threadfence_system() {}
+// L2 eviction-priority hints have no effect on results: the hinted copies are the plain ones
+inline unsigned long long l2_policy_evict_first() { return 1; }
+inline unsigned long long l2_policy_evict_last() { return 2; }
+inline void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar, unsigned long long) {
+    bulk_g2s(dst, src, bytes, bar);
+}
+inline void cp_async16_s_if_hint(unsigned smem_dst_u32, const void* gsrc, bool pred, unsigned long long) {
+    cp_async16_s_if(smem_dst_u32, gsrc, pred);
+}
+// global atomics: the emulated CUDA threads are OS threads
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }

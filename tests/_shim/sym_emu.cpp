@@ -12,6 +12,12 @@ extern "C" {
 void emu_set_async_late(int late) { emu::g_async_late = late; }
 #endif
 
+// dynamic group schedule (SymLaunch::sched): the counter is never reset between launches
+static int g_dyn = 0;
+static unsigned g_sched_ctr = 0, g_sched_total = 0;
+void emu_set_dynsched(int on) { g_dyn = on; }
+long long emu_sched_counter(void) { return g_sched_ctr == g_sched_total ? (long long)g_sched_ctr : -1; }
+
 // One call = nt difference-form RK4 steps (the stage plan of run_stage in
 // heom_kernels.cu) on host arrays.  `state` holds the four ADO arrays Y, SA, SB,
 // ACC ([nmax][N][N] complex128 each, contiguous); `links` are the (slot, meta)
@@ -27,7 +33,7 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
     *err = none;
     if (heom_sym_supported(N, K, M, L, err)) return 1;
     std::vector<int2> links2((size_t)std::max(1ll, nlinks));
-    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 0, nullptr, err))
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
         return 1;
     const long long NN = (long long)N * N, asz = nmax * NN;
     double2* Y = reinterpret_cast<double2*>(state);
@@ -74,6 +80,10 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
             s.sm_count = sm_count;
             s.batch_elems = asz;
             s.traj_bstride = (long long)(nt + 1) * NN;
+            if (g_dyn) {
+                s.sched = &g_sched_ctr;
+                s.sched_total = &g_sched_total;
+            }
             for (int p = 0; p < nparts; ++p) {
                 s.part_lo = parts[2 * p];
                 s.part_hi = parts[2 * p + 1];
@@ -96,7 +106,7 @@ int emu_sym_stage(int N, int K, int M, int L, const double* H, const double* ops
     static const char* none = "";
     *err = none;
     std::vector<int2> links2((size_t)std::max(1ll, nlinks));
-    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 0, nullptr, err))
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
         return 1;
     long long step_base = 0;
     SymLaunch s{};
@@ -144,7 +154,7 @@ int emu_packed_run(int N, int K, int M, int L, long long nmax, const double* H, 
     *err = none;
     if (heom_sym_supported(N, K, M, L, err)) return 1;
     std::vector<int2> links2((size_t)std::max(1ll, nlinks));
-    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 1, nullptr, err))
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
         return 1;
     const long long NN = (long long)N * N, PK = (long long)N * (N + 1) / 2;
     const size_t arr = ((size_t)(nmax * PK) * sizeof(double2) + 255) / 256 * 256;
@@ -178,6 +188,10 @@ int emu_packed_run(int N, int K, int M, int L, long long nmax, const double* H, 
     r.sm_count = sm_count;
     r.prefetch = prefetch;
     r.stream = nullptr;
+    if (g_dyn) {
+        r.sched = &g_sched_ctr;
+        r.sched_total = &g_sched_total;
+    }
     return heom_packed_propagate(r, err);
 }
 

@@ -145,6 +145,36 @@ def save_bath():
     for n in (1, 2, 3, 6):
         p, r = ref_deom.pade_approximation_distribution(n, 1, 1)
         out[f"psd_pole_{n}"], out[f"psd_resi_{n}"] = np.asarray(p), np.asarray(r)
+        for pade in (2, 3):   # [N/N] and [N+1/N] (deom.py:119-207)
+            p, r = ref_deom.pade_approximation_distribution(n, 1, pade)
+            out[f"psd{pade}_pole_{n}"], out[f"psd{pade}_resi_{n}"] = np.asarray(p), np.asarray(r)
+    more = {
+        "drude_q2": (cases["drude_p2"][0], 1.0, 2, 2),
+        "drude_q3": (cases["drude_p2"][0], 1.0, 3, 3),
+        "bo_q2": (cases["bo_p3"][0], 0.8, 3, 2),
+        "bo_q3": (cases["bo_p3"][0], 0.8, 2, 3),
+    }
+    for name, (spe, beta, npsd, pade) in more.items():
+        etal, etar, etaa, expn = ref_deom.decompose_spectrum_pade(spe, w_sp, beta, npsd, pade=pade)
+        out[f"{name}_etal"], out[f"{name}_etar"] = np.asarray(etal), np.asarray(etar)
+        out[f"{name}_etaa"], out[f"{name}_expn"] = np.asarray(etaa), np.asarray(expn)
+        out[f"{name}_args"] = np.array([beta, npsd, pade], dtype=float)
+    # poles of J without the Bose factor (deom.py:310-425)
+    for name, fn, spe in (("real_drude", ref_deom.decompose_spectrum_pade_real, cases["drude_p2"][0]),
+                          ("imag_bo", ref_deom.decompose_spectrum_pade_imag, cases["bo_p3"][0])):
+        etal, etar, etaa, expn = fn(spe, w_sp)
+        out[f"{name}_etal"], out[f"{name}_etar"] = np.asarray(etal), np.asarray(etar)
+        out[f"{name}_etaa"], out[f"{name}_expn"] = np.asarray(etaa), np.asarray(expn)
+    # Prony refits of a Drude bath (deom.py:428-543); monic denominator (gamma = 1)
+    prony = {"prony_3": (3, dict(scale=20, n=200, npsd=4)), "prony_4": (4, dict(scale=30, n=400, npsd=6)),
+             "prony_3a": ([3, "a"], dict(scale=20, n=200, npsd=4))}
+    spe = 2 * 0.5 * 1.0 * w_sp / (1.0 ** 2 + w_sp ** 2)
+    for name, (nind, kw) in prony.items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            etal, etar, etaa, expn = ref_deom.decompose_spectrum_prony(
+                spe, w_sp, 0.7, list(nind) if isinstance(nind, list) else nind, **kw)
+        out[f"{name}_etal"], out[f"{name}_etar"] = np.asarray(etal), np.asarray(etar)
+        out[f"{name}_etaa"], out[f"{name}_expn"] = np.asarray(etaa), np.asarray(expn)
     etal, etar, etaa, expn = ref_deom.single_oscillator(1.3, w_sp, 0.9, 2)
     out["so_etal"], out["so_etar"], out["so_etaa"], out["so_expn"] = etal, etar, etaa, expn
     np.savez_compressed(os.path.join(HERE, "bath.npz"), **out)
@@ -283,6 +313,9 @@ def main():
         return
     if len(sys.argv) > 1 and sys.argv[1] == "propagators":
         save_propagators()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "bath":
+        save_bath()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "generator":
         save_generator()

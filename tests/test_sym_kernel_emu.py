@@ -205,6 +205,24 @@ def test_owned_ranges_and_rotation(emu):
     check(emu, w, nt=2, scramble=1, sm_count=2, warps=1)   # whole hierarchy: kernel 7 too
 
 
+def test_dynamic_group_schedule(emu):
+    """Groups handed out by the global counter (SymArgs::sched) instead of the static stride:
+    several launches share one never-reset counter, every warp draws exactly one index past the
+    end (the host's running total must equal the device counter), full and packed storage,
+    one and two owned ranges."""
+    w = W.fmo(lmax=3, n_matsubara=0)
+    emu.emu_set_dynsched(ctypes.c_int(1))
+    emu.emu_sched_counter.restype = ctypes.c_longlong
+    try:
+        before = emu.emu_sched_counter()
+        check(emu, w, nt=2, sm_count=2, warps=2)
+        check(emu, w, nt=2, parts=[0, 57, 57, 120], sm_count=1, warps=3)
+        after = emu.emu_sched_counter()
+        assert after > before >= 0     # the dynamic path ran, and host total == device counter
+    finally:
+        emu.emu_set_dynsched(ctypes.c_int(0))
+
+
 def test_more_warps_than_groups(emu):
     w = projector_problem(3, 1, 2, seed=5, complex_h=True)   # 10 ADOs = 1 group of 10
     check(emu, w, nt=3, sm_count=4, warps=4)
