@@ -173,6 +173,52 @@ int pyqed_heom_chain_euler(int device, void* stream, int N, int nado, int batch,
 int pyqed_heom_set_push_table(pyqed_heom_plan* plan, const int32_t* d_push_ptr,
                               const uint8_t* d_push_ent, const uint64_t* peer_state_ptrs, int world);
 
+/* ---- Sharded propagation with rank-local arrays (one process per GPU; csrc/heom_shard.cu) ----
+ * Specification: SURVEY.md section 8e (the reference is a single Python loop, deom.py:1072-1114).
+ * Each rank owns the storage slots [lo, hi) of the blocked-lexicographic order (set_order 2).
+ * Its four ADO arrays hold n_own_max ADOs followed by a pool of pool_max halo rows (N elements
+ * each): one row for every (foreign ADO, matrix row) a link of an owned ADO reads.  The owners
+ * store those rows there themselves, from the stage kernel's epilogue, with bulk stores on
+ * peer addresses (NVLink); a flag barrier in peer memory closes every stage.  Only for the
+ * problems kernels 6 / 7 take (Hermitian ADOs, one-entry diagonal Q_m, time-independent H),
+ * batch = 1.  Everything else shards through set_partition / halo_pack / halo_push.
+ *
+ * shared_alloc / open / close / free: device memory that other processes on this box can map
+ * (cudaMalloc + CUDA IPC; handle = 64 bytes to be sent to the peers by the caller's transport).
+ * shard_state_bytes: size of a rank's state buffer and the offset of its flag block, given
+ * the largest owned range and the largest pool over all ranks (identical layouts everywhere).
+ * shard_setup: bind that buffer (allocated with shared_alloc), the peers' mapped addresses,
+ * this rank's sorted unique need list d_need[n_need] (items slot*8+row, device, int64) and
+ * its push table (CSR over the owned slots: d_push_ptr[n_own+1]; entry i = two int32,
+ * d_push_ent[2i] = row index in the destination's pool, d_push_ent[2i+1] = peer << 4 | row),
+ * and rewrite the links of the owned range to local slots / pool rows.  Collective in spirit:
+ * every rank calls it, then the caller synchronises the ranks once on the host.
+ * device_barrier = 1: every rank has its own GPU and shard_propagate may spin on peer flags;
+ * 0 (ranks share a GPU): drive the run with shard_begin / shard_stage / shard_end and a host
+ * barrier (stream synchronise + transport barrier) after begin and after every stage.
+ * shard_set_state: zero the arrays, ADO 0 = rho0 on its owner (callers barrier afterwards).
+ * shard_get_owned: this rank's ADOs and their reference ids (DEOMSolver.ddos is their union).
+ * shard_error: 0, or q+1 if a device barrier gave up waiting for rank q (20 s). */
+int pyqed_heom_shared_alloc(int device, size_t bytes, void** d_ptr, uint8_t* handle64);
+int pyqed_heom_shared_open(int device, const uint8_t* handle64, void** d_ptr);
+int pyqed_heom_shared_close(int device, void* d_ptr);
+int pyqed_heom_shared_free(int device, void* d_ptr);
+int pyqed_heom_shard_state_bytes(pyqed_heom_plan* plan, int64_t n_own_max, int64_t pool_max,
+                                 size_t* state_bytes, size_t* flag_offset);
+int pyqed_heom_shard_setup(pyqed_heom_plan* plan, int rank, int world, int64_t lo, int64_t hi,
+                           int64_t n_own_max, int64_t pool_max, const int64_t* d_need, int64_t n_need,
+                           const int32_t* d_push_ptr, const int32_t* d_push_ent, int64_t n_push,
+                           void* d_state, size_t state_bytes, const uint64_t* peer_state_ptrs,
+                           int device_barrier);
+int pyqed_heom_shard_set_state(pyqed_heom_plan* plan, const double* rho0_host);
+int pyqed_heom_shard_get_owned(pyqed_heom_plan* plan, double* ados_host, int32_t* ids_host);
+int pyqed_heom_shard_begin(pyqed_heom_plan* plan, double dt, int64_t nt, double* d_traj);
+int pyqed_heom_shard_stage(pyqed_heom_plan* plan, int64_t step, int stage);
+int pyqed_heom_shard_end(pyqed_heom_plan* plan);
+int pyqed_heom_shard_barrier(pyqed_heom_plan* plan);
+int pyqed_heom_shard_propagate(pyqed_heom_plan* plan, double dt, int64_t nt, double* d_traj);
+int pyqed_heom_shard_error(pyqed_heom_plan* plan, int* code);
+
 /* Tr(op_e rho) for npts density matrices per trajectory:
  * d_rho [batch][npts][N][N] (device), ops_host [n_ops][N][N] (host),
  * d_out [batch][n_ops][npts] complex128 (device).  Replaces
@@ -198,14 +244,15 @@ int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
  * cp.async staging (N <= 8, diagonal Q_m), 4 cluster-resident propagation
  * (whole hierarchy in distributed shared memory, small hierarchies only;
  * chosen automatically when it fits), 6 Hermitian-symmetric stage kernel and
- * 7 the same on packed (upper-triangle) storage for whole propagate calls -
- * both opt-in, both fall back to kernel 3 where they do not apply (they need
+ * 7 the same on packed (upper-triangle) storage for whole propagate calls.
+ * Kernel 0 picks 7, then 6, then 3 / 1 / 2 by applicability: 6 and 7 need
  * Hermitian ADOs, one-entry diagonal Q_m and a time-independent H; 7 also one
- * trajectory and the whole hierarchy on this GPU).  Choose the kernel before
- * pyqed_heom_table_bytes: kernels 6 / 7 add a second link table to the table
- * buffer.  warps per CTA for kernels 1, 3, 6 and 7;
- * use_graph: reserved (ignored): small hierarchies are propagated by a single
- * cluster-resident launch instead of a graph. */
+ * trajectory and the whole hierarchy on this GPU; both fall back to kernel 3
+ * where they do not apply.  Choose the kernel and set system, coupling and bath
+ * before pyqed_heom_table_bytes: kernels 6 / 7 add a second link table to the
+ * table buffer.  warps per CTA for kernels 1, 3, 6 and 7;
+ * use_graph: reserved, must be 0 (small hierarchies are propagated by a single
+ * cluster-resident launch instead of a graph). */
 int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
                           int use_graph);
 
@@ -229,6 +276,11 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *                element-parallel kernel 5)
  *   "prefetch"   1 = kernel 7 keeps the streamed tiles in two buffer sets and fetches
  *                them one group ahead (default 0)
+ *   "packed"     0 = never run on packed Hermitian storage (kernel 7)
+ *   "dynsched"   0 = kernels 6 / 7 visit their groups with a static stride instead of
+ *                drawing them from a global work counter (the counter keeps the groups
+ *                in flight on the whole chip inside one short window of the storage
+ *                order, which is what lets neighbour rows hit in L2)
  *   "debug_sync" synchronise and check after every launch
  * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "sym", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
  * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes", "sym_launches" (stage launches done by

@@ -54,6 +54,22 @@ SIGNATURES = {
                                        C.POINTER(C.c_uint64), C.c_int]),
     "pyqed_heom_set_push_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
                                             C.c_int]),
+    "pyqed_heom_shared_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), _c_uint8_p]),
+    "pyqed_heom_shared_open": (C.c_int, [C.c_int, _c_uint8_p, C.POINTER(C.c_void_p)]),
+    "pyqed_heom_shared_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "pyqed_heom_shared_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "pyqed_heom_shard_state_bytes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _c_size_p, _c_size_p]),
+    "pyqed_heom_shard_setup": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_size_t, C.POINTER(C.c_uint64), C.c_int]),
+    "pyqed_heom_shard_set_state": (C.c_int, [C.c_void_p, _c_double_p]),
+    "pyqed_heom_shard_get_owned": (C.c_int, [C.c_void_p, _c_double_p, C.POINTER(C.c_int32)]),
+    "pyqed_heom_shard_begin": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, C.c_void_p]),
+    "pyqed_heom_shard_stage": (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
+    "pyqed_heom_shard_end": (C.c_int, [C.c_void_p]),
+    "pyqed_heom_shard_barrier": (C.c_int, [C.c_void_p]),
+    "pyqed_heom_shard_propagate": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, C.c_void_p]),
+    "pyqed_heom_shard_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "pyqed_heom_apply_operator": (C.c_int, [C.c_void_p, _c_double_p, C.c_int]),
     "pyqed_heom_chain_euler": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, _c_double_p,
                                          _c_double_p, C.c_double, C.c_double, C.c_double, C.c_double,
@@ -192,22 +208,28 @@ class Plan:
         self._check(self.lib.pyqed_heom_state_bytes(self._h, C.byref(sb)))
         return sb.value
 
-    def build(self, state=None):
+    def build(self, state=None, tables_only=False):
         """Allocate the device buffers (torch), bind them and build the tables.
         ``state``: optional caller-provided uint8 tensor for the ADO arrays
-        (e.g. symmetric memory shared with peer ranks)."""
+        (e.g. symmetric memory shared with peer ranks).  ``tables_only``: bind no
+        state buffer (sharded runs bind a rank-local one in ``shard_setup``)."""
         torch = self.torch
         tb, sb = C.c_size_t(), C.c_size_t()
         self._check(self.lib.pyqed_heom_table_bytes(self._h, C.byref(tb)))
         self._check(self.lib.pyqed_heom_state_bytes(self._h, C.byref(sb)))
         dev = torch.device("cuda", self.device)
         self._tables = torch.empty(tb.value, dtype=torch.uint8, device=dev)
-        self._state = state if state is not None else torch.empty(sb.value, dtype=torch.uint8, device=dev)
-        assert self._state.numel() >= sb.value and self._state.dtype == torch.uint8
-        self.table_bytes, self.state_bytes = tb.value, sb.value
+        self.table_nbytes, self.state_nbytes = tb.value, sb.value
         stream = torch.cuda.current_stream(dev).cuda_stream
-        self._check(self.lib.pyqed_heom_bind(self._h, self._tables.data_ptr(), tb.value,
-                                             self._state.data_ptr(), sb.value, C.c_void_p(stream)))
+        if tables_only:
+            self._state = None
+            self._check(self.lib.pyqed_heom_bind(self._h, self._tables.data_ptr(), tb.value, None, 0,
+                                                 C.c_void_p(stream)))
+        else:
+            self._state = state if state is not None else torch.empty(sb.value, dtype=torch.uint8, device=dev)
+            assert self._state.numel() >= sb.value and self._state.dtype == torch.uint8
+            self._check(self.lib.pyqed_heom_bind(self._h, self._tables.data_ptr(), tb.value,
+                                                 self._state.data_ptr(), sb.value, C.c_void_p(stream)))
         self._check(self.lib.pyqed_heom_build_hierarchy(self._h))
 
     # -- state -------------------------------------------------------------

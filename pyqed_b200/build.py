@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = [os.path.join(CSRC, "heom_kernels.cu"), os.path.join(CSRC, "heom_stage_sym.cu"),
-           os.path.join(CSRC, "heom_inst.cu")]
+           os.path.join(CSRC, "heom_inst.cu"), os.path.join(CSRC, "heom_shard.cu")]
 SRC = SOURCES[0]
 SIZES = range(2, 9)   # system sizes N with templated kernels (one object file each)
 
@@ -21,7 +21,8 @@ SIZES = range(2, 9)   # system sizes N with templated kernels (one object file e
 def compile_units():
     """(source, object name, extra defines): the C ABI / builder unit, the common part of kernels
     6 / 7, and one unit per system size N for each of the two N-templated kernel families."""
-    units = [(SOURCES[0], "heom_kernels.o", []), (SOURCES[1], "heom_stage_sym.o", ["HEOM_SYM_SPLIT"])]
+    units = [(SOURCES[0], "heom_kernels.o", []), (SOURCES[1], "heom_stage_sym.o", ["HEOM_SYM_SPLIT"]),
+             (SOURCES[3], "heom_shard.o", [])]
     for n in SIZES:
         units.append((SOURCES[1], f"heom_stage_sym_n{n}.o", [f"HEOM_SYM_INST_N={n}"]))
         units.append((SOURCES[2], f"heom_inst_n{n}.o", [f"HEOM_INST_N={n}"]))
@@ -60,6 +61,7 @@ def _run(cmd):
 _COMMON = ["heom_core.cuh", "heom_device.cuh"]
 HEADER_DEPS = {
     "heom_stage_sym.cu": _COMMON + ["heom_stage_sym.cuh"],
+    "heom_shard.cu": _COMMON + ["heom_plan.cuh", "heom_stage_sym.cuh", "../../include/pyqed_heom.h"],
     "heom_inst.cu": _COMMON + ["heom_plan.cuh", "heom_stage_sym.cuh", "heom_stage_async.cuh", "heom_stage_rows.cuh",
                                "heom_resident.cuh", "../../include/pyqed_heom.h"],
     "heom_kernels.cu": _COMMON + ["heom_plan.cuh", "heom_stage_sym.cuh", "heom_stage_async.cuh", "heom_hierarchy.cuh",

@@ -200,7 +200,7 @@ static int try_resident(pyqed_heom_plan* p) {
 static bool sym_eligible(const pyqed_heom_plan* p, const StageArgs& a, bool tdep) {
     return (p->kernel == 0 || p->kernel == 6 || p->kernel == 7) && p->links2_built && !tdep && a.herm &&
            p->single_support && p->opt_sym != 0 &&
-           (!a.push_ptr || p->B == 1) && a.scheme == 1 && !(a.first && a.last);
+           !a.push_ptr && a.scheme == 1 && !(a.first && a.last);   // (legacy fused push: kernel 3)
 }
 static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
     SymLaunch s{};
@@ -380,6 +380,7 @@ void pyqed_heom_plan_destroy(pyqed_heom_plan* p) {
     if (p->d_fsys) cudaFree(p->d_fsys);
     if (p->d_fcoup) cudaFree(p->d_fcoup);
     if (p->d_peer) cudaFree(p->d_peer);
+    if (p->shard.d_peer) cudaFree(p->shard.d_peer);
     delete p;
 }
 
@@ -442,7 +443,8 @@ int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
 int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
     REQUIRE(p, "null plan");
     REQUIRE((kernel >= 0 && kernel <= 4) || kernel == 6 || kernel == 7, "kernel must be 0..4, 6 or 7");
-    REQUIRE(warps >= 0 && warps <= 8, "warps_per_cta must be in [0, 8]");
+    REQUIRE(warps >= 0 && warps <= 16, "warps_per_cta must be in [0, 16]");
+    REQUIRE(use_graph == 0, "use_graph is reserved and must be 0");
     p->kernel = kernel;
     p->warps = warps;
     p->use_graph = use_graph;
@@ -490,6 +492,10 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "array_bytes") return (int64_t)p->array_bytes;
     if (n == "part_lo") return p->part_lo;
     if (n == "part_hi") return p->part_hi;
+    if (n == "sym_inputs") return sym_wanted(p) ? 1 : 0;
+    if (n == "off_links2") return p->links2_built ? (int64_t)p->tl.links2 : -1;
+    if (n == "shard_packed") return p->shard.on ? (p->shard.packed ? 1 : 0) : -1;
+    if (n == "shard_epoch") return p->shard.epoch;
     return -1;
 }
 
@@ -508,10 +514,11 @@ int pyqed_heom_state_bytes(pyqed_heom_plan* p, size_t* bytes) {
 
 int pyqed_heom_bind(pyqed_heom_plan* p, void* d_tables, size_t table_bytes, void* d_state,
                     size_t state_bytes, void* stream) {
-    REQUIRE(p && d_tables && d_state, "bind: null argument");
+    REQUIRE(p && d_tables, "bind: null argument");
     compute_layout(p);
     REQUIRE(table_bytes >= p->tl.total, "bind: table buffer too small");
-    REQUIRE(state_bytes >= 4 * p->array_bytes, "bind: state buffer too small");
+    // d_state may be NULL for a sharded run: pyqed_heom_shard_setup binds the rank-local state buffer
+    REQUIRE(!d_state || state_bytes >= 4 * p->array_bytes, "bind: state buffer too small");
     REQUIRE(((uintptr_t)d_tables % 256) == 0 && ((uintptr_t)d_state % 256) == 0,
             "bind: buffers must be 256-byte aligned");
     p->d_tables = (char*)d_tables;
@@ -741,6 +748,7 @@ int pyqed_heom_get_keys(pyqed_heom_plan* p, uint8_t* keys_host) {
 
 int pyqed_heom_set_state(pyqed_heom_plan* p, const double* rho0_host) {
     REQUIRE(p && p->built && rho0_host, "set_state: build the hierarchy first");
+    REQUIRE(p->d_state && !p->shard.on, "set_state: no full-size state buffer bound (sharded plans use shard_set_state)");
     CU_TRY(cudaSetDevice(p->device));
     const size_t NN = (size_t)p->N * p->N;
     {
@@ -778,6 +786,7 @@ static int permute(pyqed_heom_plan* p, double2* dst, const double2* src, bool to
 
 int pyqed_heom_load_ados(pyqed_heom_plan* p, const double* ados_host) {
     REQUIRE(p && p->built && ados_host, "load_ados: build the hierarchy first");
+    REQUIRE(p->d_state && !p->shard.on, "load_ados: no full-size state buffer bound");
     CU_TRY(cudaSetDevice(p->device));
     p->herm_state = false;  // arbitrary ADOs: do not assume Hermiticity
     const size_t bytes = sizeof(double2) * (size_t)p->B * p->nmax * p->N * p->N;
@@ -793,6 +802,7 @@ int pyqed_heom_load_ados(pyqed_heom_plan* p, const double* ados_host) {
 
 int pyqed_heom_get_ados(pyqed_heom_plan* p, double* ados_host) {
     REQUIRE(p && p->built && ados_host, "get_ados: build the hierarchy first");
+    REQUIRE(p->d_state && !p->shard.on, "get_ados: no full-size state buffer bound (sharded plans use shard_get_owned)");
     CU_TRY(cudaSetDevice(p->device));
     const size_t bytes = sizeof(double2) * (size_t)p->B * p->nmax * p->N * p->N;
     const double2* src = p->arr(ARR_Y);
@@ -911,6 +921,7 @@ static int run_stage(pyqed_heom_plan* p, long long step, int stage) {
 int pyqed_heom_propagate_begin(pyqed_heom_plan* p, double dt, int64_t nt, const double* fsys,
                                const double* fcoup, double* d_traj) {
     REQUIRE(p && p->built, "propagate: build the hierarchy first");
+    REQUIRE(p->d_state && !p->shard.on, "propagate: no full-size state buffer bound (sharded plans use shard_propagate)");
     REQUIRE(nt >= 0, "propagate: nt must be >= 0");
     CU_TRY(cudaSetDevice(p->device));
     const int NN = p->N * p->N;
@@ -1180,6 +1191,7 @@ __global__ void apply_operator_kernel(double2* y, const double2* A, long long na
 
 int pyqed_heom_apply_operator(pyqed_heom_plan* p, const double* op_host, int side) {
     REQUIRE(p && p->built && op_host && (side == 0 || side == 1), "apply_operator: bad argument");
+    REQUIRE(p->d_state && !p->shard.on, "apply_operator: no full-size state buffer bound");
     CU_TRY(cudaSetDevice(p->device));
     const size_t NN = (size_t)p->N * p->N;
     double2* d_op = nullptr;

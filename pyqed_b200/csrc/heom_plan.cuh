@@ -105,6 +105,20 @@ struct pyqed_heom_plan {
     const int* push_ptr = nullptr;
     const unsigned char* push_ent = nullptr;
     unsigned long long* d_peer = nullptr;
+    // sharded run with rank-local arrays (heom_shard.cu): own ADOs [lo, hi) followed by a pool of
+    // halo rows; only kernels 6 / 7
+    struct Shard {
+        bool on = false, packed = false, device_barrier = false;
+        int rank = 0, world = 1;
+        long long lo = 0, hi = 0, n_own_max = 0, pool_max = 0;
+        size_t arr_full = 0, arr_packed = 0;     // array strides (double2 elements), identical on all ranks
+        const int* push_ptr = nullptr;           // caller-owned device tables (CSR over owned slots)
+        const int2* push_ent = nullptr;
+        unsigned long long* d_peer = nullptr;    // device copy of the peers' state buffer addresses
+        unsigned long long peer_flags[16] = {0}; // address of every rank's flag block (world uint32 + error word)
+        unsigned epoch = 0;                      // barriers done so far
+        long long pushed_rows = 0;               // rows per stage this rank stores into its peers
+    } shard;
     // context of the propagation in progress (propagate_begin)
     bool ctx_valid = false, ctx_tdep = false, ctx_use_fs = false, ctx_use_fc = false;
     double ctx_dt = 0.0;

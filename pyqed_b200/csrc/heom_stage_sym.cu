@@ -108,7 +108,7 @@ using HParamOf = typename std::conditional<HREAL, HParamReal<N>, HParam<N>>::typ
 template <int N, bool HREAL, int STAGE, bool PACKED, bool DB, bool PUSH>
 __global__ void __launch_bounds__(sym_max_threads(STAGE), 1)
 stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL> hp) {
-    static_assert(!PUSH || (!PACKED && !DB), "the fused push works on full matrices");
+    static_assert(!PUSH || !DB, "the fused push has no double-buffered variant");
     constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE_R = APW * N * LD;
     constexpr int KLD = sym_kld(), KSUB = sym_ksub(N), NBSUB = sym_nbsub(N);
@@ -226,7 +226,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         const unsigned r0 = (unsigned)r.y & 15u;
         unsigned off = PACKED ? (unsigned)r.x * (unsigned)PK + (unsigned)trow[r0 * N]
                               : ((unsigned)r.x * (unsigned)N + r0) * (unsigned)N + (unsigned)row;
-        if (r.y & SYM_LINK_POOL) off = (unsigned)r.x + (unsigned)row;
+        if (r.y & SYM_LINK_POOL) off = a.pool_off + (unsigned)r.x * (unsigned)N + (unsigned)row;
         return a.yin + off;
     };
     const char* const cq_row = (const char*)cq_s;
@@ -533,6 +533,15 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         __syncwarp();
 
         // ---- epilogue from shared memory, streaming stores
+        // PUSH: the stage output goes back into the k tile as full rows (packed storage: the
+        // element below the diagonal too), from where the halo rows leave as bulk stores
+        auto put_k = [&](int ko, const double2 v) {
+            k_s[ko] = v;
+            if (PACKED) {
+                const int kk = ko % KSUB, i = kk / KLD, j = kk - i * KLD;
+                if (i != j) k_s[ko + (KLD - 1) * (j - i)] = make_double2(v.x, -v.y);
+            }
+        };
         int e0 = -1;   // LAST: flat offset of ADO 0 (rho_sys) inside this group, if it is here
         if (LAST && a.traj) {
             const long long d0 = a.slot0 - base;
@@ -552,7 +561,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     res.x = fma(2.0 * third, s2.x, res.x);
                     res.y = fma(2.0 * third, s2.y, res.y);
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH) k_s[kofs[it]] = res;
+                    if (PUSH) put_k(kofs[it], res);
                     if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)EL) {
                         if (PACKED) {   // the trajectory holds full matrices
                             const int kk = kofs[it] - (e0 / EL) * KSUB, i = kk / KLD, j = kk - i * KLD;
@@ -566,7 +575,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     const double2 yv = FIRST ? rho_s[rofs(it)] : y_s[e];
                     const double2 res = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH) k_s[kofs[it]] = res;
+                    if (PUSH) put_k(kofs[it], res);
                 }
             }
         }
@@ -578,15 +587,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                 fence_proxy_async();   // this lane's tile writes are ordered before the bulk stores
                 __syncwarp();
                 for (int q = pb + row; q < pe; q += N) {
-                    const int ent = a.push_ent[q], r = ent & 15;
-                    double2* dst = reinterpret_cast<double2*>(__ldg(a.peer + (ent >> 4))) + a.out_elem_off +
-                                   (gbase + (unsigned)(sub * NN));
-                    if (r == 15) {
-#pragma unroll
-                        for (int rr = 0; rr < N; ++rr) bulk_s2g(dst + rr * N, ksub + rr * KLD, N * 16u);
-                    } else {
-                        bulk_s2g(dst + r * N, ksub + r * KLD, N * 16u);
-                    }
+                    const int2 ent = a.push_ent[q];
+                    double2* dst = reinterpret_cast<double2*>(__ldg(a.peer + (ent.y >> 4))) + a.out_elem_off +
+                                   (size_t)(unsigned)ent.x * N;
+                    bulk_s2g(dst, ksub + (ent.y & 15) * KLD, N * 16u);
                 }
                 bulk_commit();
             }
@@ -732,9 +736,10 @@ template <int N>
 int sym_launch_n(const SymLaunch& s) {
     // the double-buffered variant exists for packed storage only (its tiles are small enough
     // to keep nearly all warps)
+    // sharded runs: the epilogue stores the halo rows into the peers' row pools
+    if (s.push) return s.packed ? sym_launch_p<N, true, false, true>(s) : sym_launch_p<N, false, false, true>(s);
     if (s.packed) return s.prefetch ? sym_launch_p<N, true, true>(s) : sym_launch_p<N, true, false>(s);
-    // full matrices: with push tables the epilogue stores the halo rows into the peers' arrays
-    return s.a.push_ptr ? sym_launch_p<N, false, false, true>(s) : sym_launch_p<N, false, false>(s);
+    return sym_launch_p<N, false, false>(s);
 }
 
 }  // namespace
@@ -822,6 +827,23 @@ int heom_sym_launch(const SymLaunch& s, const char** err) {
 // the roles of Y, SA, SB, ACC in run_stage's difference-form plan (heom_kernels.cu) - and
 // unpacked back into Y at the end.
 // ---------------------------------------------------------------------------
+// full [n][N][N] -> upper triangles (unpack = 0) or back (unpack = 1), n ADOs
+int heom_sym_pack(double2* tri, double2* full, long long n, int N, int unpack, void* stream) {
+    if (n <= 0) return 0;
+    const long long total = n * (N * (N + 1) / 2);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    if (unpack) {
+        HEOM_LAUNCH(sym_unpack_kernel, blocks, threads, 0, stream, full, (const double2*)tri, n, N);
+    } else {
+        HEOM_LAUNCH(sym_pack_kernel, blocks, threads, 0, stream, tri, (const double2*)full, n, N);
+    }
+#ifndef HEOM_HOST_EMU
+    if (cudaGetLastError() != cudaSuccess) return 1;
+#endif
+    return 0;
+}
+
 int heom_packed_propagate(const PackedRun& r, const char** err) {
     const int N = r.N, PK = N * (N + 1) / 2;
     const long long tri = r.nmax * PK;

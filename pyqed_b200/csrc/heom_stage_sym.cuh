@@ -48,12 +48,19 @@ struct SymArgs {
     long long ngroups, slot_lo, slot_hi, slot0;
     double a, w;
     int local_step, scramble, nind, nmod, lmax;
-    // fused multi-GPU halo (PUSH instantiations): rows of the stage output that other ranks
-    // need are stored into their arrays by the epilogue (same tables as kernel 3's fused push)
-    const int* push_ptr;            // [owned+1] CSR over the owned slots, or null
-    const unsigned char* push_ent;  // entries: peer << 4 | row (15 = every row)
-    const unsigned long long* peer; // [world] base address of every rank's state buffer
-    long long out_elem_off;         // offset (double2) of this stage's output array in the state buffer
+    // Sharded runs (heom_shard.cu).  A rank's arrays hold its own ADOs followed by a pool of halo
+    // rows (N elements each) that the owning ranks store there; pool links (SYM_LINK_POOL) read
+    // row x of the pool, pool_off = offset (double2) of the pool from the array base.
+    // PUSH instantiations: the epilogue stores the rows of the stage output that other ranks read
+    // into their pools - push_ptr[owned+1] is a CSR over the owned slots, an entry is
+    // (x = row index in the destination's pool, y = peer << 4 | matrix row), peer[q] the base
+    // address of rank q's state buffer and out_elem_off the offset (double2) of the pool of this
+    // stage's output array inside a state buffer (the same on every rank).
+    unsigned pool_off;
+    const int* push_ptr;
+    const int2* push_ent;
+    const unsigned long long* peer;
+    long long out_elem_off;
     // dynamic group schedule: global counter (never reset; sched_base = its value at launch), or null
     unsigned* sched;
     unsigned sched_base;
@@ -94,11 +101,7 @@ inline SymArgs sym_args_from_stage(const StageArgs& a, const int2* links2) {
     s.nind = a.nind;
     s.nmod = a.nmod;
     s.lmax = a.lmax;
-    s.push_ptr = a.push_ptr;
-    s.push_ent = a.push_ent;
-    s.peer = a.peer;
-    s.out_elem_off = a.out_elem_off;
-    return s;
+    return s;   // (the fused push of sharded runs is set up by heom_shard.cu, not through StageArgs)
 }
 inline int sym_stage_kind(const StageArgs& a) { return a.first ? 0 : (a.last ? 2 : 1); }
 
@@ -109,6 +112,7 @@ struct SymLaunch {
     int stage;            // 0 first, 1 middle, 2 last
     int hreal;            // H has no imaginary part
     int packed;           // kernel 7: the ADO arrays hold upper triangles (N(N+1)/2 elements per ADO)
+    int push;             // sharded run: PUSH instantiation (a.push_ptr, a.push_ent, a.peer set)
     int prefetch;         // packed only: double-buffered tiles, fetched one group ahead
     int warps;            // 0 = automatic
     int sm_count;
@@ -148,3 +152,5 @@ struct PackedRun {
     unsigned* sched_total;
 };
 int heom_packed_propagate(const PackedRun& r, const char** err);
+// full [n][N][N] -> upper triangles [n][N(N+1)/2] (unpack = 0) or back (unpack = 1)
+int heom_sym_pack(double2* tri, double2* full, long long n, int N, int unpack, void* stream);

@@ -75,6 +75,7 @@ class HaloPlan:
         assert self.recv_counts[rank] == 0, "a rank never needs its own slots"
         # counts[q][r] = number of items rank q needs from rank r
         all_counts = transport.allgather_counts(self.recv_counts)
+        self.all_counts = [[int(x) for x in row] for row in all_counts]
         self.send_counts = [int(all_counts[q][rank]) for q in range(world)]
         chunks = torch.split(self.need, self.recv_counts)
         got = transport.exchange_lists(list(chunks), self.send_counts)
@@ -136,6 +137,14 @@ class DistTransport:
         self._p2p(list(torch.split(host_send, ss)), list(torch.split(host_recv, rs)))
         recvbuf.copy_(host_recv)
 
+    def allgather_object(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
     def broadcast(self, t, src):
         if self.nccl or not t.is_cuda:
             self.dist.broadcast(t, src, group=self.group)
@@ -157,13 +166,14 @@ class ShardedDEOM:
 
     def __init__(self, system, system_dipole, coupling, coupling_dipole, expn, etal, etar, etaa,
                  mode, lmax, transport, device=0, order=1, options=None, tuning=None, peer_push=None,
-                 fused_push=None):
+                 fused_push=None, native=None):
         from .._cabi import Plan
         self.tr = transport
         self.rank, self.world = transport.rank, transport.world
         n = np.shape(system)[0]
         m = int(np.max(mode)) + 1
         self.n = n
+        self.device = device
         self.plan = p = Plan(n, len(expn), m, lmax, batch=1, device=device, order=order)
         p.set_system(system, system_dipole)
         p.set_coupling(np.asarray(coupling)[:m], coupling_dipole)
@@ -172,6 +182,30 @@ class ShardedDEOM:
             p.set_tuning(**tuning)
         for k, v in (options or {}).items():
             p.set_option(k, v)
+        # Rank-local arrays + fused peer stores (csrc/heom_shard.cu) for the problems kernels 6 / 7
+        # take; ``native``: None = where it applies, True = required, False = never.
+        self.native = False
+        self.symm = None
+        self.fused = False
+        if native is not False and hasattr(transport, "allgather_object"):
+            p.build(tables_only=True)
+            if p.info("off_links2") >= 0 and p.info("sym_inputs") == 1 and order == 2:
+                self._init_native(p)
+                return
+            if native:
+                raise ValueError("the rank-local sharded layout needs storage order 2 and a problem for "
+                                 "kernels 6 / 7 (Hermitian operators and bath, one-entry diagonal Q_m)")
+            p.close()
+            self.plan = p = Plan(n, len(expn), m, lmax, batch=1, device=device, order=order)
+            p.set_system(system, system_dipole)
+            p.set_coupling(np.asarray(coupling)[:m], coupling_dipole)
+            p.set_bath(expn, etal, etar, etaa, mode)
+            if tuning:
+                p.set_tuning(**tuning)
+            for k, v in (options or {}).items():
+                p.set_option(k, v)
+        elif native:
+            raise ValueError("the rank-local sharded layout needs a multi-process transport")
         # peer_push: None = use it when NCCL + symmetric memory are available
         self.symm = None
         state = None
@@ -249,6 +283,116 @@ class ShardedDEOM:
         self.owner_of_sys = next(r for r in range(self.world)
                                  if self.bounds[r] <= p.info("slot0") < self.bounds[r + 1])
 
+    # -- rank-local layout: own ADOs + pool of halo rows, rows stored by their owners --------
+    def _init_native(self, p):
+        import ctypes as C
+        tr, world, rank = self.tr, self.world, self.rank
+        self.nmax = p.nmax
+        tables = p._tables
+        dev = tables.device
+        lp_off, lk_off = p.info("off_link_ptr"), p.info("off_links")
+        self.link_ptr = tables[lp_off:lp_off + 4 * (self.nmax + 1)].view(torch.int32)
+        nlinks = p.info("nlinks")
+        links = tables[lk_off:lk_off + 8 * nlinks].view(torch.int32).view(nlinks, 2)
+        self.bounds = cost_balanced_bounds(self.link_ptr.cpu().numpy(), world)
+        self.bounds = ([0] + [min(self.nmax, (b + 32) // 64 * 64) for b in self.bounds[1:-1]] + [self.nmax])
+        self.lo, self.hi = lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        n_own = hi - lo
+        l0, l1 = int(self.link_ptr[lo]), int(self.link_ptr[hi])
+        need = needed_items(links[l0:l1, 0], links[l0:l1, 1], lo, hi, True)
+        self.row_items = True
+        self.halo = h = HaloPlan(self.bounds, rank, world, need, True, tr)
+        self.need64 = h.need.contiguous()
+        # push table: for every row a peer q asked for, its index in q's pool = position in q's
+        # sorted need list = (rows q gets from lower ranks) + position inside q's request to me
+        si = h.send_items
+        counts = torch.tensor(h.send_counts, dtype=torch.int64, device=si.device)
+        dest = torch.repeat_interleave(torch.arange(world, device=si.device), counts)
+        first = torch.cumsum(counts, 0) - counts
+        base = torch.tensor([sum(h.all_counts[q][:rank]) for q in range(world)], dtype=torch.int64, device=si.device)
+        dst_row = base[dest] + torch.arange(si.numel(), device=si.device) - first[dest]
+        loc, rowc = (si >> 3) - lo, si & 7
+        order_ix = torch.argsort(loc, stable=True)
+        cnt = torch.bincount(loc, minlength=n_own) if si.numel() else torch.zeros(n_own, dtype=torch.int64, device=si.device)
+        ptr = torch.zeros(n_own + 1, dtype=torch.int32, device=si.device)
+        ptr[1:] = torch.cumsum(cnt, 0).to(torch.int32)
+        ent = torch.stack([dst_row, dest * 16 + rowc], dim=1).to(torch.int32)[order_ix]
+        self._push_ptr = ptr.to(dev).contiguous()
+        self._push_ent = (ent.to(dev).contiguous() if ent.numel()
+                          else torch.zeros((1, 2), dtype=torch.int32, device=dev))
+        sizes = tr.allgather_counts([n_own, int(self.need64.numel()), int(self.device)])
+        n_own_max, pool_max = max(x[0] for x in sizes), max(x[1] for x in sizes)
+        self.device_barrier = len({x[2] for x in sizes}) == world   # every rank on its own GPU
+        sb, fo = C.c_size_t(), C.c_size_t()
+        p._check(p.lib.pyqed_heom_shard_state_bytes(p._h, n_own_max, pool_max, C.byref(sb), C.byref(fo)))
+        self.state_nbytes = sb.value
+        ptr_own, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        p._check(p.lib.pyqed_heom_shared_alloc(self.device, sb.value, C.byref(ptr_own), handle))
+        self._state_ptr = ptr_own.value
+        handles = tr.allgather_object(bytes(handle))
+        self._peer_ptrs = []
+        for q in range(world):
+            if q == rank:
+                self._peer_ptrs.append(self._state_ptr)
+                continue
+            hq, pq = (C.c_uint8 * 64).from_buffer_copy(handles[q]), C.c_void_p()
+            p._check(p.lib.pyqed_heom_shared_open(self.device, hq, C.byref(pq)))
+            self._peer_ptrs.append(pq.value)
+        peers = (C.c_uint64 * world)(*self._peer_ptrs)
+        need_dev = self.need64.to(dev)
+        self._keep = (need_dev,)
+        p._check(p.lib.pyqed_heom_shard_setup(
+            p._h, rank, world, lo, hi, n_own_max, pool_max, C.c_void_p(need_dev.data_ptr()), need_dev.numel(),
+            C.c_void_p(self._push_ptr.data_ptr()), C.c_void_p(self._push_ent.data_ptr()), int(si.numel()),
+            C.c_void_p(self._state_ptr), sb.value, peers, int(self.device_barrier)))
+        self.native = True
+        self.fused = True
+        self.elems = 2 * self.n
+        self.owner_of_sys = next(r for r in range(world) if self.bounds[r] <= p.info("slot0") < self.bounds[r + 1])
+        tr.barrier()   # every rank's flags are zeroed and its buffer mapped before anyone pushes
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (rank-local layout only)."""
+        if getattr(self, "plan", None) is None:
+            return
+        if self.native and getattr(self, "_state_ptr", None):
+            p = self.plan
+            self.tr.barrier()
+            for q, ptr in enumerate(self._peer_ptrs):
+                if q != self.rank:
+                    p.lib.pyqed_heom_shared_close(self.device, ptr)
+            p.lib.pyqed_heom_shared_free(self.device, self._state_ptr)
+            self._state_ptr = None
+        self.plan.close()
+
+    def _host_barrier(self):
+        self.plan.synchronize()
+        self.tr.barrier()
+
+    def _native_propagate(self, dt, nt, traj):
+        import ctypes as C
+        p = self.plan
+        tp = None if traj is None else C.c_void_p(traj.data_ptr())
+        if self.device_barrier:
+            p._check(p.lib.pyqed_heom_shard_propagate(p._h, float(dt), int(nt), tp))
+            return
+        # ranks sharing a GPU: a spinning barrier kernel would keep the peer's kernels off the
+        # device, so the ranks meet on the host after every stage
+        p._check(p.lib.pyqed_heom_shard_begin(p._h, float(dt), int(nt), tp))
+        self._host_barrier()
+        for i in range(nt):
+            for st in range(4):
+                p._check(p.lib.pyqed_heom_shard_stage(p._h, i, st))
+                self._host_barrier()
+        p._check(p.lib.pyqed_heom_shard_end(p._h))
+
+    def check_barriers(self):
+        import ctypes as C
+        code = C.c_int()
+        self.plan._check(self.plan.lib.pyqed_heom_shard_error(self.plan._h, C.byref(code)))
+        if code.value:
+            raise RuntimeError(f"rank {self.rank}: a device barrier gave up waiting for rank {code.value - 1}")
+
     # -- one halo exchange of array `array_id` -----------------------------
     def exchange(self, array_id):
         import ctypes as C
@@ -276,6 +420,8 @@ class ShardedDEOM:
                                             C.c_void_p(self.recvbuf.data_ptr()), 1))
 
     def halo_bytes_per_stage(self):
+        if self.native:
+            return self.need64.numel() * self.elems * 8
         return self.need32.numel() * self.elems * 8
 
     # -- propagation ---------------------------------------------------------
@@ -283,6 +429,12 @@ class ShardedDEOM:
         rho0 = np.asarray(rho0, dtype=C128).reshape(1, self.n, self.n)
         if self.row_items and not np.array_equal(rho0[0], rho0[0].conj().T):
             raise ValueError("row halos assume Hermitian ADOs; rho0 is not Hermitian")
+        if self.native:
+            from .._cabi import _dptr
+            r = np.ascontiguousarray(rho0[0])
+            self.plan._check(self.plan.lib.pyqed_heom_shard_set_state(self.plan._h, _dptr(r.view(np.float64))))
+            self._host_barrier()   # peers store into this rank's pools: nobody starts before all are zeroed
+            return
         self.plan.set_state(rho0)
         if self.symm is not None:
             # peers store into this rank's arrays: nobody may start pushing before
@@ -296,6 +448,11 @@ class ShardedDEOM:
         import ctypes as C
         p = self.plan
         dp = C.POINTER(C.c_double)
+        if self.native:
+            if fsys is not None or fcoup is not None:
+                raise NotImplementedError("the rank-local sharded layout propagates time-independent "
+                                          "operators only: construct ShardedDEOM(native=False) for pulses")
+            return self._native_propagate(dt, nt, traj)
 
         def field(f):
             if f is None:
@@ -328,6 +485,21 @@ class ShardedDEOM:
         """All ADOs in reference id order on every rank (test helper: each rank
         contributes the slots it owns)."""
         p = self.plan
+        if self.native:
+            from .._cabi import _dptr
+            import ctypes as C
+            n_own = self.hi - self.lo
+            own = np.zeros((max(n_own, 1), self.n, self.n), dtype=C128)
+            ids = np.zeros(max(n_own, 1), dtype=np.int32)
+            p._check(p.lib.pyqed_heom_shard_get_owned(p._h, _dptr(own.view(np.float64)),
+                                                      ids.ctypes.data_as(C.POINTER(C.c_int32))))
+            full = np.zeros((self.nmax, self.n, self.n), dtype=C128)
+            full[ids[:n_own]] = own[:n_own]
+            t = torch.from_numpy(np.ascontiguousarray(full).view(np.float64))
+            if self.tr.nccl:
+                t = t.cuda()
+            self.tr.allreduce_sum(t)
+            return t.cpu().numpy().view(C128).reshape(self.nmax, self.n, self.n)
         full = p.get_ados()[0]
         off = p.info("off_id_of_slot")
         id_of_slot = p._tables[off:off + 4 * self.nmax].view(torch.int32).cpu().numpy()

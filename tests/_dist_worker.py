@@ -145,7 +145,8 @@ def gpu_mode(args):
                            tr, device=dev, order=args.order,
                            tuning=dict(kernel=args.kernel, warps_per_cta=0, use_graph=0),
                            peer_push={-1: None, 0: False, 1: True}[args.push],
-                           fused_push={-1: None, 0: False, 1: True}[args.fused])
+                           fused_push={-1: None, 0: False, 1: True}[args.fused],
+                           native={-1: None, 0: False, 1: True}[args.native])
         nt = int(g["nt"])
         from conftest import pulse_from_samples
         dt = float(g["dt"])
@@ -161,8 +162,13 @@ def gpu_mode(args):
             assert sum(sh.halo.recv_counts) > 0   # a proper sub-range always has foreign neighbours
         if args.kernel == 6:   # did the stages really go through kernel 6 where it applies?
             print(f"rank {tr.rank}: {name} kernel6 stage launches {sh.plan.info('sym_launches')} of {4 * nt}", flush=True)
-        print(f"rank {tr.rank}: {name} push={sh.symm is not None} fused={sh.fused} ok (owned {sh.hi - sh.lo} of {sh.nmax}, halo items "
-              f"{sh.need32.numel()}, row items {sh.row_items}, err {err:.1e})", flush=True)
+        items = sh.halo_bytes_per_stage() // (sh.elems * 8)
+        if sh.native:
+            sh.check_barriers()
+        print(f"rank {tr.rank}: {name} native={sh.native} packed={sh.plan.info('shard_packed')} "
+              f"push={sh.symm is not None} fused={sh.fused} ok (owned {sh.hi - sh.lo} of {sh.nmax}, halo items "
+              f"{items}, row items {sh.row_items}, err {err:.1e})", flush=True)
+        sh.close()
 
 
 if __name__ == "__main__":
@@ -174,6 +180,7 @@ if __name__ == "__main__":
     ap.add_argument("--push", type=int, default=-1)
     ap.add_argument("--fused", type=int, default=-1)
     ap.add_argument("--kernel", type=int, default=0, help="stage kernel (tuning), e.g. 6")
+    ap.add_argument("--native", type=int, default=-1, help="rank-local arrays + fused peer stores: 1 require, 0 never")
     a = ap.parse_args()
     dist.init_process_group(a.backend)
     try:

@@ -76,35 +76,77 @@ int main(int argc, char** argv) {
         emu_async_run(N, K, M, L, nmax, H.data(), ops.data(), cbase.data(), kmode.data(), supp.data(), damp.data(),
                       link_ptr.data(), links.data(), s3g.data(), dtv[0], nt, hreal, 0, 0, 3, 2, parts, 2, 0, 0,
                       nullptr);
-        // two ranks with their own state buffers and kernel 6's fused push (no exchange by the
-        // host): every rank must end up with kernel 6's single-rank result on the slots it owns
-        {
+        // two ranks with rank-local arrays (own ADOs + pool of halo rows, heom_shard.cu in miniature)
+        // and the fused push, on full matrices (kernel 6) and on upper triangles (kernel 7): every
+        // rank must end up with kernel 6's single-rank result on the slots it owns.  The arrays are
+        // sized exactly, so any access outside them is an AddressSanitizer error.
+        for (int packed = 0; packed < 2; ++packed) {
             const long long lo[2] = {0, nmax / 2 + 1}, hi[2] = {nmax / 2 + 1, nmax};
-            std::vector<std::vector<double>> st(2, std::vector<double>(4 * asz, std::nan("")));
+            const int PK = N * (N + 1) / 2, EL = packed ? PK : (int)NN;
+            std::vector<int> links2(2 * (size_t)nlinks);
+            if (emu_convert_links(links.data(), links2.data(), nlinks, N, L, &err)) return 1;
+            std::vector<std::vector<long long>> need(2);
+            std::vector<std::vector<int>> loc(2, links2);
             for (int r = 0; r < 2; ++r) {
-                for (size_t i = 0; i < asz; ++i) st[r][i] = 0.0;           // Y: every rank starts from the full state
-                for (size_t i = 0; i < 2 * NN; ++i) st[r][i] = rho0[i];
-            }
-            std::vector<std::vector<int>> pptr(2);
-            std::vector<std::vector<unsigned char>> pent(2);
-            for (int r = 0; r < 2; ++r) {   // rows of rank r's slots that the other rank's links read
-                std::vector<std::vector<unsigned char>> per((size_t)(hi[r] - lo[r]));
-                const int q = 1 - r;
-                for (long long n = lo[q]; n < hi[q]; ++n)
-                    for (int l = link_ptr[n]; l < link_ptr[n + 1]; ++l) {
-                        const long long nb = links[2 * l];
-                        const unsigned char ent = (unsigned char)((q << 4) | ((links[2 * l + 1] >> 16) & 0xf));
-                        if (nb >= lo[r] && nb < hi[r]) {
-                            auto& v = per[(size_t)(nb - lo[r])];
-                            if (std::find(v.begin(), v.end(), ent) == v.end()) v.push_back(ent);
-                        }
+                for (int l = link_ptr[lo[r]]; l < link_ptr[hi[r]]; ++l) {
+                    const long long nb = links2[2 * l];
+                    if (nb < lo[r] || nb >= hi[r]) need[r].push_back(nb * 8 + (links2[2 * l + 1] & 15));
+                }
+                std::sort(need[r].begin(), need[r].end());
+                need[r].erase(std::unique(need[r].begin(), need[r].end()), need[r].end());
+                for (int l = link_ptr[lo[r]]; l < link_ptr[hi[r]]; ++l) {
+                    const long long nb = loc[r][2 * l];
+                    if (nb >= lo[r] && nb < hi[r]) {
+                        loc[r][2 * l] = (int)(nb - lo[r]);
+                    } else {
+                        const long long item = nb * 8 + (loc[r][2 * l + 1] & 15);
+                        loc[r][2 * l] = (int)(std::lower_bound(need[r].begin(), need[r].end(), item) - need[r].begin());
+                        loc[r][2 * l + 1] |= 16;
                     }
+                }
+            }
+            const long long n_own_max = std::max(hi[0] - lo[0], hi[1] - lo[1]);
+            const long long pool_max = (long long)std::max(need[0].size(), need[1].size());
+            const long long pool_off = n_own_max * EL, arr = pool_off + pool_max * N;
+            std::vector<std::vector<double>> st(2, std::vector<double>(2 * 4 * (size_t)arr, std::nan("")));
+            auto elem = [&](long long slot_local, int i, int j) {   // offset (double2) of element (i, j), i <= j if packed
+                return packed ? slot_local * EL + i * N - i * (i - 1) / 2 + (j - i) : slot_local * EL + i * N + j;
+            };
+            for (int r = 0; r < 2; ++r) {   // Y: zeros, ADO 0 = rho0 on its owner
+                for (long long e = 0; e < (hi[r] - lo[r]) * EL; ++e) st[r][2 * e] = st[r][2 * e + 1] = 0.0;
+                if (lo[r] == 0)
+                    for (int i = 0; i < N; ++i)
+                        for (int j = packed ? i : 0; j < N; ++j) {
+                            st[r][2 * elem(0, i, j)] = rho0[2 * (i * N + j)];
+                            st[r][2 * elem(0, i, j) + 1] = rho0[2 * (i * N + j) + 1];
+                        }
+            }
+            auto row_value = [&](int r, long long slot, int row, int j, int arrid, int part) {   // element (row, j) of an owned ADO
+                const int i0 = packed ? std::min(row, j) : row, j0 = packed ? std::max(row, j) : j;
+                const double v = st[r][2 * ((size_t)arrid * arr + elem(slot - lo[r], i0, j0)) + part];
+                return (packed && part == 1 && j < row) ? -v : v;
+            };
+            for (int r = 0; r < 2; ++r)   // halo rows of the stage-0 input (what shard_begin pushes)
+                for (size_t i = 0; i < need[r].size(); ++i)
+                    for (int j = 0; j < N; ++j)
+                        for (int part = 0; part < 2; ++part)
+                            st[r][2 * (pool_off + (long long)i * N + j) + part] =
+                                row_value(1 - r, need[r][i] >> 3, (int)(need[r][i] & 7), j, 0, part);
+            std::vector<std::vector<int>> pptr(2), pent(2);
+            for (int r = 0; r < 2; ++r) {   // rows of rank r's slots that the other rank's links read
+                std::vector<std::vector<int>> per((size_t)(hi[r] - lo[r]));
+                const int q = 1 - r;
+                for (size_t i = 0; i < need[q].size(); ++i) {
+                    auto& v = per[(size_t)((need[q][i] >> 3) - lo[r])];
+                    v.push_back((int)i);
+                    v.push_back((q << 4) | (int)(need[q][i] & 7));
+                }
                 pptr[r].push_back(0);
                 for (auto& v : per) {
                     pent[r].insert(pent[r].end(), v.begin(), v.end());
-                    pptr[r].push_back((int)pent[r].size());
+                    pptr[r].push_back((int)pent[r].size() / 2);
                 }
-                if (pent[r].empty()) pent[r].push_back(0);
+                if (pent[r].empty()) pent[r].assign(2, 0);
             }
             const unsigned long long peers[2] = {(unsigned long long)(uintptr_t)st[0].data(),
                                                  (unsigned long long)(uintptr_t)st[1].data()};
@@ -115,22 +157,25 @@ int main(int argc, char** argv) {
                 for (const auto& p : plan)
                     for (int r = 0; r < 2; ++r) {
                         double* b = st[r].data();
-                        if (emu_sym_stage(N, K, M, L, H.data(), ops.data(), cbase.data(), kmode.data(), damp.data(),
-                                          link_ptr.data(), links.data(), nlinks, b + p.yin * asz, b, b + asz,
-                                          b + 2 * asz, b + p.out * asz, p.a, p.w, p.kind, hreal, 2, 2, lo[r], hi[r],
-                                          nmax, pptr[r].data(), pent[r].data(), peers, (long long)p.out * nmax * NN,
-                                          &err)) {
+                        if (emu_sym_stage(N, K, M, L, H.data(), ops.data(), cbase.data(), kmode.data(),
+                                          damp.data() + 2 * lo[r], link_ptr.data() + lo[r], loc[r].data(),
+                                          b + 2 * p.yin * arr, b, b + 2 * arr, b + 4 * arr, b + 2 * p.out * arr, p.a, p.w,
+                                          p.kind, hreal, 2, 2, hi[r] - lo[r], packed, pool_off, pptr[r].data(),
+                                          pent[r].data(), peers, (long long)p.out * arr + pool_off, &err)) {
                             std::cerr << "fused push failed: " << err << "\n";
                             return 1;
                         }
                     }
             double dpush = 0.0;
             for (int r = 0; r < 2; ++r)
-                for (size_t i = 2 * NN * (size_t)lo[r]; i < 2 * NN * (size_t)hi[r]; ++i) {
-                    const double d = std::fabs(st[r][i] - s6[i]);
-                    if (!(d <= dpush)) dpush = d;
-                }
-            std::cout << "late=" << late << " |fused-push ranks - k6|=" << dpush << "\n";
+                for (long long slot = lo[r]; slot < hi[r]; ++slot)
+                    for (int i = 0; i < N; ++i)
+                        for (int j = 0; j < N; ++j)
+                            for (int part = 0; part < 2; ++part) {
+                                const double d = std::fabs(row_value(r, slot, i, j, 0, part) - s6[2 * ((size_t)slot * NN + i * N + j) + part]);
+                                if (!(d <= dpush)) dpush = d;
+                            }
+            std::cout << "late=" << late << " packed=" << packed << " |fused-push ranks - k6|=" << dpush << "\n";
             if (!(dpush == 0.0)) bad = 1;
         }
         s6.resize(asz);

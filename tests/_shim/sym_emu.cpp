@@ -95,19 +95,27 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
     return 0;
 }
 
-// One stage of one rank: kernel 6 over the owned range [lo, hi) of the arrays given (a sharded
-// run in miniature - the caller moves the halo rows between the ranks' arrays).
+// links (slot, meta) -> links2 with the product's converter
+int emu_convert_links(const int* links, int* links2, long long nlinks, int N, int L, const char** err) {
+    static const char* none = "";
+    *err = none;
+    return heom_sym_convert_links(reinterpret_cast<const int2*>(links), reinterpret_cast<int2*>(links2), nlinks, N, L,
+                                  nullptr, err);
+}
+
+// One stage of one rank of a sharded run with rank-local arrays (heom_shard.cu in miniature): the
+// arrays hold the rank's n_own ADOs (full matrices or upper triangles) followed by its pool of
+// halo rows; `links2` is the rank's localized link table (local slots / pool rows), `link_ptr`
+// the CSR offsets of its owned slots.  With push tables the PUSH instantiation stores the rows
+// other ranks read into their pools (peer[q] = base address of rank q's state).
 int emu_sym_stage(int N, int K, int M, int L, const double* H, const double* ops, const double* cbase,
-                  const int* kmode, const double* damp, const int* link_ptr, const int* links, long long nlinks,
+                  const int* kmode, const double* damp, const int* link_ptr, const int* links2,
                   const double* yin, const double* y, const double* s1, const double* s2, double* out, double a,
-                  double w, int stage_kind, int hreal, int sm_count, int warps, long long lo, long long hi,
-                  long long nmax, const int* push_ptr, const unsigned char* push_ent,
+                  double w, int stage_kind, int hreal, int sm_count, int warps, long long n_own, int packed,
+                  long long pool_off, const int* push_ptr, const int* push_ent,
                   const unsigned long long* peer, long long out_elem_off, const char** err) {
     static const char* none = "";
     *err = none;
-    std::vector<int2> links2((size_t)std::max(1ll, nlinks));
-    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
-        return 1;
     long long step_base = 0;
     SymLaunch s{};
     s.a.yin = reinterpret_cast<const double2*>(yin);
@@ -117,29 +125,37 @@ int emu_sym_stage(int N, int K, int M, int L, const double* H, const double* ops
     s.a.out = reinterpret_cast<double2*>(out);
     s.a.damp = reinterpret_cast<const double2*>(damp);
     s.a.link_ptr = link_ptr;
-    s.a.links2 = links2.data();
+    s.a.links2 = reinterpret_cast<const int2*>(links2);
     s.a.cbase = reinterpret_cast<const double2*>(cbase);
     s.a.kmode = kmode;
     s.a.ops = reinterpret_cast<const double2*>(ops);
     s.a.step_base = &step_base;
+    s.a.slot0 = -1;
     s.a.a = a;
     s.a.w = w;
     s.a.nind = K;
     s.a.nmod = M;
     s.a.lmax = L;
+    s.a.pool_off = (unsigned)pool_off;
     s.a.push_ptr = push_ptr;     // null: no fused push
-    s.a.push_ent = push_ent;
+    s.a.push_ent = reinterpret_cast<const int2*>(push_ent);
     s.a.peer = peer;
     s.a.out_elem_off = out_elem_off;
+    s.push = push_ptr ? 1 : 0;
+    s.packed = packed;
     s.H = H;
     s.N = N; s.K = K; s.M = M; s.L = L; s.B = 1;
     s.stage = stage_kind;
     s.hreal = hreal;
     s.warps = warps;
     s.sm_count = sm_count;
-    s.part_lo = lo;
-    s.part_hi = hi;
-    s.batch_elems = nmax * N * N;
+    s.part_lo = 0;
+    s.part_hi = n_own;
+    s.batch_elems = 0;
+    if (g_dyn) {
+        s.sched = &g_sched_ctr;
+        s.sched_total = &g_sched_total;
+    }
     return heom_sym_launch(s, err);
 }
 

@@ -200,7 +200,7 @@ def test_kernel6_sharded_ranks_sharing_one_device(world, order):
     exchanged on full matrices; gloo transport staged through the host).  Projector
     couplings go through kernel 6, sigma_z and dense ones fall back."""
     from test_sharded import _launch
-    out = _launch(world, ["gpu", "--backend", "gloo", "--order", str(order), "--kernel", "6", "--cases",
+    out = _launch(world, ["gpu", "--backend", "gloo", "--order", str(order), "--kernel", "6", "--native", "0", "--cases",
                           "deom_fmo_K21_L2,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
     assert out.count(" ok (owned") == 4 * world
     import re
@@ -221,7 +221,8 @@ def test_kernel6_fused_push_two_gpus():
     out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", "1", "--fused", "1", "--kernel", "6",
                       "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_spin_boson_L10"])
     assert out.count(" ok (owned") == 6
-    assert out.count("fused=True") == 6
+    # FMO: rank-local layout (fused by construction); sigma_z: legacy fused push of kernel 3
+    assert out.count("fused=True") == 6 and out.count("native=True") == 4
     import re
     for m in re.finditer(r"rank \d+: (\S+) kernel6 stage launches (\d+) of (\d+)", out):
         assert int(m.group(2)) == (int(m.group(3)) if "fmo" in m.group(1) else 0), m.group(0)

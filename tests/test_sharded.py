@@ -49,9 +49,26 @@ def test_cost_balanced_bounds():
 def test_sharded_gpu_ranks_sharing_one_device(world, order):
     """The real kernels and pack/unpack with several ranks on one GPU (gloo
     transport staged through the host); projector, sigma_z and dense couplings."""
-    out = _launch(world, ["gpu", "--backend", "gloo", "--order", str(order), "--cases",
+    out = _launch(world, ["gpu", "--backend", "gloo", "--order", str(order), "--native", "0", "--cases",
                           "deom_fmo_K21_L2,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
     assert out.count(" ok (owned") == 4 * world
+    assert out.count("native=False") == 4 * world
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,kernel", [(2, 0), (3, 0), (2, 6), (4, 7)])
+def test_rank_local_layout_ranks_sharing_one_device(world, kernel):
+    """The rank-local layout (``csrc/heom_shard.cu``): arrays of own ADOs + halo row pool,
+    localized link table, rows stored into the peers' pools by the stage kernel's epilogue
+    through CUDA-IPC mappings.  Several ranks share the one GPU of the test box (gloo for the
+    plumbing, a host barrier per stage instead of the device flag barrier); the peer stores, the
+    push tables and the pool reads are the ones a multi-GPU run uses.  FMO cases take the layout
+    (kernel 7 = packed storage unless kernel 6 is asked for), the others fall back."""
+    out = _launch(world, ["gpu", "--backend", "gloo", "--order", "2", "--kernel", str(kernel), "--cases",
+                          "deom_fmo_K21_L3,deom_fmo_K21_L2,deom_fmo_K7_L4,deom_spin_boson_L10"])
+    assert out.count(" ok (owned") == 4 * world
+    assert out.count("native=True") == 3 * world and out.count("native=False") == world
+    assert out.count("native=True packed=%d" % (0 if kernel == 6 else 1)) == 3 * world
 
 
 @pytest.mark.gpu
@@ -63,8 +80,22 @@ def test_sharded_nccl_two_gpus(push, fused):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", str(push), "--fused", str(fused),
+                      "--native", "0",
                       "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
     assert out.count(" ok (owned") == 8
     assert out.count(f"push={bool(push)}") == 8
     # the dense-Q case cannot use the fused path (it needs the diagonal-Q kernel)
     assert out.count("fused=True") == (6 if fused else 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", [0, 6])
+def test_rank_local_layout_two_gpus(kernel):
+    """The same on two GPUs: peer stores over NVLink and the device flag barrier
+    (``pyqed_heom_shard_propagate``: no host round trip inside a run)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--kernel", str(kernel), "--native", "1",
+                      "--cases", "deom_fmo_K21_L3,deom_fmo_K21_L2,deom_fmo_K7_L4"])
+    assert out.count(" ok (owned") == 6 and out.count("native=True") == 6

@@ -228,73 +228,119 @@ def test_more_warps_than_groups(emu):
     check(emu, w, nt=3, sm_count=4, warps=4)
 
 
+def _pack(full):
+    n = full.shape[-1]
+    iu = np.triu_indices(n)
+    return np.ascontiguousarray(full[..., iu[0], iu[1]])
+
+
+def _unpack(tri, n):
+    iu = np.triu_indices(n)
+    full = np.zeros(tri.shape[:-1] + (n, n), dtype=C128)
+    full[..., iu[0], iu[1]] = tri
+    low = np.conj(np.swapaxes(full, -1, -2))
+    idx = np.tril_indices(n, -1)
+    full[..., idx[0], idx[1]] = low[..., idx[0], idx[1]]
+    return full
+
+
 @pytest.mark.parametrize("shape", ["fmo N=7", "even N=4"])
+@pytest.mark.parametrize("packed", [False, True])
 @pytest.mark.parametrize("fused", [False, True])
-def test_sharded_ranks_read_only_their_halo_rows(emu, fused, shape):
-    """Two ranks with separate arrays: everything a rank does not own is NaN except
-    the rows its links point at (the halo rows ``sharded.needed_items`` exchanges).
-    Kernel 6 must reproduce the oracle from that alone - one NaN read would poison
-    the result.  ``fused``: no exchange by the test at all - the PUSH instantiation's
-    epilogue stores the rows the other rank needs into that rank's arrays itself
-    (bulk shared->global stores, push tables as ``ShardedDEOM`` builds them)."""
-    # odd N: unpadded tiles; even N: padded k tile (row stride N + 1)
+def test_sharded_ranks_with_local_arrays(emu, fused, packed, shape):
+    """The rank-local layout of ``csrc/heom_shard.cu`` with two ranks: a rank's arrays hold only
+    its own ADOs (full matrices, or upper triangles = kernel 7) followed by a pool of halo rows,
+    its link table points at local slots and pool rows.  Everything starts as NaN, so a read of
+    anything that was not owned or exchanged would poison the result.  ``fused``: no exchange by
+    the test at all - the PUSH instantiation's epilogue stores the rows the other rank reads
+    into that rank's pool (bulk shared->global stores, tables as ``ShardedDEOM`` builds them)."""
     w = W.fmo(lmax=3, n_matsubara=0) if "fmo" in shape else projector_problem(4, 2, 3, seed=31, complex_h=True)
     o, t = host_tables(w)
     N, nmax, dt, nt = t["N"], o.nmax, w["dt"], 2
+    EL = N * (N + 1) // 2 if packed else N * N
     bounds = [0, 53, nmax]
     ptr, links = t["link_ptr"], t["links"]
-    need = []   # per rank: (slot, row) pairs of foreign rows its owned ADOs read
+    err = ctypes.c_char_p()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    links2 = np.zeros_like(links)
+    assert emu.emu_convert_links(p(links), p(links2), ctypes.c_longlong(len(links)), ctypes.c_int(N),
+                                 ctypes.c_int(o.lmax), ctypes.byref(err)) == 0
+    need, local_links = [], []   # per rank: sorted (slot, row) of foreign rows; localized link table
     for r in range(2):
         lo, hi = bounds[r], bounds[r + 1]
-        rec = links[ptr[lo]:ptr[hi]]
+        rec = links2[ptr[lo]:ptr[hi]]
         foreign = (rec[:, 0] < lo) | (rec[:, 0] >= hi)
-        need.append(sorted({(int(s_), int((m_ >> 16) & 0xf)) for s_, m_ in rec[foreign]}))
-        assert need[-1]
-    state = np.full((2, 4, nmax, N, N), np.nan, dtype=C128)   # rank, (Y, SA, SB, ACC)
+        nd = sorted({(int(s_), int(y_ & 15)) for s_, y_ in rec[foreign]})
+        assert nd
+        need.append(nd)
+        pos = {item: i for i, item in enumerate(nd)}
+        loc = links2.copy()
+        for l in range(ptr[lo], ptr[hi]):
+            nb, y_ = int(loc[l, 0]), int(loc[l, 1])
+            if lo <= nb < hi:
+                loc[l, 0] = nb - lo
+            else:
+                loc[l] = (pos[(nb, y_ & 15)], y_ | 16)      # SYM_LINK_POOL
+        local_links.append(loc)
+    n_own = [bounds[1], nmax - bounds[1]]
+    n_own_max, pool_max = max(n_own), max(len(x) for x in need)
+    pool_off = n_own_max * EL
+    arr_elems = pool_off + pool_max * N
+    state = np.full((2, 4, arr_elems), np.nan, dtype=C128)   # rank, (Y, SA, SB, ACC)
     y0 = np.zeros((nmax, N, N), C128)
     y0[0] = w["rho0"]
     for r in range(2):
-        state[r, 0, bounds[r]:bounds[r + 1]] = y0[bounds[r]:bounds[r + 1]]
+        own = y0[bounds[r]:bounds[r + 1]]
+        state[r, 0, :n_own[r] * EL] = (_pack(own) if packed else own).reshape(-1)
+
+    def own_ados(r, arr):
+        flat = state[r, arr, :n_own[r] * EL]
+        return _unpack(flat.reshape(n_own[r], EL), N) if packed else flat.reshape(n_own[r], N, N)
 
     def exchange(arr):
+        full = [own_ados(r, arr) for r in range(2)]
         for r in range(2):
-            for slot, row in need[r]:
-                state[r, arr, slot, row] = state[1 - r, arr, slot, row]
+            for i, (slot, row) in enumerate(need[r]):
+                src = full[1 - r][slot - bounds[1 - r], row]
+                state[r, arr, pool_off + i * N: pool_off + (i + 1) * N] = src
     exchange(0)
-    # push tables of rank r: CSR over its owned slots, entry = peer << 4 | row
+    # push tables of rank r: CSR over its owned slots, entry = (row index in the peer's pool, peer << 4 | row)
     push_ptr, push_ent = [], []
     for r in range(2):
         lo, hi = bounds[r], bounds[r + 1]
         per_slot = [[] for _ in range(hi - lo)]
-        for slot, row in need[1 - r]:          # what the other rank reads from this one
-            per_slot[slot - lo].append(((1 - r) << 4) | row)
+        for i, (slot, row) in enumerate(need[1 - r]):          # what the other rank reads from this one
+            per_slot[slot - lo].append((i, ((1 - r) << 4) | row))
         push_ptr.append(np.concatenate([[0], np.cumsum([len(x) for x in per_slot])]).astype(np.int32))
-        push_ent.append(np.array([e for x in per_slot for e in x] or [0], dtype=np.uint8))
+        push_ent.append(np.array([e for x in per_slot for e in x] or [(0, 0)], dtype=np.int32))
     peers = np.array([state[0].ctypes.data, state[1].ctypes.data], dtype=np.uint64)
     H = np.ascontiguousarray(o.H0)
-    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     emu.emu_sym_stage.restype = ctypes.c_int
     plan = [(0, 1, 0, dt / 2, 0.0), (1, 2, 1, dt / 2, 0.0), (2, 3, 1, dt, 0.0), (3, 0, 2, 2.0 / dt, dt / 6)]
     for _ in range(nt):
         for yin, out, kind, a, wgt in plan:
             for r in range(2):
-                err = ctypes.c_char_p()
                 st = state[r]
+                lo, hi = bounds[r], bounds[r + 1]
+                damp_r = np.ascontiguousarray(t["damp"][lo:hi])
+                ptr_r = np.ascontiguousarray(ptr[lo:hi + 1])
                 rc = emu.emu_sym_stage(
                     ctypes.c_int(N), ctypes.c_int(t["K"]), ctypes.c_int(t["M"]), ctypes.c_int(o.lmax), p(H),
-                    p(t["ops"]), p(t["cbase"]), p(t["kmode"]), p(t["damp"]), p(ptr), p(links),
-                    ctypes.c_longlong(len(links)), p(st[yin]), p(st[0]), p(st[1]), p(st[2]), p(st[out]),
+                    p(t["ops"]), p(t["cbase"]), p(t["kmode"]), p(damp_r), p(ptr_r), p(local_links[r]),
+                    p(st[yin]), p(st[0]), p(st[1]), p(st[2]), p(st[out]),
                     ctypes.c_double(a), ctypes.c_double(wgt), ctypes.c_int(kind),
                     ctypes.c_int(int(np.all(H.imag == 0))), ctypes.c_int(2), ctypes.c_int(2),
-                    ctypes.c_longlong(bounds[r]), ctypes.c_longlong(bounds[r + 1]), ctypes.c_longlong(nmax),
+                    ctypes.c_longlong(n_own[r]), ctypes.c_int(int(packed)), ctypes.c_longlong(pool_off),
                     p(push_ptr[r]) if fused else None, p(push_ent[r]) if fused else None,
-                    p(peers) if fused else None, ctypes.c_longlong(out * nmax * N * N), ctypes.byref(err))
+                    p(peers) if fused else None, ctypes.c_longlong(out * arr_elems + pool_off), ctypes.byref(err))
                 assert rc == 0, err.value
             if not fused:
                 exchange(out)
     o.run(w["rho0"], dt, nt)
-    got = np.concatenate([state[0, 0, :bounds[1]], state[1, 0, bounds[1]:]])
+    got = np.concatenate([own_ados(0, 0), own_ados(1, 0)])
     assert np.isfinite(got).all()
     assert np.abs(got - o.ddos).max() < 1e-12
-    # what a rank does not own and does not need was never written
-    assert np.isnan(state[0, 0, bounds[1]:]).any() and np.isnan(state[1, 0, :bounds[1]]).any()
+    # pool rows nobody asked for were never written
+    for r in range(2):
+        if len(need[r]) < pool_max:
+            assert np.isnan(state[r, 0, pool_off + len(need[r]) * N:]).all()
