@@ -51,15 +51,15 @@ DEFAULT_WORKLOAD = "fmo7_K21_L8"
 
 def measured_traffic(workload, kernel, order):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/r01_traffic.json), if it was taken for this workload/kernel/order."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as fh:
-            t = json.load(fh)
-        if (t["workload"], t["kernel"]) == (workload, kernel) and t["storage_order"] == order:
-            return t["dram_bytes_per_launch_avg"]
-    except Exception:
-        pass
+    (profiles/r02_traffic.json, r01_traffic.json), if it was taken for this workload/kernel/order."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                t = json.load(fh)
+            if (t["workload"], t["kernel"]) == (workload, kernel) and t["storage_order"] == order:
+                return t["dram_bytes_per_launch_avg"]
+        except Exception:
+            pass
     return None
 
 
@@ -175,7 +175,9 @@ def cpu_native_leg(workload_name, budget_s=10.0, steps=None):
     from oracle import c_oracle
     w = WORKLOADS[workload_name]()
     nind, depth = len(w["expn"]), w["lmax"]
-    while depth > 1 and comb(depth + nind, depth) > 70000:
+    # largest depth whose arrays are well out of the last-level cache but whose step still takes
+    # well under a second (K = 21: depth 6, 296 010 ADOs, 232 MB per array)
+    while depth > 1 and comb(depth + nind, depth) > 300000:
         depth -= 1
     nmax = comb(depth + nind, depth)
     # every core this process may run on (torchrun's OMP_NUM_THREADS=1 default is not a limit)
@@ -191,11 +193,15 @@ def cpu_native_leg(workload_name, budget_s=10.0, steps=None):
     t1 = go(1)
     nt = steps if steps is not None else max(2, min(400, int(budget_s / max(t1, 1e-4))))
     el = go(nt)
-    return dict(value=nmax * nt / el, unit=UNIT, cores=threads, kind="port",
-                sample=(f"{workload_name} operators and bath at depth {depth} ({nmax} ADOs) instead of "
-                        f"{w['lmax']}, {nt} RK4 steps in {el:.1f} s, C/OpenMP restatement of "
+    full = comb(w["lmax"] + nind, w["lmax"])
+    return dict(value=nmax * nt / el, unit=UNIT, cores=threads, kind="port", n_ado=nmax, depth=depth,
+                sample=(f"{workload_name} operators and bath at depth {depth} ({nmax} ADOs, "
+                        f"{nmax * w['system'].shape[0] ** 2 * 16 / 1e6:.0f} MB per array) instead of depth "
+                        f"{w['lmax']} ({full} ADOs), {nt} RK4 steps in {el:.1f} s, C/OpenMP restatement of "
                         f"generate_dot_element/rk4 (deom.py:641-766), dense N x N products per term, "
-                        f"{threads} threads")), el, nt
+                        f"{threads} threads; the work per ADO-step does not depend on the depth, so ADO-steps/s "
+                        f"at full depth is expected to be the same or lower (more cache misses): "
+                        f"{full / (nmax * nt / el):.1f} s per RK4 step extrapolated")), el, nt
 
 
 def cpu_batched_leg(workload_name, budget_s=6.0):
@@ -263,7 +269,9 @@ def run_reference_arm(args):
         "data": "synthetic",
         "config": {"workload": args.workload, "nsys": int(w["system"].shape[0]),
                    "nind": int(len(w["expn"])), "lmax": int(w["lmax"]),
-                   "note": "CPU leg runs a bounded sample, see cpu_baseline.sample"},
+                   "sample_depth": cb["depth"], "sample_n_ado": cb["n_ado"],
+                   "note": "CPU leg runs a bounded sample of the workload (same operators and bath, reduced "
+                           "hierarchy depth), see cpu_baseline.sample"},
         "cpu_baseline": cb,
         "cpu_baseline_python_loop": py,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -273,122 +281,47 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------
-# kernel 6 (opt-in stage kernel, heom_stage_sym.cu): measured beside the headline
-# in a child process so that nothing it does can disturb the headline numbers
+# correctness evidence carried by the bench line
 # ---------------------------------------------------------------------------
-def kernel6_child(args):
-    """Runs in its own process: for kernel 6 and kernel 7 (packed Hermitian storage),
-    parity against kernel 3 on a small hierarchy, then the device-timed propagation
-    of the workload.  Prints one JSON object."""
-    import torch
+RHO_REF = os.path.join(ROOT, "profiles", "r02_rho_sys_n1.json")
+
+
+def fixture_parity(multi, transport, device, order, tuning, options, native):
+    """The path that is being timed, run on the reference's own output: the fixture
+    tests/golden/deom_fmo_K21_L3.npz (same operators and bath as the headline workload at depth
+    3, trajectory and final ADOs written by the unmodified reference, tests/golden/make_golden.py).
+    Returns max |rho_sys(t) - reference| over the trajectory (and over all final ADOs)."""
     from pyqed_b200.heom import DEOMSolver, Bath
-    from pyqed_b200 import workloads as W
-    torch.cuda.set_device(0)
-
-    def solver_for(w, kernel, prefetch=0):
-        bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
-        s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
-                       w["pulse_system_func"], w["pulse_coupling_func"], lmax=int(w["lmax"]), device=0,
-                       alias_rho0=False)
-        s.tuning = dict(kernel=kernel, warps_per_cta=0, use_graph=0)
-        s.options = {"resident": 0, "prefetch": prefetch}
-        return s
-
-    def ran(plan, kernel, nt):
-        if kernel == 6:
-            return plan.info("sym_launches") == 4 * nt
-        return plan.info("packed_steps") == nt
-
-    # ---- parity first: K=21, depth 3 (2024 ADOs), 12 steps, every ADO
-    small, nt_small = W.fmo(lmax=3, n_matsubara=2), 12
-    ref = solver_for(small, 3)
-    _, traj3 = ref.run(small["rho0"].copy(), small["dt"], nt_small)
-    traj3, ados3 = np.asarray(traj3), np.array(ref.ddos)
-    scale = max(1.0, float(np.abs(ados3).max()))
-    peak, peak_src = peaks()
-    out = {}
-    for kernel, prefetch, label in ((6, 0, "kernel6"), (7, 0, "kernel7_packed"),
-                                    (7, 1, "kernel7_packed_prefetch")):
-        o = {}
-        out[label] = o
-        try:
-            s = solver_for(small, kernel, prefetch)
-            _, traj = s.run(small["rho0"].copy(), small["dt"], nt_small)
-            traj, ados = np.asarray(traj), np.array(s.ddos)
-            o["parity_vs_kernel3"] = {
-                "workload": "fmo7 K=21 L=3 (2024 ADOs), %d RK4 steps" % nt_small,
-                "max_abs_diff_trajectory": float(np.max(np.abs(traj3 - traj))),
-                "max_abs_diff_all_ados": float(np.max(np.abs(ados3 - ados))),
-                "ados_bitwise_hermitian": bool(np.array_equal(ados, ados.conj().transpose(0, 2, 1))),
-                "went_through_the_kernel": bool(ran(s._plan, kernel, nt_small)),
-            }
-            ok = (o["parity_vs_kernel3"]["went_through_the_kernel"]
-                  and o["parity_vs_kernel3"]["max_abs_diff_all_ados"] < 1e-12 * scale
-                  and o["parity_vs_kernel3"]["max_abs_diff_trajectory"] < 1e-12)
-            o["parity_ok"] = bool(ok)
-            if not ok:
-                continue
-            # ---- timing, same recipe as the headline arm (CUDA events, inputs resident in HBM)
-            w = WORKLOADS[args.workload]()
-            K, Wm, dt = args.steps, args.warmup, w["dt"]
-            s = solver_for(w, kernel, prefetch)
-            _, tr1 = s.run(w["rho0"].copy(), dt, 1)
-            plan = s._plan
-            plan.set_state(w["rho0"][None])
-            plan.propagate(dt, Wm, None, None, None, 0)
-            plan.synchronize()
-            plan.stage_timing(True)
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            plan.propagate(dt, K, None, None, None, 0)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms = ev0.elapsed_time(ev1)
-            stage_ms, stage_n = plan.stage_timing(False)
-            # kernel 7 runs the whole propagation in one call (no per-stage events): its stage
-            # time is the step time / 4, pack and unpack passes included
-            avg_launch_ms = stage_ms / stage_n if stage_n else ms / (4 * K)
-            n, nmax = int(w["system"].shape[0]), plan.nmax
-            achieved = 64.0 * n * n * nmax / (avg_launch_ms * 1e-3) / 1e9
-            o.update({
-                "value": nmax * K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
-                "warmup": Wm, "kernel": "stage_rows_sym_kernel" + ("<PACKED>" if kernel == 7 else "")
-                                                    + (" double-buffered tiles" if prefetch else ""),
-                "trace_rho_sys_after_1_step": float(np.trace(np.asarray(tr1)[-1]).real),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "peak_source": peak_src,
-                             "avg_launch_ms": avg_launch_ms,
-                             "note": "algorithmic bytes 256 N^2 per ADO-step as for the headline"
-                                     + ("; kernel 7 moves fewer bytes than that (upper triangles only)"
-                                        if kernel == 7 else "")},
-            })
-            del s, plan
-            torch.cuda.empty_cache()
-        except Exception as exc:  # noqa: BLE001 - report, then try the next kernel
-            o["error"] = repr(exc)[-400:]
-    print(json.dumps(out), flush=True)
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "deom_fmo_K21_L3.npz"), allow_pickle=False))
+    dt, nt = float(g["dt"]), int(g["nt"])
+    if not multi:
+        bath = Bath(expn=g["expn"], etal=g["etal"], etar=g["etar"], etaa=g["etaa"], mode=g["mode"])
+        s = DEOMSolver(g["system"], g["system_dipole"], bath, g["coupling"], g["coupling_dipole"],
+                       lmax=int(g["lmax"]), device=device, order=order, alias_rho0=False)
+        s.tuning, s.options = tuning, dict(options, resident=0)
+        _, traj = s.run(g["rho0"].copy(), dt, nt)
+        ados = np.array(s.ddos)
+    else:
+        from pyqed_b200.heom.sharded import ShardedDEOM
+        sh = ShardedDEOM(g["system"], g["system_dipole"], g["coupling"], g["coupling_dipole"], g["expn"],
+                         g["etal"], g["etar"], g["etaa"], g["mode"], int(g["lmax"]), transport, device=device,
+                         order=order, options=dict(options, resident=0), tuning=tuning, native=native)
+        _, traj = sh.run(g["rho0"], dt, nt)
+        ados = sh.gather_ados()
+        sh.close()
+    return {"fixture": "tests/golden/deom_fmo_K21_L3.npz (reference output, 2024 ADOs, %d steps)" % nt,
+            "max_abs_diff_trajectory": float(np.max(np.abs(np.asarray(traj) - g["traj"]))),
+            "max_abs_diff_all_ados": float(np.max(np.abs(ados - g["ados_final"])))}
 
 
-def kernel6_leg(args):
-    """Parent side: run ``kernel6_child`` in a child process with a time limit."""
-    import subprocess
-    import sys
-    cmd = [sys.executable, os.path.abspath(__file__), "--kernel6-child", "--workload", args.workload,
-           "--steps", str(args.steps), "--warmup", str(args.warmup)]
-    note = ("opt-in stage kernels (tuning kernel=6 / 7), written after this round's GPU budget was spent; "
-            "measured here in a child process, not part of the headline value")
+def rho_reference(workload, steps):
     try:
-        res = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
-        lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
-        if res.returncode != 0 or not lines:
-            return {"note": note, "error": (res.stderr or res.stdout)[-400:], "returncode": res.returncode}
-        out = json.loads(lines[-1])
-        out["note"] = note
-        return out
-    except subprocess.TimeoutExpired:
-        return {"note": note, "error": "child process exceeded 180 s"}
-    except Exception as exc:  # noqa: BLE001 - this leg must never take the bench line down
-        return {"note": note, "error": repr(exc)}
+        with open(RHO_REF) as fh:
+            ref = json.load(fh)
+        v = ref.get(workload, {}).get(str(steps))
+        return None if v is None else np.array(v, dtype=np.float64).view(np.complex128).reshape(-1)
+    except Exception:
+        return None
 
 
 # ---------------------------------------------------------------------------
@@ -406,7 +339,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     if multi:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    order = args.order if args.order >= 0 else (2 if multi else 0)
+    order = args.order if args.order >= 0 else 2   # blocked lexicographic: L2 locality of the neighbour rows
 
     w = WORKLOADS[args.workload]()
     n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
@@ -453,7 +386,10 @@ def run_gpu_arm(args):
                          w["expn"], w["etal"], w["etar"], w["etaa"], w["mode"], lmax,
                          DistTransport(), device=local, order=order, options=options, tuning=tuning,
                          peer_push={-1: None, 0: False, 1: True}[args.push],
-                         fused_push={-1: None, 0: False, 1: True}[args.fused])
+                         fused_push={-1: None, 0: False, 1: True}[args.fused],
+                         native={-1: None, 0: False, 1: True}[args.native])
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
         sh.run(w["rho0"], dt, 1, w["pulse_system_func"], w["pulse_coupling_func"])
         setup_s = time.perf_counter() - t0
         plan = sh.plan
@@ -470,6 +406,8 @@ def run_gpu_arm(args):
         def propagate(nsteps):
             sh.propagate(dt, nsteps, None, None if fs is None else fs[:nsteps], None)
         sh.set_state(w["rho0"])
+        if sh.native:
+            sh.check_barriers()
     nmax = plan.nmax
 
     # ---- device-resident timing
@@ -513,6 +451,35 @@ def run_gpu_arm(args):
                     for x in allr]
 
     tr = complex(np.trace(rho_end))
+    # correctness evidence: (1) the timed path on the reference's own fixture; (2) rho_sys after
+    # `steps` RK4 steps of the timed e2e call - at N > 1 against the committed 1-GPU values
+    # (1-GPU-vs-N-GPU agreement at full depth); the trace alone would be blind to a
+    # broken halo exchange (it is conserved whatever the neighbour rows hold)
+    check = {"trace_rho_sys": [tr.real, tr.imag],
+             "rho_sys_final": np.ascontiguousarray(rho_end.reshape(-1)).view(np.float64).reshape(-1, 2).tolist()}
+    try:
+        check["reference_fixture"] = fixture_parity(multi, DistTransport() if multi else None, local, order,
+                                                    tuning, options, {-1: None, 0: False, 1: True}[args.native])
+        check["reference_fixture"]["ok"] = bool(check["reference_fixture"]["max_abs_diff_trajectory"] < 1e-10
+                                                and check["reference_fixture"]["max_abs_diff_all_ados"] < 1e-10)
+    except Exception as exc:  # noqa: BLE001
+        check["reference_fixture"] = {"error": repr(exc)[-300:], "ok": False}
+    ref1 = rho_reference(args.workload, K)
+    if ref1 is not None:
+        check["max_abs_diff_vs_n1"] = float(np.max(np.abs(rho_end.reshape(-1) - ref1)))
+        check["n1_reference"] = "profiles/r02_rho_sys_n1.json (1 GPU, same workload and steps)"
+    else:
+        check["max_abs_diff_vs_n1"] = None
+    if args.save_rho_ref and rank == 0 and not multi:
+        os.makedirs(os.path.dirname(args.save_rho_ref) or ".", exist_ok=True)
+        try:
+            with open(args.save_rho_ref) as fh:
+                store = json.load(fh)
+        except Exception:
+            store = {}
+        store.setdefault(args.workload, {})[str(K)] = check["rho_sys_final"]
+        with open(args.save_rho_ref, "w") as fh:
+            json.dump(store, fh)
     if rank == 0:
         peak, peak_src = peaks()
         bytes_per_step = 256.0 * n * n * nmax          # 16 array passes x 16 B x N^2
@@ -545,13 +512,18 @@ def run_gpu_arm(args):
                 "l2": ("inputs larger than L2 (4 arrays of %.0f MB); no flush needed" % state_mb) if state_mb > 200
                       else "state is cache-resident by construction (time stepping re-reads its own output); no flush",
                 "parallelism": "single GPU" if not multi else
-                               (f"hierarchy sharded over {world} GPUs (contiguous ranges of the lexicographic order, "
-                                f"cost balanced); one halo exchange of neighbour rows per RK stage "
-                                + (("(rows stored into peer memory over NVLink by the stage kernel's epilogue"
-                                    if sh.fused else "(rows stored into peer memory over NVLink by a push kernel")
-                                   + " + symmetric-memory barrier)"
-                                   if sh.symm is not None else "(NCCL all_to_all_single)")),
+                               (f"hierarchy sharded over {world} GPUs (contiguous ranges of the blocked lexicographic "
+                                f"order, cost balanced); one exchange of neighbour rows per RK stage "
+                                + ("(rank-local arrays = own ADOs + halo row pool; rows stored into the peers' pools "
+                                   "over NVLink by the stage kernel's epilogue, CUDA-IPC mappings, flag barrier in "
+                                   "peer memory, whole run in one C call)" if sh.native else
+                                   (("(rows stored into peer memory over NVLink by the stage kernel's epilogue"
+                                     if sh.fused else "(rows stored into peer memory over NVLink by a push kernel")
+                                    + " + symmetric-memory barrier)"
+                                    if sh.symm is not None else "(NCCL all_to_all_single)"))),
                 "setup_s_first_call": setup_s,
+                "setup_breakdown_s": (dict(getattr(sh, "timings", {}), construct_total=build_s) if multi else None),
+                "state_mb_per_rank": (sh.state_nbytes / 1e6 if (multi and sh.native) else 4 * state_mb),
             },
             "clocks": clocks,
             "e2e": {"value": nmax * K / e2e_s, "unit": UNIT,
@@ -567,7 +539,7 @@ def run_gpu_arm(args):
                          "avg_launch_ms": avg_launch_ms, "launches_timed": stage_n,
                          "whole_job_gbs": bytes_per_step * K / (ms * 1e-3) / 1e9,
                          "whole_job_frac_of_aggregate_peak": bytes_per_step * K / (ms * 1e-3) / 1e9 / (peak * world)},
-            "check": {"trace_rho_sys": [tr.real, tr.imag]},
+            "check": check,
         }
         if per_rank:
             line["ranks"] = per_rank
@@ -586,9 +558,6 @@ def run_gpu_arm(args):
             aux("cpu_baseline", lambda: cpu_native_leg(args.workload)[0])
             aux("cpu_baseline_python_loop", lambda: cpu_reference_leg(args.workload, budget_s=8.0)[0])
             aux("cpu_baseline_batched", lambda: cpu_batched_leg(args.workload))
-        if (world == 1 and args.kernel == 0 and not args.no_cpu
-                and os.environ.get("PYQED_B200_BENCH_KERNEL6", "1") != "0"):
-            line["experimental"] = kernel6_leg(args)
         print(json.dumps(line), flush=True)
     if multi:
         dist.destroy_process_group()
@@ -612,7 +581,8 @@ def main():
     ap.add_argument("--resident", type=int, default=-1, help="0 off, 4 force kernel 4, default auto (kernel 5)")
     ap.add_argument("--fused", type=int, default=-1, help="multi-GPU: stage kernel stores halo rows itself")
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
-    ap.add_argument("--kernel6-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--native", type=int, default=-1, help="multi-GPU: 1 require / 0 forbid the rank-local layout")
+    ap.add_argument("--save-rho-ref", default=None, help="1 GPU: merge rho_sys after `steps` steps into this JSON")
     ap.add_argument("--prefetch", type=int, default=0, help="kernel 7: double-buffered tiles fetched one group ahead")
     ap.add_argument("--dynsched", type=int, default=-1, help="kernels 6/7: 0 = static group stride, default: global work counter")
     ap.add_argument("--packed", type=int, default=-1, help="0: never use packed Hermitian storage (kernel 7)")
@@ -621,9 +591,7 @@ def main():
     if args.steps is None:
         args.steps = 20
     args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
-    if args.kernel6_child:
-        kernel6_child(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

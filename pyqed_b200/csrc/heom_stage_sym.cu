@@ -207,7 +207,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             i = j / N;
             j -= i * N;
         }
-        kofs[it] = s * KSUB + i * KLD + j;
+        // low half: offset of (i, j) in the k tile, high half: offset of (j, i)
+        kofs[it] = (s * KSUB + i * KLD + j) | ((s * KSUB + j * KLD + i) << 16);
         if (!(PACKED || BULK_TILE)) rofs_[it] = (s * N + i) * LD + j;   // padded rows (even N)
     }
     // bulk-copied tiles (packed, or odd N) keep the flat layout of the global array
@@ -500,9 +501,14 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         }
         if (cur_rr >= 0) flush();
         __syncwarp();
-        // ---- k = P' + P'^dagger: this lane finishes its diagonal element and the pairs
-        //      (row, row+d), d = 1..(N-1)/2 (and d = N/2 from the lower half when N is even)
-        if (on) {
+        // ---- k = P' + P'^dagger.  FUSE_HERM: formed by the epilogue, which reads (i, j) and (j, i)
+        //      of P' for every element it writes - no separate pass over the tile.  (Full storage
+        //      with the fused push keeps the pass: there (i, j) and (j, i) belong to different lanes
+        //      and the output goes back into the tile.)  Otherwise this lane finishes its diagonal
+        //      element and the pairs (row, row+d), d = 1..(N-1)/2 (and d = N/2 from the lower half
+        //      when N is even).
+        constexpr bool FUSE_HERM = PACKED || !PUSH;
+        if (!FUSE_HERM && on) {
             {
                 double2* pd = ksub + row * KLD + row;
                 const double2 v = *pd;
@@ -535,12 +541,19 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         // ---- epilogue from shared memory, streaming stores
         // PUSH: the stage output goes back into the k tile as full rows (packed storage: the
         // element below the diagonal too), from where the halo rows leave as bulk stores
-        auto put_k = [&](int ko, const double2 v) {
-            k_s[ko] = v;
-            if (PACKED) {
-                const int kk = ko % KSUB, i = kk / KLD, j = kk - i * KLD;
-                if (i != j) k_s[ko + (KLD - 1) * (j - i)] = make_double2(v.x, -v.y);
+        // (only in groups that push anything)
+        const bool any_push = PUSH && __reduce_max_sync(0xffffffffu, pe - pb) > 0;
+        auto put_k = [&](int kk, const double2 v) {
+            k_s[kk & 0xffff] = v;
+            if (PACKED && (kk >> 16) != (kk & 0xffff)) k_s[kk >> 16] = make_double2(v.x, -v.y);
+        };
+        auto get_k = [&](int kk) {
+            double2 v = k_s[kk & 0xffff];
+            if (FUSE_HERM) {
+                const double2 m = k_s[kk >> 16];
+                v = make_double2(v.x + m.x, v.y - m.y);
             }
+            return v;
         };
         int e0 = -1;   // LAST: flat offset of ADO 0 (rho_sys) inside this group, if it is here
         if (LAST && a.traj) {
@@ -551,7 +564,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         for (int it = 0; it < EIT; ++it) {
             const int e = lane + 32 * it;
             if (e < nelem) {
-                const double2 k = k_s[kofs[it]];
+                const double2 k = get_k(kofs[it]);
                 if (LAST) {
                     // y' = -y/3 + S1/3 + 2 S2/3 + w (k4 + (2/dt) S3)   (S3's share is already in k)
                     const double2 y0 = y_s[e], s1 = acc_s[e], s2 = rho_s[rofs(it)];
@@ -561,10 +574,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     res.x = fma(2.0 * third, s2.x, res.x);
                     res.y = fma(2.0 * third, s2.y, res.y);
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH) put_k(kofs[it], res);
+                    if (PUSH && any_push) put_k(kofs[it], res);
                     if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)EL) {
                         if (PACKED) {   // the trajectory holds full matrices
-                            const int kk = kofs[it] - (e0 / EL) * KSUB, i = kk / KLD, j = kk - i * KLD;
+                            const int kk = (kofs[it] & 0xffff) - (e0 / EL) * KSUB, i = kk / KLD, j = kk - i * KLD;
                             a.traj[(step + 1) * NN + i * N + j] = res;
                             if (i != j) a.traj[(step + 1) * NN + j * N + i] = make_double2(res.x, -res.y);
                         } else {
@@ -575,15 +588,14 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     const double2 yv = FIRST ? rho_s[rofs(it)] : y_s[e];
                     const double2 res = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH) put_k(kofs[it], res);
+                    if (PUSH && any_push) put_k(kofs[it], res);
                 }
             }
         }
         if (PUSH) {
             // rows of this group's output that other ranks read: from the k tile straight into
             // their arrays.  The N lanes of an ADO share its entries.
-            const bool any = __reduce_max_sync(0xffffffffu, pe - pb) > 0;
-            if (any) {
+            if (any_push) {
                 fence_proxy_async();   // this lane's tile writes are ordered before the bulk stores
                 __syncwarp();
                 for (int q = pb + row; q < pe; q += N) {

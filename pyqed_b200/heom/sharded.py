@@ -286,7 +286,16 @@ class ShardedDEOM:
     # -- rank-local layout: own ADOs + pool of halo rows, rows stored by their owners --------
     def _init_native(self, p):
         import ctypes as C
+        import time
         tr, world, rank = self.tr, self.world, self.rank
+        self.timings = tm = {}
+        t_last = [time.perf_counter()]
+
+        def lap(name):
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            tm[name] = now - t_last[0]
+            t_last[0] = now
         self.nmax = p.nmax
         tables = p._tables
         dev = tables.device
@@ -298,10 +307,13 @@ class ShardedDEOM:
         self.bounds = ([0] + [min(self.nmax, (b + 32) // 64 * 64) for b in self.bounds[1:-1]] + [self.nmax])
         self.lo, self.hi = lo, hi = self.bounds[rank], self.bounds[rank + 1]
         n_own = hi - lo
+        lap("bounds")
         l0, l1 = int(self.link_ptr[lo]), int(self.link_ptr[hi])
         need = needed_items(links[l0:l1, 0], links[l0:l1, 1], lo, hi, True)
         self.row_items = True
+        lap("need_list")
         self.halo = h = HaloPlan(self.bounds, rank, world, need, True, tr)
+        lap("request_exchange")
         self.need64 = h.need.contiguous()
         # push table: for every row a peer q asked for, its index in q's pool = position in q's
         # sorted need list = (rows q gets from lower ranks) + position inside q's request to me
@@ -320,6 +332,7 @@ class ShardedDEOM:
         self._push_ptr = ptr.to(dev).contiguous()
         self._push_ent = (ent.to(dev).contiguous() if ent.numel()
                           else torch.zeros((1, 2), dtype=torch.int32, device=dev))
+        lap("push_table")
         sizes = tr.allgather_counts([n_own, int(self.need64.numel()), int(self.device)])
         n_own_max, pool_max = max(x[0] for x in sizes), max(x[1] for x in sizes)
         self.device_barrier = len({x[2] for x in sizes}) == world   # every rank on its own GPU
@@ -339,6 +352,7 @@ class ShardedDEOM:
             p._check(p.lib.pyqed_heom_shared_open(self.device, hq, C.byref(pq)))
             self._peer_ptrs.append(pq.value)
         peers = (C.c_uint64 * world)(*self._peer_ptrs)
+        lap("state_alloc_and_ipc")
         need_dev = self.need64.to(dev)
         self._keep = (need_dev,)
         p._check(p.lib.pyqed_heom_shard_setup(
@@ -350,6 +364,7 @@ class ShardedDEOM:
         self.elems = 2 * self.n
         self.owner_of_sys = next(r for r in range(world) if self.bounds[r] <= p.info("slot0") < self.bounds[r + 1])
         tr.barrier()   # every rank's flags are zeroed and its buffer mapped before anyone pushes
+        lap("localize_links_and_barrier")
 
     def close(self):
         """Unmap the peers' buffers and free this rank's (rank-local layout only)."""
