@@ -501,13 +501,12 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         }
         if (cur_rr >= 0) flush();
         __syncwarp();
-        // ---- k = P' + P'^dagger.  FUSE_HERM: formed by the epilogue, which reads (i, j) and (j, i)
-        //      of P' for every element it writes - no separate pass over the tile.  (Full storage
-        //      with the fused push keeps the pass: there (i, j) and (j, i) belong to different lanes
-        //      and the output goes back into the tile.)  Otherwise this lane finishes its diagonal
+        // ---- k = P' + P'^dagger.  FUSE_HERM (packed storage): formed by the epilogue, which reads
+        //      (i, j) and (j, i) of P' for each of the N(N+1)/2 elements it writes - no separate pass
+        //      over the tile.  Full storage keeps the pass: this lane finishes its diagonal
         //      element and the pairs (row, row+d), d = 1..(N-1)/2 (and d = N/2 from the lower half
         //      when N is even).
-        constexpr bool FUSE_HERM = PACKED || !PUSH;
+        constexpr bool FUSE_HERM = PACKED;   // (full storage: the transposed reads of all N*N elements cost more than the pass)
         if (!FUSE_HERM && on) {
             {
                 double2* pd = ksub + row * KLD + row;

@@ -53,7 +53,7 @@ def sample_pulse(func, dt, nt):
 class DEOMSolver:
     def __init__(self, system=None, system_dipole=None, bath=None, coupling=None,
                  coupling_dipole=None, pulse_system_func=None, pulse_coupling_func=None,
-                 lmax=None, device=0, order=0, alias_rho0=True):
+                 lmax=None, device=0, order=None, alias_rho0=True, shard=None):
         self.system = system
         self.system_dipole = system_dipole
         self.coupling = coupling
@@ -68,8 +68,16 @@ class DEOMSolver:
         self.nmod = 0
         self.comb_list = []
         self.device = device
+        # device storage order of the ADOs (results are always in the reference's id order):
+        # None = blocked lexicographic for large hierarchies (L2 locality), the reference's otherwise
         self.order = order
         self.alias_rho0 = alias_rho0
+        # multi-GPU: under an initialised torch.distributed job with more than one rank, ``run``
+        # shards the hierarchy over the ranks (one process per GPU, ``device`` = this rank's GPU;
+        # every rank calls ``run`` with the same arguments and gets the same result).
+        # None = only for hierarchies of 2^18 ADOs or more, True = always, False = never.
+        self.shard = shard
+        self._sharded = None
         self.tuning = dict(kernel=0, warps_per_cta=0, use_graph=0)
         self.options = {}  # named C-ABI options, e.g. {"qdiag": 0, "hermitian": 0}
         self._plan = None
@@ -138,15 +146,69 @@ class DEOMSolver:
             Qd = np.stack([np.broadcast_to(qd[i], (n, n)) for i in range(m)])
         return H, mu, Q, Qd
 
+    def _order(self):
+        if self.order is not None:
+            return self.order
+        return 2 if self.nmax >= (1 << 16) else 0
+
+    def _shard_transport(self, batch):
+        """The transport to shard over, or None (single-GPU run)."""
+        if self.shard is False or batch != 1:
+            return None
+        try:
+            import torch.distributed as dist
+            active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        except Exception:  # noqa: BLE001
+            active = False
+        if not active:
+            if self.shard is True:
+                raise RuntimeError("shard=True needs an initialised torch.distributed job with more than one rank")
+            return None
+        if self.shard is None and self.nmax < (1 << 18):
+            return None
+        from .sharded import DistTransport
+        return DistTransport()
+
+    def _run_sharded(self, tr, rho0, dt, nt, p1, fs, fc):
+        """``run`` over all ranks of the job (``heom/sharded.py``): rank-local arrays and fused peer
+        stores where kernels 6 / 7 apply and there is no pulse, the general exchange otherwise."""
+        import hashlib
+        from .sharded import ShardedDEOM
+        H, mu, Q, Qd = self._operators()
+        b = self.bath
+        pulses = sample_pulse(fs, dt, nt) is not None or sample_pulse(fc, dt, nt) is not None
+        hh = hashlib.sha1()
+        for arr in (H, mu, Q, Qd, b.expn, b.etal, b.etar, b.etaa, np.asarray(b.mode, dtype=np.int64)):
+            hh.update(np.ascontiguousarray(arr).tobytes())
+        hh.update(repr((self.lmax, self.device, pulses, sorted(self.tuning.items()),
+                        sorted(self.options.items()))).encode())
+        digest = hh.hexdigest()
+        if self._sharded is None or self._sharded[0] != digest:
+            if self._sharded is not None:
+                self._sharded[1].close()
+            sh = ShardedDEOM(H, mu, Q, Qd, b.expn, b.etal, b.etar, b.etaa, b.mode, self.lmax, tr,
+                             device=self.device, order=2, options=self.options, tuning=self.tuning,
+                             native=False if pulses else None)
+            self._sharded = (digest, sh)
+        sh = self._sharded[1]
+        t_save, traj = sh.run(np.asarray(rho0, dtype=C128), dt, nt, fs, fc)
+        self._keys, self._ddos = None, None
+        self._ddos_from = sh
+        self._rho_sys_final = traj[None, -1]
+        if p1 is None:
+            return t_save, traj[None]
+        p1 = np.asarray(p1, dtype=C128)
+        return t_save, np.einsum("ij,tji->t", p1, traj)[None]
+
     def _ensure_plan(self, batch):
         H, mu, Q, Qd = self._operators()
         b = self.bath
-        key = (self.nsys, self.nind, self.nmod, self.lmax, batch, self.device, self.order)
+        key = (self.nsys, self.nind, self.nmod, self.lmax, batch, self.device, self._order())
         if self._plan is None or self._plan_key != key:
             if self._plan is not None:
                 self._plan.close()
             self._plan = Plan(self.nsys, self.nind, self.nmod, self.lmax, batch=batch,
-                              device=self.device, order=self.order)
+                              device=self.device, order=self._order())
             self._plan_key = key
             fresh = True
         else:
@@ -181,9 +243,11 @@ class DEOMSolver:
     def keys(self):
         """``keys[nmax, K]`` (int64), reference id order (``deom.py:1062-1064``)."""
         if self._keys is None:
-            if self._plan is None:
+            sharded = getattr(self, "_ddos_from", None)
+            plan = sharded.plan if sharded is not None else self._plan
+            if plan is None:
                 raise AttributeError("keys are available after run()")
-            self._keys = self._plan.get_keys().astype(np.int64)
+            self._keys = plan.get_keys().astype(np.int64)
         return self._keys
 
     @property
@@ -191,6 +255,9 @@ class DEOMSolver:
         """All ADOs after ``run`` as ``[nmax, N, N]`` (``[batch, nmax, N, N]``
         after ``run_batch``), reference id order."""
         if self._ddos is None:
+            if getattr(self, "_ddos_from", None) is not None:   # sharded run: every rank gathers all ADOs
+                self._ddos = self._ddos_from.gather_ados()
+                return self._ddos
             if self._plan is None:
                 raise AttributeError("ddos are available after run()")
             a = self._plan.get_ados()
@@ -360,6 +427,10 @@ class DEOMSolver:
     def _run(self, rho0s, dt, nt, p1, fs, fc):
         import torch
         nb = len(rho0s)
+        tr = self._shard_transport(nb)
+        if tr is not None:
+            return self._run_sharded(tr, rho0s[0], dt, nt, p1, fs[0], fc[0])
+        self._ddos_from = None
         plan = self._ensure_plan(nb)
         n = self.nsys
         rho0 = np.stack([np.asarray(r, dtype=C128).reshape(n, n) for r in rho0s])

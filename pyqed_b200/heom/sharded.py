@@ -77,8 +77,22 @@ class HaloPlan:
         all_counts = transport.allgather_counts(self.recv_counts)
         self.all_counts = [[int(x) for x in row] for row in all_counts]
         self.send_counts = [int(all_counts[q][rank]) for q in range(world)]
-        chunks = torch.split(self.need, self.recv_counts)
-        got = transport.exchange_lists(list(chunks), self.send_counts)
+        if hasattr(transport, "allgather_lists"):
+            # one all-gather of the (sorted) need lists instead of pairwise sends: every rank cuts
+            # the part that falls into its own range out of each peer's list.  (Pairwise NCCL
+            # sends set up a connection per pair of ranks - seconds at 8 ranks.)
+            lists = transport.allgather_lists(self.need, [sum(row) for row in self.all_counts])
+            lo_item = self.bounds[rank] * (8 if row_items else 1)
+            hi_item = self.bounds[rank + 1] * (8 if row_items else 1)
+            got = []
+            for q in range(world):
+                cut = torch.searchsorted(lists[q], torch.tensor([lo_item, hi_item], dtype=torch.int64,
+                                                                device=lists[q].device))
+                got.append(lists[q][int(cut[0]):int(cut[1])].to(self.need.device))
+                assert got[-1].numel() == self.send_counts[q]
+        else:
+            chunks = torch.split(self.need, self.recv_counts)
+            got = transport.exchange_lists(list(chunks), self.send_counts)
         self.send_items = (torch.cat(got) if sum(self.send_counts) else
                            torch.zeros(0, dtype=torch.int64, device=self.need.device))
         lo, hi = self.bounds[rank], self.bounds[rank + 1]
@@ -136,6 +150,16 @@ class DistTransport:
         host_recv = torch.empty(recvbuf.shape, dtype=recvbuf.dtype)
         self._p2p(list(torch.split(host_send, ss)), list(torch.split(host_recv, rs)))
         recvbuf.copy_(host_recv)
+
+    def allgather_lists(self, mine, sizes):
+        """Every rank's int64 list (``sizes[q]`` entries from rank q) on every rank."""
+        wire = mine.device if self.nccl else torch.device("cpu")
+        cap = max(max(sizes), 1)
+        buf = torch.zeros(cap, dtype=torch.int64, device=wire)
+        buf[:mine.numel()] = mine.to(wire)
+        out = [torch.empty(cap, dtype=torch.int64, device=wire) for _ in range(self.world)]
+        self.dist.all_gather(out, buf, group=self.group)
+        return [o[:n] for o, n in zip(out, sizes)]
 
     def allgather_object(self, obj):
         out = [None] * self.world

@@ -171,9 +171,41 @@ def gpu_mode(args):
         sh.close()
 
 
+def solver_mode(args):
+    """``DEOMSolver.run`` itself under a multi-rank job: every rank calls it with the same arguments
+    and gets the reference's trajectory, observable, keys and ADOs (drop-in API, sharded inside)."""
+    from conftest import golden, pulse_from_samples
+    from pyqed_b200.heom import DEOMSolver, Bath
+    rank = dist.get_rank()
+    dev = int(os.environ.get("LOCAL_RANK", "0")) if args.backend == "nccl" else 0
+    torch.cuda.set_device(dev)
+    for name in args.cases.split(","):
+        g = golden(name)
+        dt, nt = float(g["dt"]), int(g["nt"])
+        bath = Bath(expn=g["expn"], etal=g["etal"], etar=g["etar"], etaa=g["etaa"], mode=g["mode"])
+        s = DEOMSolver(g["system"], g["system_dipole"], bath, g["coupling"], g["coupling_dipole"],
+                       pulse_from_samples(g["pulse_system"], dt), pulse_from_samples(g["pulse_coupling"], dt),
+                       lmax=int(g["lmax"]), device=dev, shard=True)
+        p1 = g["p1"] if "p1" in g and g["p1"].ndim == 2 else None
+        rho0 = g["rho0"].copy()
+        t_save, out = s.run(rho0, dt, nt, p1)
+        ref = g["traj"]
+        err = np.max(np.abs(np.asarray(out) - ref))
+        assert err < 1e-12, (name, err)
+        assert np.allclose(t_save, np.arange(nt + 1) * dt)
+        if "keys" in g:
+            assert np.array_equal(s.keys, g["keys"])
+        if "ados_final" in g:
+            assert np.max(np.abs(s.ddos - g["ados_final"])) < 1e-12
+            assert np.max(np.abs(rho0 - g["ados_final"][0])) < 1e-12     # rho0 aliasing of the reference
+        sh = s._sharded[1]
+        print(f"rank {rank}: {name} solver ok native={sh.native} p1={p1 is not None} err {err:.1e}", flush=True)
+        sh.close()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["cpu", "gpu"])
+    ap.add_argument("mode", choices=["cpu", "gpu", "solver"])
     ap.add_argument("--backend", default="gloo")
     ap.add_argument("--cases", default="deom_fmo_K21_L2")
     ap.add_argument("--order", type=int, default=1)
@@ -184,6 +216,6 @@ if __name__ == "__main__":
     a = ap.parse_args()
     dist.init_process_group(a.backend)
     try:
-        cpu_mode(a) if a.mode == "cpu" else gpu_mode(a)
+        {"cpu": cpu_mode, "gpu": gpu_mode, "solver": solver_mode}[a.mode](a)
     finally:
         dist.destroy_process_group()

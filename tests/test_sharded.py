@@ -99,3 +99,14 @@ def test_rank_local_layout_two_gpus(kernel):
     out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--kernel", str(kernel), "--native", "1",
                       "--cases", "deom_fmo_K21_L3,deom_fmo_K21_L2,deom_fmo_K7_L4"])
     assert out.count(" ok (owned") == 6 and out.count("native=True") == 6
+
+
+@pytest.mark.gpu
+def test_deomsolver_run_shards_under_torch_distributed():
+    """The drop-in class itself: ``DEOMSolver(..., shard=True).run`` on every rank of a 2-rank job
+    (ranks sharing the test box's GPU) returns the reference's results - rank-local layout for the
+    FMO case, general exchange for the pulsed / sigma_z / p1 cases."""
+    out = _launch(2, ["solver", "--backend", "gloo", "--cases",
+                      "deom_fmo_K21_L2,deom_spin_boson_L10,deom_example_L10_p1,deom_aggregate_L3_T37"])
+    assert out.count(" solver ok") == 8
+    assert out.count("native=True") == 2 and out.count("p1=True") >= 2
