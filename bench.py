@@ -356,6 +356,8 @@ def run_gpu_arm(args):
         from pyqed_b200.heom.deom import sample_pulse
         fs = sample_pulse(w["pulse_system_func"], dt, max(K, Wm))
 
+    if args.batch > 1:
+        return run_batch_arm(args, w, world, rank, local, multi, order, tuning, options)
     if not multi:
         bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
         solver = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
@@ -563,6 +565,105 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_batch_arm(args, w, world, rank, local, multi, order, tuning, options):
+    """Waiting-time scan (BASELINE configs[4]): ``--batch B`` trajectories of the same hierarchy that
+    differ in their field tables, through ``DEOMSolver.run_batch``.  The reference runs them one
+    after the other (B serial ``DEOMSolver.run`` calls, deom.py:1072).  Several GPUs: replicas only -
+    the batch axis is split over the ranks, no communication."""
+    import torch
+    import torch.distributed as dist
+    from pyqed_b200.heom import DEOMSolver, Bath
+    from pyqed_b200.heom.deom import sample_pulse
+    if args.workload != "aggregate7_K6_L6":
+        raise SystemExit("--batch is defined for the waiting-time workload aggregate7_K6_L6")
+    B = args.batch
+    mine = list(range(rank, B, world))           # waiting indices of this rank
+    n, nind, lmax = int(w["system"].shape[0]), int(len(w["expn"])), int(w["lmax"])
+    K, Wm, dt = args.steps, args.warmup, w["dt"]
+    fields = [W.aggregate_2des(lmax=lmax, waiting_index=b)["pulse_system_func"] for b in mine]
+    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+    solver = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"],
+                        None, None, lmax=lmax, device=local, order=order, alias_rho0=False, shard=False)
+    solver.tuning, solver.options = tuning, options
+    rho0s = [w["rho0"]] * len(mine)
+    t0 = time.perf_counter()
+    solver.run_batch(rho0s, dt, 2, p1=w["observable"], pulse_system_funcs=fields)
+    setup_s = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, sig = solver.run_batch(rho0s, dt, K, p1=w["observable"], pulse_system_funcs=fields)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    plan = solver._plan
+    fs = np.stack([sample_pulse(f, dt, max(K, Wm)) for f in fields])
+    plan.set_state(np.stack(rho0s))
+    plan.propagate(dt, Wm, fs[:, :Wm], None, None, 0)
+    plan.synchronize()
+    launches0 = plan.launch_count()
+    plan.stage_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    plan.propagate(dt, K, fs[:, :K], None, None, 0)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else {}
+    stage_ms, stage_n = plan.stage_timing(False)
+    launches = plan.launch_count() - launches0
+    if multi:
+        tt = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(tt[0]), float(tt[1])
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt[0])
+    if rank == 0:
+        peak, peak_src = peaks()
+        nmax = plan.nmax
+        value = B * nmax * K / (ms * 1e-3)
+        resident = plan.info("resident_launches") > 0
+        kname = ({4: "resident_cluster_kernel", 5: "resident_elem_kernel"}[plan.info("resident_kind")] if resident
+                 else "stage_rows_async_kernel")
+        algo = 256.0 * n * n * nmax * len(mine) * K
+        achieved = algo / (ms * 1e-3) / 1e9
+        in_bytes = sum(np.asarray(w[k]).nbytes for k in ("system", "system_dipole", "coupling", "coupling_dipole",
+                                                         "expn", "etal", "etar", "etaa", "mode")) + \
+            B * (w["rho0"].nbytes + 3 * K * 8)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if multi else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "batch": B, "nsys": n, "nind": nind, "lmax": lmax, "n_ado": nmax,
+                       "dt": dt, "waiting_times": "T_b = 0.05 b, b = 0..%d (pump/probe field tables)" % (B - 1),
+                       "l2": "state is resident in distributed shared memory / L2 by construction; no flush",
+                       "parallelism": "single GPU" if not multi else
+                                      f"replicas only: the {B} trajectories are split over {world} GPUs, no communication",
+                       "setup_s_first_call": setup_s},
+            "clocks": clocks,
+            "e2e": {"value": B * nmax * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": in_bytes / K,
+                    "d2h_bytes_per_step": B * (K + 1) * 16 / K,
+                    "call": "DEOMSolver.run_batch(rho0s, dt, nt=steps, p1=mu, pulse_system_funcs=[...]) with host arrays"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": kname,
+                         "note": "the whole batch (%.0f MB of state) lives in distributed shared memory for all steps "
+                                 "(one launch): the HBM fraction only says how far below the streaming bound the "
+                                 "latency/issue-bound resident kernel runs" % (B * nmax * n * n * 16 * 4 / 1e6)
+                                 if resident else "per-stage launches",
+                         "launches_timed": stage_n},
+            "check": {"signal_last": [float(np.real(sig[0][-1])), float(np.imag(sig[0][-1]))]},
+        }
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -581,6 +682,7 @@ def main():
     ap.add_argument("--resident", type=int, default=-1, help="0 off, 4 force kernel 4, default auto (kernel 5)")
     ap.add_argument("--fused", type=int, default=-1, help="multi-GPU: stage kernel stores halo rows itself")
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
+    ap.add_argument("--batch", type=int, default=1, help="aggregate7_K6_L6: number of waiting times (config 5: 64)")
     ap.add_argument("--native", type=int, default=-1, help="multi-GPU: 1 require / 0 forbid the rank-local layout")
     ap.add_argument("--save-rho-ref", default=None, help="1 GPU: merge rho_sys after `steps` steps into this JSON")
     ap.add_argument("--prefetch", type=int, default=0, help="kernel 7: double-buffered tiles fetched one group ahead")

@@ -129,6 +129,7 @@ static int compute_layout(pyqed_heom_plan* p) {
 #include "heom_stage_async.cuh"   // AsyncTables (shared-memory layout, also used by the resident kernels)
 #include "heom_resident.cuh"      // ResidentArgs; the kernels are instantiated in heom_inst.cu
 #include "heom_stage_generic.cuh"
+#include "heom_dataflow.cuh"
 
 extern "C" {
 static void fill_stage_args(pyqed_heom_plan* p, StageArgs& a);
@@ -191,6 +192,67 @@ static int try_resident(pyqed_heom_plan* p) {
     }
     if (rcode == 0) p->resident_launches++;
     return rcode;
+}
+
+// ---- kernel 8: persistent, ADO-to-ADO synchronised propagation of small hierarchies with N > 8 ----
+// returns 0 = done, -1 = not applicable (caller falls back to per-stage launches), 1 = error
+static int try_dataflow(pyqed_heom_plan* p) {
+    const bool whole = p->part_lo == 0 && p->part_hi == p->nmax;
+    if (!(p->kernel == 0 || p->kernel == 8) || stage_kernel_of(p) != 2 || p->ctx_tdep || !whole || p->ctx_nt <= 0 ||
+        p->N > 32 || p->opt_resident == 0)
+        return -1;
+    const int N = p->N, NN = N * N;
+    const size_t M1 = 1 + (size_t)p->M;
+    const size_t smem = sizeof(double2) * (NN + M1 * NN + 2 * 2 * (size_t)p->K) + sizeof(int2) * 2 * (size_t)p->K +
+                        sizeof(short) * 2 * (M1 * NN + M1 * (N + 1)) + 16;
+    if (smem > 200 * 1024) return -1;
+    static PerDeviceOnce attr;
+    if (attr.need(p->device))
+        CU_TRY(cudaFuncSetAttribute(stage_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int coop = 0, per_sm = 0;
+    CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_dataflow_kernel, DATAFLOW_THREADS, smem));
+    const long long cap = (long long)per_sm * sm_count_of(p->device);
+    const long long total = p->nmax * (long long)p->B;
+    // worth it while a stage is latency bound: a few ADOs per CTA at most
+    if (!coop || cap < 1 || (p->kernel != 8 && total > 8 * cap)) return -1;
+    if ((size_t)total > p->flags_cap) {
+        if (p->d_flags) cudaFree(p->d_flags);
+        p->d_flags = nullptr;
+        CU_TRY(cudaMalloc(&p->d_flags, sizeof(unsigned) * total));
+        p->flags_cap = (size_t)total;
+    }
+    CU_TRY(cudaMemsetAsync(p->d_flags, 0, sizeof(unsigned) * total, p->stream));
+    DataflowArgs da;
+    fill_stage_args(p, da.s);
+    da.Y = p->arr(ARR_Y);
+    da.SA = p->arr(ARR_SA);
+    da.SB = p->arr(ARR_SB);
+    da.ACC = p->arr(ARR_ACC);
+    da.flags = p->d_flags;
+    da.dt = p->ctx_dt;
+    da.nt = p->ctx_nt;
+    da.B = p->B;
+    if (p->timing) {
+        if (p->ev_used == p->ev.size()) {
+            cudaEvent_t e0, e1;
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            p->ev.emplace_back(e0, e1);
+        }
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].first, p->stream));
+    }
+    void* kargs[] = {&da};
+    const unsigned grid = (unsigned)std::min<long long>(total, cap);
+    CU_TRY(cudaLaunchCooperativeKernel((void*)stage_dataflow_kernel, dim3(grid), dim3(DATAFLOW_THREADS), kargs, smem,
+                                       p->stream));
+    if (post_launch(p, "stage_dataflow_kernel")) return 1;
+    if (p->timing) {
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].second, p->stream));
+        p->ev_used++;
+    }
+    p->dataflow_launches++;
+    return 0;
 }
 
 // kernel 6 (heom_stage_sym.cu) takes the difference-form RK4 stages of kernel 3 when every
@@ -381,6 +443,7 @@ void pyqed_heom_plan_destroy(pyqed_heom_plan* p) {
     if (p->d_fcoup) cudaFree(p->d_fcoup);
     if (p->d_peer) cudaFree(p->d_peer);
     if (p->shard.d_peer) cudaFree(p->shard.d_peer);
+    if (p->d_flags) cudaFree(p->d_flags);
     delete p;
 }
 
@@ -442,7 +505,7 @@ int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
 
 int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
     REQUIRE(p, "null plan");
-    REQUIRE((kernel >= 0 && kernel <= 4) || kernel == 6 || kernel == 7, "kernel must be 0..4, 6 or 7");
+    REQUIRE((kernel >= 0 && kernel <= 4) || (kernel >= 6 && kernel <= 8), "kernel must be 0..4 or 6..8");
     REQUIRE(warps >= 0 && warps <= 16, "warps_per_cta must be in [0, 16]");
     REQUIRE(use_graph == 0, "use_graph is reserved and must be 0");
     p->kernel = kernel;
@@ -481,6 +544,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "resident_kind") return p->resident_kind;
     if (n == "sym_launches") return p->sym_launches;
     if (n == "packed_steps") return p->packed_steps;
+    if (n == "dataflow_launches") return p->dataflow_launches;
     if (n == "rk_scheme") return rk_scheme(p) ? 1 : 0;
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
@@ -1019,6 +1083,10 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
         if (rr == 0) return 0;
         if (rr > 0) return 1;
         REQUIRE(p->kernel != 4, "kernel 4 (cluster-resident) is not applicable to this problem");
+        const int df = try_dataflow(p);
+        if (df == 0) return 0;
+        if (df > 0) return 1;
+        REQUIRE(p->kernel != 8, "kernel 8 (persistent dataflow) is not applicable to this problem");
         if (packed_eligible(p)) return run_packed(p, dt, nt);
         for (int64_t i = 0; i < nt; ++i)
             for (int st = 0; st < 4; ++st)

@@ -79,6 +79,9 @@ struct pyqed_heom_plan {
     long long resident_launches = 0;
     long long sym_launches = 0;  // stage launches that went to kernel 6
     long long packed_steps = 0;  // RK4 steps done by kernel 7 (packed Hermitian storage)
+    long long dataflow_launches = 0;  // propagations done by kernel 8 (one persistent launch each)
+    unsigned* d_flags = nullptr;      // kernel 8: per-ADO stage counters
+    size_t flags_cap = 0;
     bool links2_built = false;
     size_t bound_table_bytes = 0;
     int resident_kind = 0;  // 4 or 5: which resident kernel ran last
@@ -141,8 +144,9 @@ inline int stage_kernel_of(const pyqed_heom_plan* p) {
     // 6 = kernel 3's scheme and buffers; launch_stage hands the eligible stages to kernel 6.
     // 7 = whole propagations on packed Hermitian storage where eligible (pyqed_heom_propagate),
     //     kernel 3 otherwise
-    if (p->kernel && p->kernel != 4 && p->kernel != 6 && p->kernel != 7) return p->kernel;
-    if (p->N > 8) return 2;
+    // 8 = persistent dataflow propagation (heom_dataflow.cuh) where eligible, the generic kernel otherwise
+    if (p->kernel && p->kernel != 4 && p->kernel != 6 && p->kernel != 7 && p->kernel != 8) return p->kernel;
+    if (p->N > 8 || p->kernel == 8) return 2;
     const bool fits32 = (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
     return (p->use_qdiag && p->opt_rk13 != 0 && fits32) ? 3 : 1;
 }

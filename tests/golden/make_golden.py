@@ -314,6 +314,17 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "propagators":
         save_propagators()
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "aggregate_L6":
+        # config 5 at full depth (924 ADOs), pump/probe field on, observable Tr(mu rho); the reference
+        # needs ~5 minutes per waiting time.  Optional second argument: one waiting index.
+        for b in ([int(sys.argv[2])] if len(sys.argv) > 2 else [0, 37]):
+            w = W.aggregate_2des(lmax=6, waiting_index=b)
+            save_deom(f"aggregate_L6_T{b}", w, 400, p1=w["observable"], keep_ados=False, stride=1)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "polariton_L6":
+        # config 4 at full depth (N = 32, 210 ADOs): trajectory and every final ADO
+        save_deom("polariton32_L6", W.polariton(lmax=6), 40)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "bath":
         save_bath()
         return

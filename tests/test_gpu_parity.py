@@ -496,3 +496,58 @@ def test_frequency_domain_four_operator_response(tag, lcr):
     ref = get(f"c4_{lcr}")
     assert c.shape == ref.shape
     assert np.max(np.abs(c - ref)) < 1e-8 * max(1.0, np.max(np.abs(ref)))
+
+
+# ---- kernel 8: persistent, ADO-to-ADO synchronised propagation (csrc/heom_dataflow.cuh) ----
+@pytest.mark.parametrize("name", ["deom_polariton32_L6", "deom_polariton32_L2", "deom_polariton8_L4",
+                                  "deom_fmo_K7_L4", "deom_spin_boson_L10", "deom_fmo_K21_L2"])
+def test_dataflow_kernel_matches_reference(name):
+    """All steps in one cooperative launch, stages ordered by per-ADO release/acquire flags instead
+    of kernel boundaries: the reference's trajectory and every final ADO (N = 32 at full depth 6,
+    and smaller systems forced through the same kernel)."""
+    g = golden(name)
+    s = _solver_from(g)
+    s.tuning = dict(kernel=8, warps_per_cta=0, use_graph=0)
+    _check_against_golden(g, s)
+    assert s._plan.info("dataflow_launches") == 1 and s._plan.info("resident_launches") == 0
+
+
+def test_dataflow_kernel_is_the_default_for_config4_and_handles_batches():
+    g = golden("deom_polariton32_L6")
+    s = _solver_from(g)
+    _check_against_golden(g, s)
+    assert s._plan.info("dataflow_launches") == 1          # chosen automatically for N = 32
+    # a batch of trajectories (different initial states) in the same launch, twice in a row
+    n, nt, dt = g["rho0"].shape[0], 12, float(g["dt"])
+    rng = np.random.default_rng(5)
+    rhos = []
+    for _ in range(3):
+        a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+        r = a @ a.conj().T
+        rhos.append(r / np.trace(r))
+    b = _solver_from(g)
+    _, out = b.run_batch(rhos, dt, nt)
+    assert b._plan.info("dataflow_launches") == 1
+    for i, r in enumerate(rhos):
+        one = _solver_from(g)
+        one.tuning = dict(kernel=2, warps_per_cta=0, use_graph=0)     # per-stage launches of the generic kernel
+        _, ref = one.run(r.copy(), dt, nt)
+        assert np.max(np.abs(out[i] - np.asarray(ref))) < 1e-13
+    _, out2 = b.run_batch(rhos, dt, nt)
+    assert np.array_equal(out, out2)
+
+
+def test_waiting_time_scan_batch_matches_reference_at_depth_6():
+    """BASELINE configs[4] at its full depth (924 ADOs): two waiting times of the pump/probe scan in
+    one ``run_batch`` against the reference's two separate ``DEOMSolver.run`` calls."""
+    gs = [golden("deom_aggregate_L6_T0"), golden("deom_aggregate_L6_T37")]
+    g = gs[0]
+    dt, nt = float(g["dt"]), int(g["nt"])
+    from pyqed_b200.heom import DEOMSolver, Bath
+    bath = Bath(expn=g["expn"], etal=g["etal"], etar=g["etar"], etaa=g["etaa"], mode=g["mode"])
+    s = DEOMSolver(g["system"], g["system_dipole"], bath, g["coupling"], g["coupling_dipole"], lmax=int(g["lmax"]))
+    fields = [pulse_from_samples(x["pulse_system"], dt) for x in gs]
+    ts, sig = s.run_batch([g["rho0"], g["rho0"]], dt, nt, p1=g["p1"], pulse_system_funcs=fields)
+    for i, x in enumerate(gs):
+        assert np.max(np.abs(sig[i] - x["traj"])) < TOL
+    assert np.max(np.abs(sig[0] - sig[1])) > 1e-4      # the two waiting times really differ
