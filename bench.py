@@ -488,18 +488,42 @@ def run_gpu_arm(args):
         value = nmax * K / (ms * 1e-3)
         avg_launch_ms = stage_ms / max(stage_n, 1)
         # dominant kernel on this rank: its share of the algorithmic bytes / its mean duration
-        resident = plan.info("resident_launches") > 0
+        resident = plan.info("resident_launches") > 0 or plan.info("dataflow_launches") > 0
         bytes_per_launch = 256.0 * n * n * owned * (K if resident else 0.25)  # resident: one launch = K steps
         achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
         state_mb = nmax * n * n * 16 / 1e6
-        kname = {1: "stage_rows_kernel", 2: "stage_generic_kernel", 3: "stage_rows_async_kernel",
-                 4: "resident_cluster_kernel", 5: "resident_elem_kernel", 6: "stage_rows_async_kernel",
-                 7: "stage_rows_async_kernel"}[
-            plan.info("resident_kind") if plan.info("resident_launches") > 0 else
-            (args.kernel or (2 if n > 8 else (3 if plan.info("qdiag") else 1)))] \
-            if not (plan.info("sym_launches") > 0 or plan.info("packed_steps") > 0) else \
-            ("stage_rows_sym_kernel<PACKED>" if plan.info("packed_steps") > 0 else "stage_rows_sym_kernel")
+        if plan.info("dataflow_launches") > 0:
+            kname = "stage_dataflow_kernel"
+        elif plan.info("packed_steps") > 0:
+            kname = "stage_rows_sym_kernel<PACKED>"
+        elif plan.info("sym_launches") > 0:
+            kname = "stage_rows_sym_kernel"
+        elif plan.info("resident_launches") > 0:
+            kname = {4: "resident_cluster_kernel", 5: "resident_elem_kernel"}[plan.info("resident_kind")]
+        else:
+            k = args.kernel if args.kernel in (1, 2, 3) else (2 if n > 8 else (3 if plan.info("qdiag") else 1))
+            kname = {1: "stage_rows_kernel", 2: "stage_generic_kernel", 3: "stage_rows_async_kernel"}[k]
         order_name = ["reference", "lexicographic", "blocked lexicographic"][order]
+        fp64 = None
+        if n > 8:
+            # compute-shaped configuration (N = 32): algorithmic flops of SURVEY 8d's structured path,
+            # 4 [16 N^3 + 16 N nnz_Q M_eff] per ADO-step, against the DFMA rate measured on this GPU
+            # type (tools/fp64_peaks.cu; DMMA gives the same rate, so the commutator stays on DFMA)
+            nnz_q = int(sum(np.count_nonzero(q) for q in np.asarray(w["coupling"])))
+            flops_step = 4.0 * (16.0 * n ** 3 + 16.0 * n * nnz_q) * nmax
+            peak_tf, src = 36.7, "fallback"
+            try:
+                with open(os.path.join(ROOT, "profiles", "r02_fp64_peaks.json")) as fh:
+                    peak_tf, src = float(json.load(fh)["dfma_tflops"]), "measured (profiles/r02_fp64_peaks.json, DFMA; DMMA m8n8k4 / m16n8k8 give the same)"
+            except Exception:
+                pass
+            ach = flops_step * K / (ms * 1e-3) / 1e12
+            fp64 = {"bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                    "peak_source": src, "traffic": None, "kernel": kname,
+                    "algorithmic_flops_per_step": flops_step,
+                    "note": "H and Q_m are applied through their sparsity lists, so the executed flops are far "
+                            "below this dense-commutator count; the run is issue/latency bound "
+                            "(ncu: profiles/r02_kernel8_polariton32_ncu.txt, FP64 pipe 11 %, issue 42 %)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if multi else "weak",
@@ -533,7 +557,8 @@ def run_gpu_arm(args):
                     "call": ("DEOMSolver.run(rho0, dt, nt=steps)" if not multi else "ShardedDEOM.run(rho0, dt, nt=steps)")
                             + " with host arrays, plan cached"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": fp64 if fp64 is not None else
+                        {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": measured_traffic(args.workload, kname, order_name) if not multi else None,
                          "peak_source": peak_src, "kernel": kname,

@@ -42,13 +42,24 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 }
 
 constexpr int DATAFLOW_THREADS = 512;
+constexpr int DATAFLOW_EPT = 2;   // matrix elements per thread: N <= 32
 
+// Per ADO and stage: (A) wait for the neighbours' flags, (B) own tile -> shared memory, (C) per
+// coupling mode m: every thread sums ITS element of the mode's neighbours - S^L = sum c^L rho',
+// S^R = sum c^R rho', coalesced loads that are all in flight together - and the products
+// Q_m S^L + S^R Q_m are taken once per mode (element-wise for a diagonal Q_m, through shared
+// memory and the sparsity lists otherwise) instead of once per link, (D) -i[H, rho] from shared
+// memory, (E) the stage update.  The reference sums Q rho' per link (deom.py:656-664); by
+// linearity the per-mode form is the same number up to rounding.
 __global__ void __launch_bounds__(DATAFLOW_THREADS, 2) stage_dataflow_kernel(const DataflowArgs da) {
     extern __shared__ double2 smem[];
     const StageArgs& a = da.s;
     const int N = a.N, NN = N * N, M1 = 1 + a.nmod;
+    constexpr int EPT = DATAFLOW_EPT;
     double2* rho_s = smem;
-    double2* ops_s = rho_s + NN;
+    double2* sl_s = rho_s + NN;                         // S^L of the current mode
+    double2* sr_s = sl_s + NN;                          // S^R
+    double2* ops_s = sr_s + NN;
     const int maxl = 2 * a.nind;
     double2* lcf_s = ops_s + (size_t)M1 * NN;          // [maxl][2]
     int2* lk_s = (int2*)(lcf_s + 2 * maxl);            // [maxl]
@@ -56,6 +67,7 @@ __global__ void __launch_bounds__(DATAFLOW_THREADS, 2) stage_dataflow_kernel(con
     short* ri_s = rp_s + M1 * (N + 1);
     short* cp_s = ri_s + M1 * NN;
     short* ci_s = cp_s + M1 * (N + 1);
+    int* qdiag_s = (int*)(ci_s + M1 * NN);   // [M1]: operator o is diagonal (the four lists hold an even number of shorts)
     for (int e = threadIdx.x; e < M1 * NN; e += blockDim.x) {
         ops_s[e] = a.ops[e];
         ri_s[e] = a.row_idx[e];
@@ -64,6 +76,14 @@ __global__ void __launch_bounds__(DATAFLOW_THREADS, 2) stage_dataflow_kernel(con
     for (int e = threadIdx.x; e < M1 * (N + 1); e += blockDim.x) {
         rp_s[e] = a.row_ptr[e];
         cp_s[e] = a.col_ptr[e];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < M1; o += blockDim.x) {
+        int diag = 1;
+        for (int i = 0; i < N; ++i)
+            for (int t = rp_s[o * (N + 1) + i]; t < rp_s[o * (N + 1) + i + 1]; ++t)
+                if (ri_s[o * NN + t] != i) diag = 0;
+        qdiag_s[o] = diag;
     }
     const long long total = a.nmax * (long long)da.B;     // work items: (trajectory, ADO)
     const double dt = da.dt;
@@ -86,80 +106,126 @@ __global__ void __launch_bounds__(DATAFLOW_THREADS, 2) stage_dataflow_kernel(con
                     lk_s[t] = lk;
                     lcf_s[2 * t] = a.coef[2 * ci];
                     lcf_s[2 * t + 1] = a.coef[2 * ci + 1];
-                    // the neighbours must have published the stage input this stage reads
+                    // (A) the neighbours must have published the stage input this stage reads
                     const unsigned* f = da.flags + (long long)b * a.nmax + lk.x;
                     while (ld_acquire_u32(f) < g - 1u) __nanosleep(20);
                 }
                 __syncthreads();
-                for (int e = threadIdx.x; e < NN; e += blockDim.x) rho_s[e] = __ldcg(yin + boff + slot * NN + e);
+                // (B) own elements; the epilogue's operands are requested now as well
+                double2 own[EPT], yv[EPT], bs[EPT], v[EPT];
                 const double2 d = a.damp[slot];
-                __syncthreads();
-                for (int e = threadIdx.x; e < NN; e += blockDim.x) {
-                    const int i = e / N, j = e - i * N;
-                    const long long gi = boff + slot * NN + e;
-                    const double2 own = rho_s[e];
-                    double2 yv = own, bs = own;
-                    if (stage != 0) {
-                        bs = __ldcg(da.ACC + gi);
-                        if (stage != 3) yv = __ldcg(da.Y + gi);
+#pragma unroll
+                for (int u = 0; u < EPT; ++u) {
+                    const int e = threadIdx.x + u * DATAFLOW_THREADS;
+                    own[u] = yv[u] = bs[u] = v[u] = make_double2(0.0, 0.0);
+                    if (e < NN) {
+                        const long long gi = boff + slot * NN + e;
+                        own[u] = __ldcg(yin + gi);
+                        yv[u] = bs[u] = own[u];
+                        if (stage != 0) {
+                            bs[u] = __ldcg(da.ACC + gi);
+                            if (stage != 3) yv[u] = __ldcg(da.Y + gi);
+                        }
                     }
-                    double2 v = make_double2(-(d.x * own.x - d.y * own.y), -(d.x * own.y + d.y * own.x));
-                    for (int t = rp_s[i]; t < rp_s[i + 1]; ++t) {   // -i H rho
-                        const int l = ri_s[t];
-                        const double2 h = ops_s[i * N + l];
-                        cfma(v, make_double2(h.y, -h.x), rho_s[l * N + j]);
+                }
+#pragma unroll
+                for (int u = 0; u < EPT; ++u) {
+                    const int e = threadIdx.x + u * DATAFLOW_THREADS;
+                    if (e < NN) {
+                        rho_s[e] = own[u];
+                        v[u] = make_double2(-(d.x * own[u].x - d.y * own[u].y), -(d.x * own[u].y + d.y * own[u].x));
                     }
-                    for (int t = cp_s[j]; t < cp_s[j + 1]; ++t) {   // +i rho H
-                        const int l = ci_s[t];
-                        const double2 h = ops_s[l * N + j];
-                        cfma(v, make_double2(-h.y, h.x), rho_s[i * N + l]);
-                    }
+                }
+                // (C) coupling terms, mode by mode
+                for (int m = 0; m < a.nmod; ++m) {
+                    double2 SL[EPT], SR[EPT];
+#pragma unroll
+                    for (int u = 0; u < EPT; ++u) SL[u] = SR[u] = make_double2(0.0, 0.0);
                     for (int lp = 0; lp < nl; ++lp) {
                         const int2 lk = lk_s[lp];
+                        if (heom::meta_mode(lk.y) != m) continue;
                         const double2* __restrict__ pn = yin + boff + (long long)lk.x * NN;
-                        const int m1 = 1 + heom::meta_mode(lk.y);
-                        const double2* Qm = ops_s + m1 * NN;
+                        const double2 cl = lcf_s[2 * lp], cr = lcf_s[2 * lp + 1];
+#pragma unroll
+                        for (int u = 0; u < EPT; ++u) {
+                            const int e = threadIdx.x + u * DATAFLOW_THREADS;
+                            if (e < NN) {
+                                const double2 x = __ldcg(pn + e);
+                                cfma(SL[u], cl, x);
+                                cfma(SR[u], cr, x);
+                            }
+                        }
+                    }
+                    const int m1 = 1 + m;
+                    const double2* Qm = ops_s + m1 * NN;
+                    if (qdiag_s[m1]) {
+#pragma unroll
+                        for (int u = 0; u < EPT; ++u) {
+                            const int e = threadIdx.x + u * DATAFLOW_THREADS;
+                            if (e < NN) {
+                                const int i = e / N, j = e - i * N;
+                                cfma(v[u], Qm[i * N + i], SL[u]);
+                                cfma(v[u], Qm[j * N + j], SR[u]);
+                            }
+                        }
+                    } else {
+                        __syncthreads();   // the previous mode's products have read S^L, S^R
+#pragma unroll
+                        for (int u = 0; u < EPT; ++u) {
+                            const int e = threadIdx.x + u * DATAFLOW_THREADS;
+                            if (e < NN) {
+                                sl_s[e] = SL[u];
+                                sr_s[e] = SR[u];
+                            }
+                        }
+                        __syncthreads();
                         const short* rp = rp_s + m1 * (N + 1);
                         const short* ri = ri_s + m1 * NN;
                         const short* cp = cp_s + m1 * (N + 1);
                         const short* cx = ci_s + m1 * NN;
-                        const int r0 = rp[i], r1 = rp[i + 1], c0 = cp[j], c1 = cp[j + 1];
-                        double2 sl = make_double2(0.0, 0.0), sr = make_double2(0.0, 0.0);
-                        if (r1 - r0 <= 2 && c1 - c0 <= 2) {
-                            double2 q[4], x[4];
 #pragma unroll
-                            for (int u = 0; u < 2; ++u) {
-                                const bool lv = r0 + u < r1, rv = c0 + u < c1;
-                                const int ll = lv ? ri[r0 + u] : 0, lr = rv ? cx[c0 + u] : 0;
-                                q[u] = lv ? Qm[i * N + ll] : make_double2(0.0, 0.0);
-                                q[2 + u] = rv ? Qm[lr * N + j] : make_double2(0.0, 0.0);
-                                x[u] = lv ? __ldcg(pn + ll * N + j) : make_double2(0.0, 0.0);
-                                x[2 + u] = rv ? __ldcg(pn + i * N + lr) : make_double2(0.0, 0.0);
-                            }
-                            cfma(sl, q[0], x[0]);
-                            cfma(sl, q[1], x[1]);
-                            cfma(sr, q[2], x[2]);
-                            cfma(sr, q[3], x[3]);
-                        } else {
-                            for (int t = r0; t < r1; ++t) {
-                                const int l = ri[t];
-                                cfma(sl, Qm[i * N + l], __ldcg(pn + l * N + j));
-                            }
-                            for (int t = c0; t < c1; ++t) {
-                                const int l = cx[t];
-                                cfma(sr, Qm[l * N + j], __ldcg(pn + i * N + l));
+                        for (int u = 0; u < EPT; ++u) {
+                            const int e = threadIdx.x + u * DATAFLOW_THREADS;
+                            if (e < NN) {
+                                const int i = e / N, j = e - i * N;
+                                for (int t = rp[i]; t < rp[i + 1]; ++t) {
+                                    const int l = ri[t];
+                                    cfma(v[u], Qm[i * N + l], sl_s[l * N + j]);
+                                }
+                                for (int t = cp[j]; t < cp[j + 1]; ++t) {
+                                    const int l = cx[t];
+                                    cfma(v[u], Qm[l * N + j], sr_s[i * N + l]);
+                                }
                             }
                         }
-                        cfma(v, lcf_s[2 * lp], sl);
-                        cfma(v, lcf_s[2 * lp + 1], sr);
+                    }
+                }
+                __syncthreads();   // rho_s is complete
+                // (D) -i [H, rho] and (E) the stage update
+#pragma unroll
+                for (int u = 0; u < EPT; ++u) {
+                    const int e = threadIdx.x + u * DATAFLOW_THREADS;
+                    if (e >= NN) continue;
+                    const int i = e / N, j = e - i * N;
+                    const long long gi = boff + slot * NN + e;
+                    double2 w = v[u];
+                    for (int t = rp_s[i]; t < rp_s[i + 1]; ++t) {   // -i H rho
+                        const int l = ri_s[t];
+                        const double2 h = ops_s[i * N + l];
+                        cfma(w, make_double2(h.y, -h.x), rho_s[l * N + j]);
+                    }
+                    for (int t = cp_s[j]; t < cp_s[j + 1]; ++t) {   // +i rho H
+                        const int l = ci_s[t];
+                        const double2 h = ops_s[l * N + j];
+                        cfma(w, make_double2(-h.y, h.x), rho_s[i * N + l]);
                     }
                     if (stage == 3) {
-                        const double2 res = make_double2(fma(cw, v.x, bs.x), fma(cw, v.y, bs.y));
+                        const double2 res = make_double2(fma(cw, w.x, bs[u].x), fma(cw, w.y, bs[u].y));
                         da.Y[gi] = res;
                         if (a.traj && slot == a.slot0) a.traj[b * a.traj_bstride + (step + 1) * NN + e] = res;
                     } else {
-                        da.ACC[gi] = make_double2(fma(cw, v.x, bs.x), fma(cw, v.y, bs.y));
-                        yout[gi] = make_double2(fma(ca, v.x, yv.x), fma(ca, v.y, yv.y));
+                        da.ACC[gi] = make_double2(fma(cw, w.x, bs[u].x), fma(cw, w.y, bs[u].y));
+                        yout[gi] = make_double2(fma(ca, w.x, yv[u].x), fma(ca, w.y, yv[u].y));
                     }
                 }
                 __syncthreads();   // every element of this ADO's stage output is written ...

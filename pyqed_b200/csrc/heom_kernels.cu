@@ -203,8 +203,8 @@ static int try_dataflow(pyqed_heom_plan* p) {
         return -1;
     const int N = p->N, NN = N * N;
     const size_t M1 = 1 + (size_t)p->M;
-    const size_t smem = sizeof(double2) * (NN + M1 * NN + 2 * 2 * (size_t)p->K) + sizeof(int2) * 2 * (size_t)p->K +
-                        sizeof(short) * 2 * (M1 * NN + M1 * (N + 1)) + 16;
+    const size_t smem = sizeof(double2) * (3 * NN + M1 * NN + 2 * 2 * (size_t)p->K) + sizeof(int2) * 2 * (size_t)p->K +
+                        sizeof(short) * 2 * (M1 * NN + M1 * (N + 1)) + sizeof(int) * (M1 + 2) + 16;
     if (smem > 200 * 1024) return -1;
     static PerDeviceOnce attr;
     if (attr.need(p->device))
