@@ -118,6 +118,7 @@ struct pyqed_heom_plan {
         const int* push_ptr = nullptr;           // caller-owned device tables (CSR over owned slots)
         const int2* push_ent = nullptr;
         unsigned long long* d_peer = nullptr;    // device copy of the peers' state buffer addresses
+        unsigned long long peer_state[16] = {0}; // host copy of the peers' state buffer addresses
         unsigned long long peer_flags[16] = {0}; // address of every rank's flag block (world uint32 + error word)
         unsigned epoch = 0;                      // barriers done so far
         long long pushed_rows = 0;               // rows per stage this rank stores into its peers

@@ -249,7 +249,9 @@ int pyqed_heom_shard_setup(pyqed_heom_plan* p, int rank, int world, int64_t lo, 
     (void)NN;
     // peers: [0, 16) state buffers, [16, 32) flag blocks
     unsigned long long tab[32] = {0};
+    for (int q = 0; q < 16; ++q) sh.peer_state[q] = 0;
     for (int q = 0; q < world; ++q) {
+        sh.peer_state[q] = peer_state_ptrs[q];
         tab[q] = peer_state_ptrs[q];
         tab[16 + q] = peer_state_ptrs[q] + flag_off;
         sh.peer_flags[q] = tab[16 + q];
@@ -348,7 +350,7 @@ static int shard_stage(pyqed_heom_plan* p, int64_t step, int stage) {
     a.pool_off = (unsigned)(sh.n_own_max * EL);
     a.push_ptr = sh.push_ptr;
     a.push_ent = sh.push_ent;
-    a.peer = sh.d_peer;
+    for (int q = 0; q < 16; ++q) a.peer[q] = sh.peer_state[q];
     a.out_elem_off = pool_off_in_state(p, out, sh.packed);
     s.push = (sh.world > 1 && sh.pushed_rows > 0) ? 1 : 0;
     s.H = reinterpret_cast<const double*>(p->H.data());

@@ -60,18 +60,24 @@ constexpr int SYM_TOFS = 16;  // double2 units reserved for the packed-row offse
 // one group ahead.
 // Shared-memory layouts chosen for the banks (a 128-bit access is served per quarter warp, eight
 // 16-byte slots wide): with lane = sub N + row,
-//   k tile:         element (i, j) of ADO `sub` at sub KSUB + 8 i + j, KSUB = 9N - 8 (= N mod 8):
+//   k tile:         element (i, j) of ADO `sub` at sub KSUB + KLD i + j, KLD = 8, KSUB = 9N - 8 (= N mod 8):
 //                   column accesses (fixed i), the diagonal, the (row, row+d) diagonals and their
 //                   transposes all land in slot lane + const (mod 8) - no conflicts;
 //   neighbour rows: element `row` of link t at sub NBSUB + t N + row, NBSUB = N mod 8.
 // (The staged own tile keeps the layout of the global array, it arrives by bulk copy.)
-__host__ __device__ constexpr int sym_kld() { return 8; }
-__host__ __device__ constexpr int sym_ksub(int N) { return 9 * N - 8; }
+// Packed storage (kernel 7) forms k = P' + P'^dagger in the epilogue, which reads (and, with the
+// fused push, writes) element (j, i) next to (i, j) with consecutive lanes on consecutive j: there
+// the row stride is 9, so that the transposed accesses spread over the slots as well.
+__host__ __device__ constexpr int sym_kld(bool packed) { return packed ? 9 : 8; }
+__host__ __device__ constexpr int sym_ksub(int N, bool packed) {
+    const int base = (N - 1) * sym_kld(packed) + N;
+    return base + ((N - base) % 8 + 8) % 8;
+}
 __host__ __device__ constexpr int sym_nbsub(int N) { return N * N + ((N - N * N) % 8 + 8) % 8; }
 
 __host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed, bool db = false) {
     const int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE_R = APW * N * LD;
-    const int TILE = APW * sym_ksub(N), FLAT = APW * sym_nbsub(N);
+    const int TILE = APW * sym_ksub(N, packed), FLAT = APW * sym_nbsub(N);
     const int FE = APW * (packed ? N * (N + 1) / 2 : N * N);   // a group's elements in the global arrays
     const int RT = packed ? FE : TILE_R;                     // own tile as staged
     const int nb = db ? 2 : 1;
@@ -111,7 +117,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     static_assert(!PUSH || !DB, "the fused push has no double-buffered variant");
     constexpr bool FIRST = STAGE == 0, LAST = STAGE == 2;
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE_R = APW * N * LD;
-    constexpr int KLD = sym_kld(), KSUB = sym_ksub(N), NBSUB = sym_nbsub(N);
+    constexpr int KLD = sym_kld(PACKED), KSUB = sym_ksub(N, PACKED), NBSUB = sym_nbsub(N);
     constexpr int TILE = APW * KSUB, FLAT = APW * NBSUB;   // k tile, neighbour rows
     constexpr int PERWARP = sym_perwarp(N, STAGE, PACKED, DB), NCH = SYM_NCH;
     constexpr int NBUF = DB ? 2 : 1;
@@ -325,6 +331,9 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         const int lbeg = nx_lbeg, lend = nx_lend;
         const int nl = on ? (lend - lbeg) : 0;
         const int pb = nx_pb, pe = on ? nx_pe : nx_pb;
+        // PUSH: this lane's first push entry is requested now and used after the epilogue
+        int2 pent = make_int2(0, 0);
+        if (PUSH && pb + row < pe) pent = __ldg(a.push_ent + pb + row);
         const double dh = 0.5 * nx_damp;
         const unsigned gbase = (unsigned)base * (unsigned)EL;
         // publish this group's records, then start the prefetch of the next group's
@@ -598,8 +607,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                 fence_proxy_async();   // this lane's tile writes are ordered before the bulk stores
                 __syncwarp();
                 for (int q = pb + row; q < pe; q += N) {
-                    const int2 ent = a.push_ent[q];
-                    double2* dst = reinterpret_cast<double2*>(__ldg(a.peer + (ent.y >> 4))) + a.out_elem_off +
+                    const int2 ent = q == pb + row ? pent : a.push_ent[q];
+                    double2* dst = reinterpret_cast<double2*>(a.peer[(ent.y >> 4) & 15]) + a.out_elem_off +
                                    (size_t)(unsigned)ent.x * N;
                     bulk_s2g(dst, ksub + (ent.y & 15) * KLD, N * 16u);
                 }

