@@ -190,7 +190,7 @@ class ShardedDEOM:
 
     def __init__(self, system, system_dipole, coupling, coupling_dipole, expn, etal, etar, etaa,
                  mode, lmax, transport, device=0, order=1, options=None, tuning=None, peer_push=None,
-                 fused_push=None, native=None):
+                 fused_push=None, native=None, rebalance=None):
         from .._cabi import Plan
         self.tr = transport
         self.rank, self.world = transport.rank, transport.world
@@ -215,6 +215,11 @@ class ShardedDEOM:
             p.build(tables_only=True)
             if p.info("off_links2") >= 0 and p.info("sym_inputs") == 1 and order == 2:
                 self._init_native(p)
+                # the ranges are first balanced by a static cost (links per ADO); the time of a stage
+                # also depends on how many rows a rank stores to and reads from its peers, so large
+                # hierarchies are measured once and re-cut (None = from 2^20 ADOs per job)
+                if (rebalance if rebalance is not None else (self.nmax >= (1 << 20))) and self.world > 1:
+                    self._rebalance(p, force=(rebalance == "force"))
                 return
             if native:
                 raise ValueError("the rank-local sharded layout needs storage order 2 and a problem for "
@@ -308,7 +313,51 @@ class ShardedDEOM:
                                  if self.bounds[r] <= p.info("slot0") < self.bounds[r + 1])
 
     # -- rank-local layout: own ADOs + pool of halo rows, rows stored by their owners --------
-    def _init_native(self, p):
+    def _rebalance(self, p, steps=2, force=False):
+        """Re-cut the ranges from measured stage-kernel times: a rank that took longer per ADO gets
+        fewer ADOs (cost density assumed uniform inside a rank's old range)."""
+        n = self.n
+        rho = np.eye(n, dtype=C128) / n
+        self.set_state(rho)
+        self._native_propagate(1e-9, 1, None)            # warm-up
+        p.synchronize()
+        p.stage_timing(True)
+        self._native_propagate(1e-9, steps, None)
+        ms, cnt = p.stage_timing(False)
+        mine = ms / max(cnt, 1)
+        times = [x[0] / 1e6 for x in self.tr.allgather_counts([int(mine * 1e6)])]   # ms per stage, per rank
+        owned = [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)]
+        if min(owned) <= 0 or min(times) <= 0 or (max(times) / min(times) < 1.03 and not force):
+            self.timings["rebalance"] = {"stage_ms_before": times, "changed": False}
+            return
+        # cumulative cost over slots, piecewise linear; new boundaries at equal shares
+        edges = np.array(self.bounds, dtype=np.float64)
+        cum = np.concatenate([[0.0], np.cumsum(times)])
+        targets = cum[-1] * np.arange(1, self.world) / self.world
+        inner = np.interp(targets, cum, edges)
+        new = [0] + [int(min(self.nmax, max(0, round(b / 64.0) * 64))) for b in inner] + [self.nmax]
+        if any(b1 <= b0 for b0, b1 in zip(new, new[1:])):
+            self.timings["rebalance"] = {"stage_ms_before": times, "changed": False}
+            return
+        before = dict(self.timings)
+        self._release_native()
+        p._check(p.lib.pyqed_heom_build_hierarchy(p._h))   # fresh link table (the old one was localized in place)
+        self._init_native(p, bounds=new)
+        self.timings["first_cut"] = before
+        self.timings["rebalance"] = {"stage_ms_before": times, "changed": True, "old_bounds": [int(b) for b in edges],
+                                     "new_bounds": new}
+
+    def _release_native(self):
+        p = self.plan
+        self.tr.barrier()
+        for q, ptr in enumerate(self._peer_ptrs):
+            if q != self.rank:
+                p.lib.pyqed_heom_shared_close(self.device, ptr)
+        p.lib.pyqed_heom_shared_free(self.device, self._state_ptr)
+        self._state_ptr = None
+        self.native = False
+
+    def _init_native(self, p, bounds=None):
         import ctypes as C
         import time
         tr, world, rank = self.tr, self.world, self.rank
@@ -327,8 +376,11 @@ class ShardedDEOM:
         self.link_ptr = tables[lp_off:lp_off + 4 * (self.nmax + 1)].view(torch.int32)
         nlinks = p.info("nlinks")
         links = tables[lk_off:lk_off + 8 * nlinks].view(torch.int32).view(nlinks, 2)
-        self.bounds = cost_balanced_bounds(self.link_ptr.cpu().numpy(), world)
-        self.bounds = ([0] + [min(self.nmax, (b + 32) // 64 * 64) for b in self.bounds[1:-1]] + [self.nmax])
+        if bounds is None:
+            self.bounds = cost_balanced_bounds(self.link_ptr.cpu().numpy(), world)
+            self.bounds = ([0] + [min(self.nmax, (b + 32) // 64 * 64) for b in self.bounds[1:-1]] + [self.nmax])
+        else:
+            self.bounds = list(bounds)
         self.lo, self.hi = lo, hi = self.bounds[rank], self.bounds[rank + 1]
         n_own = hi - lo
         lap("bounds")
@@ -395,14 +447,9 @@ class ShardedDEOM:
         if getattr(self, "plan", None) is None:
             return
         if self.native and getattr(self, "_state_ptr", None):
-            p = self.plan
-            self.tr.barrier()
-            for q, ptr in enumerate(self._peer_ptrs):
-                if q != self.rank:
-                    p.lib.pyqed_heom_shared_close(self.device, ptr)
-            p.lib.pyqed_heom_shared_free(self.device, self._state_ptr)
-            self._state_ptr = None
+            self._release_native()
         self.plan.close()
+        self.plan = None
 
     def _host_barrier(self):
         self.plan.synchronize()

@@ -146,7 +146,8 @@ def gpu_mode(args):
                            tuning=dict(kernel=args.kernel, warps_per_cta=0, use_graph=0),
                            peer_push={-1: None, 0: False, 1: True}[args.push],
                            fused_push={-1: None, 0: False, 1: True}[args.fused],
-                           native={-1: None, 0: False, 1: True}[args.native])
+                           native={-1: None, 0: False, 1: True}[args.native],
+                           rebalance={0: None, 1: "force"}[args.rebalance])
         nt = int(g["nt"])
         from conftest import pulse_from_samples
         dt = float(g["dt"])
@@ -165,6 +166,8 @@ def gpu_mode(args):
         items = sh.halo_bytes_per_stage() // (sh.elems * 8)
         if sh.native:
             sh.check_barriers()
+        if args.rebalance and sh.native:
+            print(f"rank {tr.rank}: {name} rebalanced={sh.timings['rebalance']['changed']} bounds {sh.bounds}", flush=True)
         print(f"rank {tr.rank}: {name} native={sh.native} packed={sh.plan.info('shard_packed')} "
               f"push={sh.symm is not None} fused={sh.fused} ok (owned {sh.hi - sh.lo} of {sh.nmax}, halo items "
               f"{items}, row items {sh.row_items}, err {err:.1e})", flush=True)
@@ -212,6 +215,7 @@ if __name__ == "__main__":
     ap.add_argument("--push", type=int, default=-1)
     ap.add_argument("--fused", type=int, default=-1)
     ap.add_argument("--kernel", type=int, default=0, help="stage kernel (tuning), e.g. 6")
+    ap.add_argument("--rebalance", type=int, default=0, help="1: re-cut the ranges from measured stage times")
     ap.add_argument("--native", type=int, default=-1, help="rank-local arrays + fused peer stores: 1 require, 0 never")
     a = ap.parse_args()
     dist.init_process_group(a.backend)

@@ -89,6 +89,16 @@ def test_sharded_nccl_two_gpus(push, fused):
 
 
 @pytest.mark.gpu
+def test_rank_local_layout_rebalanced_ranges():
+    """Ranges re-cut from measured stage times (what large hierarchies do once at set-up): the
+    layout is torn down, the link table rebuilt and localized for the new ranges; results unchanged."""
+    out = _launch(3, ["gpu", "--backend", "gloo", "--order", "2", "--native", "1", "--rebalance", "1", "--cases",
+                      "deom_fmo_K21_L3,deom_fmo_K7_L4"])
+    assert out.count(" ok (owned") == 6 and out.count("native=True") == 6
+    assert out.count("rebalanced=True") >= 3
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("kernel", [0, 6])
 def test_rank_local_layout_two_gpus(kernel):
     """The same on two GPUs: peer stores over NVLink and the device flag barrier
