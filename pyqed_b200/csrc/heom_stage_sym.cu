@@ -75,7 +75,13 @@ __host__ __device__ constexpr int sym_ksub(int N, bool packed) {
 }
 __host__ __device__ constexpr int sym_nbsub(int N) { return N * N + ((N - N * N) % 8 + 8) % 8; }
 
-__host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed, bool db = false) {
+// fused push: per-warp staging area for the rows a group sends to other ranks (N elements each)
+#ifndef HEOM_SYM_PUSH_SLOTS
+#define HEOM_SYM_PUSH_SLOTS 12
+#endif
+constexpr int SYM_PUSH_SLOTS = HEOM_SYM_PUSH_SLOTS;
+
+__host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed, bool db = false, bool push = false) {
     const int APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE_R = APW * N * LD;
     const int TILE = APW * sym_ksub(N, packed), FLAT = APW * sym_nbsub(N);
     const int FE = APW * (packed ? N * (N + 1) / 2 : N * N);   // a group's elements in the global arrays
@@ -83,7 +89,7 @@ __host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed, boo
     const int nb = db ? 2 : 1;
     // own tile, k tile, neighbour rows, [y], [first stage buffer], record strip, mbarriers
     return nb * RT + TILE + FLAT + (stage == 0 ? 0 : nb * FE) + (stage == 2 ? nb * FE : 0) +
-           SYM_NCH * APW * N / 2 + 3;
+           SYM_NCH * APW * N / 2 + 3 + (push ? SYM_PUSH_SLOTS * N : 0);
 }
 __host__ __device__ constexpr int sym_max_threads(int stage) {
     return stage == 2 ? HEOM_SYM_LAST_THREADS : HEOM_SYM_THREADS;
@@ -119,7 +125,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     constexpr int NN = N * N, APW = 32 / N, LD = (N % 2 == 0) ? N + 1 : N, TILE_R = APW * N * LD;
     constexpr int KLD = sym_kld(PACKED), KSUB = sym_ksub(N, PACKED), NBSUB = sym_nbsub(N);
     constexpr int TILE = APW * KSUB, FLAT = APW * NBSUB;   // k tile, neighbour rows
-    constexpr int PERWARP = sym_perwarp(N, STAGE, PACKED, DB), NCH = SYM_NCH;
+    constexpr int PERWARP = sym_perwarp(N, STAGE, PACKED, DB, PUSH), NCH = SYM_NCH;
+    constexpr int PSLOTS = SYM_PUSH_SLOTS;
     constexpr int NBUF = DB ? 2 : 1;
     constexpr int PK = N * (N + 1) / 2, EL = PACKED ? PK : NN;   // elements per ADO in the global arrays
     constexpr int FE = APW * EL, RT = PACKED ? FE : TILE_R;
@@ -143,6 +150,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     unsigned long long* barA0 = (unsigned long long*)(strip + NCH * APW * N);   // own tile, per buffer set
     unsigned long long* barB0 = barA0 + NBUF;                                   // y / first stage buffer
     unsigned long long* barD = barA0 + 2 * NBUF;                                // second stage buffer
+    double2* const push_s = rho0 + PERWARP - PSLOTS * N;                        // PUSH: rows on their way to peers
     unsigned phA = 0, phB = 0, phD = 0;   // phA / phB: one phase bit per buffer set
     if (lane == 0) {
 #pragma unroll
@@ -390,7 +398,6 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             mbar_wait(barA, (phA >> buf) & 1u);
             phA ^= 1u << buf;
         }
-        if (PUSH) bulk_wait_read();   // the previous group's rows have left the k tile
         __syncwarp();
 
         // ---- P = -i H rho - (damp/2) rho, column `row` of this ADO.  The full
@@ -547,13 +554,29 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         __syncwarp();
 
         // ---- epilogue from shared memory, streaming stores
-        // PUSH: the stage output goes back into the k tile as full rows (packed storage: the
-        // element below the diagonal too), from where the halo rows leave as bulk stores
-        // (only in groups that push anything)
+        // PUSH: the rows of this group's output that other ranks read are collected in the warp's
+        // staging area while the epilogue computes them, and leave from there as bulk stores.  The
+        // group's push entries are consecutive in the table: entry t of ADO s goes to staging slot
+        // (first entry of s - first entry of the group) + t.  What does not fit (more than PSLOTS
+        // rows per group, more than N entries per ADO) takes the element-wise path below.
         const bool any_push = PUSH && __reduce_max_sync(0xffffffffu, pe - pb) > 0;
-        auto put_k = [&](int kk, const double2 v) {
-            k_s[kk & 0xffff] = v;
-            if (PACKED && (kk >> 16) != (kk & 0xffff)) k_s[kk >> 16] = make_double2(v.x, -v.y);
+        const int pb0 = PUSH ? __shfl_sync(0xffffffffu, pb, 0) : 0;
+        if (PUSH && any_push) {
+            bulk_wait_read();   // the previous group's rows have left the staging area
+            if (lane_ok) {
+                strip[sub * N + row] = pent;
+                if (row == 0) strip[APW * N + sub] = make_int2(pb - pb0, pe - pb);
+            }
+            __syncwarp();
+        }
+        auto stage_rows = [&](int e, int kk, const double2 v) {
+            const int s_ = e / EL, k0 = (kk & 0xffff) - s_ * KSUB, i = k0 / KLD, j = k0 - i * KLD;
+            const int2 hdr = strip[APW * N + s_];
+            for (int t = 0; t < hdr.y && t < N && hdr.x + t < PSLOTS; ++t) {
+                const int r = strip[s_ * N + t].y & 15;
+                if (i == r) push_s[(hdr.x + t) * N + j] = v;
+                if (PACKED && j == r && i != j) push_s[(hdr.x + t) * N + i] = make_double2(v.x, -v.y);
+            }
         };
         auto get_k = [&](int kk) {
             double2 v = k_s[kk & 0xffff];
@@ -582,7 +605,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     res.x = fma(2.0 * third, s2.x, res.x);
                     res.y = fma(2.0 * third, s2.y, res.y);
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH && any_push) put_k(kofs[it], res);
+                    if (PUSH && any_push) stage_rows(e, kofs[it], res);
                     if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)EL) {
                         if (PACKED) {   // the trajectory holds full matrices
                             const int kk = (kofs[it] & 0xffff) - (e0 / EL) * KSUB, i = kk / KLD, j = kk - i * KLD;
@@ -596,23 +619,32 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     const double2 yv = FIRST ? rho_s[rofs(it)] : y_s[e];
                     const double2 res = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH && any_push) put_k(kofs[it], res);
+                    if (PUSH && any_push) stage_rows(e, kofs[it], res);
                 }
             }
         }
-        if (PUSH) {
-            // rows of this group's output that other ranks read: from the k tile straight into
-            // their arrays.  The N lanes of an ADO share its entries.
-            if (any_push) {
-                fence_proxy_async();   // this lane's tile writes are ordered before the bulk stores
-                __syncwarp();
-                for (int q = pb + row; q < pe; q += N) {
-                    const int2 ent = q == pb + row ? pent : a.push_ent[q];
-                    double2* dst = reinterpret_cast<double2*>(a.peer[(ent.y >> 4) & 15]) + a.out_elem_off +
-                                   (size_t)(unsigned)ent.x * N;
-                    bulk_s2g(dst, ksub + (ent.y & 15) * KLD, N * 16u);
+        if (PUSH && any_push) {
+            fence_proxy_async();   // the staging writes are ordered before the bulk stores
+            __syncwarp();
+            const int slot = pb - pb0 + row;
+            if (pb + row < pe && slot < PSLOTS) {
+                double2* dst = reinterpret_cast<double2*>(a.peer[(pent.y >> 4) & 15]) + a.out_elem_off +
+                               (size_t)(unsigned)pent.x * N;
+                bulk_s2g(dst, push_s + slot * N, N * 16u);
+            }
+            bulk_commit();
+            // rare: rows beyond the staging area or beyond N entries per ADO - the N lanes of the ADO
+            // store the row element by element, read back from the output this warp has just written
+            if (pe - pb > N || pe - pb0 > PSLOTS) {
+                for (int q = pb; q < pe; ++q) {
+                    if (q - pb < N && q - pb0 < PSLOTS) continue;
+                    const int2 ent = a.push_ent[q];
+                    const int r = ent.y & 15, lo_ = min(r, row), hi_ = max(r, row);
+                    const int off = PACKED ? lo_ * N - lo_ * (lo_ - 1) / 2 + (hi_ - lo_) : r * N + row;
+                    double2 v = __ldcg(a.out + (gbase + (unsigned)(sub * EL + off)));
+                    if (PACKED && row < r) v.y = -v.y;
+                    reinterpret_cast<double2*>(a.peer[(ent.y >> 4) & 15])[a.out_elem_off + (size_t)(unsigned)ent.x * N + row] = v;
                 }
-                bulk_commit();
             }
         }
         __syncwarp();
@@ -676,7 +708,7 @@ int sym_launch_t(const SymLaunch& s) {
     args.slot_lo = s.part_lo;
     args.slot_hi = s.part_hi;
     const size_t table_bytes = sym_table_bytes(s.K, s.L);
-    const size_t per_warp = sizeof(double2) * sym_perwarp(N, STAGE, PACKED, DB);
+    const size_t per_warp = sizeof(double2) * sym_perwarp(N, STAGE, PACKED, DB, PUSH);
     if (table_bytes + per_warp > SYM_SMEM_BUDGET) {
         g_sym_err = "shared-memory tables too large for kernel 6";
         return 1;

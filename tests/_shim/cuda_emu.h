@@ -172,6 +172,7 @@ inline int __shfl_sync(unsigned mask, int v, int src) {
 // ---- memory access wrappers ---------------------------------------------------
 template <typename T> inline T __ldg(const T* p) { return *p; }
 template <typename T> inline T __ldcs(const T* p) { return *p; }
+template <typename T> inline T __ldcg(const T* p) { return *p; }
 template <typename T> inline void __stcs(T* p, const T v) { *p = v; }
 
 inline unsigned smem_u32(const void* p) {
