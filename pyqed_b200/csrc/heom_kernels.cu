@@ -546,6 +546,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "packed_steps") return p->packed_steps;
     if (n == "dataflow_launches") return p->dataflow_launches;
     if (n == "rk_scheme") return rk_scheme(p) ? 1 : 0;
+    if (n == "stage_kernel") return stage_kernel_of(p);
     if (n == "nlinks") return p->nlinks;
     if (n == "nmax") return p->nmax;
     if (n == "slot0") return p->slot0;

@@ -147,7 +147,7 @@ inline int stage_kernel_of(const pyqed_heom_plan* p) {
     //     kernel 3 otherwise
     // 8 = persistent dataflow propagation (heom_dataflow.cuh) where eligible, the generic kernel otherwise
     if (p->kernel && p->kernel != 4 && p->kernel != 6 && p->kernel != 7 && p->kernel != 8) return p->kernel;
-    if (p->N > 8 || p->kernel == 8) return 2;
+    if (p->N > 8 || p->N < 2 || p->kernel == 8) return 2;   // (the row kernels need 2 <= N <= 8)
     const bool fits32 = (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
     return (p->use_qdiag && p->opt_rk13 != 0 && fits32) ? 3 : 1;
 }

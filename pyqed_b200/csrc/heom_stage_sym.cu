@@ -730,15 +730,18 @@ int sym_launch_t(const SymLaunch& s) {
     }
     auto kern = stage_rows_sym_kernel<N, HREAL, STAGE, PACKED, DB, PUSH>;
 #ifndef HEOM_HOST_EMU
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device
+    static unsigned long long attr_done = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_done >> (dev & 63) & 1ull)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)SYM_SMEM_BUDGET);
         if (e != cudaSuccess) {
             g_sym_err = cudaGetErrorString(e);
             return 1;
         }
-        attr_set = true;
+        attr_done |= 1ull << (dev & 63);
     }
 #endif
     // dynamic schedule only where a warp processes several groups (otherwise the order is moot)

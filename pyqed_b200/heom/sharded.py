@@ -252,7 +252,10 @@ class ShardedDEOM:
         self.nmax = p.nmax
         # a diagonal Q_m only reads the rows r of a neighbour with (Q_m)_rr != 0, and
         # (for Hermitian ADOs) gets the column entries as their conjugates
-        self.row_items = bool(p.info("qdiag")) and bool(p.info("hermitian_inputs"))
+        # ... which only the row kernels (1, 3) do; the generic kernel reads whole neighbours.  Row items
+        # are slot*8+row in 32 bits.
+        self.row_items = (bool(p.info("qdiag")) and bool(p.info("hermitian_inputs"))
+                          and p.info("stage_kernel") in (1, 3) and self.nmax * 8 < 2 ** 31)
         Qa = np.asarray(coupling, dtype=C128)[:m]
         Qd = (np.zeros_like(Qa) if coupling_dipole is None
               else np.broadcast_to(np.asarray(coupling_dipole, dtype=C128), Qa.shape))
