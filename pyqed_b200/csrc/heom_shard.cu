@@ -70,7 +70,7 @@ __global__ void shard_push_rows_kernel(const double2* arr, const int* push_ptr, 
             } else {
                 v = arr[slot * EL + r * N + j];
             }
-            reinterpret_cast<double2*>(peer[ent.y >> 4])[dst_pool_off + (long long)(unsigned)ent.x * N + j] = v;
+            reinterpret_cast<double2*>(peer[ent.y >> 4])[dst_pool_off + (long long)(unsigned)ent.x * sym_pool_stride(N) + j] = v;
         }
     }
     __threadfence_system();
@@ -130,7 +130,7 @@ long long pool_off_in_state(const pyqed_heom_plan* p, int which, bool packed) {
     const int N = p->N, EL = packed ? N * (N + 1) / 2 : N * N;
     const long long arr0 = packed ? (long long)(p->array_bytes / sizeof(double2)) + (long long)which * (long long)sh.arr_packed
                                   : (long long)which * (long long)(p->array_bytes / sizeof(double2));
-    return arr0 + sh.n_own_max * EL;
+    return arr0 + sym_pool_offset(sh.n_own_max, EL);
 }
 
 int push_rows(pyqed_heom_plan* p, const double2* arr, int which, bool packed) {
@@ -185,11 +185,12 @@ int pyqed_heom_shared_free(int device, void* d_ptr) {
 
 // ---- sizes ------------------------------------------------------------------------------------
 // State buffer of a rank whose largest peer owns n_own_max ADOs and whose largest pool has
-// pool_max rows: four arrays of (n_own_max N^2 + pool_max N) elements, then the flag block.
+// pool_max rows: four arrays of (n_own_max N^2 + pool_max sym_pool_stride(N)) elements, then the flag block.
 int pyqed_heom_shard_state_bytes(pyqed_heom_plan* p, int64_t n_own_max, int64_t pool_max, size_t* state_bytes,
                                  size_t* flag_offset) {
     REQUIRE(p && state_bytes && flag_offset && n_own_max >= 0 && pool_max >= 0, "shard_state_bytes: bad argument");
-    const size_t arr = align_up(sizeof(double2) * ((size_t)n_own_max * p->N * p->N + (size_t)pool_max * p->N));
+    const size_t arr = align_up(sizeof(double2) * ((size_t)sym_pool_offset(n_own_max, p->N * p->N) +
+                                                   (size_t)pool_max * sym_pool_stride(p->N)));
     *flag_offset = 4 * arr;
     *state_bytes = 4 * arr + 256;
     return 0;
@@ -244,7 +245,8 @@ int pyqed_heom_shard_setup(pyqed_heom_plan* p, int rank, int world, int64_t lo, 
     p->d_state = (char*)d_state;
     p->array_bytes = flag_off / 4;
     sh.arr_full = p->array_bytes / sizeof(double2);
-    sh.arr_packed = align_up(sizeof(double2) * ((size_t)n_own_max * PK + (size_t)pool_max * N)) / sizeof(double2);
+    sh.arr_packed = align_up(sizeof(double2) * ((size_t)sym_pool_offset(n_own_max, PK) +
+                                                (size_t)pool_max * sym_pool_stride(N))) / sizeof(double2);
     sh.packed = (p->kernel == 0 || p->kernel == 7) && p->opt_packed != 0 && 4 * sh.arr_packed <= 3 * sh.arr_full;
     (void)NN;
     // peers: [0, 16) state buffers, [16, 32) flag blocks
@@ -347,7 +349,7 @@ static int shard_stage(pyqed_heom_plan* p, int64_t step, int stage) {
     a.nind = p->K;
     a.nmod = p->M;
     a.lmax = p->L;
-    a.pool_off = (unsigned)(sh.n_own_max * EL);
+    a.pool_off = (unsigned)sym_pool_offset(sh.n_own_max, EL);
     a.push_ptr = sh.push_ptr;
     a.push_ent = sh.push_ent;
     for (int q = 0; q < 16; ++q) a.peer[q] = sh.peer_state[q];

@@ -89,7 +89,7 @@ __host__ __device__ constexpr int sym_perwarp(int N, int stage, bool packed, boo
     const int nb = db ? 2 : 1;
     // own tile, k tile, neighbour rows, [y], [first stage buffer], record strip, mbarriers
     return nb * RT + TILE + FLAT + (stage == 0 ? 0 : nb * FE) + (stage == 2 ? nb * FE : 0) +
-           SYM_NCH * APW * N / 2 + 3 + (push ? SYM_PUSH_SLOTS * N : 0);
+           SYM_NCH * APW * N / 2 + 3 + (push ? SYM_PUSH_SLOTS * sym_pool_stride(N) : 0);
 }
 __host__ __device__ constexpr int sym_max_threads(int stage) {
     return stage == 2 ? HEOM_SYM_LAST_THREADS : HEOM_SYM_THREADS;
@@ -126,7 +126,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     constexpr int KLD = sym_kld(PACKED), KSUB = sym_ksub(N, PACKED), NBSUB = sym_nbsub(N);
     constexpr int TILE = APW * KSUB, FLAT = APW * NBSUB;   // k tile, neighbour rows
     constexpr int PERWARP = sym_perwarp(N, STAGE, PACKED, DB, PUSH), NCH = SYM_NCH;
-    constexpr int PSLOTS = SYM_PUSH_SLOTS;
+    constexpr int PSLOTS = SYM_PUSH_SLOTS, PS = sym_pool_stride(N);   // staging slots, pool row stride
     constexpr int NBUF = DB ? 2 : 1;
     constexpr int PK = N * (N + 1) / 2, EL = PACKED ? PK : NN;   // elements per ADO in the global arrays
     constexpr int FE = APW * EL, RT = PACKED ? FE : TILE_R;
@@ -150,7 +150,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     unsigned long long* barA0 = (unsigned long long*)(strip + NCH * APW * N);   // own tile, per buffer set
     unsigned long long* barB0 = barA0 + NBUF;                                   // y / first stage buffer
     unsigned long long* barD = barA0 + 2 * NBUF;                                // second stage buffer
-    double2* const push_s = rho0 + PERWARP - PSLOTS * N;                        // PUSH: rows on their way to peers
+    double2* const push_s = rho0 + PERWARP - PSLOTS * PS;                       // PUSH: rows on their way to peers
     unsigned phA = 0, phB = 0, phD = 0;   // phA / phB: one phase bit per buffer set
     if (lane == 0) {
 #pragma unroll
@@ -241,7 +241,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         const unsigned r0 = (unsigned)r.y & 15u;
         unsigned off = PACKED ? (unsigned)r.x * (unsigned)PK + (unsigned)trow[r0 * N]
                               : ((unsigned)r.x * (unsigned)N + r0) * (unsigned)N + (unsigned)row;
-        if (r.y & SYM_LINK_POOL) off = a.pool_off + (unsigned)r.x * (unsigned)N + (unsigned)row;
+        if (r.y & SYM_LINK_POOL) off = a.pool_off + (unsigned)r.x * (unsigned)PS + (unsigned)row;
         return a.yin + off;
     };
     const char* const cq_row = (const char*)cq_s;
@@ -574,8 +574,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             const int2 hdr = strip[APW * N + s_];
             for (int t = 0; t < hdr.y && t < N && hdr.x + t < PSLOTS; ++t) {
                 const int r = strip[s_ * N + t].y & 15;
-                if (i == r) push_s[(hdr.x + t) * N + j] = v;
-                if (PACKED && j == r && i != j) push_s[(hdr.x + t) * N + i] = make_double2(v.x, -v.y);
+                if (i == r) push_s[(hdr.x + t) * PS + j] = v;
+                if (PACKED && j == r && i != j) push_s[(hdr.x + t) * PS + i] = make_double2(v.x, -v.y);
             }
         };
         auto get_k = [&](int kk) {
@@ -629,8 +629,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             const int slot = pb - pb0 + row;
             if (pb + row < pe && slot < PSLOTS) {
                 double2* dst = reinterpret_cast<double2*>(a.peer[(pent.y >> 4) & 15]) + a.out_elem_off +
-                               (size_t)(unsigned)pent.x * N;
-                bulk_s2g(dst, push_s + slot * N, N * 16u);
+                               (size_t)(unsigned)pent.x * PS;
+                bulk_s2g(dst, push_s + slot * PS, PS * 16u);   // whole sectors (the pad element is never read)
             }
             bulk_commit();
             // rare: rows beyond the staging area or beyond N entries per ADO - the N lanes of the ADO
@@ -643,7 +643,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     const int off = PACKED ? lo_ * N - lo_ * (lo_ - 1) / 2 + (hi_ - lo_) : r * N + row;
                     double2 v = __ldcg(a.out + (gbase + (unsigned)(sub * EL + off)));
                     if (PACKED && row < r) v.y = -v.y;
-                    reinterpret_cast<double2*>(a.peer[(ent.y >> 4) & 15])[a.out_elem_off + (size_t)(unsigned)ent.x * N + row] = v;
+                    reinterpret_cast<double2*>(a.peer[(ent.y >> 4) & 15])[a.out_elem_off + (size_t)(unsigned)ent.x * PS + row] = v;
                 }
             }
         }

@@ -71,6 +71,13 @@ struct SymArgs {
 // offset (double2 units from the array base) of a plain N-element row: the halo rows a sharded
 // rank receives from its peers live in a row pool behind its own ADOs.
 constexpr int SYM_LINK_POOL = 16;
+// A pool row occupies an even number of elements (whole 32-byte sectors; 128 bytes = one line for
+// N = 7, 8) and the pool starts on a 128-byte boundary: the rows arrive as peer writes over NVLink,
+// and a write that covers sectors only partly would make the receiving L2 merge it with memory.
+__host__ __device__ constexpr int sym_pool_stride(int N) { return (N + 1) & ~1; }
+__host__ __device__ constexpr long long sym_pool_offset(long long n_own_max, int elems_per_ado) {
+    return (n_own_max * elems_per_ado + 7) & ~7ll;
+}
 __host__ __device__ inline int sym_link_y(int kdir, int neff, int L, int r0) {
     return ((kdir * (L + 1) + neff) << 5) | (r0 & 0xf);
 }

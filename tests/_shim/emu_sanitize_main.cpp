@@ -107,7 +107,8 @@ int main(int argc, char** argv) {
             }
             const long long n_own_max = std::max(hi[0] - lo[0], hi[1] - lo[1]);
             const long long pool_max = (long long)std::max(need[0].size(), need[1].size());
-            const long long pool_off = n_own_max * EL, arr = pool_off + pool_max * N;
+            const int PS = (N + 1) & ~1;                                 // sym_pool_stride
+            const long long pool_off = (n_own_max * EL + 7) & ~7ll, arr = pool_off + pool_max * PS;
             std::vector<std::vector<double>> st(2, std::vector<double>(2 * 4 * (size_t)arr, std::nan("")));
             auto elem = [&](long long slot_local, int i, int j) {   // offset (double2) of element (i, j), i <= j if packed
                 return packed ? slot_local * EL + i * N - i * (i - 1) / 2 + (j - i) : slot_local * EL + i * N + j;
@@ -130,7 +131,7 @@ int main(int argc, char** argv) {
                 for (size_t i = 0; i < need[r].size(); ++i)
                     for (int j = 0; j < N; ++j)
                         for (int part = 0; part < 2; ++part)
-                            st[r][2 * (pool_off + (long long)i * N + j) + part] =
+                            st[r][2 * (pool_off + (long long)i * PS + j) + part] =
                                 row_value(1 - r, need[r][i] >> 3, (int)(need[r][i] & 7), j, 0, part);
             std::vector<std::vector<int>> pptr(2), pent(2);
             for (int r = 0; r < 2; ++r) {   // rows of rank r's slots that the other rank's links read

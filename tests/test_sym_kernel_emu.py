@@ -284,8 +284,9 @@ def test_sharded_ranks_with_local_arrays(emu, fused, packed, shape):
         local_links.append(loc)
     n_own = [bounds[1], nmax - bounds[1]]
     n_own_max, pool_max = max(n_own), max(len(x) for x in need)
-    pool_off = n_own_max * EL
-    arr_elems = pool_off + pool_max * N
+    PS = (N + 1) & ~1                       # sym_pool_stride: whole sectors per pool row
+    pool_off = (n_own_max * EL + 7) & ~7    # sym_pool_offset
+    arr_elems = pool_off + pool_max * PS
     state = np.full((2, 4, arr_elems), np.nan, dtype=C128)   # rank, (Y, SA, SB, ACC)
     y0 = np.zeros((nmax, N, N), C128)
     y0[0] = w["rho0"]
@@ -302,7 +303,7 @@ def test_sharded_ranks_with_local_arrays(emu, fused, packed, shape):
         for r in range(2):
             for i, (slot, row) in enumerate(need[r]):
                 src = full[1 - r][slot - bounds[1 - r], row]
-                state[r, arr, pool_off + i * N: pool_off + (i + 1) * N] = src
+                state[r, arr, pool_off + i * PS: pool_off + i * PS + N] = src
     exchange(0)
     # push tables of rank r: CSR over its owned slots, entry = (row index in the peer's pool, peer << 4 | row)
     push_ptr, push_ent = [], []
@@ -343,4 +344,4 @@ def test_sharded_ranks_with_local_arrays(emu, fused, packed, shape):
     # pool rows nobody asked for were never written
     for r in range(2):
         if len(need[r]) < pool_max:
-            assert np.isnan(state[r, 0, pool_off + len(need[r]) * N:]).all()
+            assert np.isnan(state[r, 0, pool_off + len(need[r]) * PS:]).all()

@@ -26,5 +26,4 @@ while [ $n -le $N ]; do
   n=$((n*2))
 done
 tr native_n${N}_k20 $N --steps 20
-tr native_n${N}_static_cut $N --steps $K --rebalance 0
 ls "$out"
