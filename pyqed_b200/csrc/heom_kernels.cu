@@ -558,6 +558,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "part_lo") return p->part_lo;
     if (n == "part_hi") return p->part_hi;
     if (n == "sym_inputs") return sym_wanted(p) ? 1 : 0;
+    if (n == "push_slots") return heom_sym_push_slots();
     if (n == "off_links2") return p->links2_built ? (int64_t)p->tl.links2 : -1;
     if (n == "shard_packed") return p->shard.on ? (p->shard.packed ? 1 : 0) : -1;
     if (n == "shard_epoch") return p->shard.epoch;

@@ -70,7 +70,7 @@ __global__ void shard_push_rows_kernel(const double2* arr, const int* push_ptr, 
             } else {
                 v = arr[slot * EL + r * N + j];
             }
-            reinterpret_cast<double2*>(peer[ent.y >> 4])[dst_pool_off + (long long)(unsigned)ent.x * sym_pool_stride(N) + j] = v;
+            reinterpret_cast<double2*>(peer[(ent.y >> 4) & 15])[dst_pool_off + (long long)(unsigned)ent.x * sym_pool_stride(N) + j] = v;
         }
     }
     __threadfence_system();

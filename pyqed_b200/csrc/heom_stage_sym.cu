@@ -221,8 +221,8 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             i = j / N;
             j -= i * N;
         }
-        // low half: offset of (i, j) in the k tile, high half: offset of (j, i)
-        kofs[it] = (s * KSUB + i * KLD + j) | ((s * KSUB + j * KLD + i) << 16);
+        // bits 0-9: offset of (i, j) in the k tile, 10-19: offset of (j, i), 20-22: i, 23-25: j, 26-30: ADO
+        kofs[it] = (s * KSUB + i * KLD + j) | ((s * KSUB + j * KLD + i) << 10) | (i << 20) | (j << 23) | (s << 26);
         if (!(PACKED || BULK_TILE)) rofs_[it] = (s * N + i) * LD + j;   // padded rows (even N)
     }
     // bulk-copied tiles (packed, or odd N) keep the flat layout of the global array
@@ -556,32 +556,35 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         // ---- epilogue from shared memory, streaming stores
         // PUSH: the rows of this group's output that other ranks read are collected in the warp's
         // staging area while the epilogue computes them, and leave from there as bulk stores.  The
-        // group's push entries are consecutive in the table: entry t of ADO s goes to staging slot
-        // (first entry of s - first entry of the group) + t.  What does not fit (more than PSLOTS
-        // rows per group, more than N entries per ADO) takes the element-wise path below.
+        // push table gives every distinct (ADO, row) of the group a staging slot (bits 8-15 of an
+        // entry's y; 255 = no slot left, element-wise path below); rowmap[ADO][row] = slot or 255.
         const bool any_push = PUSH && __reduce_max_sync(0xffffffffu, pe - pb) > 0;
-        const int pb0 = PUSH ? __shfl_sync(0xffffffffu, pb, 0) : 0;
+        unsigned char* const rowmap = reinterpret_cast<unsigned char*>(strip);   // (the strip is free after the link loop)
         if (PUSH && any_push) {
             bulk_wait_read();   // the previous group's rows have left the staging area
-            if (lane_ok) {
-                strip[sub * N + row] = pent;
-                if (row == 0) strip[APW * N + sub] = make_int2(pb - pb0, pe - pb);
+            if (lane_ok) rowmap[sub * 8 + row] = 255;
+            __syncwarp();
+            if (pb + row < pe) rowmap[sub * 8 + (pent.y & 15)] = (unsigned char)(pent.y >> 8);
+            for (int q = pb + row + N; q < pe; q += N) {   // (more than N entries per ADO: rare)
+                const int y_ = a.push_ent[q].y;
+                rowmap[sub * 8 + (y_ & 15)] = (unsigned char)(y_ >> 8);
             }
             __syncwarp();
         }
-        auto stage_rows = [&](int e, int kk, const double2 v) {
-            const int s_ = e / EL, k0 = (kk & 0xffff) - s_ * KSUB, i = k0 / KLD, j = k0 - i * KLD;
-            const int2 hdr = strip[APW * N + s_];
-            for (int t = 0; t < hdr.y && t < N && hdr.x + t < PSLOTS; ++t) {
-                const int r = strip[s_ * N + t].y & 15;
-                if (i == r) push_s[(hdr.x + t) * PS + j] = v;
-                if (PACKED && j == r && i != j) push_s[(hdr.x + t) * PS + i] = make_double2(v.x, -v.y);
+        auto stage_rows = [&](int kk, const double2 v) {
+            const int i = (kk >> 20) & 7, j = (kk >> 23) & 7;
+            const unsigned char* const rm = rowmap + ((kk >> 26) & 31) * 8;
+            const int mi = rm[i];
+            if (mi < PSLOTS) push_s[mi * PS + j] = v;
+            if (PACKED && i != j) {
+                const int mj = rm[j];
+                if (mj < PSLOTS) push_s[mj * PS + i] = make_double2(v.x, -v.y);
             }
         };
         auto get_k = [&](int kk) {
-            double2 v = k_s[kk & 0xffff];
+            double2 v = k_s[kk & 0x3ff];
             if (FUSE_HERM) {
-                const double2 m = k_s[kk >> 16];
+                const double2 m = k_s[(kk >> 10) & 0x3ff];
                 v = make_double2(v.x + m.x, v.y - m.y);
             }
             return v;
@@ -605,10 +608,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     res.x = fma(2.0 * third, s2.x, res.x);
                     res.y = fma(2.0 * third, s2.y, res.y);
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH && any_push) stage_rows(e, kofs[it], res);
+                    if (PUSH && any_push) stage_rows(kofs[it], res);
                     if (e0 >= 0 && (unsigned)(e - e0) < (unsigned)EL) {
                         if (PACKED) {   // the trajectory holds full matrices
-                            const int kk = (kofs[it] & 0xffff) - (e0 / EL) * KSUB, i = kk / KLD, j = kk - i * KLD;
+                            const int i = (kofs[it] >> 20) & 7, j = (kofs[it] >> 23) & 7;
                             a.traj[(step + 1) * NN + i * N + j] = res;
                             if (i != j) a.traj[(step + 1) * NN + j * N + i] = make_double2(res.x, -res.y);
                         } else {
@@ -619,26 +622,32 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     const double2 yv = FIRST ? rho_s[rofs(it)] : y_s[e];
                     const double2 res = make_double2(fma(a.a, k.x, yv.x), fma(a.a, k.y, yv.y));
                     st_stream(a.out + (gbase + e), res);
-                    if (PUSH && any_push) stage_rows(e, kofs[it], res);
+                    if (PUSH && any_push) stage_rows(kofs[it], res);
                 }
             }
         }
         if (PUSH && any_push) {
             fence_proxy_async();   // the staging writes are ordered before the bulk stores
             __syncwarp();
-            const int slot = pb - pb0 + row;
-            if (pb + row < pe && slot < PSLOTS) {
-                double2* dst = reinterpret_cast<double2*>(a.peer[(pent.y >> 4) & 15]) + a.out_elem_off +
-                               (size_t)(unsigned)pent.x * PS;
-                bulk_s2g(dst, push_s + slot * PS, PS * 16u);   // whole sectors (the pad element is never read)
+            bool overflow = false;
+            for (int q = pb + row; q < pe; q += N) {
+                const int2 ent = q == pb + row ? pent : a.push_ent[q];
+                const int slot = (ent.y >> 8) & 255;
+                if (slot < PSLOTS) {
+                    double2* dst = reinterpret_cast<double2*>(a.peer[(ent.y >> 4) & 15]) + a.out_elem_off +
+                                   (size_t)(unsigned)ent.x * PS;
+                    bulk_s2g(dst, push_s + slot * PS, PS * 16u);   // whole sectors (the pad element is never read)
+                } else {
+                    overflow = true;
+                }
             }
             bulk_commit();
-            // rare: rows beyond the staging area or beyond N entries per ADO - the N lanes of the ADO
-            // store the row element by element, read back from the output this warp has just written
-            if (pe - pb > N || pe - pb0 > PSLOTS) {
+            // rare: rows that got no staging slot - the N lanes of the ADO store such a row element by
+            // element, read back from the output this warp has just written
+            if (__reduce_max_sync(0xffffffffu, overflow ? 1 : 0) > 0) {
                 for (int q = pb; q < pe; ++q) {
-                    if (q - pb < N && q - pb0 < PSLOTS) continue;
                     const int2 ent = a.push_ent[q];
+                    if (((ent.y >> 8) & 255) < PSLOTS) continue;
                     const int r = ent.y & 15, lo_ = min(r, row), hi_ = max(r, row);
                     const int off = PACKED ? lo_ * N - lo_ * (lo_ - 1) / 2 + (hi_ - lo_) : r * N + row;
                     double2 v = __ldcg(a.out + (gbase + (unsigned)(sub * EL + off)));
@@ -812,6 +821,8 @@ int HEOM_SYM_CAT(heom_sym_launch_n, HEOM_SYM_INST_N)(const SymLaunch& s, const c
     return rc;
 }
 #else
+int heom_sym_push_slots(void) { return SYM_PUSH_SLOTS; }
+
 int heom_sym_supported(int N, int K, int M, int L, const char** err) {
     (void)M;
     const char* why = nullptr;

@@ -53,7 +53,9 @@ struct SymArgs {
     // row x of the pool, pool_off = offset (double2) of the pool from the array base.
     // PUSH instantiations: the epilogue stores the rows of the stage output that other ranks read
     // into their pools - push_ptr[owned+1] is a CSR over the owned slots, an entry is
-    // (x = row index in the destination's pool, y = peer << 4 | matrix row), peer[q] the base
+    // (x = row index in the destination's pool, y = staging slot << 8 | peer << 4 | matrix row;
+    // the staging slot numbers the distinct (ADO, row) pairs inside a group of 32/N consecutive
+    // ADOs, 255 = beyond heom_sym_push_slots()), peer[q] the base
     // address of rank q's state buffer and out_elem_off the offset (double2) of the pool of this
     // stage's output array inside a state buffer (the same on every rank).
     unsigned pool_off;
@@ -135,6 +137,7 @@ struct SymLaunch {
 
 // All return 0 on success; on failure *err points to a static message.
 int heom_sym_supported(int N, int K, int M, int L, const char** err);
+int heom_sym_push_slots(void);   // staging slots per group of the fused push
 int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
                            const char** err);
 int heom_sym_launch(const SymLaunch& L, const char** err);

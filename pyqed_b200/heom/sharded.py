@@ -403,11 +403,28 @@ class ShardedDEOM:
         base = torch.tensor([sum(h.all_counts[q][:rank]) for q in range(world)], dtype=torch.int64, device=si.device)
         dst_row = base[dest] + torch.arange(si.numel(), device=si.device) - first[dest]
         loc, rowc = (si >> 3) - lo, si & 7
-        order_ix = torch.argsort(loc, stable=True)
+        # entries ordered by (owned slot, row, destination); every distinct (slot, row) inside a group
+        # of 32/N consecutive slots (= the ADOs one warp processes together) gets a staging slot
+        key = loc * 8 + rowc
+        order_ix = torch.argsort(key * 16 + dest, stable=True)
+        key_s, dest_s, dst_s = key[order_ix], dest[order_ix], dst_row[order_ix]
         cnt = torch.bincount(loc, minlength=n_own) if si.numel() else torch.zeros(n_own, dtype=torch.int64, device=si.device)
         ptr = torch.zeros(n_own + 1, dtype=torch.int32, device=si.device)
         ptr[1:] = torch.cumsum(cnt, 0).to(torch.int32)
-        ent = torch.stack([dst_row, dest * 16 + rowc], dim=1).to(torch.int32)[order_ix]
+        if si.numel():
+            apw, nslots = 32 // self.n, p.info("push_slots")
+            new = torch.ones_like(key_s)
+            new[1:] = (key_s[1:] != key_s[:-1]).to(new.dtype)
+            c = torch.cumsum(new, 0) - 1
+            grp = (key_s >> 3) // apw
+            gstart = torch.ones_like(grp, dtype=torch.bool)
+            gstart[1:] = grp[1:] != grp[:-1]
+            base = c[gstart][torch.cumsum(gstart.to(torch.int64), 0) - 1]
+            slot_id = torch.clamp(c - base, max=255)
+            slot_id = torch.where(slot_id >= nslots, torch.full_like(slot_id, 255), slot_id)
+            ent = torch.stack([dst_s, slot_id * 256 + dest_s * 16 + (key_s & 7)], dim=1).to(torch.int32)
+        else:
+            ent = torch.zeros((0, 2), dtype=torch.int32, device=si.device)
         self._push_ptr = ptr.to(dev).contiguous()
         self._push_ent = (ent.to(dev).contiguous() if ent.numel()
                           else torch.zeros((1, 2), dtype=torch.int32, device=dev))

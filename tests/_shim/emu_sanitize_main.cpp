@@ -135,17 +135,27 @@ int main(int argc, char** argv) {
                                 row_value(1 - r, need[r][i] >> 3, (int)(need[r][i] & 7), j, 0, part);
             std::vector<std::vector<int>> pptr(2), pent(2);
             for (int r = 0; r < 2; ++r) {   // rows of rank r's slots that the other rank's links read
-                std::vector<std::vector<int>> per((size_t)(hi[r] - lo[r]));
-                const int q = 1 - r;
-                for (size_t i = 0; i < need[q].size(); ++i) {
-                    auto& v = per[(size_t)((need[q][i] >> 3) - lo[r])];
-                    v.push_back((int)i);
-                    v.push_back((q << 4) | (int)(need[q][i] & 7));
-                }
+                std::vector<std::vector<std::pair<int, int>>> per((size_t)(hi[r] - lo[r]));   // (row, pool index)
+                const int q = 1 - r, apw = 32 / N;
+                for (size_t i = 0; i < need[q].size(); ++i)
+                    per[(size_t)((need[q][i] >> 3) - lo[r])].push_back({(int)(need[q][i] & 7), (int)i});
                 pptr[r].push_back(0);
-                for (auto& v : per) {
-                    pent[r].insert(pent[r].end(), v.begin(), v.end());
-                    pptr[r].push_back((int)pent[r].size() / 2);
+                for (size_t g0 = 0; g0 < per.size(); g0 += apw) {   // staging slots: distinct (ADO, row) per group
+                    int next_id = 0;
+                    for (size_t sl = g0; sl < std::min(per.size(), g0 + apw); ++sl) {
+                        std::sort(per[sl].begin(), per[sl].end());
+                        int last_row = -1, sid = 255;
+                        for (auto& e : per[sl]) {
+                            if (e.first != last_row) {
+                                sid = next_id < 12 ? next_id : 255;
+                                ++next_id;
+                                last_row = e.first;
+                            }
+                            pent[r].push_back(e.second);
+                            pent[r].push_back((sid << 8) | (q << 4) | e.first);
+                        }
+                        pptr[r].push_back((int)pent[r].size() / 2);
+                    }
                 }
                 if (pent[r].empty()) pent[r].assign(2, 0);
             }

@@ -305,15 +305,26 @@ def test_sharded_ranks_with_local_arrays(emu, fused, packed, shape):
                 src = full[1 - r][slot - bounds[1 - r], row]
                 state[r, arr, pool_off + i * PS: pool_off + i * PS + N] = src
     exchange(0)
-    # push tables of rank r: CSR over its owned slots, entry = (row index in the peer's pool, peer << 4 | row)
+    # push tables of rank r: CSR over its owned slots, entry = (row index in the peer's pool,
+    # staging slot << 8 | peer << 4 | row); the distinct (ADO, row) pairs of a group of 32/N
+    # consecutive ADOs are numbered in order, 255 beyond the kernel's staging area (12 slots)
     push_ptr, push_ent = [], []
+    apw = 32 // N
     for r in range(2):
         lo, hi = bounds[r], bounds[r + 1]
         per_slot = [[] for _ in range(hi - lo)]
         for i, (slot, row) in enumerate(need[1 - r]):          # what the other rank reads from this one
-            per_slot[slot - lo].append((i, ((1 - r) << 4) | row))
+            per_slot[slot - lo].append((row, i))
+        ents = []
+        for g0 in range(0, hi - lo, apw):
+            ids = {}
+            for sl in range(g0, min(g0 + apw, hi - lo)):
+                per_slot[sl].sort()
+                for row, i in per_slot[sl]:
+                    sid = ids.setdefault((sl, row), len(ids))
+                    ents.append((i, (min(sid, 255) if sid < 12 else 255) << 8 | ((1 - r) << 4) | row))
         push_ptr.append(np.concatenate([[0], np.cumsum([len(x) for x in per_slot])]).astype(np.int32))
-        push_ent.append(np.array([e for x in per_slot for e in x] or [(0, 0)], dtype=np.int32))
+        push_ent.append(np.array(ents or [(0, 0)], dtype=np.int32))
     peers = np.array([state[0].ctypes.data, state[1].ctypes.data], dtype=np.uint64)
     H = np.ascontiguousarray(o.H0)
     emu.emu_sym_stage.restype = ctypes.c_int
