@@ -24,7 +24,7 @@ from test_sym_kernel_emu import host_tables, projector_problem, C128, ROOT
 def emu_lib(tmp_path_factory):
     out = tmp_path_factory.mktemp("emu3") / "libasync_emu.so"
     src = os.path.join(ROOT, "tests", "_shim", "async_emu.cpp")
-    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++",
+    subprocess.check_call(["g++", "-O0", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++",
                            "-o", str(out), src])
     lib = ctypes.CDLL(str(out))
     lib.emu_async_run.restype = ctypes.c_int

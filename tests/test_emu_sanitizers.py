@@ -51,7 +51,7 @@ def binaries(tmp_path_factory):
 
     def build(sanitizer):
         exe = str(d / f"emu_{sanitizer}")
-        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-pthread", f"-fsanitize={sanitizer}",
+        subprocess.check_call(["g++", "-O0", "-g", "-std=c++17", "-pthread", f"-fsanitize={sanitizer}",
                                "-fno-omit-frame-pointer", "-DHEOM_EMU_FEW_N", "-o", exe, src])
         return exe
     with ThreadPoolExecutor(2) as pool:

@@ -23,7 +23,7 @@ from test_sym_kernel_emu import ROOT, C128, link_meta, host_tables
 @pytest.fixture(scope="module")
 def hier(tmp_path_factory):
     out = tmp_path_factory.mktemp("hier") / "libhier_emu.so"
-    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++", "-o", str(out),
+    subprocess.check_call(["g++", "-O0", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++", "-o", str(out),
                            os.path.join(ROOT, "tests", "_shim", "hier_emu.cpp")])
     lib = ctypes.CDLL(str(out))
     lib.emu_build_hierarchy.restype = ctypes.c_int
@@ -104,7 +104,7 @@ def test_kernels_6_and_7_on_device_built_blocked_order(hier):
     builder kernels, rotated visiting order, state and results permuted through
     ``slot_of_id`` as the C ABI does."""
     out = os.path.join(os.path.dirname(hier._name), "libsym_emu.so")
-    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++", "-o", out,
+    subprocess.check_call(["g++", "-O0", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++", "-o", out,
                            "-DHEOM_EMU_FEW_N", os.path.join(ROOT, "tests", "_shim", "sym_emu.cpp")])
     emu = ctypes.CDLL(out)
     emu.emu_sym_run.restype = ctypes.c_int

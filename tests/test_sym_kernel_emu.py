@@ -27,7 +27,7 @@ C128 = np.complex128
 def emu_lib(tmp_path_factory):
     out = tmp_path_factory.mktemp("emu") / "libsym_emu.so"
     src = os.path.join(ROOT, "tests", "_shim", "sym_emu.cpp")
-    subprocess.check_call(["g++", "-O1", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++",
+    subprocess.check_call(["g++", "-O0", "-shared", "-fPIC", "-std=c++17", "-pthread", "-x", "c++",
                            "-o", str(out), src])
     lib = ctypes.CDLL(str(out))
     lib.emu_sym_run.restype = ctypes.c_int
