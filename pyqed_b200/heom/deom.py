@@ -289,7 +289,34 @@ class DEOMSolver:
         nb = len(rho0s)
         fs = pulse_system_funcs or [self.pulse_system_func] * nb
         fc = pulse_coupling_funcs or [self.pulse_coupling_func] * nb
-        return self._run(list(rho0s), dt, nt, p1, fs, fc)
+        split = self._batch_split(nb)
+        if split is None:
+            return self._run(list(rho0s), dt, nt, p1, fs, fc)
+        # several ranks: replicas only - every rank propagates its share of the trajectories
+        # (no communication during the run) and the results are gathered at the end
+        dist, rank, world = split
+        mine = list(range(rank, nb, world))
+        t_save, out = self._run([rho0s[b] for b in mine], dt, nt, p1, [fs[b] for b in mine],
+                                [fc[b] for b in mine])
+        parts = [None] * world
+        dist.all_gather_object(parts, (mine, np.asarray(out)))
+        full = np.empty((nb,) + np.asarray(out).shape[1:], dtype=C128)
+        for idx, arr in parts:
+            full[idx] = arr
+        return t_save, full
+
+    def _batch_split(self, nb):
+        """(dist, rank, world) when a batch should be split over the ranks of the job."""
+        if self.shard is False:
+            return None
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+                    and nb >= dist.get_world_size():
+                return dist, dist.get_rank(), dist.get_world_size()
+        except Exception:  # noqa: BLE001
+            pass
+        return None
 
     # ---- HEOM-space correlation functions by time propagation ------------------
     def operator_action_ddos(self, operator, side="left"):

@@ -72,20 +72,20 @@ def test_rank_local_layout_ranks_sharing_one_device(world, kernel):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("push,fused", [(0, 0), (1, 0), (1, 1)])
-def test_sharded_nccl_two_gpus(push, fused):
-    """NCCL all_to_all halo (push=0), peer-memory stores by a separate kernel
-    (push=1, fused=0) and by the stage kernel's epilogue (fused=1)."""
+def test_sharded_nccl_two_gpus():
+    """The general exchange on two GPUs: NCCL all_to_all halo (push=0), peer-memory stores by a
+    separate kernel (push=1, fused=0) and by kernel 3's epilogue (fused=1)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", str(push), "--fused", str(fused),
-                      "--native", "0",
-                      "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
-    assert out.count(" ok (owned") == 8
-    assert out.count(f"push={bool(push)}") == 8
-    # the dense-Q case cannot use the fused path (it needs the diagonal-Q kernel)
-    assert out.count("fused=True") == (6 if fused else 0)
+    for push, fused in [(0, 0), (1, 0), (1, 1)]:
+        out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--push", str(push), "--fused", str(fused),
+                          "--native", "0",
+                          "--cases", "deom_fmo_K21_L3,deom_fmo_K7_L4,deom_spin_boson_L10,deom_random4_herm"])
+        assert out.count(" ok (owned") == 8
+        assert out.count(f"push={bool(push)}") == 8
+        # the dense-Q case cannot use the fused path (it needs the diagonal-Q kernel)
+        assert out.count("fused=True") == (6 if fused else 0)
 
 
 @pytest.mark.gpu
@@ -99,24 +99,27 @@ def test_rank_local_layout_rebalanced_ranges():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel", [0, 6])
-def test_rank_local_layout_two_gpus(kernel):
-    """The same on two GPUs: peer stores over NVLink and the device flag barrier
-    (``pyqed_heom_shard_propagate``: no host round trip inside a run)."""
+def test_rank_local_layout_two_gpus():
+    """The rank-local layout on two GPUs: peer stores over NVLink and the device flag barrier
+    (``pyqed_heom_shard_propagate``: no host round trip inside a run); packed (kernel 7) and full
+    (kernel 6) storage."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--kernel", str(kernel), "--native", "1",
-                      "--cases", "deom_fmo_K21_L3,deom_fmo_K21_L2,deom_fmo_K7_L4"])
-    assert out.count(" ok (owned") == 6 and out.count("native=True") == 6
+    for kernel in (0, 6):
+        out = _launch(2, ["gpu", "--backend", "nccl", "--order", "2", "--kernel", str(kernel), "--native", "1",
+                          "--cases", "deom_fmo_K21_L3,deom_fmo_K21_L2,deom_fmo_K7_L4"])
+        assert out.count(" ok (owned") == 6 and out.count("native=True") == 6
 
 
 @pytest.mark.gpu
 def test_deomsolver_run_shards_under_torch_distributed():
     """The drop-in class itself: ``DEOMSolver(..., shard=True).run`` on every rank of a 2-rank job
     (ranks sharing the test box's GPU) returns the reference's results - rank-local layout for the
-    FMO case, general exchange for the pulsed / sigma_z / p1 cases."""
+    FMO case, general exchange for the pulsed / sigma_z / p1 cases - and ``run_batch`` splits its
+    trajectories over the ranks."""
     out = _launch(2, ["solver", "--backend", "gloo", "--cases",
                       "deom_fmo_K21_L2,deom_spin_boson_L10,deom_example_L10_p1,deom_aggregate_L3_T37"])
     assert out.count(" solver ok") == 8
     assert out.count("native=True") == 2 and out.count("p1=True") >= 2
+    assert out.count("batch split ok") == 2
