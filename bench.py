@@ -191,7 +191,7 @@ def cpu_native_leg(workload_name, budget_s=10.0, steps=None):
         return time.perf_counter() - t0
     t1 = go(1)  # warm-up (also builds the library on first use)
     t1 = go(1)
-    nt = steps if steps is not None else max(2, min(400, int(budget_s / max(t1, 1e-4))))
+    nt = steps if steps is not None else max(10, min(400, int(budget_s / max(t1, 1e-4))))   # (each call first-touches ~1 GB: keep the run long enough)
     el = go(nt)
     full = comb(w["lmax"] + nind, w["lmax"])
     return dict(value=nmax * nt / el, unit=UNIT, cores=threads, kind="port", n_ado=nmax, depth=depth,
