@@ -264,7 +264,22 @@ static bool sym_eligible(const pyqed_heom_plan* p, const StageArgs& a, bool tdep
            p->single_support && p->opt_sym != 0 &&
            !a.push_ptr && a.scheme == 1 && !(a.first && a.last);   // (legacy fused push: kernel 3)
 }
+// kernels 6 / 7 read link records resolved for their storage (heom_stage_sym.cuh): (re)write the
+// table from the general link table when the storage changes - one pass over 8 bytes per link
+static int ensure_links2(pyqed_heom_plan* p, int packed) {
+    if (p->links2_mode == packed) return 0;
+    REQUIRE(!p->shard.on, "the link table of a sharded plan is resolved for its rank-local layout");
+    const char* err = "";
+    if (heom_sym_convert_links(p->tab<int2>(p->tl.links), p->tab<int2>(p->tl.links2), p->nlinks, p->N, p->L, packed,
+                               p->stream, &err))
+        return fail(std::string("sym_convert_links_kernel launch: ") + err);
+    p->launches++;
+    p->links2_mode = packed;
+    return 0;
+}
+
 static int launch_sym(pyqed_heom_plan* p, const StageArgs& a, int sm_count) {
+    if (ensure_links2(p, 0)) return 1;
     SymLaunch s{};
     s.a = sym_args_from_stage(a, p->tab<int2>(p->tl.links2));
     s.H = reinterpret_cast<const double*>(p->H.data());
@@ -779,13 +794,9 @@ int pyqed_heom_build_hierarchy(pyqed_heom_plan* p) {
     p->slot0 = slot0;
     p->links2_built = false;
     if (sym_wanted(p)) {
-        const char* err = "";
         if (t.links2 + sizeof(int2) * (size_t)p->nlinks <= p->bound_table_bytes) {   // (options changed after bind)
-            if (heom_sym_convert_links(h.links, p->tab<int2>(t.links2), p->nlinks, N, L, s, &err))
-                return fail(std::string("sym_convert_links_kernel launch: ") + err);
-            p->launches++;
-            CU_TRY(cudaStreamSynchronize(s));
-            p->links2_built = true;
+            p->links2_built = true;   // (filled for full or packed storage when a propagation needs it)
+            p->links2_mode = -1;
         }
     }
     if (p->part_hi <= p->part_lo) {
@@ -1024,6 +1035,7 @@ static bool packed_eligible(const pyqed_heom_plan* p) {
            p->part_lo == 0 && p->part_hi == p->nmax && rk_scheme(p) && 4 * tri <= 3 * p->array_bytes;
 }
 static int run_packed(pyqed_heom_plan* p, double dt, int64_t nt) {
+    if (ensure_links2(p, 1)) return 1;
     const int sm_count = sm_count_of(p->device);
     const TableLayout& t = p->tl;
     PackedRun r{};

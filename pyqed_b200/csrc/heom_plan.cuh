@@ -83,6 +83,7 @@ struct pyqed_heom_plan {
     unsigned* d_flags = nullptr;      // kernel 8: per-ADO stage counters
     size_t flags_cap = 0;
     bool links2_built = false;
+    int links2_mode = -1;        // what links2 is resolved for: 0 full matrices, 1 packed storage, -1 neither
     size_t bound_table_bytes = 0;
     int resident_kind = 0;  // 4 or 5: which resident kernel ran last
     TableLayout tl{};

@@ -7,8 +7,8 @@
 // Layout of a rank: every ADO array holds the rank's own ADOs [lo, hi) (full matrices, or
 // upper triangles while kernel 7 runs) followed by a POOL of halo rows - for each (foreign
 // ADO, row) that a link of an owned ADO reads, N elements.  The link table of the owned range
-// is rewritten once: a local neighbour becomes a local slot, a foreign one a pool row
-// (SYM_LINK_POOL).  The owners store those rows themselves: the stage kernel's epilogue
+// is written for that layout: a local neighbour is addressed by its local slot, a foreign one
+// by its pool row.  The owners store those rows themselves: the stage kernel's epilogue
 // (PUSH instantiations of kernels 6 / 7) sends each row of its output that a peer reads from
 // shared memory straight into that peer's pool with one bulk store (cp.async.bulk
 // shared -> global on a peer address, i.e. over NVLink), in flight while the warp works on
@@ -63,10 +63,9 @@ __global__ void shard_push_rows_kernel(const double2* arr, const int* push_ptr, 
             const int2 ent = push_ent[q];
             const int r = ent.y & 15, j = lane % N;
             double2 v;
-            if (packed) {
+            if (packed) {   // as a gather through the triangle delivers the row: (min, max), not conjugated
                 const int lo = min(r, j), hi = max(r, j);
                 v = arr[slot * EL + lo * N - lo * (lo - 1) / 2 + (hi - lo)];
-                if (j < r) v.y = -v.y;   // element (r, j) below the diagonal = conj of (j, r)
             } else {
                 v = arr[slot * EL + r * N + j];
             }
@@ -76,20 +75,24 @@ __global__ void shard_push_rows_kernel(const double2* arr, const int* push_ptr, 
     __threadfence_system();
 }
 
-// ---- link table of the owned range: local slots and pool rows --------------------------------
-// need[] = sorted unique items (slot * 8 + row) this rank reads from other ranks
-__global__ void shard_localize_links_kernel(int2* links2, const int* link_ptr, long long lo, long long hi,
-                                            const long long* need, long long n_need, int* bad) {
+// ---- link table of the owned range: local rows and pool rows -----------------------------------
+// need[] = sorted unique items (slot * 8 + row) this rank reads from other ranks.  Written from the
+// plan's general link table (slot, meta), so it can be redone for other ranges.
+__global__ void shard_localize_links_kernel(int2* links2, const int2* links, const int* link_ptr, long long lo,
+                                            long long hi, const long long* need, long long n_need, int N, int L,
+                                            int packed, unsigned pool_off, int* bad) {
     const long long slot = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (slot >= hi) return;
     for (int l = link_ptr[slot]; l < link_ptr[slot + 1]; ++l) {
-        int2 r = links2[l];
-        if (r.y & SYM_LINK_POOL) continue;   // already localized (plan reused)
+        const int2 r = links[l];
         const long long nb = r.x;
+        const int r0 = heom::meta_r0(r.y);
+        unsigned x;
+        int table_row = r0;
         if (nb >= lo && nb < hi) {
-            r.x = (int)(nb - lo);
+            x = sym_link_x((unsigned)(nb - lo), r0, N, packed != 0);
         } else {
-            const long long item = nb * 8 + (r.y & 15);
+            const long long item = nb * 8 + r0;
             long long a = 0, b = n_need;
             while (a < b) {
                 const long long m = (a + b) >> 1;
@@ -100,10 +103,10 @@ __global__ void shard_localize_links_kernel(int2* links2, const int* link_ptr, l
                 atomicExch(bad, 1);
                 continue;
             }
-            r.x = (int)a;
-            r.y |= SYM_LINK_POOL;
+            x = pool_off + (unsigned)a * (unsigned)sym_pool_stride(N);
+            table_row = N;   // pool rows: N consecutive elements
         }
-        links2[l] = r;
+        links2[l] = make_int2((int)x, sym_link_y(heom::meta_kdir(r.y), heom::meta_neff(r.y), L, r0, table_row));
     }
 }
 
@@ -215,16 +218,25 @@ int pyqed_heom_shard_setup(pyqed_heom_plan* p, int rank, int world, int64_t lo, 
     size_t need_bytes = 0, flag_off = 0;
     if (pyqed_heom_shard_state_bytes(p, n_own_max, pool_max, &need_bytes, &flag_off)) return 1;
     REQUIRE(state_bytes >= need_bytes, "shard_setup: state buffer too small");
-    // link table of the owned range -> local slots / pool rows
+    // storage of this run (identical decision on every rank: it depends on the maxima only)
+    const size_t arr_full_bytes = flag_off / 4;
+    const size_t arr_packed = align_up(sizeof(double2) * ((size_t)sym_pool_offset(n_own_max, PK) +
+                                                          (size_t)pool_max * sym_pool_stride(N))) / sizeof(double2);
+    const bool packed = (p->kernel == 0 || p->kernel == 7) && p->opt_packed != 0 &&
+                        4 * arr_packed * sizeof(double2) <= 3 * arr_full_bytes;
+    // link table of the owned range -> local rows / pool rows
     int* d_bad = nullptr;
     CU_TRY(cudaMalloc(&d_bad, sizeof(int)));
     CU_TRY(cudaMemsetAsync(d_bad, 0, sizeof(int), p->stream));
     if (hi > lo) {
         const unsigned blocks = (unsigned)((hi - lo + 127) / 128);
-        shard_localize_links_kernel<<<blocks, 128, 0, p->stream>>>(p->tab<int2>(p->tl.links2), p->tab<int>(p->tl.link_ptr),
-                                                                   lo, hi, (const long long*)d_need, n_need, d_bad);
+        shard_localize_links_kernel<<<blocks, 128, 0, p->stream>>>(
+            p->tab<int2>(p->tl.links2), p->tab<int2>(p->tl.links), p->tab<int>(p->tl.link_ptr), lo, hi,
+            (const long long*)d_need, n_need, N, p->L, packed ? 1 : 0,
+            (unsigned)sym_pool_offset(n_own_max, packed ? PK : NN), d_bad);
         if (post_launch(p, "shard_localize_links_kernel")) return 1;
     }
+    p->links2_mode = -1;   // the table no longer describes the whole hierarchy
     int bad = 0;
     CU_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     CU_TRY(cudaStreamSynchronize(p->stream));
@@ -243,12 +255,10 @@ int pyqed_heom_shard_setup(pyqed_heom_plan* p, int rank, int world, int64_t lo, 
     sh.device_barrier = device_barrier != 0;
     sh.epoch = 0;
     p->d_state = (char*)d_state;
-    p->array_bytes = flag_off / 4;
+    p->array_bytes = arr_full_bytes;
     sh.arr_full = p->array_bytes / sizeof(double2);
-    sh.arr_packed = align_up(sizeof(double2) * ((size_t)sym_pool_offset(n_own_max, PK) +
-                                                (size_t)pool_max * sym_pool_stride(N))) / sizeof(double2);
-    sh.packed = (p->kernel == 0 || p->kernel == 7) && p->opt_packed != 0 && 4 * sh.arr_packed <= 3 * sh.arr_full;
-    (void)NN;
+    sh.arr_packed = arr_packed;
+    sh.packed = packed;
     // peers: [0, 16) state buffers, [16, 32) flag blocks
     unsigned long long tab[32] = {0};
     for (int q = 0; q < 16; ++q) sh.peer_state[q] = 0;

@@ -52,7 +52,7 @@ namespace {
 
 constexpr int SYM_NCH = 4;   // link chunks (of N links) whose records are prefetched per ADO
 
-constexpr int SYM_TOFS = 16;  // double2 units reserved for the packed-row offset table (N*N ints)
+constexpr int SYM_TOFS = 20;  // double2 units reserved for the packed-row offset table ((N+1)*N ints)
 
 // per-warp shared memory in double2 units.  `packed`: the ADO arrays hold the upper
 // triangle only (N(N+1)/2 elements per ADO, row-major), see stage_rows_sym_kernel.
@@ -175,9 +175,10 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
         cq_s[2 * e + 1] = make_double2(0.5 * (c1.x * sq), 0.5 * (c1.y * sq));
     }
     if (PACKED) {
-        for (int e = threadIdx.x; e < NN; e += blockDim.x) {
+        // [r0][j] -> offset of element (min(r0, j), max(r0, j)) in the triangle; row N: identity (pool rows)
+        for (int e = threadIdx.x; e < NN + N; e += blockDim.x) {
             const int r0 = e / N, j = e - r0 * N, lo = min(r0, j), hi = max(r0, j);
-            tofs_s[e] = lo * N - lo * (lo - 1) / 2 + (hi - lo);
+            tofs_s[e] = r0 < N ? lo * N - lo * (lo - 1) / 2 + (hi - lo) : j;
         }
     }
     __syncthreads();
@@ -234,14 +235,13 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     const unsigned nbrow_u32 = smem_u32(nbrow);
     // + (c*APW*N + t): record t of chunk c (idle lanes stay inside the strip)
     const int2* const strip_sub = strip + (lane_ok ? sub * N : 0);
-    // this lane's element of the neighbour row of link record r (links2): the neighbour's slot and
-    // the row r0 = r.y & 15, or - SYM_LINK_POOL set - the element offset of a row that lies
-    // outside the ADOs of this rank (halo row pool of a sharded run, rows stored as N elements)
+    // this lane's element of the neighbour row of link record r (links2): x is the element offset
+    // of the row's storage - full matrices: the row itself; packed: the neighbour's triangle, the
+    // lane's element sits at trow[table row * N] behind it (table row = r0, or N = identity for the
+    // halo rows of a sharded run, which lie as N consecutive elements in the pool)
     auto row_src = [&](const int2 r) -> const double2* {
-        const unsigned r0 = (unsigned)r.y & 15u;
-        unsigned off = PACKED ? (unsigned)r.x * (unsigned)PK + (unsigned)trow[r0 * N]
-                              : ((unsigned)r.x * (unsigned)N + r0) * (unsigned)N + (unsigned)row;
-        if (r.y & SYM_LINK_POOL) off = a.pool_off + (unsigned)r.x * (unsigned)PS + (unsigned)row;
+        const unsigned off = PACKED ? (unsigned)r.x + (unsigned)trow[((unsigned)r.y >> 28) * N]
+                                    : (unsigned)r.x + (unsigned)row;
         return a.yin + off;
     };
     const char* const cq_row = (const char*)cq_s;
@@ -501,15 +501,16 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     if (c0 + t < nl) {
                         const int rr = ry[t] & 15;
                         double2 Aj = nbrow[t * N];
-                        // read through the triangle as (row, r0): conjugate (pool rows are plain rows)
-                        if (PACKED && row < rr && !(ry[t] & SYM_LINK_POOL)) Aj.y = -Aj.y;
+                        // read through the triangle as (row, r0): conjugate (packed pool rows are stored
+                        // the way the triangle would deliver them, so the same rule holds)
+                        if (PACKED && row < rr) Aj.y = -Aj.y;
                         if (rr != cur_rr) {
                             if (cur_rr >= 0) flush();
                             cur_rr = rr;
                             X = make_double2(0.0, 0.0);
                         }
                         const double2 cf =
-                            *(const double2*)(cq_row + ((ry[t] & ~31) + (row == rr ? 16 : 0)));
+                            *(const double2*)(cq_row + ((ry[t] & 0x0fffffe0) + (row == rr ? 16 : 0)));
                         cfma(X, cf, Aj);
                     }
                 }
@@ -578,7 +579,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
             if (mi < PSLOTS) push_s[mi * PS + j] = v;
             if (PACKED && i != j) {
                 const int mj = rm[j];
-                if (mj < PSLOTS) push_s[mj * PS + i] = make_double2(v.x, -v.y);
+                if (mj < PSLOTS) push_s[mj * PS + i] = v;   // row j, position i < j: as read through the triangle
             }
         };
         auto get_k = [&](int kk) {
@@ -650,8 +651,7 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
                     if (((ent.y >> 8) & 255) < PSLOTS) continue;
                     const int r = ent.y & 15, lo_ = min(r, row), hi_ = max(r, row);
                     const int off = PACKED ? lo_ * N - lo_ * (lo_ - 1) / 2 + (hi_ - lo_) : r * N + row;
-                    double2 v = __ldcg(a.out + (gbase + (unsigned)(sub * EL + off)));
-                    if (PACKED && row < r) v.y = -v.y;
+                    const double2 v = __ldcg(a.out + (gbase + (unsigned)(sub * EL + off)));   // (packed: as read through the triangle)
                     reinterpret_cast<double2*>(a.peer[(ent.y >> 4) & 15])[a.out_elem_off + (size_t)(unsigned)ent.x * PS + row] = v;
                 }
             }
@@ -666,12 +666,14 @@ stage_rows_sym_kernel(const SymArgs a, const __grid_constant__ HParamOf<N, HREAL
     }
 }
 
-// links -> links2 (one thread per link): x = neighbour slot, y = coefficient byte offset | row
-__global__ void sym_convert_links_kernel(const int2* links, int2* links2, long long nlinks, int L) {
+// links -> links2 (one thread per link) for full or packed storage
+__global__ void sym_convert_links_kernel(const int2* links, int2* links2, long long nlinks, int N, int L, int packed) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= nlinks) return;
     const int2 r = links[i];
-    links2[i] = make_int2(r.x, sym_link_y(heom::meta_kdir(r.y), heom::meta_neff(r.y), L, heom::meta_r0(r.y)));
+    const int r0 = heom::meta_r0(r.y);
+    links2[i] = make_int2((int)sym_link_x((unsigned)r.x, r0, N, packed != 0),
+                          sym_link_y(heom::meta_kdir(r.y), heom::meta_neff(r.y), L, r0, r0));
 }
 
 thread_local const char* g_sym_err = "";
@@ -835,13 +837,12 @@ int heom_sym_supported(int N, int K, int M, int L, const char** err) {
     return why ? 1 : 0;
 }
 
-int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
+int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, int packed, void* stream,
                            const char** err) {
-    (void)N;
     if (nlinks <= 0) return 0;
     const int threads = 256;
     const unsigned blocks = (unsigned)((nlinks + threads - 1) / threads);
-    HEOM_LAUNCH(sym_convert_links_kernel, blocks, threads, 0, stream, links, links2, nlinks, L);
+    HEOM_LAUNCH(sym_convert_links_kernel, blocks, threads, 0, stream, links, links2, nlinks, N, L, packed);
 #ifndef HEOM_HOST_EMU
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -39,7 +39,7 @@ struct SymArgs {
     double2* out;         // next stage input, or the end-of-step state in the last stage
     const double2* damp;
     const int* link_ptr;
-    const int2* links2;   // x: neighbour slot (or pool element offset), y: coefficient byte offset | flags | row
+    const int2* links2;   // x: element offset of the neighbour row's storage, y: coefficient byte offset | row | table row << 28
     const double2* cbase; // [K][4]
     const int* kmode;     // [K]: mode | first support row << 8
     const double2* ops;   // [1+M][N*N] (diagonal entries of Q_m are read)
@@ -49,8 +49,8 @@ struct SymArgs {
     double a, w;
     int local_step, scramble, nind, nmod, lmax;
     // Sharded runs (heom_shard.cu).  A rank's arrays hold its own ADOs followed by a pool of halo
-    // rows (N elements each) that the owning ranks store there; pool links (SYM_LINK_POOL) read
-    // row x of the pool, pool_off = offset (double2) of the pool from the array base.
+    // rows that the owning ranks store there (sym_pool_stride(N) elements apart, starting pool_off
+    // elements behind the array base); the link table of the owned range points into it.
     // PUSH instantiations: the epilogue stores the rows of the stage output that other ranks read
     // into their pools - push_ptr[owned+1] is a CSR over the owned slots, an entry is
     // (x = row index in the destination's pool, y = staging slot << 8 | peer << 4 | matrix row;
@@ -68,11 +68,19 @@ struct SymArgs {
     unsigned sched_base;
 };
 
-// links2 record: x = neighbour slot, y = ((2k+dir) * (L+1) + n_eff) << 5 | r0.  One table serves
-// full and packed (kernel 7) storage.  With SYM_LINK_POOL set in y, x is instead the element
-// offset (double2 units from the array base) of a plain N-element row: the halo rows a sharded
-// rank receives from its peers live in a row pool behind its own ADOs.
-constexpr int SYM_LINK_POOL = 16;
+// links2 record, resolved for the storage the kernel runs on (a plan converts the table when it
+// switches between kernel 6 and kernel 7):
+//   x = element offset (double2 units from the array base) of the neighbour row's storage -
+//       full matrices: (slot N + r0) N, the row itself; packed: slot N(N+1)/2, the neighbour's
+//       triangle; sharded runs, row received from a peer: its place in the halo-row pool;
+//   y = ((2k+dir) (L+1) + n_eff) << 5 | r0, plus in bits 28-31 the row of the kernel's offset table
+//       that places the lane's element behind x (packed storage): r0, or N for pool rows.
+__host__ __device__ inline unsigned sym_link_x(unsigned slot, int r0, int N, bool packed) {
+    return packed ? slot * (unsigned)(N * (N + 1) / 2) : (slot * (unsigned)N + (unsigned)r0) * (unsigned)N;
+}
+__host__ __device__ inline int sym_link_y(int kdir, int neff, int L, int r0, int table_row) {
+    return (int)((((unsigned)(kdir * (L + 1) + neff)) << 5) | (unsigned)(r0 & 0xf) | ((unsigned)table_row << 28));
+}
 // A pool row occupies an even number of elements (whole 32-byte sectors; 128 bytes = one line for
 // N = 7, 8) and the pool starts on a 128-byte boundary: the rows arrive as peer writes over NVLink,
 // and a write that covers sectors only partly would make the receiving L2 merge it with memory.
@@ -138,7 +146,7 @@ struct SymLaunch {
 // All return 0 on success; on failure *err points to a static message.
 int heom_sym_supported(int N, int K, int M, int L, const char** err);
 int heom_sym_push_slots(void);   // staging slots per group of the fused push
-int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, void* stream,
+int heom_sym_convert_links(const int2* links, int2* links2, long long nlinks, int N, int L, int packed, void* stream,
                            const char** err);
 int heom_sym_launch(const SymLaunch& L, const char** err);
 

@@ -344,8 +344,7 @@ class ShardedDEOM:
             return
         before = dict(self.timings)
         self._release_native()
-        p._check(p.lib.pyqed_heom_build_hierarchy(p._h))   # fresh link table (the old one was localized in place)
-        self._init_native(p, bounds=new)
+        self._init_native(p, bounds=new)   # (the rank-local link table is rewritten from the general one)
         self.timings["first_cut"] = before
         self.timings["rebalance"] = {"stage_ms_before": times, "changed": True, "old_bounds": [int(b) for b in edges],
                                      "new_bounds": new}

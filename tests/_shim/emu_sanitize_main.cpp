@@ -84,31 +84,39 @@ int main(int argc, char** argv) {
             const long long lo[2] = {0, nmax / 2 + 1}, hi[2] = {nmax / 2 + 1, nmax};
             const int PK = N * (N + 1) / 2, EL = packed ? PK : (int)NN;
             std::vector<int> links2(2 * (size_t)nlinks);
-            if (emu_convert_links(links.data(), links2.data(), nlinks, N, L, &err)) return 1;
+            if (emu_convert_links(links.data(), links2.data(), nlinks, N, L, packed, &err)) return 1;
             std::vector<std::vector<long long>> need(2);
-            std::vector<std::vector<int>> loc(2, links2);
             for (int r = 0; r < 2; ++r) {
                 for (int l = link_ptr[lo[r]]; l < link_ptr[hi[r]]; ++l) {
-                    const long long nb = links2[2 * l];
-                    if (nb < lo[r] || nb >= hi[r]) need[r].push_back(nb * 8 + (links2[2 * l + 1] & 15));
+                    const long long nb = links[2 * l];
+                    if (nb < lo[r] || nb >= hi[r]) need[r].push_back(nb * 8 + ((links[2 * l + 1] >> 16) & 15));
                 }
                 std::sort(need[r].begin(), need[r].end());
                 need[r].erase(std::unique(need[r].begin(), need[r].end()), need[r].end());
-                for (int l = link_ptr[lo[r]]; l < link_ptr[hi[r]]; ++l) {
-                    const long long nb = loc[r][2 * l];
-                    if (nb >= lo[r] && nb < hi[r]) {
-                        loc[r][2 * l] = (int)(nb - lo[r]);
-                    } else {
-                        const long long item = nb * 8 + (loc[r][2 * l + 1] & 15);
-                        loc[r][2 * l] = (int)(std::lower_bound(need[r].begin(), need[r].end(), item) - need[r].begin());
-                        loc[r][2 * l + 1] |= 16;
-                    }
-                }
             }
+            const int PS = (N + 1) & ~1;                                 // sym_pool_stride
             const long long n_own_max = std::max(hi[0] - lo[0], hi[1] - lo[1]);
             const long long pool_max = (long long)std::max(need[0].size(), need[1].size());
-            const int PS = (N + 1) & ~1;                                 // sym_pool_stride
             const long long pool_off = (n_own_max * EL + 7) & ~7ll, arr = pool_off + pool_max * PS;
+            // rank-local link tables (shard_localize_links_kernel restated)
+            std::vector<std::vector<int>> loc(2, links2);
+            for (int r = 0; r < 2; ++r)
+                for (int l = link_ptr[lo[r]]; l < link_ptr[hi[r]]; ++l) {
+                    const long long nb = links[2 * l];
+                    const int r0 = (links[2 * l + 1] >> 16) & 15;
+                    unsigned x, tr;
+                    if (nb >= lo[r] && nb < hi[r]) {
+                        x = packed ? (unsigned)(nb - lo[r]) * PK : ((unsigned)(nb - lo[r]) * N + r0) * N;
+                        tr = r0;
+                    } else {
+                        const long long item = nb * 8 + r0;
+                        x = (unsigned)pool_off +
+                            (unsigned)(std::lower_bound(need[r].begin(), need[r].end(), item) - need[r].begin()) * PS;
+                        tr = N;
+                    }
+                    loc[r][2 * l] = (int)x;
+                    loc[r][2 * l + 1] = (int)(((unsigned)links2[2 * l + 1] & 0x0fffffffu) | (tr << 28));
+                }
             std::vector<std::vector<double>> st(2, std::vector<double>(2 * 4 * (size_t)arr, std::nan("")));
             auto elem = [&](long long slot_local, int i, int j) {   // offset (double2) of element (i, j), i <= j if packed
                 return packed ? slot_local * EL + i * N - i * (i - 1) / 2 + (j - i) : slot_local * EL + i * N + j;
@@ -131,7 +139,8 @@ int main(int argc, char** argv) {
                 for (size_t i = 0; i < need[r].size(); ++i)
                     for (int j = 0; j < N; ++j)
                         for (int part = 0; part < 2; ++part)
-                            st[r][2 * (pool_off + (long long)i * PS + j) + part] =
+                            st[r][2 * (pool_off + (long long)i * PS + j) + part] =   // packed: as read through the triangle
+                                (packed && part == 1 && j < (int)(need[r][i] & 7) ? -1.0 : 1.0) *
                                 row_value(1 - r, need[r][i] >> 3, (int)(need[r][i] & 7), j, 0, part);
             std::vector<std::vector<int>> pptr(2), pent(2);
             for (int r = 0; r < 2; ++r) {   // rows of rank r's slots that the other rank's links read

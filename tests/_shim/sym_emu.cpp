@@ -33,7 +33,7 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
     *err = none;
     if (heom_sym_supported(N, K, M, L, err)) return 1;
     std::vector<int2> links2((size_t)std::max(1ll, nlinks));
-    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 0, nullptr, err))
         return 1;
     const long long NN = (long long)N * N, asz = nmax * NN;
     double2* Y = reinterpret_cast<double2*>(state);
@@ -96,11 +96,11 @@ int emu_sym_run(int N, int K, int M, int L, long long nmax, const double* H, con
 }
 
 // links (slot, meta) -> links2 with the product's converter
-int emu_convert_links(const int* links, int* links2, long long nlinks, int N, int L, const char** err) {
+int emu_convert_links(const int* links, int* links2, long long nlinks, int N, int L, int packed, const char** err) {
     static const char* none = "";
     *err = none;
     return heom_sym_convert_links(reinterpret_cast<const int2*>(links), reinterpret_cast<int2*>(links2), nlinks, N, L,
-                                  nullptr, err);
+                                  packed, nullptr, err);
 }
 
 // One stage of one rank of a sharded run with rank-local arrays (heom_shard.cu in miniature): the
@@ -171,7 +171,7 @@ int emu_packed_run(int N, int K, int M, int L, long long nmax, const double* H, 
     *err = none;
     if (heom_sym_supported(N, K, M, L, err)) return 1;
     std::vector<int2> links2((size_t)std::max(1ll, nlinks));
-    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, nullptr, err))
+    if (heom_sym_convert_links(reinterpret_cast<const int2*>(links), links2.data(), nlinks, N, L, 1, nullptr, err))
         return 1;
     const long long NN = (long long)N * N, PK = (long long)N * (N + 1) / 2;
     const size_t arr = ((size_t)(nmax * PK) * sizeof(double2) + 255) / 256 * 256;

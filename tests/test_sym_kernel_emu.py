@@ -264,29 +264,40 @@ def test_sharded_ranks_with_local_arrays(emu, fused, packed, shape):
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     links2 = np.zeros_like(links)
     assert emu.emu_convert_links(p(links), p(links2), ctypes.c_longlong(len(links)), ctypes.c_int(N),
-                                 ctypes.c_int(o.lmax), ctypes.byref(err)) == 0
-    need, local_links = [], []   # per rank: sorted (slot, row) of foreign rows; localized link table
+                                 ctypes.c_int(o.lmax), ctypes.c_int(int(packed)), ctypes.byref(err)) == 0
+    need = []   # per rank: sorted (slot, row) of the foreign rows its links read
     for r in range(2):
         lo, hi = bounds[r], bounds[r + 1]
-        rec = links2[ptr[lo]:ptr[hi]]
+        rec = links[ptr[lo]:ptr[hi]]
         foreign = (rec[:, 0] < lo) | (rec[:, 0] >= hi)
-        nd = sorted({(int(s_), int(y_ & 15)) for s_, y_ in rec[foreign]})
+        nd = sorted({(int(s_), int((m_ >> 16) & 0xf)) for s_, m_ in rec[foreign]})
         assert nd
         need.append(nd)
-        pos = {item: i for i, item in enumerate(nd)}
-        loc = links2.copy()
-        for l in range(ptr[lo], ptr[hi]):
-            nb, y_ = int(loc[l, 0]), int(loc[l, 1])
-            if lo <= nb < hi:
-                loc[l, 0] = nb - lo
-            else:
-                loc[l] = (pos[(nb, y_ & 15)], y_ | 16)      # SYM_LINK_POOL
-        local_links.append(loc)
     n_own = [bounds[1], nmax - bounds[1]]
     n_own_max, pool_max = max(n_own), max(len(x) for x in need)
     PS = (N + 1) & ~1                       # sym_pool_stride: whole sectors per pool row
     pool_off = (n_own_max * EL + 7) & ~7    # sym_pool_offset
     arr_elems = pool_off + pool_max * PS
+    # the rank-local link tables (shard_localize_links_kernel restated): x = element offset of the row's
+    # storage (local ADO: as the converter resolves it for the local slot; foreign: its pool row),
+    # table row (bits 28-31 of y) = r0, or N for pool rows
+    local_links = []
+    for r in range(2):
+        lo, hi = bounds[r], bounds[r + 1]
+        pos = {item: i for i, item in enumerate(need[r])}
+        loc = links2.copy()
+        for l in range(ptr[lo], ptr[hi]):
+            nb, r0 = int(links[l, 0]), int((links[l, 1] >> 16) & 0xf)
+            y_ = int(links2[l, 1]) & 0x0fffffff
+            if lo <= nb < hi:
+                x_ = (nb - lo) * EL if packed else ((nb - lo) * N + r0) * N
+                tr = r0
+            else:
+                x_ = pool_off + pos[(nb, r0)] * PS
+                tr = N
+            yy = y_ | (tr << 28)
+            loc[l] = (x_, yy - (1 << 32) if yy >= (1 << 31) else yy)
+        local_links.append(loc)
     state = np.full((2, 4, arr_elems), np.nan, dtype=C128)   # rank, (Y, SA, SB, ACC)
     y0 = np.zeros((nmax, N, N), C128)
     y0[0] = w["rho0"]
@@ -302,7 +313,9 @@ def test_sharded_ranks_with_local_arrays(emu, fused, packed, shape):
         full = [own_ados(r, arr) for r in range(2)]
         for r in range(2):
             for i, (slot, row) in enumerate(need[r]):
-                src = full[1 - r][slot - bounds[1 - r], row]
+                src = full[1 - r][slot - bounds[1 - r], row].copy()
+                if packed:   # as a gather through the triangle delivers the row: (min, max), not conjugated
+                    src[:row] = np.conj(src[:row])
                 state[r, arr, pool_off + i * PS: pool_off + i * PS + N] = src
     exchange(0)
     # push tables of rank r: CSR over its owned slots, entry = (row index in the peer's pool,
