@@ -390,7 +390,7 @@ def run_gpu_arm(args):
                          peer_push={-1: None, 0: False, 1: True}[args.push],
                          fused_push={-1: None, 0: False, 1: True}[args.fused],
                          native={-1: None, 0: False, 1: True}[args.native],
-                         rebalance={-1: None, 0: False, 1: True}[args.rebalance])
+                         rebalance={-1: None, 0: False, 1: True, 2: "force"}[args.rebalance])
         torch.cuda.synchronize()
         build_s = time.perf_counter() - t0
         sh.run(w["rho0"], dt, 1, w["pulse_system_func"], w["pulse_coupling_func"])
@@ -710,7 +710,7 @@ def main():
     ap.add_argument("--push", type=int, default=-1, help="multi-GPU halo: 1 peer-memory stores, 0 NCCL all_to_all")
     ap.add_argument("--batch", type=int, default=1, help="aggregate7_K6_L6: number of waiting times (config 5: 64)")
     ap.add_argument("--native", type=int, default=-1, help="multi-GPU: 1 require / 0 forbid the rank-local layout")
-    ap.add_argument("--rebalance", type=int, default=-1, help="multi-GPU: 0 = keep the static cut of the ranges")
+    ap.add_argument("--rebalance", type=int, default=-1, help="multi-GPU: 0 = keep the static cut of the ranges, 2 = re-cut even if the ranks are balanced")
     ap.add_argument("--save-rho-ref", default=None, help="1 GPU: merge rho_sys after `steps` steps into this JSON")
     ap.add_argument("--prefetch", type=int, default=0, help="kernel 7: double-buffered tiles fetched one group ahead")
     ap.add_argument("--dynsched", type=int, default=-1, help="kernels 6/7: 0 = static group stride, default: global work counter")
