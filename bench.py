@@ -493,7 +493,9 @@ def run_gpu_arm(args):
         bytes_per_launch = 256.0 * n * n * owned * (K if resident else 0.25)  # resident: one launch = K steps
         achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
         state_mb = nmax * n * n * 16 / 1e6
-        if plan.info("dataflow_launches") > 0:
+        if plan.info("dataflow_tma_launches") > 0:
+            kname = "stage_dataflow_tma_kernel"
+        elif plan.info("dataflow_launches") > 0:
             kname = "stage_dataflow_kernel"
         elif plan.info("packed_steps") > 0:
             kname = "stage_rows_sym_kernel<PACKED>"

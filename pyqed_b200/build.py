@@ -32,7 +32,7 @@ def compile_units():
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpyqed_heom.so")
 DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("heom_core.cuh", "heom_device.cuh", "heom_plan.cuh", "heom_hierarchy.cuh", "heom_stage_rows.cuh", "heom_stage_async.cuh",
-                                                 "heom_resident.cuh", "heom_stage_generic.cuh", "heom_stage_sym.cuh", "heom_plan.cuh", "heom_dataflow.cuh")] + \
+                                                 "heom_resident.cuh", "heom_stage_generic.cuh", "heom_stage_sym.cuh", "heom_plan.cuh", "heom_dataflow.cuh", "heom_dataflow_tma.cuh")] + \
     [os.path.join(os.path.dirname(HERE), "include", "pyqed_heom.h")]
 
 
@@ -65,7 +65,7 @@ HEADER_DEPS = {
     "heom_inst.cu": _COMMON + ["heom_plan.cuh", "heom_stage_sym.cuh", "heom_stage_async.cuh", "heom_stage_rows.cuh",
                                "heom_resident.cuh", "../../include/pyqed_heom.h"],
     "heom_kernels.cu": _COMMON + ["heom_plan.cuh", "heom_stage_sym.cuh", "heom_stage_async.cuh", "heom_hierarchy.cuh",
-                                  "heom_resident.cuh", "heom_stage_generic.cuh", "heom_dataflow.cuh", "../../include/pyqed_heom.h"],
+                                  "heom_resident.cuh", "heom_stage_generic.cuh", "heom_dataflow.cuh", "heom_dataflow_tma.cuh", "../../include/pyqed_heom.h"],
 }
 
 

@@ -130,6 +130,7 @@ static int compute_layout(pyqed_heom_plan* p) {
 #include "heom_resident.cuh"      // ResidentArgs; the kernels are instantiated in heom_inst.cu
 #include "heom_stage_generic.cuh"
 #include "heom_dataflow.cuh"
+#include "heom_dataflow_tma.cuh"
 
 extern "C" {
 static void fill_stage_args(pyqed_heom_plan* p, StageArgs& a);
@@ -194,11 +195,95 @@ static int try_resident(pyqed_heom_plan* p) {
     return rcode;
 }
 
+// ---- kernel 9: kernel 8's scheme for Hermitian problems with one CTA per ADO (heom_dataflow_tma.cuh) ----
+// returns 0 = done, -1 = not applicable (kernel 8 or per-stage launches take it), 1 = error
+extern "C" {
+static void sparsity(const pyqed_heom_plan* p, int o, std::vector<short>& row_ptr, std::vector<short>& row_idx,
+                     std::vector<short>& col_ptr, std::vector<short>& col_idx);
+}
+static int try_dataflow_tma(pyqed_heom_plan* p) {
+    const bool whole = p->part_lo == 0 && p->part_hi == p->nmax;
+    if (!(p->kernel == 0 || p->kernel == 9) || stage_kernel_of(p) != 2 || p->ctx_tdep || !whole || p->ctx_nt <= 0 ||
+        p->N > 32 || p->N < 2 || p->opt_resident == 0 || p->opt_dataflow_tma == 0)
+        return -1;
+    if (!(p->herm_inputs && p->herm_state && p->opt_herm != 0) || p->ctx_nt >= (1ll << 29)) return -1;
+    const int N = p->N, M1 = 1 + p->M, maxl = p->K + std::min(p->K, p->L);
+    const long long total = p->nmax * (long long)p->B;
+    const int nsm = sm_count_of(p->device);
+    if (total > 2ll * nsm || M1 > DF9_MAXOPS || maxl > DF9_MAXL) return -1;
+    int nnz = 0;
+    for (int o = 0; o < M1; ++o) {
+        std::vector<short> a, b, c, d;
+        sparsity(p, o, a, b, c, d);
+        nnz += a[N];
+    }
+    if (nnz > DF9_MAXNNZ) return -1;
+    const int units = N * (N - 1) / 2 + (N + 1) / 2;   // element pairs + pairs of diagonal elements
+    const size_t smem = sizeof(Df9Smem);               // > 227 KB / 3: at most two CTAs per SM (the placement counts on it)
+    static_assert(sizeof(Df9Smem) <= 113 * 1024 && sizeof(Df9Smem) > 78 * 1024, "two CTAs per SM");
+    static PerDeviceOnce attr;
+    if (attr.need(p->device))
+        CU_TRY(cudaFuncSetAttribute(stage_dataflow_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    int coop = 0, per_sm = 0;
+    CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_dataflow_tma_kernel, DF9_THREADS, smem));
+    const long long grid = total <= nsm ? total : 2ll * nsm;
+    if (!coop || (long long)per_sm * nsm < grid) return -1;
+    const size_t nflag = (size_t)total * DF9_FLAG_STRIDE;
+    const size_t words = nflag + DF9_CTRL + DF9_MAXSM + (size_t)total;   // flags, control block, work order
+    if (words > p->df9_cap) {
+        if (p->d_df9) cudaFree(p->d_df9);
+        p->d_df9 = nullptr;
+        p->df9_cap = 0;
+        CU_TRY(cudaMalloc(&p->d_df9, sizeof(unsigned) * words));
+        p->df9_cap = words;
+    }
+    CU_TRY(cudaMemsetAsync(p->d_df9, 0, sizeof(unsigned) * (nflag + DF9_CTRL + DF9_MAXSM), p->stream));
+    Dataflow9Args da;
+    fill_stage_args(p, da.s);
+    if (!da.s.herm) return -1;
+    da.Y = p->arr(ARR_Y);
+    da.P0 = p->arr(ARR_ACC);   // packed stage outputs live in the three work arrays
+    da.P1 = p->arr(ARR_SA);
+    da.P2 = p->arr(ARR_SB);
+    da.units = units;
+    da.flags = p->d_df9;
+    da.ctrl = p->d_df9 + nflag;
+    int* order = (int*)(p->d_df9 + nflag + DF9_CTRL + DF9_MAXSM);
+    da.order = order;
+    da.dt = p->ctx_dt;
+    da.nt = p->ctx_nt;
+    da.timeout_ns = 2000000000ull;
+    da.B = p->B;
+    if (p->timing) {
+        if (p->ev_used == p->ev.size()) {
+            cudaEvent_t e0, e1;
+            CU_TRY(cudaEventCreate(&e0));
+            CU_TRY(cudaEventCreate(&e1));
+            p->ev.emplace_back(e0, e1);
+        }
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].first, p->stream));
+    }
+    dataflow_order_kernel<<<1, 512, 0, p->stream>>>(da.s.link_ptr, p->nmax, total, order);
+    if (post_launch(p, "dataflow_order_kernel")) return 1;
+    void* kargs[] = {&da};
+    CU_TRY(cudaLaunchCooperativeKernel((void*)stage_dataflow_tma_kernel, dim3((unsigned)grid), dim3(DF9_THREADS), kargs,
+                                       smem, p->stream));
+    if (post_launch(p, "stage_dataflow_tma_kernel")) return 1;
+    if (p->timing) {
+        CU_TRY(cudaEventRecord(p->ev[p->ev_used].second, p->stream));
+        p->ev_used++;
+    }
+    p->dataflow_launches++;
+    p->dataflow_tma_launches++;
+    return 0;
+}
+
 // ---- kernel 8: persistent, ADO-to-ADO synchronised propagation of small hierarchies with N > 8 ----
 // returns 0 = done, -1 = not applicable (caller falls back to per-stage launches), 1 = error
 static int try_dataflow(pyqed_heom_plan* p) {
     const bool whole = p->part_lo == 0 && p->part_hi == p->nmax;
-    if (!(p->kernel == 0 || p->kernel == 8) || stage_kernel_of(p) != 2 || p->ctx_tdep || !whole || p->ctx_nt <= 0 ||
+    if (!(p->kernel == 0 || p->kernel == 8 || p->kernel == 9) || stage_kernel_of(p) != 2 || p->ctx_tdep || !whole || p->ctx_nt <= 0 ||
         p->N > 32 || p->opt_resident == 0)
         return -1;
     const int N = p->N, NN = N * N;
@@ -459,6 +544,7 @@ void pyqed_heom_plan_destroy(pyqed_heom_plan* p) {
     if (p->d_peer) cudaFree(p->d_peer);
     if (p->shard.d_peer) cudaFree(p->shard.d_peer);
     if (p->d_flags) cudaFree(p->d_flags);
+    if (p->d_df9) cudaFree(p->d_df9);
     delete p;
 }
 
@@ -520,7 +606,7 @@ int pyqed_heom_set_order(pyqed_heom_plan* p, int order) {
 
 int pyqed_heom_set_tuning(pyqed_heom_plan* p, int kernel, int warps, int use_graph) {
     REQUIRE(p, "null plan");
-    REQUIRE((kernel >= 0 && kernel <= 4) || (kernel >= 6 && kernel <= 8), "kernel must be 0..4 or 6..8");
+    REQUIRE((kernel >= 0 && kernel <= 4) || (kernel >= 6 && kernel <= 9), "kernel must be 0..4 or 6..9");
     REQUIRE(warps >= 0 && warps <= 16, "warps_per_cta must be in [0, 16]");
     REQUIRE(use_graph == 0, "use_graph is reserved and must be 0");
     p->kernel = kernel;
@@ -541,6 +627,7 @@ int pyqed_heom_set_option(pyqed_heom_plan* p, const char* name, int value) {
     else if (n == "prefetch") p->opt_prefetch = value;
     else if (n == "dynsched") p->opt_dynsched = value;
     else if (n == "packed") p->opt_packed = value;
+    else if (n == "dataflow_tma") p->opt_dataflow_tma = value;
     else if (n == "debug_sync") p->debug_sync = value != 0;
     else return fail("unknown option '" + n + "'");
     return 0;
@@ -560,6 +647,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "sym_launches") return p->sym_launches;
     if (n == "packed_steps") return p->packed_steps;
     if (n == "dataflow_launches") return p->dataflow_launches;
+    if (n == "dataflow_tma_launches") return p->dataflow_tma_launches;
     if (n == "rk_scheme") return rk_scheme(p) ? 1 : 0;
     if (n == "stage_kernel") return stage_kernel_of(p);
     if (n == "nlinks") return p->nlinks;
@@ -1097,10 +1185,13 @@ int pyqed_heom_propagate(pyqed_heom_plan* p, double dt, int64_t nt, const double
         if (rr == 0) return 0;
         if (rr > 0) return 1;
         REQUIRE(p->kernel != 4, "kernel 4 (cluster-resident) is not applicable to this problem");
+        const int d9 = try_dataflow_tma(p);
+        if (d9 == 0) return 0;
+        if (d9 > 0) return 1;
         const int df = try_dataflow(p);
         if (df == 0) return 0;
         if (df > 0) return 1;
-        REQUIRE(p->kernel != 8, "kernel 8 (persistent dataflow) is not applicable to this problem");
+        REQUIRE(p->kernel != 8 && p->kernel != 9, "kernels 8 / 9 (persistent dataflow) are not applicable to this problem");
         if (packed_eligible(p)) return run_packed(p, dt, nt);
         for (int64_t i = 0; i < nt; ++i)
             for (int st = 0; st < 4; ++st)

@@ -80,6 +80,10 @@ struct pyqed_heom_plan {
     long long sym_launches = 0;  // stage launches that went to kernel 6
     long long packed_steps = 0;  // RK4 steps done by kernel 7 (packed Hermitian storage)
     long long dataflow_launches = 0;  // propagations done by kernel 8 (one persistent launch each)
+    long long dataflow_tma_launches = 0;  // ... of which by kernel 9 (Hermitian, one CTA per ADO, TMA staging)
+    int opt_dataflow_tma = -1;        // kernel 9 where eligible (-1/1 on, 0 off: kernel 8)
+    unsigned* d_df9 = nullptr;        // kernel 9: stage counters, control block, work order
+    size_t df9_cap = 0;
     unsigned* d_flags = nullptr;      // kernel 8: per-ADO stage counters
     size_t flags_cap = 0;
     bool links2_built = false;
@@ -147,8 +151,8 @@ inline int stage_kernel_of(const pyqed_heom_plan* p) {
     // 7 = whole propagations on packed Hermitian storage where eligible (pyqed_heom_propagate),
     //     kernel 3 otherwise
     // 8 = persistent dataflow propagation (heom_dataflow.cuh) where eligible, the generic kernel otherwise
-    if (p->kernel && p->kernel != 4 && p->kernel != 6 && p->kernel != 7 && p->kernel != 8) return p->kernel;
-    if (p->N > 8 || p->N < 2 || p->kernel == 8) return 2;   // (the row kernels need 2 <= N <= 8)
+    if (p->kernel && p->kernel != 4 && p->kernel != 6 && p->kernel != 7 && p->kernel != 8 && p->kernel != 9) return p->kernel;
+    if (p->N > 8 || p->N < 2 || p->kernel == 8 || p->kernel == 9) return 2;   // (the row kernels need 2 <= N <= 8)
     const bool fits32 = (unsigned long long)p->nmax * p->N * p->N < (1ull << 32);
     return (p->use_qdiag && p->opt_rk13 != 0 && fits32) ? 3 : 1;
 }

@@ -512,11 +512,50 @@ def test_dataflow_kernel_matches_reference(name):
     assert s._plan.info("dataflow_launches") == 1 and s._plan.info("resident_launches") == 0
 
 
+# ---- kernel 9: the same scheme for Hermitian problems, one CTA per ADO (csrc/heom_dataflow_tma.cuh) ----
+@pytest.mark.parametrize("name", ["deom_polariton32_L6", "deom_polariton32_L2", "deom_polariton8_L4",
+                                  "deom_spin_boson_L10", "deom_fmo_K21_L2"])
+def test_dataflow_tma_kernel_matches_reference(name):
+    """Kernel 9: y and the accumulator in registers for the whole run, k = W + W^dagger, neighbour
+    matrices by bulk copies behind per-link flags; N = 32 at full depth 6 (210 CTAs on 148 SMs: the
+    per-SM placement with spare CTAs) and smaller systems forced through the same kernel."""
+    g = golden(name)
+    s = _solver_from(g)
+    s.tuning = dict(kernel=9, warps_per_cta=0, use_graph=0)
+    _check_against_golden(g, s)
+    assert s._plan.info("dataflow_tma_launches") == 1 and s._plan.info("resident_launches") == 0
+
+
+def test_dataflow_tma_kernel_repeated_runs_and_fallback():
+    """Two propagations in a row continue from the evolved state (bit-identical to kernel 8's
+    restart behaviour within rounding); a non-Hermitian initial state is not taken by kernel 9."""
+    g = golden("deom_polariton32_L2")
+    n, dt, nt = g["rho0"].shape[0], float(g["dt"]), int(g["nt"])
+    a = _solver_from(g)
+    a.tuning = dict(kernel=9, warps_per_cta=0, use_graph=0)
+    b = _solver_from(g)
+    b.tuning = dict(kernel=2, warps_per_cta=0, use_graph=0)
+    for s in (a, b):
+        s.run(g["rho0"].copy(), dt, nt)
+    assert a._plan.info("dataflow_tma_launches") == 1
+    assert np.max(np.abs(a.ddos - b.ddos)) < 1e-13
+    rng = np.random.default_rng(11)
+    r = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))       # not Hermitian
+    c = _solver_from(g)
+    _, out = c.run(r.copy(), dt, nt)
+    assert c._plan.info("dataflow_tma_launches") == 0 and c._plan.info("dataflow_launches") == 1
+    d = _solver_from(g)
+    d.tuning = dict(kernel=2, warps_per_cta=0, use_graph=0)
+    _, ref = d.run(r.copy(), dt, nt)
+    assert np.max(np.abs(np.asarray(out) - np.asarray(ref))) < 1e-12
+
+
 def test_dataflow_kernel_is_the_default_for_config4_and_handles_batches():
     g = golden("deom_polariton32_L6")
     s = _solver_from(g)
     _check_against_golden(g, s)
     assert s._plan.info("dataflow_launches") == 1          # chosen automatically for N = 32
+    assert s._plan.info("dataflow_tma_launches") == 1      # Hermitian problem, 210 ADOs <= 2 CTAs per SM: kernel 9
     # a batch of trajectories (different initial states) in the same launch, twice in a row
     n, nt, dt = g["rho0"].shape[0], 12, float(g["dt"])
     rng = np.random.default_rng(5)
