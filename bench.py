@@ -248,11 +248,17 @@ def small_workload_leg(name, device, nt=2000):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    if plan.info("dataflow_tma_launches"):
+        kernel, note = "stage_dataflow_tma_kernel", ("one cooperative launch, one CTA per ADO, state in registers / shared "
+                                                     "memory, stage outputs exchanged through L2; latency bound")
+    elif plan.info("dataflow_launches"):
+        kernel, note = "stage_dataflow_kernel", "one cooperative launch, state in L2; latency bound"
+    else:
+        kernel = {0: "per-stage kernels", 4: "resident_cluster_kernel", 5: "resident_elem_kernel"}[
+            plan.info("resident_kind") if plan.info("resident_launches") else 0]
+        note = "state resident in distributed shared memory; an HBM fraction is not meaningful here"
     return {"value": plan.nmax * nt / (ms * 1e-3), "unit": UNIT, "n_ado": plan.nmax, "steps": nt,
-            "us_per_step": 1e3 * ms / nt,
-            "kernel": {0: "per-stage kernels", 4: "resident_cluster_kernel", 5: "resident_elem_kernel"}[
-                plan.info("resident_kind") if plan.info("resident_launches") else 0],
-            "note": "state resident in distributed shared memory; an HBM fraction is not meaningful here"}
+            "us_per_step": 1e3 * ms / nt, "kernel": kernel, "note": note}
 
 
 def run_reference_arm(args):
@@ -524,9 +530,11 @@ def run_gpu_arm(args):
             fp64 = {"bound": "fp64", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                     "peak_source": src, "traffic": None, "kernel": kname,
                     "algorithmic_flops_per_step": flops_step,
-                    "note": "H and Q_m are applied through their sparsity lists, so the executed flops are far "
-                            "below this dense-commutator count; the run is issue/latency bound "
-                            "(ncu: profiles/r02_kernel8_polariton32_ncu.txt, FP64 pipe 11 %, issue 42 %)"}
+                    "note": "H and Q_m are applied through their sparsity lists (and, in kernel 9, only W of "
+                            "k = W + W^dagger is formed), so the executed flops are far below this dense-commutator "
+                            "count; the run is bound by the flag/fetch latency between ADOs and by shared-memory "
+                            "wavefronts (ncu: profiles/r02_kernel9_polariton32_ncu.txt; kernel 8: "
+                            "profiles/r02_kernel8_polariton32_ncu.txt)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if multi else "weak",
@@ -583,7 +591,8 @@ def run_gpu_arm(args):
         if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_cpu:
             # BASELINE.json configs[1] (330 ADOs, cache resident) measured beside the
             # headline workload so that both readings of "the configuration" are on record
-            aux("other_workloads", lambda: {"fmo7_K7_L4": small_workload_leg("fmo7_K7_L4", local)})
+            aux("other_workloads", lambda: {"fmo7_K7_L4": small_workload_leg("fmo7_K7_L4", local),
+                                            "polariton32_K4_L6": small_workload_leg("polariton32_K4_L6", local)})
         if world == 1 and not args.no_cpu:
             aux("cpu_baseline", lambda: cpu_native_leg(args.workload)[0])
             aux("cpu_baseline_python_loop", lambda: cpu_reference_leg(args.workload, budget_s=8.0)[0])

@@ -248,7 +248,12 @@ int pyqed_heom_stage_timing(pyqed_heom_plan* plan, int enable, double* total_ms,
  * Kernel 0 picks 7, then 6, then 3 / 1 / 2 by applicability: 6 and 7 need
  * Hermitian ADOs, one-entry diagonal Q_m and a time-independent H; 7 also one
  * trajectory and the whole hierarchy on this GPU; both fall back to kernel 3
- * where they do not apply.  Choose the kernel and set system, coupling and bath
+ * where they do not apply.  8 and 9: ONE cooperative launch for all steps of a
+ * small hierarchy with 8 < N <= 32 (or any N when asked for), the ADOs
+ * synchronised by per-ADO release/acquire flags instead of kernel boundaries;
+ * 9 (Hermitian problems, at most two ADOs per SM, sparse operators) keeps one
+ * CTA per ADO with the state in registers / shared memory and exchanges packed
+ * Hermitian stage outputs; kernel 0 picks 9, then 8, for N > 8.  Choose the kernel and set system, coupling and bath
  * before pyqed_heom_table_bytes: kernels 6 / 7 add a second link table to the
  * table buffer.  warps per CTA for kernels 1, 3, 6 and 7;
  * use_graph: reserved, must be 0 (small hierarchies are propagated by a single
@@ -281,10 +286,12 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  *                drawing them from a global work counter (the counter keeps the groups
  *                in flight on the whole chip inside one short window of the storage
  *                order, which is what lets neighbour rows hit in L2)
+ *   "dataflow_tma" 0 = never use kernel 9 (kernel 8 takes its problems)
  *   "debug_sync" synchronise and check after every launch
  * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "sym", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
  * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes", "sym_launches" (stage launches done by
- * kernel 6), "packed_steps" (RK4 steps done by kernel 7)); -1 for an unknown name. */
+ * kernel 6), "packed_steps" (RK4 steps done by kernel 7), "dataflow_launches" (propagations done by kernels 8 / 9),
+ * "dataflow_tma_launches" (... by kernel 9)); -1 for an unknown name. */
 int pyqed_heom_set_option(pyqed_heom_plan* plan, const char* name, int value);
 int64_t pyqed_heom_get_info(pyqed_heom_plan* plan, const char* name);
 

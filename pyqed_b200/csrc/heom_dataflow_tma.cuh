@@ -50,15 +50,16 @@ struct __align__(128) Df9Smem {
     double2 rho[DF9_NMAX * DF9_NP];         // own stage input, full matrix
     double2 buf[DF9_NMAX * DF9_NP];         // S_m of a non-diagonal mode
     double2 acc[DF9_THREADS];               // RK4 accumulator (thread-private)
-    double2 val[DF9_MAXNNZ];                // operator entries: -iH, Q_1, ...
+    double2 val[DF9_MAXNNZ];                // operator entries (-iH, Q_1, ...), padded rows: [obase[o] + k N + row] = k-th entry of the row
     double2 lcf[DF9_MAXL];                  // alphaL per link (links sorted by mode)
     int lnb[DF9_MAXL];                      // neighbour slot per link
     int mord[DF9_MAXOPS];                   // modes in processing order: non-diagonal Q_m first
     int mend[DF9_MAXOPS];                   // end of the k-th processed mode's links in the sorted list
-    int rp[DF9_MAXOPS][DF9_NP];             // row starts in val / ri
+    int obase[DF9_MAXOPS];                  // first entry of operator o in val / ri
+    int mrow[DF9_MAXOPS];                   // entries per (padded) row of operator o
     int qdiag[DF9_MAXOPS];
     int misc[8];
-    short ri[DF9_MAXNNZ];                   // column of an entry
+    short ri[DF9_MAXNNZ];                   // column of an entry (padding: value 0, column = the row itself)
 };
 
 struct Dataflow9Args {
@@ -106,22 +107,17 @@ __device__ __forceinline__ void df9_wait_flag(const unsigned* f, unsigned need, 
     }
 }
 
-// wa += sum_t val[t] src[col(t)][ja] over row ia of a sparse operator, the same for (wb, ib, jb): the two
-// dependent chains advance together (small code on purpose)
-__device__ __forceinline__ void df9_rows2(double2& wa, double2& wb, const int* rp, int ia, int ib, bool hasb,
-                                          const double2* val, const short* ri, const double2* src, int ja, int jb) {
-    int ta = rp[ia], tb = rp[ib];
-    const int ea = rp[ia + 1], eb = hasb ? rp[ib + 1] : tb;
+// wa += sum_k val[k][ia] src[col[k][ia]][ja] over the (padded) row ia of a sparse operator, the same for
+// (wb, ib, jb).  Rows are padded to the operator's longest row with zero entries, stored entry-major
+// ([k][row]): the trip count is uniform, lanes with consecutive rows read consecutive words, and there
+// are no row pointers to load - the stage loop is bound by shared-memory wavefronts and issue slots.
+__device__ __forceinline__ void df9_rows2(double2& wa, double2& wb, int n, int nrow, const double2* val, const short* ri,
+                                          const double2* src, int ia, int ib, int ja, int jb) {
 #pragma unroll 1
-    while (ta < ea || tb < eb) {
-        if (ta < ea) {
-            cfma(wa, val[ta], src[ri[ta] * DF9_NP + ja]);
-            ++ta;
-        }
-        if (tb < eb) {
-            cfma(wb, val[tb], src[ri[tb] * DF9_NP + jb]);
-            ++tb;
-        }
+    for (int k = 0; k < n; ++k) {
+        const int ea = k * nrow + ia, eb = k * nrow + ib;
+        cfma(wa, val[ea], src[ri[ea] * DF9_NP + ja]);
+        cfma(wb, val[eb], src[ri[eb] * DF9_NP + jb]);
     }
 }
 
@@ -199,19 +195,41 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
         sm.misc[7] = (a.traj && slot == a.slot0) ? 1 : 0;
     }
 
-    // ---- operators: compact sparse rows, H pre-multiplied by -i ----
+    // ---- operators: padded sparse rows, entry-major, H pre-multiplied by -i ----
+    if (tid < M1) {
+        int longest = 0, diag = 1;
+        for (int i = 0; i < N; ++i) {
+            const int t0 = a.row_ptr[tid * (N + 1) + i], t1 = a.row_ptr[tid * (N + 1) + i + 1];
+            longest = max(longest, t1 - t0);
+            for (int t = t0; t < t1; ++t)
+                if (a.row_idx[tid * NN + t] != i) diag = 0;
+        }
+        sm.mrow[tid] = longest;
+        sm.qdiag[tid] = diag;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int base = 0;
+        for (int o = 0; o < M1; ++o) {
+            sm.obase[o] = base;
+            base += sm.mrow[o] * N;
+        }
+    }
+    __syncthreads();
     for (int r = tid; r < M1 * N; r += DF9_THREADS) {
         const int o = r / N, i = r - o * N;
-        int base = 0;
-        for (int q = 0; q < o; ++q) base += a.row_ptr[q * (N + 1) + N];
-        const int t0 = a.row_ptr[o * (N + 1) + i], t1 = a.row_ptr[o * (N + 1) + i + 1];
-        sm.rp[o][i] = base + t0;
-        if (i == N - 1) sm.rp[o][N] = base + t1;
-        for (int t = t0; t < t1; ++t) {
-            const int l = a.row_idx[o * NN + t];
-            const double2 x = a.ops[o * NN + i * N + l];
-            sm.ri[base + t] = (short)l;
-            sm.val[base + t] = o == 0 ? make_double2(x.y, -x.x) : x;
+        const int t0 = a.row_ptr[o * (N + 1) + i], len = a.row_ptr[o * (N + 1) + i + 1] - t0;
+        for (int k = 0; k < sm.mrow[o]; ++k) {
+            const int e = sm.obase[o] + k * N + i;
+            if (k < len) {
+                const int l = a.row_idx[o * NN + t0 + k];
+                const double2 x = a.ops[o * NN + i * N + l];
+                sm.ri[e] = (short)l;
+                sm.val[e] = o == 0 ? make_double2(x.y, -x.x) : x;
+            } else {
+                sm.ri[e] = (short)i;
+                sm.val[e] = make_double2(0.0, 0.0);
+            }
         }
     }
     // ---- links of this ADO, sorted by coupling mode ----
@@ -221,13 +239,6 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
         const int2 lk = __ldg(a.links + lbeg + t);
         ltmp[2 * t] = lk.x;
         ltmp[2 * t + 1] = lk.y;
-    }
-    for (int o = tid; o < M1; o += DF9_THREADS) {
-        int diag = 1;
-        for (int i = 0; i < N; ++i)
-            for (int t = a.row_ptr[o * (N + 1) + i]; t < a.row_ptr[o * (N + 1) + i + 1]; ++t)
-                if (a.row_idx[o * NN + t] != i) diag = 0;
-        sm.qdiag[o] = diag;
     }
     __syncthreads();
     // modes with a non-diagonal Q_m first: their S_m goes through shared memory, and the barrier of
@@ -322,22 +333,25 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
         for (int stage = 0; stage < 4; ++stage) {
             const unsigned need = 4u * (unsigned)step + (unsigned)stage + 1u;   // outputs the neighbours must have published
             const double2* yin = (stage == 0 ? da.P0 : (stage == 2 ? da.P2 : da.P1)) + pbase + tid;
-            // (A) the neighbours' flags: one lane of warp 0 per link (the other warps start on the own term)
-            if (warp == 0) {
-                const unsigned* bflags = da.flags + (sm.misc[6] / a.nmax) * a.nmax * DF9_FLAG_STRIDE;
-                for (int lp = lane; lp < nl; lp += 32)
-                    df9_wait_flag(bflags + (long long)sm.lnb[lp] * DF9_FLAG_STRIDE, need, da.ctrl, da.timeout_ns);
-                __syncwarp();
-                asm volatile("fence.acq_rel.gpu;\n" ::: "memory");   // acquire: the polls above were relaxed
-            }
-            DF9_MARK(0);
-            // (B) own term: W = (-iH - gamma/2) rho for both elements of the unit
+            // (A) own term: W = (-iH - gamma/2) rho for both elements of the unit (needs no neighbour)
             double2 wa = make_double2(0.0, 0.0), wb = wa;
             if (valid) {
                 const double2 oa = sm.rho[ia * DF9_NP + ja], ob = sm.rho[ib * DF9_NP + jb];
                 wa = make_double2(hg * oa.x, hg * oa.y);
-                if (hasb) wb = make_double2(hg * ob.x, hg * ob.y);
-                df9_rows2(wa, wb, sm.rp[0], ia, ib, hasb, sm.val, sm.ri, sm.rho, ja, jb);
+                wb = make_double2(hg * ob.x, hg * ob.y);
+                df9_rows2(wa, wb, sm.mrow[0], N, sm.val, sm.ri, sm.rho, ia, ib, ja, jb);
+            }
+            DF9_MARK(0);
+            // (B) the neighbours' flags: one lane of warp 0 per link - after warp 0's share of the own term,
+            // so that nothing but the barrier stands between the last flag and the fetch
+            if (warp == 0) {
+                const unsigned* bflags = da.flags + (sm.misc[6] / a.nmax) * a.nmax * DF9_FLAG_STRIDE;
+                for (int lp = lane; lp < nl; lp += 32) {
+                    const unsigned* f = bflags + (long long)sm.lnb[lp] * DF9_FLAG_STRIDE;
+                    df9_wait_flag(f, need, da.ctrl, da.timeout_ns);
+                    (void)ld_acquire_u32(f);   // the polls were relaxed: one acquire load of the final value
+                }
+                __syncwarp();
             }
             __syncthreads();   // the flags are acquired; rho may be overwritten by the epilogue from here on
             DF9_MARK(1);
@@ -345,19 +359,17 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
             int lp = 0;
             int pend = -1;   // non-diagonal mode whose S is in buf, products not taken yet (the readers of the
                              // previous stage are behind the end-of-stage barrier)
+            // S_A = sum alphaL x_A, S_B = sum alphaL x_B from four real sums (x = xr + i xi, alphaL = cr + i ci):
+            // A1 = sum cr xr, A2 = sum ci xi, A3 = sum cr xi, A4 = sum ci xr; pair units (x_A = x, x_B = conj x):
+            // S_A = (A1 - A2, A3 + A4), S_B = (A1 + A2, A4 - A3); diagonal units (x_A = xr, x_B = xi real):
+            // S_A = (A1, A4), S_B = (A3, A2) - the loop is the same for both, four independent chains
+            double A1 = 0.0, A2 = 0.0, A3 = 0.0, A4 = 0.0;
+            int k = 0;
 #pragma unroll 1
-            for (int k = 0; k < a.nmod; ++k) {
-                const int lend = sm.mend[k], m = sm.mord[k];
-                if (lend == lp) continue;
-                // S_A = sum alphaL x_A, S_B = sum alphaL x_B from four real sums (x = xr + i xi, alphaL = cr + i ci):
-                // A1 = sum cr xr, A2 = sum ci xi, A3 = sum cr xi, A4 = sum ci xr; pair units (x_A = x, x_B = conj x):
-                // S_A = (A1 - A2, A3 + A4), S_B = (A1 + A2, A4 - A3); diagonal units (x_A = xr, x_B = xi real):
-                // S_A = (A1, A4), S_B = (A3, A2) - the loop is the same for both, four independent chains
-                double A1 = 0.0, A2 = 0.0, A3 = 0.0, A4 = 0.0;
-#pragma unroll 1
-                for (; lp < lend; ++lp) {
-                    const int q = lp & (DF9_SLOTS - 1);
-                    if (q == 0) {
+            while (k < a.nmod) {
+                const int lend = sm.mend[k];
+                if (lp < lend) {
+                    if ((lp & (DF9_SLOTS - 1)) == 0) {
                         // next batch: thread u fetches ITS value of up to eight neighbours (thread-private
                         // places: no barrier around the staging slots)
                         const int cnt = min(DF9_SLOTS, nl - lp);
@@ -369,39 +381,66 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
                         cp_async_wait<0>();
                         DF9_MARK(2);
                     }
-                    const double2 cl = sm.lcf[lp];
-                    const double2 x = sm.slot[q][tid];
-                    A1 = fma(cl.x, x.x, A1);
-                    A2 = fma(cl.y, x.y, A2);
-                    A3 = fma(cl.x, x.y, A3);
-                    A4 = fma(cl.y, x.x, A4);
+                    const int stop = min(lend, (lp | (DF9_SLOTS - 1)) + 1);   // this mode's links inside the batch
+#pragma unroll 1
+                    for (; lp + 2 <= stop; lp += 2) {   // two links at a time: the loads of both before the sums
+                        const int q = lp & (DF9_SLOTS - 1);
+                        const double2 c0 = sm.lcf[lp], c1 = sm.lcf[lp + 1];
+                        const double2 x0 = sm.slot[q][tid], x1 = sm.slot[q + 1][tid];
+                        A1 = fma(c0.x, x0.x, A1);
+                        A2 = fma(c0.y, x0.y, A2);
+                        A3 = fma(c0.x, x0.y, A3);
+                        A4 = fma(c0.y, x0.x, A4);
+                        A1 = fma(c1.x, x1.x, A1);
+                        A2 = fma(c1.y, x1.y, A2);
+                        A3 = fma(c1.x, x1.y, A3);
+                        A4 = fma(c1.y, x1.x, A4);
+                    }
+                    if (lp < stop) {
+                        const double2 c0 = sm.lcf[lp];
+                        const double2 x0 = sm.slot[lp & (DF9_SLOTS - 1)][tid];
+                        A1 = fma(c0.x, x0.x, A1);
+                        A2 = fma(c0.y, x0.y, A2);
+                        A3 = fma(c0.x, x0.y, A3);
+                        A4 = fma(c0.y, x0.x, A4);
+                        ++lp;
+                    }
+                    if (lp < lend) continue;   // the mode goes on in the next batch
+                    DF9_MARK(3);
+                    // the mode is complete: Q_m S_m
+                    const int m = sm.mord[k];
+                    const double2 Sa = isdiag ? make_double2(A1, A4) : make_double2(A1 - A2, A3 + A4);
+                    const double2 Sb = isdiag ? make_double2(A3, A2) : make_double2(A1 + A2, A4 - A3);
+                    A1 = A2 = A3 = A4 = 0.0;
+                    if (sm.qdiag[1 + m]) {   // at most one entry per row, on the diagonal
+                        if (valid && sm.mrow[1 + m]) {
+                            const int ob = sm.obase[1 + m];
+                            cfma(wa, sm.val[ob + ia], Sa);
+                            cfma(wb, sm.val[ob + ib], Sb);
+                        }
+                    } else {
+                        if (pend >= 0) {   // finish the previous exchange before buf is overwritten
+                            __syncthreads();
+                            if (valid)
+                                df9_rows2(wa, wb, sm.mrow[1 + pend], N, sm.val + sm.obase[1 + pend], sm.ri + sm.obase[1 + pend],
+                                          sm.buf, ia, ib, ja, jb);
+                            __syncthreads();
+                        }
+                        if (valid) {
+                            sm.buf[ia * DF9_NP + ja] = Sa;
+                            if (hasb) sm.buf[ib * DF9_NP + jb] = Sb;
+                        }
+                        pend = m;
+                    }
+                    DF9_MARK(4);
                 }
-                const double2 Sa = isdiag ? make_double2(A1, A4) : make_double2(A1 - A2, A3 + A4);
-                const double2 Sb = isdiag ? make_double2(A3, A2) : make_double2(A1 + A2, A4 - A3);
-                DF9_MARK(3);
-                if (sm.qdiag[1 + m]) {   // at most one entry per row
-                    const int* rp = sm.rp[1 + m];
-                    if (valid) {
-                        if (rp[ia] < rp[ia + 1]) cfma(wa, sm.val[rp[ia]], Sa);
-                        if (hasb && rp[ib] < rp[ib + 1]) cfma(wb, sm.val[rp[ib]], Sb);
-                    }
-                } else {
-                    if (pend >= 0) {   // finish the previous exchange before buf is overwritten
-                        __syncthreads();
-                        if (valid) df9_rows2(wa, wb, sm.rp[1 + pend], ia, ib, hasb, sm.val, sm.ri, sm.buf, ja, jb);
-                        __syncthreads();
-                    }
-                    if (valid) {
-                        sm.buf[ia * DF9_NP + ja] = Sa;
-                        if (hasb) sm.buf[ib * DF9_NP + jb] = Sb;
-                    }
-                    pend = m;
-                }
-                DF9_MARK(4);
+                ++k;
             }
             if (pend >= 0) {
                 __syncthreads();
-                if (valid) df9_rows2(wa, wb, sm.rp[1 + pend], ia, ib, hasb, sm.val, sm.ri, sm.buf, ja, jb);
+                if (valid)
+                    df9_rows2(wa, wb, sm.mrow[1 + pend], N, sm.val + sm.obase[1 + pend], sm.ri + sm.obase[1 + pend], sm.buf, ia,
+                              ib, ja, jb);
             }
             DF9_MARK(4);
             // (D) k = W + W^dagger inside the thread, (E) stage update; the output goes to shared

@@ -211,11 +211,13 @@ static int try_dataflow_tma(pyqed_heom_plan* p) {
     const long long total = p->nmax * (long long)p->B;
     const int nsm = sm_count_of(p->device);
     if (total > 2ll * nsm || M1 > DF9_MAXOPS || maxl > DF9_MAXL) return -1;
-    int nnz = 0;
+    int nnz = 0;   // entries of the padded rows (every row of an operator as long as its longest)
     for (int o = 0; o < M1; ++o) {
         std::vector<short> a, b, c, d;
         sparsity(p, o, a, b, c, d);
-        nnz += a[N];
+        int longest = 0;
+        for (int i = 0; i < N; ++i) longest = std::max(longest, (int)a[i + 1] - (int)a[i]);
+        nnz += longest * N;
     }
     if (nnz > DF9_MAXNNZ) return -1;
     const int units = N * (N - 1) / 2 + (N + 1) / 2;   // element pairs + pairs of diagonal elements
@@ -253,7 +255,9 @@ static int try_dataflow_tma(pyqed_heom_plan* p) {
     da.order = order;
     da.dt = p->ctx_dt;
     da.nt = p->ctx_nt;
-    da.timeout_ns = 2000000000ull;
+    da.timeout_ns = 2000000000ull;   // a flag that does not arrive in 2 s poisons the result instead of hanging the GPU
+    if (const char* t = std::getenv("PYQED_HEOM_DATAFLOW_TIMEOUT_MS"))   // (compute-sanitizer runs are 100x slower)
+        da.timeout_ns = 1000000ull * std::strtoull(t, nullptr, 10);
     da.B = p->B;
     if (p->timing) {
         if (p->ev_used == p->ev.size()) {

@@ -1,6 +1,6 @@
 """Tiny propagation used under compute-sanitizer (racecheck is slow): the async row
 kernel, the plain-load row kernel, both resident kernels, the generic kernel, kernels 6 and 7
-(full and packed Hermitian storage) and the persistent dataflow kernel 8 on a 36-ADO
+(full and packed Hermitian storage) and the persistent dataflow kernels 8 and 9 on a 36-ADO
 hierarchy, two RK4 steps each, checked against the oracle."""
 import os
 import sys
@@ -21,7 +21,7 @@ bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode
 for tuning, opts in [(dict(kernel=3), {"resident": 0}), (dict(kernel=1), {"resident": 0}),
                      (dict(kernel=2), {"resident": 0}), (dict(kernel=0), {"resident": 1}),
                      (dict(kernel=0), {"resident": 4}), (dict(kernel=6), {"resident": 0}),
-                     (dict(kernel=7), {"resident": 0}), (dict(kernel=8), {})]:
+                     (dict(kernel=7), {"resident": 0}), (dict(kernel=8), {}), (dict(kernel=9), {})]:
     s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"], lmax=w["lmax"])
     s.tuning = dict(kernel=tuning["kernel"], warps_per_cta=0, use_graph=0)
     s.options = opts
