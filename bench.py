@@ -456,7 +456,11 @@ def run_gpu_arm(args):
         mine = torch.tensor([owned, halo_bytes, stage_ms / max(stage_n, 1)], dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = [dict(owned_ados=int(x[0]), halo_bytes_per_stage=int(x[1]), avg_stage_kernel_ms=float(x[2]))
+        # NVLink rate a rank's halo rows arrive with, averaged over a whole stage period (kernel +
+        # barrier): bytes its pool receives per stage / (step time / 4)
+        stage_s = ms * 1e-3 / K / 4.0
+        per_rank = [dict(owned_ados=int(x[0]), halo_bytes_per_stage=int(x[1]), avg_stage_kernel_ms=float(x[2]),
+                         nvlink_in_gbs=float(x[1]) / stage_s / 1e9)
                     for x in allr]
 
     tr = complex(np.trace(rho_end))

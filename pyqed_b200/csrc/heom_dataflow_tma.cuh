@@ -18,11 +18,14 @@
 //    and one double2 per unit (rho_ij, or the two real diagonal entries) is the whole state.  The
 //    stage outputs are published in this packed unit order - N(N-1)/2 + ceil(N/2) values, 8 KB
 //    instead of 16 KB for N = 32 - and a reader's thread u needs exactly value u of each neighbour.
-//  * neighbours: one lane per link waits for that neighbour's flag while the other warps already
-//    evaluate the own term; then every thread fetches ITS value of every neighbour with cp.async
-//    (LDGSTS.128, all links in flight, no registers) into thread-private places of eight staging
-//    slots - no barrier and no mbarrier around them.  (A first version used one cp.async.bulk per
-//    link: the per-lane issue loop with its generic->async proxy fence cost ~800 cycles per copy.)
+//  * neighbours: after its share of the own term, warp w (< 8) owns link w: its lane 0 waits for that
+//    neighbour's flag (relaxed polls, one acquire), then the warp copies the neighbour's packed matrix
+//    with cp.async (LDGSTS.128) into staging slot w - every link is fetched as soon as ITS flag is
+//    there, and only one CTA barrier stands between the last arrival and the link sums, in which
+//    thread u reads value u of every slot.  (Measured on the way: one cp.async.bulk per link cost
+//    ~800 cycles per copy - UBLKCP takes uniform operands, so per-lane copies become a serial loop,
+//    each with its generic->async proxy fence; every thread fetching its own values after a
+//    poll-all-flags + barrier was 5 % slower than the per-warp scheme.)
 //  * operators as compact sparse rows in shared memory (values pre-multiplied, no dense copies,
 //    no column lists); links sorted by coupling mode once.
 //  * placement: CTAs are numbered per SM after a one-off grid barrier; the first CTA of every SM
@@ -46,7 +49,7 @@ constexpr int DF9_MAXOPS = 8;      // 1 + coupling modes
 // Shared memory of a CTA: every section at a compile-time offset (the kernel is register bound -
 // with run-time section offsets ptxas re-derived them inside every loop)
 struct __align__(128) Df9Smem {
-    double2 slot[DF9_SLOTS][DF9_THREADS];   // packed neighbour matrices; value u only ever touched by thread u
+    double2 slot[DF9_SLOTS][DF9_THREADS];   // packed neighbour matrices: slot w filled by warp w, value u read by thread u
     double2 rho[DF9_NMAX * DF9_NP];         // own stage input, full matrix
     double2 buf[DF9_NMAX * DF9_NP];         // S_m of a non-diagonal mode
     double2 acc[DF9_THREADS];               // RK4 accumulator (thread-private)
@@ -332,7 +335,27 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
             const unsigned need = 4u * (unsigned)step + (unsigned)stage + 1u;   // outputs the neighbours must have published
-            const double2* yin = (stage == 0 ? da.P0 : (stage == 2 ? da.P2 : da.P1)) + pbase + tid;
+            const double2* yin = (stage == 0 ? da.P0 : (stage == 2 ? da.P2 : da.P1)) + pbase;
+            // warp w (< 8) owns link first + w of a batch: its lane 0 waits for that neighbour's flag, then the
+            // warp copies the neighbour's packed matrix into staging slot w - every link is fetched as soon as
+            // ITS flag is there, and only the CTA barrier stands between the last arrival and the sums
+            auto fetch_batch = [&](int first) {
+                const int lp = first + warp;
+                if (warp < DF9_SLOTS && lp < nl) {
+                    const int nb = sm.lnb[lp];
+                    if (lane == 0) {
+                        const unsigned* f = da.flags + ((sm.misc[6] / a.nmax) * a.nmax + nb) * DF9_FLAG_STRIDE;
+                        df9_wait_flag(f, need, da.ctrl, da.timeout_ns);
+                        (void)ld_acquire_u32(f);   // the polls were relaxed: one acquire load of the final value
+                    }
+                    __syncwarp();
+                    const double2* src = yin + (long long)nb * U;
+#pragma unroll 4
+                    for (int c = lane; c < U; c += 32) cp_async16(&sm.slot[warp][c], src + c);
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                }
+            };
             // (A) own term: W = (-iH - gamma/2) rho for both elements of the unit (needs no neighbour)
             double2 wa = make_double2(0.0, 0.0), wb = wa;
             if (valid) {
@@ -342,18 +365,9 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
                 df9_rows2(wa, wb, sm.mrow[0], N, sm.val, sm.ri, sm.rho, ia, ib, ja, jb);
             }
             DF9_MARK(0);
-            // (B) the neighbours' flags: one lane of warp 0 per link - after warp 0's share of the own term,
-            // so that nothing but the barrier stands between the last flag and the fetch
-            if (warp == 0) {
-                const unsigned* bflags = da.flags + (sm.misc[6] / a.nmax) * a.nmax * DF9_FLAG_STRIDE;
-                for (int lp = lane; lp < nl; lp += 32) {
-                    const unsigned* f = bflags + (long long)sm.lnb[lp] * DF9_FLAG_STRIDE;
-                    df9_wait_flag(f, need, da.ctrl, da.timeout_ns);
-                    (void)ld_acquire_u32(f);   // the polls were relaxed: one acquire load of the final value
-                }
-                __syncwarp();
-            }
-            __syncthreads();   // the flags are acquired; rho may be overwritten by the epilogue from here on
+            // (B) the neighbours' stage outputs (first batch), after this warp's share of the own term
+            fetch_batch(0);
+            __syncthreads();   // the staging slots are filled; rho may be overwritten by the epilogue from here on
             DF9_MARK(1);
             // (C) coupling terms, mode by mode: S_m summed link by link from the staging slots, then Q_m S_m
             int lp = 0;
@@ -369,16 +383,10 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
             while (k < a.nmod) {
                 const int lend = sm.mend[k];
                 if (lp < lend) {
-                    if ((lp & (DF9_SLOTS - 1)) == 0) {
-                        // next batch: thread u fetches ITS value of up to eight neighbours (thread-private
-                        // places: no barrier around the staging slots)
-                        const int cnt = min(DF9_SLOTS, nl - lp);
-                        if (valid) {
-#pragma unroll 4
-                            for (int c = 0; c < cnt; ++c) cp_async16(&sm.slot[c][tid], yin + (long long)sm.lnb[lp + c] * U);
-                        }
-                        cp_async_commit();
-                        cp_async_wait<0>();
+                    if ((lp & (DF9_SLOTS - 1)) == 0 && lp > 0) {   // more than eight links: next batch
+                        __syncthreads();   // the slots are consumed
+                        fetch_batch(lp);
+                        __syncthreads();
                         DF9_MARK(2);
                     }
                     const int stop = min(lend, (lp | (DF9_SLOTS - 1)) + 1);   // this mode's links inside the batch

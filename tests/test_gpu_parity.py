@@ -550,6 +550,27 @@ def test_dataflow_tma_kernel_repeated_runs_and_fallback():
     assert np.max(np.abs(np.asarray(out) - np.asarray(ref))) < 1e-12
 
 
+def test_dataflow_tma_kernel_handles_batches():
+    """Several trajectories (different Hermitian initial states) in one kernel-9 launch: 3 x 15 ADOs,
+    each against its own per-stage run of the generic kernel."""
+    g = golden("deom_polariton32_L2")
+    n, nt, dt = g["rho0"].shape[0], int(g["nt"]), float(g["dt"])
+    rng = np.random.default_rng(7)
+    rhos = []
+    for _ in range(3):
+        a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+        r = a @ a.conj().T
+        rhos.append(r / np.trace(r))
+    b = _solver_from(g)
+    _, out = b.run_batch(rhos, dt, nt)
+    assert b._plan.info("dataflow_tma_launches") == 1
+    for i, r in enumerate(rhos):
+        one = _solver_from(g)
+        one.tuning = dict(kernel=2, warps_per_cta=0, use_graph=0)
+        _, ref = one.run(r.copy(), dt, nt)
+        assert np.max(np.abs(out[i] - np.asarray(ref))) < 1e-13
+
+
 def test_dataflow_kernel_is_the_default_for_config4_and_handles_batches():
     g = golden("deom_polariton32_L6")
     s = _solver_from(g)
