@@ -13,5 +13,5 @@ PY
 }
 tr() { label=$1; shift; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --no-cpu --warmup 3 "$@" > "$out/bench_$label.json" 2> "$out/bench_$label.err"; show "$out/bench_$label.json" $label; }
 tr n2 --steps 20
-tr n2_forced_recut --steps 20 --rebalance 2
-tr n2_batch --workload aggregate7_K6_L6 --batch 64 --steps 700
+
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus 2 --no-cpu --warmup 3 --workload aggregate7_K6_L6 --batch 64 --steps 700 > "$out/bench_n2_batch.json" 2> "$out/bench_n2_batch.err"; tail -c 600 "$out/bench_n2_batch.json"
