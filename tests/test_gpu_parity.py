@@ -550,6 +550,26 @@ def test_dataflow_tma_kernel_repeated_runs_and_fallback():
     assert np.max(np.abs(np.asarray(out) - np.asarray(ref))) < 1e-12
 
 
+def test_dataflow_tma_kernel_long_run_agrees_with_kernel8():
+    """Config 4 as benchmarked (N = 32, 210 ADOs) over 1500 RK4 steps: kernel 9 (k = W + W^dagger, packed
+    units, S from four real sums) against kernel 8 (the reference's product order) on every final ADO;
+    rho_sys stays Hermitian with unit trace."""
+    from pyqed_b200 import workloads as W
+    from pyqed_b200.heom import DEOMSolver, Bath
+    w = W.polariton(lmax=6)
+    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+    out = {}
+    for kern in (9, 8):
+        s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"], lmax=w["lmax"])
+        s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
+        _, traj = s.run(w["rho0"].copy(), w["dt"], 1500)
+        assert s._plan.info("dataflow_tma_launches") == (1 if kern == 9 else 0)
+        out[kern] = (np.asarray(traj[-1]), s.ddos.copy())
+    assert np.max(np.abs(out[9][1] - out[8][1])) < 1e-12
+    rho = out[9][0]
+    assert abs(np.trace(rho) - 1) < 1e-12 and np.array_equal(rho, rho.conj().T)
+
+
 def test_dataflow_tma_kernel_handles_batches():
     """Several trajectories (different Hermitian initial states) in one kernel-9 launch: 3 x 15 ADOs,
     each against its own per-stage run of the generic kernel."""
