@@ -26,7 +26,7 @@ struct DataflowArgs {
     double2* SA;
     double2* SB;
     double2* ACC;
-    unsigned* flags;      // [B * nmax] stage counters, zero on entry
+    unsigned* flags;      // [B * nmax][DATAFLOW_FLAG_STRIDE] stage counters, zero on entry
     double dt;
     long long nt;
     int B;                // trajectories
@@ -42,6 +42,8 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 }
 
 constexpr int DATAFLOW_THREADS = 512;
+constexpr int DATAFLOW_FLAG_STRIDE = 32;   // one flag per 128-byte line: a flag is polled by up to 2K CTAs while its owner
+                                           // writes it (dense flags cost kernel 9 a fifth of its time)
 constexpr int DATAFLOW_EPT = 2;   // matrix elements per thread: N <= 32
 
 // Per ADO and stage: (A) wait for the neighbours' flags, (B) own tile -> shared memory, (C) per
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(DATAFLOW_THREADS, 2) stage_dataflow_kernel(con
                     lcf_s[2 * t] = a.coef[2 * ci];
                     lcf_s[2 * t + 1] = a.coef[2 * ci + 1];
                     // (A) the neighbours must have published the stage input this stage reads
-                    const unsigned* f = da.flags + (long long)b * a.nmax + lk.x;
+                    const unsigned* f = da.flags + ((long long)b * a.nmax + lk.x) * DATAFLOW_FLAG_STRIDE;
                     while (ld_acquire_u32(f) < g - 1u) __nanosleep(20);
                 }
                 __syncthreads();
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(DATAFLOW_THREADS, 2) stage_dataflow_kernel(con
                 __syncthreads();   // every element of this ADO's stage output is written ...
                 if (threadIdx.x == 0) {
                     __threadfence();
-                    st_release_u32(da.flags + (long long)b * a.nmax + slot, g);   // ... and published
+                    st_release_u32(da.flags + ((long long)b * a.nmax + slot) * DATAFLOW_FLAG_STRIDE, g);   // ... and published
                 }
             }
         }

@@ -305,13 +305,15 @@ static int try_dataflow(pyqed_heom_plan* p) {
     const long long total = p->nmax * (long long)p->B;
     // worth it while a stage is latency bound: a few ADOs per CTA at most
     if (!coop || cap < 1 || (p->kernel != 8 && total > 8 * cap)) return -1;
-    if ((size_t)total > p->flags_cap) {
+    const size_t nflag = (size_t)total * DATAFLOW_FLAG_STRIDE;
+    if (nflag > p->flags_cap) {
         if (p->d_flags) cudaFree(p->d_flags);
         p->d_flags = nullptr;
-        CU_TRY(cudaMalloc(&p->d_flags, sizeof(unsigned) * total));
-        p->flags_cap = (size_t)total;
+        p->flags_cap = 0;
+        CU_TRY(cudaMalloc(&p->d_flags, sizeof(unsigned) * nflag));
+        p->flags_cap = nflag;
     }
-    CU_TRY(cudaMemsetAsync(p->d_flags, 0, sizeof(unsigned) * total, p->stream));
+    CU_TRY(cudaMemsetAsync(p->d_flags, 0, sizeof(unsigned) * nflag, p->stream));
     DataflowArgs da;
     fill_stage_args(p, da.s);
     da.Y = p->arr(ARR_Y);
