@@ -6,9 +6,9 @@
 //
 // Same equations (generate_dot_element, pyqed/heom/deom.py:641-664; accumulator form of rk4,
 // deom.py:725-766).  What is different:
-//  * one CTA per (trajectory, ADO) for the whole run: y and the RK4 accumulator stay in
-//    registers, the own stage input stays in shared memory; global memory only carries the stage
-//    outputs that the neighbours read.
+//  * one CTA per (trajectory, ADO) for the whole run: y stays in a register, the RK4 accumulator
+//    and the own stage input in shared memory; global memory only carries the stage outputs that
+//    the neighbours read.
 //  * Hermitian form: with Hermitian operators, a real-exponent bath (eta_r = conj eta_l) and a
 //    Hermitian state the link coefficients obey alphaR = conj(alphaL), so
 //        d rho/dt = W + W^dagger,  W = (-iH - gamma/2) rho + sum_m Q_m S_m,  S_m = sum_{links of m} alphaL rho'
@@ -26,11 +26,14 @@
 //    ~800 cycles per copy - UBLKCP takes uniform operands, so per-lane copies become a serial loop,
 //    each with its generic->async proxy fence; every thread fetching its own values after a
 //    poll-all-flags + barrier was 5 % slower than the per-warp scheme.)
-//  * operators as compact sparse rows in shared memory (values pre-multiplied, no dense copies,
-//    no column lists); links sorted by coupling mode once.
-//  * placement: CTAs are numbered per SM after a one-off grid barrier; the first CTA of every SM
-//    takes the ADOs with the most links, second CTAs take the lightest ones - with 210 ADOs on
-//    148 SMs the 8-link ADOs run alone on their SM.
+//  * S_m of both elements of a unit from four real sums over the links (4 DFMA per link, the same
+//    loop for pair and diagonal units); operators as zero-padded, entry-major sparse rows in shared
+//    memory (values pre-multiplied, uniform trip count, no row pointers); links sorted by coupling
+//    mode once; one flag per 128-byte line.
+//  * placement: CTAs are numbered per SM after a one-off grid barrier; SMs that host one CTA take
+//    the ADOs with the most links, shared SMs the lighter ones - with 210 ADOs on 148 SMs the
+//    8-link ADOs run alone on their SM.
+// The kernel name keeps "tma" from its first version; the neighbour copies are plain cp.async now.
 // Every wait is bounded (globaltimer); a run that times out poisons Y with NaN instead of
 // hanging the GPU.
 #pragma once
