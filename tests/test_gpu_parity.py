@@ -570,6 +570,34 @@ def test_dataflow_tma_kernel_long_run_agrees_with_kernel8():
     assert abs(np.trace(rho) - 1) < 1e-12 and np.array_equal(rho, rho.conj().T)
 
 
+def test_dense_operators_at_n32_against_the_oracle():
+    """SURVEY 8d's stress variant of config 4: N = 32 with a dense random Hermitian H (seed 0) and the
+    polariton couplings.  Dense rows do not fit kernel 9's operator table, so the automatic choice is
+    kernel 8; both it and the per-stage generic kernel must match the oracle (test infrastructure, here
+    as the checker) on the trajectory and on every ADO."""
+    from oracle.deom_oracle import DeomOracle
+    from pyqed_b200 import workloads as W
+    from pyqed_b200.heom import DEOMSolver, Bath
+    w = W.polariton(lmax=2)
+    n = w["system"].shape[0]
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+    H = 0.1 * (a + a.conj().T) / 2 + w["system"]
+    nt, dt = 8, w["dt"]
+    o = DeomOracle(H, w["system_dipole"], w["coupling"], w["coupling_dipole"], w["expn"], w["etal"], w["etar"],
+                   w["etaa"], w["mode"], w["lmax"])
+    _, ref = o.run(w["rho0"], dt, nt)
+    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+    for kern in (0, 2):
+        s = DEOMSolver(H, w["system_dipole"], bath, w["coupling"], w["coupling_dipole"], lmax=w["lmax"])
+        s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
+        _, got = s.run(w["rho0"].copy(), dt, nt)
+        assert np.max(np.abs(np.asarray(got) - np.asarray(ref))) < TOL
+        assert np.max(np.abs(s.ddos - o.ddos)) < TOL
+        if kern == 0:
+            assert s._plan.info("dataflow_launches") == 1 and s._plan.info("dataflow_tma_launches") == 0
+
+
 def test_dataflow_tma_kernel_handles_batches():
     """Several trajectories (different Hermitian initial states) in one kernel-9 launch: 3 x 15 ADOs,
     each against its own per-stage run of the generic kernel."""
