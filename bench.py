@@ -44,6 +44,8 @@ WORKLOADS = {
     "fmo7_K7_L4": lambda: W.fmo(lmax=4, n_matsubara=0),
     "spin_boson_K2_L10": lambda: W.spin_boson(lmax=10),
     "polariton32_K4_L6": lambda: W.polariton(lmax=6),
+    # SURVEY 8d's stress variant of config 4: dense random Hermitian H (every operator row full)
+    "polariton32_dense_K4_L6": lambda: W.polariton(lmax=6, dense_h=True),
     "aggregate7_K6_L6": lambda: W.aggregate_2des(lmax=6),
 }
 DEFAULT_WORKLOAD = "fmo7_K21_L8"
@@ -503,7 +505,9 @@ def run_gpu_arm(args):
         bytes_per_launch = 256.0 * n * n * owned * (K if resident else 0.25)  # resident: one launch = K steps
         achieved = bytes_per_launch / (avg_launch_ms * 1e-3) / 1e9 if stage_n else None
         state_mb = nmax * n * n * 16 / 1e6
-        if plan.info("dataflow_tma_launches") > 0:
+        if plan.info("dataflow_dense_launches") > 0:
+            kname = "stage_dataflow_tma_kernel<DENSE_H>"
+        elif plan.info("dataflow_tma_launches") > 0:
             kname = "stage_dataflow_tma_kernel"
         elif plan.info("dataflow_launches") > 0:
             kname = "stage_dataflow_kernel"

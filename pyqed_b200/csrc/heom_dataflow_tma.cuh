@@ -142,6 +142,15 @@ __global__ void dataflow_order_kernel(const int* link_ptr, long long nmax, long 
     }
 }
 
+// DENSE_H: H has (nearly) full rows - the N = 32 stress variant of config 4.  Its rows do not
+// fit the operator table, and a row-per-unit product would read a different row in every lane.  Instead the
+// own term W_own = -i H rho is formed as a plain matrix product: warp w owns rows w and w + 16, lane = column,
+// so H[row][l] is one broadcast read for the whole warp and rho[l][:] one conflict-free row read; the product
+// goes through the (still unused) S tile to the units' owners.  H (16 KB) is copied with cp.async into the
+// last two staging slots at the end of every stage - they are free until the next stage's fetch - so the
+// copy hides behind the publication.  32768 complex FMAs per ADO and stage.  (A first version kept -iH in
+// the kernel's parameter space: 16 warps reading 32 different rows thrash the constant cache - 157 us/step.)
+template <bool DENSE_H>
 __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(const Dataflow9Args da) {
     extern __shared__ Df9Smem df9_smem[];   // typed: every access is a shared-space access at a constant offset
 #define sm df9_smem[0]
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
             for (int t = t0; t < t1; ++t)
                 if (a.row_idx[tid * NN + t] != i) diag = 0;
         }
-        sm.mrow[tid] = longest;
+        sm.mrow[tid] = (DENSE_H && tid == 0) ? 0 : longest;   // (dense H: not in the table)
         sm.qdiag[tid] = diag;
     }
     __syncthreads();
@@ -326,6 +335,13 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
     unsigned* const myflag = da.flags + (long long)sm.misc[6] * DF9_FLAG_STRIDE;
     if (tid == 0) st_release_u32(myflag, 1u);   // the packed initial state is published
 
+    // DENSE_H: H lives in the last two staging slots between the end of a stage and the next stage's fetch
+    double2* const Hs = &sm.slot[DF9_SLOTS - 2][0];
+    auto prefetch_h = [&]() {
+        for (int e = tid; e < NN; e += DF9_THREADS) cp_async16(Hs + e, a.ops + e);
+        cp_async_commit();
+    };
+    if (DENSE_H) prefetch_h();
 #ifdef DF9_PROFILE
     long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
 #define DF9_MARK(k) do { if (tid == 0) { const long long t_ = clock64(); pf[k] += t_ - pt; pt = t_; } } while (0)
@@ -361,7 +377,25 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
             };
             // (A) own term: W = (-iH - gamma/2) rho for both elements of the unit (needs no neighbour)
             double2 wa = make_double2(0.0, 0.0), wb = wa;
-            if (valid) {
+            if (DENSE_H) {
+                cp_async_wait<0>();
+                __syncthreads();   // H has arrived in the last two slots
+                // rows `warp` and `warp + 16` of H rho, column `lane`; -i H rho goes into the S tile
+                const int r0 = warp, r1 = warp + DF9_THREADS / 32;
+                if (lane < N && r0 < N) {
+                    double2 t0 = make_double2(0.0, 0.0), t1 = t0;
+                    const bool two = r1 < N;
+#pragma unroll 4
+                    for (int l = 0; l < N; ++l) {
+                        const double2 x = sm.rho[l * DF9_NP + lane];
+                        cfma(t0, Hs[r0 * N + l], x);
+                        if (two) cfma(t1, Hs[r1 * N + l], x);
+                    }
+                    sm.buf[r0 * DF9_NP + lane] = make_double2(t0.y, -t0.x);
+                    if (two) sm.buf[r1 * DF9_NP + lane] = make_double2(t1.y, -t1.x);
+                }
+                __syncthreads();   // every warp is done with H before links 6 and 7 are fetched over it
+            } else if (valid) {
                 const double2 oa = sm.rho[ia * DF9_NP + ja], ob = sm.rho[ib * DF9_NP + jb];
                 wa = make_double2(hg * oa.x, hg * oa.y);
                 wb = make_double2(hg * ob.x, hg * ob.y);
@@ -371,6 +405,15 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
             // (B) the neighbours' stage outputs (first batch), after this warp's share of the own term
             fetch_batch(0);
             __syncthreads();   // the staging slots are filled; rho may be overwritten by the epilogue from here on
+            if (DENSE_H) {
+                if (valid) {   // the units pick up their two elements of A rho
+                    const double2 oa = sm.rho[ia * DF9_NP + ja], ob = sm.rho[ib * DF9_NP + jb];
+                    const double2 pa = sm.buf[ia * DF9_NP + ja], pb = sm.buf[ib * DF9_NP + jb];
+                    wa = make_double2(fma(hg, oa.x, pa.x), fma(hg, oa.y, pa.y));
+                    wb = make_double2(fma(hg, ob.x, pb.x), fma(hg, ob.y, pb.y));
+                }
+                __syncthreads();   // the S tile is free for the coupling modes; rho for the epilogue
+            }
             DF9_MARK(1);
             // (C) coupling terms, mode by mode: S_m summed link by link from the staging slots, then Q_m S_m
             int lp = 0;
@@ -482,6 +525,7 @@ __global__ void __launch_bounds__(DF9_THREADS, 2) stage_dataflow_tma_kernel(cons
             DF9_MARK(5);
             __syncthreads();   // every value of this stage's output is written ...
             DF9_MARK(6);
+            if (DENSE_H) prefetch_h();   // the staging slots are free until the next stage's fetch
             if (tid == 0) st_release_u32(myflag, need + 1u);   // ... and published (release: bar.sync + cumulativity)
             DF9_MARK(7);
         }

@@ -211,24 +211,30 @@ static int try_dataflow_tma(pyqed_heom_plan* p) {
     const long long total = p->nmax * (long long)p->B;
     const int nsm = sm_count_of(p->device);
     if (total > 2ll * nsm || M1 > DF9_MAXOPS || maxl > DF9_MAXL) return -1;
-    int nnz = 0;   // entries of the padded rows (every row of an operator as long as its longest)
+    int nnz = 0, nnz_h = 0;   // entries of the padded rows (every row of an operator as long as its longest)
     for (int o = 0; o < M1; ++o) {
         std::vector<short> a, b, c, d;
         sparsity(p, o, a, b, c, d);
         int longest = 0;
         for (int i = 0; i < N; ++i) longest = std::max(longest, (int)a[i + 1] - (int)a[i]);
-        nnz += longest * N;
+        (o == 0 ? nnz_h : nnz) += longest * N;
     }
-    if (nnz > DF9_MAXNNZ) return -1;
+    // H with long rows: as a dense matrix in parameter space instead of the operator table
+    const bool dense_h = nnz_h + nnz > DF9_MAXNNZ || nnz_h > 8 * N;
+    if ((dense_h ? nnz : nnz + nnz_h) > DF9_MAXNNZ) return -1;
+    const void* kern = dense_h ? (const void*)stage_dataflow_tma_kernel<true> : (const void*)stage_dataflow_tma_kernel<false>;
     const int units = N * (N - 1) / 2 + (N + 1) / 2;   // element pairs + pairs of diagonal elements
     const size_t smem = sizeof(Df9Smem);               // > 227 KB / 3: at most two CTAs per SM (the placement counts on it)
     static_assert(sizeof(Df9Smem) <= 113 * 1024 && sizeof(Df9Smem) > 78 * 1024, "two CTAs per SM");
-    static PerDeviceOnce attr;
-    if (attr.need(p->device))
-        CU_TRY(cudaFuncSetAttribute(stage_dataflow_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    static PerDeviceOnce attr[2];
+    if (attr[dense_h].need(p->device))
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     int coop = 0, per_sm = 0;
     CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_dataflow_tma_kernel, DF9_THREADS, smem));
+    if (dense_h)
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_dataflow_tma_kernel<true>, DF9_THREADS, smem));
+    else
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_dataflow_tma_kernel<false>, DF9_THREADS, smem));
     const long long grid = total <= nsm ? total : 2ll * nsm;
     if (!coop || (long long)per_sm * nsm < grid) return -1;
     const size_t nflag = (size_t)total * DF9_FLAG_STRIDE;
@@ -271,8 +277,8 @@ static int try_dataflow_tma(pyqed_heom_plan* p) {
     dataflow_order_kernel<<<1, 512, 0, p->stream>>>(da.s.link_ptr, p->nmax, total, order);
     if (post_launch(p, "dataflow_order_kernel")) return 1;
     void* kargs[] = {&da};
-    CU_TRY(cudaLaunchCooperativeKernel((void*)stage_dataflow_tma_kernel, dim3((unsigned)grid), dim3(DF9_THREADS), kargs,
-                                       smem, p->stream));
+    CU_TRY(cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3(DF9_THREADS), kargs, smem, p->stream));
+    if (dense_h) p->dataflow_dense_launches++;
     if (post_launch(p, "stage_dataflow_tma_kernel")) return 1;
     if (p->timing) {
         CU_TRY(cudaEventRecord(p->ev[p->ev_used].second, p->stream));
@@ -654,6 +660,7 @@ int64_t pyqed_heom_get_info(pyqed_heom_plan* p, const char* name) {
     if (n == "packed_steps") return p->packed_steps;
     if (n == "dataflow_launches") return p->dataflow_launches;
     if (n == "dataflow_tma_launches") return p->dataflow_tma_launches;
+    if (n == "dataflow_dense_launches") return p->dataflow_dense_launches;
     if (n == "rk_scheme") return rk_scheme(p) ? 1 : 0;
     if (n == "stage_kernel") return stage_kernel_of(p);
     if (n == "nlinks") return p->nlinks;

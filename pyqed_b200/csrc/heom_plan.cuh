@@ -81,6 +81,7 @@ struct pyqed_heom_plan {
     long long packed_steps = 0;  // RK4 steps done by kernel 7 (packed Hermitian storage)
     long long dataflow_launches = 0;  // propagations done by kernel 8 (one persistent launch each)
     long long dataflow_tma_launches = 0;  // ... of which by kernel 9 (Hermitian, one CTA per ADO, TMA staging)
+    long long dataflow_dense_launches = 0;  // ... of which with H as a dense matrix in parameter space
     int opt_dataflow_tma = -1;        // kernel 9 where eligible (-1/1 on, 0 off: kernel 8)
     unsigned* d_df9 = nullptr;        // kernel 9: stage counters, control block, work order
     size_t df9_cap = 0;

@@ -122,7 +122,7 @@ def fmo(lmax=4, n_matsubara=0, dt=None, nt=1000, lam_cm=35.0, gam_cm=106.18,
 
 
 def polariton(lmax=6, nfock=16, wc=1.0, w0=1.0, g=0.1, lam=0.05, gam=1.0, beta=1.0,
-              dt=0.005, nt=500):
+              dt=0.005, nt=500, dense_h=False):
     """Config 4: two-level molecule x ``nfock`` photon states (N = 2 nfock),
     non-RWA dipole-gauge coupling i g mu (a - a^dag) + g^2/wc mu^2 as in the
     reference's ``Polariton.getH`` (``pyqed/polariton/cavity.py:608-678``);
@@ -135,6 +135,10 @@ def polariton(lmax=6, nfock=16, wc=1.0, w0=1.0, g=0.1, lam=0.05, gam=1.0, beta=1
     hcav = wc * (ad @ a)
     H = (np.kron(hmol, ic) + np.kron(s0, hcav) + 1j * g * np.kron(sx, a - ad)
          + g * g / wc * np.kron(sx @ sx, ic))
+    if dense_h:  # SURVEY 8d's stress variant: a dense random Hermitian perturbation (seed 0)
+        rng = np.random.default_rng(0)
+        r = rng.normal(size=H.shape) + 1j * rng.normal(size=H.shape)
+        H = H + 0.05 * (r + r.conj().T) / 2
     Q = np.stack([np.kron(sz, ic), np.kron(s0, a + ad)])
     e1, l1, r1, a1 = drude_exponents(lam, gam, beta, 1, 1)
     expn, etal, etar, etaa = (np.tile(x, 2) for x in (e1, l1, r1, a1))

@@ -572,9 +572,10 @@ def test_dataflow_tma_kernel_long_run_agrees_with_kernel8():
 
 def test_dense_operators_at_n32_against_the_oracle():
     """SURVEY 8d's stress variant of config 4: N = 32 with a dense random Hermitian H (seed 0) and the
-    polariton couplings.  Dense rows do not fit kernel 9's operator table, so the automatic choice is
-    kernel 8; both it and the per-stage generic kernel must match the oracle (test infrastructure, here
-    as the checker) on the trajectory and on every ADO."""
+    polariton couplings.  Dense rows do not fit kernel 9's operator table: the automatic choice is its
+    DENSE_H instantiation (A = -iH in parameter space, the own term as a matrix product by rows); it,
+    kernel 8 and the per-stage generic kernel must match the oracle (test infrastructure, here as the
+    checker) on the trajectory and on every ADO."""
     from oracle.deom_oracle import DeomOracle
     from pyqed_b200 import workloads as W
     from pyqed_b200.heom import DEOMSolver, Bath
@@ -588,14 +589,33 @@ def test_dense_operators_at_n32_against_the_oracle():
                    w["etaa"], w["mode"], w["lmax"])
     _, ref = o.run(w["rho0"], dt, nt)
     bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
-    for kern in (0, 2):
+    for kern in (0, 8, 2):
         s = DEOMSolver(H, w["system_dipole"], bath, w["coupling"], w["coupling_dipole"], lmax=w["lmax"])
         s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
         _, got = s.run(w["rho0"].copy(), dt, nt)
         assert np.max(np.abs(np.asarray(got) - np.asarray(ref))) < TOL
         assert np.max(np.abs(s.ddos - o.ddos)) < TOL
         if kern == 0:
+            assert s._plan.info("dataflow_dense_launches") == 1
+        if kern == 8:
             assert s._plan.info("dataflow_launches") == 1 and s._plan.info("dataflow_tma_launches") == 0
+
+
+def test_dense_h_instantiation_at_full_depth_agrees_with_kernel8():
+    """The dense-H variant of config 4 at depth 6 (210 ADOs on 148 SMs), 200 steps: kernel 9<DENSE_H>
+    against kernel 8 on every ADO."""
+    from pyqed_b200 import workloads as W
+    from pyqed_b200.heom import DEOMSolver, Bath
+    w = W.polariton(lmax=6, dense_h=True)
+    bath = Bath(expn=w["expn"], etal=w["etal"], etar=w["etar"], etaa=w["etaa"], mode=w["mode"])
+    out = {}
+    for kern in (0, 8):
+        s = DEOMSolver(w["system"], w["system_dipole"], bath, w["coupling"], w["coupling_dipole"], lmax=w["lmax"])
+        s.tuning = dict(kernel=kern, warps_per_cta=0, use_graph=0)
+        s.run(w["rho0"].copy(), w["dt"], 200)
+        assert s._plan.info("dataflow_dense_launches") == (1 if kern == 0 else 0)
+        out[kern] = s.ddos.copy()
+    assert np.max(np.abs(out[0] - out[8])) < 1e-12
 
 
 def test_dataflow_tma_kernel_handles_batches():
