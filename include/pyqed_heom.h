@@ -291,7 +291,8 @@ int pyqed_heom_set_tuning(pyqed_heom_plan* plan, int kernel, int warps_per_cta,
  * get_info reports resolved properties ("qdiag", "q_diagonal", "hermitian", "sym", "real_h", "off_link_ptr", "off_links" (byte offsets into the table buffer),
  * "array_bytes", "part_lo", "part_hi", "nlinks", "nmax", "slot0", "table_bytes", "sym_launches" (stage launches done by
  * kernel 6), "packed_steps" (RK4 steps done by kernel 7), "dataflow_launches" (propagations done by kernels 8 / 9),
- * "dataflow_tma_launches" (... by kernel 9)); -1 for an unknown name. */
+ * "dataflow_tma_launches" (... by kernel 9), "dataflow_dense_launches" (... by its dense-H instantiation)); -1 for an
+ * unknown name. */
 int pyqed_heom_set_option(pyqed_heom_plan* plan, const char* name, int value);
 int64_t pyqed_heom_get_info(pyqed_heom_plan* plan, const char* name);
 
